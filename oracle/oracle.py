@@ -75,6 +75,7 @@ class Oracle:
         L.oracle_direct_g_rhf.restype = _L
         L.oracle_direct_g_rhf.argtypes = [_P, _D, ctypes.POINTER(_D), ctypes.POINTER(_D), _L, _L, ctypes.POINTER(_L)]
         L.oracle_cart_norm.restype = _D; L.oracle_cart_norm.argtypes = [_I, _I]
+        L.oracle_basis_set_center.argtypes = [_P, _I, _D, _D, _D]
 
     def basis(self, patin_path):
         h = self.lib.oracle_basis_read(os.fsencode(patin_path))

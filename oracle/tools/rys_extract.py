@@ -424,12 +424,12 @@ def emit_cuda(res, path):
         f.write("// unomol_b200/csrc/rys_roots.cuh -- Rys quadrature roots and weights, 1..5 roots, FP64.\n/*\n" + HDR_NOTE +
                 " * Product code (host+device).  r[i] = t_i^2/(1-t_i^2), w[i] = weights, as in reference Rys.hpp:145-164.\n"
                 " * Horner steps are explicit fma() so the coefficients become FP64 immediates / constant-bank operands.\n */\n")
-        f.write("#pragma once\n#include <math.h>\n\n#ifdef __CUDACC__\n#define UNOMOL_HD __host__ __device__ __forceinline__\n#else\n#define UNOMOL_HD inline\n#endif\n\nnamespace unomol_b200 {\n\n")
+        f.write("#pragma once\n#include <math.h>\n\n#ifdef __CUDACC__\n#define UNOMOL_HD __host__ __device__ __forceinline__\n#else\n#define UNOMOL_HD inline\n#endif\n\nnamespace ub200 {\n\n")
         f.write("template <int N> UNOMOL_HD void rys_roots(double x, double *r, double *w);\n\n")
         for n in sorted(bodies):
             f.write("template <> UNOMOL_HD void rys_roots<%d>(double x, double *r, double *w) {\n" % n)
             f.write("\n".join(drop_unused_locals(bodies[n])) + "\n}\n\n")
-        f.write("}  // namespace unomol_b200\n")
+        f.write("}  // namespace ub200\n")
 
 
 def main():

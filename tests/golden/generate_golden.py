@@ -1,0 +1,119 @@
+#!/usr/bin/env python3
+"""tests/golden/generate_golden.py -- regenerates the committed fixtures from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference and oracle/_ref built by oracle/Makefile):
+    python tests/golden/generate_golden.py [--with-sf6]
+Writes, next to this script:
+  inputs/patin.dat.*      verbatim copies of the reference's test INPUT files (data, not source)
+  short_dat.json          the reference's own golden energies test/short.dat.* (E_iter0, E_final, dE)
+  ref_runs.json           fresh runs of oracle/_ref/Unomol (finite-field flag off): E_iter0, E_final, iterations
+  rys_grid.npz            roots/weights of the reference's Rys::root1..5 on a fixed X grid
+  eri_3g_h2o.npz          every stored unique integral of H2O/STO-3G (reference cache dump)
+  eri_631_nh3.npz, eri_631_co.npz   ditto (108 345 computed each)
+  g_<input>.npz           reference formGmatrix for seeded random P (RHF and UHF), several inputs
+  quartets_<input>.npz    reference calc_two_electron_ints_rys blocks for seeded random ordered shell quartets
+"""
+import json, os, re, shutil, subprocess, sys, tempfile
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle.oracle import Reference  # noqa: E402
+
+REFT = "/root/reference/test"
+INPUTS = ["3g.h2", "3g.h2o", "3g.hf", "3g.nh3", "3g.ch4", "3g.co", "3g.n2", "431.h2o", "431.nh3", "631.h2", "631.hf",
+          "631.h2o", "631.nh3", "631.co", "631.n2", "631.ch4", "b.dhdz", "c.dhdz", "o.dhdz", "f.dhdz", "d6s3p.h2",
+          "dh95.co2", "dh95.c2h2", "tz2p.sf6"]
+
+
+def run_unomol(name):
+    d = tempfile.mkdtemp()
+    try:
+        txt = open(os.path.join(REFT, "patin.dat." + name)).read().split("\n")
+        # 4th data line is 'int_flag[0] int_flag[1]' -> finite-field off so only the ground-state SCF runs
+        k = [i for i, l in enumerate(txt) if l.strip()][3]
+        txt[k] = " 0 0"
+        open(os.path.join(d, "patin.dat"), "w").write("\n".join(txt))
+        p = subprocess.run([Reference.UNOMOL], cwd=d, capture_output=True, text=True, timeout=3600)
+        s = [float(x) for x in open(os.path.join(d, "short.gs.out")).read().split()]
+        out = open(os.path.join(d, "scfout.gs.out")).read()
+        its = int(re.search(r"Final Iteration\s*=\s*(\d+)", out).group(1))
+        conv = "NOT_ REACHED" not in out
+        m = re.search(r"Time for Two Electrons Integrals = ([\d.e+-]+)", p.stderr)
+        m2 = re.search(r"SCF time = ([\d.e+-]+)", p.stderr)
+        ev = [float(x.split()[1]) for x in re.findall(r"^\s+\d+\s+[-\d.e+]+\s+\d+\s*$", out, flags=re.M)]
+        return dict(e_init=s[0], e_final=s[1], de=s[2], iterations=its, converged=conv,
+                    eri_seconds=float(m.group(1)) if m else None, scf_seconds=float(m2.group(1)) if m2 else None,
+                    orbital_energies=ev)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def main():
+    with_sf6 = "--with-sf6" in sys.argv
+    R = Reference()
+    os.makedirs(os.path.join(HERE, "inputs"), exist_ok=True)
+    for n in INPUTS:
+        shutil.copyfile(os.path.join(REFT, "patin.dat." + n), os.path.join(HERE, "inputs", "patin.dat." + n))
+    short = {}
+    for f in sorted(os.listdir(REFT)):
+        if f.startswith("short.dat."):
+            short[f[len("short.dat."):]] = [float(x) for x in open(os.path.join(REFT, f)).read().split()]
+    json.dump(short, open(os.path.join(HERE, "short_dat.json"), "w"), indent=1)
+    # Rys grid
+    xs = np.concatenate([np.linspace(0.0, 60.0, 1201), [1e-9, 3e-7, 3.1e-7, 15.05, 16.0, 18.0, 20.0, 25.0, 28.0, 33.0,
+                                                        33.01, 40.0, 40.01, 47.01, 53.01, 59.01, 80.0, 500.0]])
+    rys = {"x": xs}
+    for n in range(1, 6):
+        rr = np.zeros((len(xs), n)); ww = np.zeros((len(xs), n))
+        for i, x in enumerate(xs):
+            rr[i], ww[i] = R.rys_roots(n, x)
+        rys["r%d" % n] = rr; rys["w%d" % n] = ww
+    np.savez_compressed(os.path.join(HERE, "rys_grid.npz"), **rys)
+    # stored integral lists
+    for n in ["3g.h2o", "631.nh3", "631.co"]:
+        h = R.basis(os.path.join(REFT, "patin.dat." + n)); t = R.tints(h)
+        vals, ijkl = R.tints_dump(t)
+        np.savez_compressed(os.path.join(HERE, "eri_%s.npz" % n.replace(".", "_")), vals=vals, ijkl=ijkl)
+        R.tints_destroy(t); R.basis_close(h)
+    # G matrices for seeded random P, and random quartet blocks
+    for n in ["3g.h2o", "631.nh3", "631.co", "b.dhdz", "dh95.co2", "dh95.c2h2"] + (["tz2p.sf6"] if with_sf6 else []):
+        h = R.basis(os.path.join(REFT, "patin.dat." + n))
+        nbf = R.lib.ref_basis_norb(h); no2 = nbf * (nbf + 1) // 2
+        rng = np.random.default_rng(12345)
+        P = rng.standard_normal(no2); PB = rng.standard_normal(no2)
+        t = R.tints(h)
+        G, _ = R.form_g_rhf(t, P)
+        GA, GB, _ = R.form_g_uhf(t, P, PB)
+        S, T, H = R.one_electron(h)
+        np.savez_compressed(os.path.join(HERE, "g_%s.npz" % n.replace(".", "_")), P=P, PB=PB, G=G, GA=GA, GB=GB, S=S, T=T, H=H)
+        R.tints_destroy(t)
+        shells = R.basis_shells(h)
+        ns = len(shells)
+        nq = 60 if nbf > 50 else 120
+        quart = rng.integers(0, ns, size=(nq, 4))
+        blocks = []
+        for (i, j, k, l) in quart:
+            nc = lambda s: (shells[s][1] + 1) * (shells[s][1] + 2) // 2
+            blocks.append(R.quartet_block(h, (nc(i), nc(j), nc(k), nc(l)), int(i), int(j), int(k), int(l)).ravel())
+        np.savez_compressed(os.path.join(HERE, "quartets_%s.npz" % n.replace(".", "_")), quartets=quart,
+                            offsets=np.cumsum([0] + [len(b) for b in blocks]), values=np.concatenate(blocks))
+        R.basis_close(h)
+    # fresh reference SCF runs
+    runs = {}
+    path = os.path.join(HERE, "ref_runs.json")
+    if os.path.exists(path):
+        runs = json.load(open(path))
+    for n in INPUTS:
+        if n == "tz2p.sf6" and not with_sf6:
+            continue
+        if n in runs:
+            continue
+        runs[n] = run_unomol(n)
+        print(n, runs[n]["e_final"], runs[n]["iterations"], flush=True)
+        json.dump(runs, open(path, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

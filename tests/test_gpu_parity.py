@@ -1,0 +1,186 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI (unomol_b200.capi -> libunomol_b200.so), against the
+CPU oracle on the same inputs and against the committed reference fixtures.
+
+Tolerances are BASELINE.json's: per-quartet ERIs within 1e-12 absolute; G within 1e-12 relative to max|G|
+(G sums up to ~nbf^2 integrals); SCF energies within 1e-9 Eh (tests/test_gpu_scf.py)."""
+import os
+import numpy as np
+import pytest
+from conftest import GOLDEN, golden_input
+
+pytestmark = pytest.mark.gpu
+
+ERI_TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from unomol_b200 import capi as c
+    return c
+
+
+def _handle(capi, name, **kw):
+    from unomol_b200.basis import Basis
+    b = Basis.from_patin(golden_input(name))
+    return b, capi.Handle(b, **kw)
+
+
+@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "b.dhdz", "dh95.co2", "dh95.c2h2", "tz2p.sf6"])
+def test_quartet_blocks_vs_reference_fixture(capi, name):
+    path = os.path.join(GOLDEN, "quartets_%s.npz" % name.replace(".", "_"))
+    g = np.load(path)
+    b, h = _handle(capi, name)
+    worst = 0.0
+    for q, (i, j, k, l) in enumerate(g["quartets"]):
+        ref = g["values"][g["offsets"][q]:g["offsets"][q + 1]]
+        blk = h.eri_quartet(int(i), int(j), int(k), int(l)).ravel()
+        worst = max(worst, np.max(np.abs(blk - ref)))
+    assert worst < ERI_TOL, worst
+
+
+def test_every_shell_quartet_h2o_sto3g_vs_oracle(capi, oracle):
+    b, h = _handle(capi, "3g.h2o")
+    ob = oracle.basis(golden_input("3g.h2o"))
+    ns = b.nshell
+    worst = 0.0
+    for i in range(ns):
+        for j in range(ns):
+            for k in range(ns):
+                for l in range(ns):
+                    worst = max(worst, np.max(np.abs(h.eri_quartet(i, j, k, l) - oracle.quartet_block(ob, i, j, k, l))))
+    assert worst < ERI_TOL, worst
+
+
+@pytest.mark.parametrize("name", ["dh95.co2", "tz2p.sf6"])
+def test_random_d_shell_quartets_vs_oracle(capi, oracle, name):
+    """covers every class up to (dd|dd) with all orderings of the four shells"""
+    b, h = _handle(capi, name)
+    ob = oracle.basis(golden_input(name))
+    rng = np.random.default_rng(7)
+    by_l = {l: [s for s in range(b.nshell) if b.lv[s] == l] for l in (0, 1, 2)}
+    worst = 0.0
+    for la in (0, 1, 2):
+        for lb in (0, 1, 2):
+            for lc in (0, 1, 2):
+                for ld in (0, 1, 2):
+                    for _ in range(2):
+                        i, j, k, l = (int(rng.choice(by_l[x])) for x in (la, lb, lc, ld))
+                        d = np.max(np.abs(h.eri_quartet(i, j, k, l) - oracle.quartet_block(ob, i, j, k, l)))
+                        worst = max(worst, d)
+    assert worst < ERI_TOL, worst
+
+
+@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "631.co"])
+def test_unique_integral_list_vs_reference_cache(capi, name):
+    """all stored integrals of the reference (|val| > 1e-14), same records in the same order"""
+    g = np.load(os.path.join(GOLDEN, "eri_%s.npz" % name.replace(".", "_")))
+    b, h = _handle(capi, name)
+    # thresholding at 1e-14 can flip for values within rounding of the threshold: compare as dense maps
+    vals, ijkl = h.dump_eris(0.0)
+    got = {tuple(r): v for r, v in zip(ijkl.tolist(), vals)}
+    worst = 0.0
+    for r, v in zip(g["ijkl"].tolist(), g["vals"]):
+        worst = max(worst, abs(got.get(tuple(r), 0.0) - v))
+    assert worst < ERI_TOL, worst
+    vals14, ijkl14 = h.dump_eris(1e-14)
+    assert abs(len(vals14) - len(g["vals"])) <= 2      # borderline |val| ~ 1e-14 records only
+    # everything the reference dropped is below its threshold here too
+    ref_keys = set(map(tuple, g["ijkl"].tolist()))
+    extra = [abs(v) for r, v in got.items() if r not in ref_keys]
+    assert not extra or max(extra) < 1e-14 + ERI_TOL
+
+
+@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "631.co", "b.dhdz", "dh95.co2", "dh95.c2h2", "tz2p.sf6"])
+def test_g_matrices_vs_reference_fixture(capi, name):
+    g = np.load(os.path.join(GOLDEN, "g_%s.npz" % name.replace(".", "_")))
+    b, h = _handle(capi, name)
+    h.set_option("schwarz_tau", 0.0)        # no screening: the reference has none
+    G = h.fock_rhf(g["P"])
+    GA, GB = h.fock_uhf(g["P"], g["PB"])
+    scale = max(1.0, np.max(np.abs(g["G"])))
+    assert np.max(np.abs(G - g["G"])) < 1e-12 * scale
+    assert np.max(np.abs(GA - g["GA"])) < 1e-12 * scale
+    assert np.max(np.abs(GB - g["GB"])) < 1e-12 * scale
+    # default Schwarz screening (tau = 1e-12) must stay inside the same tolerance
+    h.set_option("schwarz_tau", 1e-12)
+    G2 = h.fock_rhf(g["P"])
+    assert np.max(np.abs(G2 - g["G"])) < 2e-12 * scale * max(1.0, np.max(np.abs(g["P"])))
+
+
+def test_g_accumulates_like_the_reference(capi):
+    """formGmatrix does G += ... (reference RHF.hpp:89-93: the caller zeroes G)"""
+    g = np.load(os.path.join(GOLDEN, "g_631_nh3.npz"))
+    b, h = _handle(capi, "631.nh3")
+    G0 = np.full(b.no2, 0.25)
+    G = h.fock_rhf(g["P"], G0.copy())
+    assert np.max(np.abs(G - 0.25 - g["G"])) < 1e-12 * max(1.0, np.max(np.abs(g["G"])))
+
+
+def test_linearity_and_spin_consistency(capi):
+    """size-independent properties: G is linear in P; UHF with PA=PB=P gives GA=GB=G_RHF(P)"""
+    b, h = _handle(capi, "dh95.c2h2")
+    rng = np.random.default_rng(11)
+    P1 = rng.standard_normal(b.no2); P2 = rng.standard_normal(b.no2)
+    G1 = h.fock_rhf(P1); G2 = h.fock_rhf(P2); G12 = h.fock_rhf(2.0 * P1 - 0.5 * P2)
+    s = np.max(np.abs(G12))
+    assert np.max(np.abs(G12 - (2.0 * G1 - 0.5 * G2))) < 1e-12 * s
+    GA, GB = h.fock_uhf(P1, P1)
+    assert np.max(np.abs(GA - G1)) < 1e-12 * s and np.max(np.abs(GB - G1)) < 1e-12 * s
+
+
+def test_start_shell_matches_oracle(capi, oracle):
+    """start_shell > 0 (reference TwoElectronInts.cpp:541; used by findPolarizationPotential)"""
+    name = "631.h2o"
+    from unomol_b200.basis import Basis
+    b = Basis.from_patin(golden_input(name))
+    ob = oracle.basis(golden_input(name))
+    start = b.nshell - 3
+    h = capi.Handle(b, start_shell=start)
+    h.set_option("schwarz_tau", 0.0)
+    rng = np.random.default_rng(2)
+    P = rng.standard_normal(b.no2)
+    vals, ijkl, _ = oracle.unique_eris(ob, start_shell=start)
+    Gref = oracle.form_g_rhf(vals, ijkl, P)
+    G = h.fock_rhf(P)
+    assert np.max(np.abs(G - Gref)) < 1e-12 * max(1.0, np.max(np.abs(Gref)))
+
+
+def test_two_rank_partials_sum_to_full(capi):
+    """the multi-GPU split: partial G's of rank 0/2 and 1/2 on one device add up to the 1-rank G"""
+    from unomol_b200.basis import Basis
+    b = Basis.from_patin(golden_input("dh95.co2"))
+    rng = np.random.default_rng(4)
+    P = rng.standard_normal(b.no2)
+    full = capi.Handle(b).fock_rhf(P)
+    parts = [capi.Handle(b, rank=r, nranks=2).fock_rhf(P) for r in range(2)]
+    assert np.max(np.abs(parts[0] + parts[1] - full)) < 1e-12 * np.max(np.abs(full))
+    assert np.max(np.abs(parts[0])) > 0 and np.max(np.abs(parts[1])) > 0
+
+
+def test_set_geometry_recalculates(capi, oracle):
+    from unomol_b200.basis import Basis
+    b = Basis.from_patin(golden_input("631.h2o"))
+    h = capi.Handle(b)
+    h.set_option("schwarz_tau", 0.0)
+    xyz = b.xyz.copy(); xyz[0] += [0.1, -0.2, 0.05]
+    h.set_geometry(xyz)
+    ob = oracle.basis(golden_input("631.h2o"))
+    oracle.lib.oracle_basis_set_center(ob.h, 0, *[float(v) for v in xyz[0]])
+    rng = np.random.default_rng(9)
+    P = rng.standard_normal(b.no2)
+    vals, ijkl, _ = oracle.unique_eris(ob)
+    Gref = oracle.form_g_rhf(vals, ijkl, P)
+    assert np.max(np.abs(h.fock_rhf(P) - Gref)) < 1e-12 * max(1.0, np.max(np.abs(Gref)))
+
+
+def test_schwarz_bounds_bound_the_integrals(capi, oracle):
+    b, h = _handle(capi, "631.nh3")
+    ob = oracle.basis(golden_input("631.nh3"))
+    Q = h.schwarz()
+    ns = b.nshell
+    rng = np.random.default_rng(1)
+    for _ in range(40):
+        i, j, k, l = (int(x) for x in rng.integers(0, ns, 4))
+        blk = oracle.quartet_block(ob, i, j, k, l)
+        qa = Q[max(i, j) * (max(i, j) + 1) // 2 + min(i, j)]; qb = Q[max(k, l) * (max(k, l) + 1) // 2 + min(k, l)]
+        assert np.max(np.abs(blk)) <= qa * qb * (1 + 1e-9) + 1e-13

@@ -1,0 +1,773 @@
+// unomol_b200/csrc/engine.cu -- host engine + C ABI of libunomol_b200.so (see include/unomol_b200.h).
+//
+// Replaces the reference's TwoElectronInts (TwoElectronInts.hpp:79-110, TwoElectronInts.cpp:511-869) with an
+// integral-direct GPU Fock build:
+//   create / set_geometry : shell-pair + primitive-pair tables (the quantities the reference recomputes per
+//                           quartet at TwoElectronInts.cpp:439-460), pairs binned by angular class,
+//                           Schwarz bounds from the diagonal quartets on the GPU, pairs sorted by bound,
+//                           per-bra ket prefix counts for the Q_ab*Q_cd >= tau test;
+//   fock_rhf / fock_uhf   : P packed -> square, 21 class launches of the fused ERI+digestion kernel,
+//                           symmetrise + pack -> G.
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <numeric>
+#include "engine.h"
+
+using namespace ub200;
+
+#define CUDA_TRY(h, expr)                                                                        \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            (h)->last_error = std::string(#expr) + ": " + cudaGetErrorString(_e);                \
+            fprintf(stderr, "unomol_b200: CUDA error %s\n", (h)->last_error.c_str());            \
+            return UNOMOL_E_CUDA;                                                                \
+        }                                                                                        \
+    } while (0)
+
+namespace ub200 {
+
+// bra-class launchers (eri_class_<n>.cu)
+#define DECL_BRA(a, b)                                                                                         \
+    cudaError_t launch_bra_class_##a##b(int ket_class, const ClassTask &task, int mode, int grid, cudaStream_t); \
+    int groups_bra_class_##a##b(int ket_class);
+DECL_BRA(0, 0) DECL_BRA(1, 0) DECL_BRA(1, 1) DECL_BRA(2, 0) DECL_BRA(2, 1) DECL_BRA(2, 2)
+#undef DECL_BRA
+
+cudaError_t launch_quartet_class(int cb, int ck, const ClassTask &task, int mode, int grid, cudaStream_t s) {
+    switch (cb) {
+        case 0: return launch_bra_class_00(ck, task, mode, grid, s);
+        case 1: return launch_bra_class_10(ck, task, mode, grid, s);
+        case 2: return launch_bra_class_11(ck, task, mode, grid, s);
+        case 3: return launch_bra_class_20(ck, task, mode, grid, s);
+        case 4: return launch_bra_class_21(ck, task, mode, grid, s);
+        case 5: return launch_bra_class_22(ck, task, mode, grid, s);
+    }
+    return cudaErrorInvalidValue;
+}
+int class_groups_per_cta(int cb, int ck) {
+    switch (cb) {
+        case 0: return groups_bra_class_00(ck);
+        case 1: return groups_bra_class_10(ck);
+        case 2: return groups_bra_class_11(ck);
+        case 3: return groups_bra_class_20(ck);
+        case 4: return groups_bra_class_21(ck);
+        case 5: return groups_bra_class_22(ck);
+    }
+    return 1;
+}
+
+// algorithmic FLOPs of the reference's Rys algorithm per PRIMITIVE quartet.
+double model_flops_per_primitive_quartet(int la, int lb, int lc, int ld) {
+    const int La = la + lb, Lb = lc + ld, n = (La + Lb) / 2 + 1;
+    auto mx = [](int a) { return a > 0 ? a : 0; };
+    double R = (La < 2 && Lb < 2) ? 2.0 : 2.0 + 10.0 * mx(Lb - 1) + mx(La - 1) * (8.0 + 7.0 * mx(Lb - 1));
+    auto S = [](int a, int b) { return 4.0 * (a + 1) * (b + 1) + 2.0 * (a + 1); };
+    double F = 40.0 + (48.0 * n + 10.0) + 3.0 * n * R;
+    auto comps = [](int l, std::vector<std::array<int, 3>> &v) {
+        for (int lx = l; lx >= 0; --lx)
+            for (int ly = l - lx; ly >= 0; --ly) v.push_back({lx, ly, l - lx - ly});
+    };
+    std::vector<std::array<int, 3>> cb, cd;
+    comps(lb, cb);
+    comps(ld, cd);
+    const int na = (la + 1) * (la + 2) / 2, nc = (lc + 1) * (lc + 2) / 2;
+    double comp = 0.0;
+    for (auto &b : cb)
+        for (auto &d : cd) comp += n * (S(b[0], d[0]) + S(b[1], d[1]) + S(b[2], d[2]) + 4.0) + 2.0;
+    F += comp * na * nc;
+    return F;
+}
+
+// ---------------------------------------------------------------- small utility kernels
+__global__ void unpack_density_kernel(const double *__restrict__ PA, const double *__restrict__ PB, int n, int nspin,
+                                      double *__restrict__ PJ, double *__restrict__ PK0, double *__restrict__ PK1) {
+    // packed lower-triangular -> square symmetric.  RHF: PJ = 4P (G = 2J-K with J,K symmetrised from half
+    // accumulators), UHF: PJ = 2(PA+PB).
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t nn = (size_t)n * n;
+    if (idx >= nn) return;
+    int i = (int)(idx / n), j = (int)(idx % n);
+    int a = i > j ? i : j, b = i > j ? j : i;
+    size_t p = (size_t)a * (a + 1) / 2 + b;
+    double pa = PA[p];
+    if (nspin == 1) {
+        PJ[idx] = 4.0 * pa;
+        PK0[idx] = pa;
+    } else {
+        double pb = PB[p];
+        PJ[idx] = 2.0 * (pa + pb);
+        PK0[idx] = pa;
+        PK1[idx] = pb;
+    }
+}
+
+__global__ void pack_fock_kernel(const double *__restrict__ J, const double *__restrict__ K0,
+                                 const double *__restrict__ K1, int n, int nspin, double *__restrict__ G0,
+                                 double *__restrict__ G1) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t no2 = (size_t)n * (n + 1) / 2;
+    if (idx >= no2) return;
+    // invert idx = i(i+1)/2 + j
+    int i = (int)floor((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+    while ((size_t)i * (i + 1) / 2 > idx) --i;
+    while ((size_t)(i + 1) * (i + 2) / 2 <= idx) ++i;
+    int j = (int)(idx - (size_t)i * (i + 1) / 2);
+    size_t ij = (size_t)i * n + j, ji = (size_t)j * n + i;
+    double jj = J[ij] + J[ji];
+    G0[idx] = jj - (K0[ij] + K0[ji]);
+    if (nspin == 2) G1[idx] = jj - (K1[ij] + K1[ji]);
+}
+
+}  // namespace ub200
+
+// ---------------------------------------------------------------- pair tables
+static void free_pairs(unomol_b200 *h) {
+    for (int c = 0; c < NPAIRCLASS; ++c) {
+        if (h->cls[c].d_pairs) cudaFree(h->cls[c].d_pairs);
+        h->cls[c].d_pairs = nullptr;
+        h->cls[c].pairs.clear();
+        h->cls[c].n = 0;
+    }
+    if (h->d_prims) cudaFree(h->d_prims);
+    h->d_prims = nullptr;
+    for (auto &p : h->plans)
+        if (p.d_ket_count) cudaFree(p.d_ket_count);
+    h->plans.clear();
+    h->pairs_ready = false;
+}
+
+static int build_plans(unomol_b200 *h);
+
+// Shell-pair + primitive-pair precompute (host), Schwarz bounds (GPU), sort, upload.
+static int build_pairs(unomol_b200 *h) {
+    free_pairs(h);
+    cudaEventRecord(h->ev2, h->stream);
+    const HostBasis &B = h->basis;
+    const int ns = B.nshell;
+    h->pair_cls.assign((size_t)ns * (ns + 1) / 2, -1);
+    h->pair_pos.assign((size_t)ns * (ns + 1) / 2, -1);
+    h->h_prims.clear();
+    // pass 1: every primitive pair of every shell pair; track the global maximum of u for the exact prune
+    struct TmpPair { ShellPair sp; std::vector<PrimPair> pp; int cls; };
+    std::vector<TmpPair> tmp;
+    tmp.reserve((size_t)ns * (ns + 1) / 2);
+    double umax = 0.0;
+    for (int i = 0; i < ns; ++i)
+        for (int j = 0; j <= i; ++j) {
+            // first shell = higher l (reference swaps so that l1 >= l2, TwoElectronInts.cpp:563-580)
+            int a = i, b = j;
+            if (B.lv[i] < B.lv[j]) { a = j; b = i; }
+            TmpPair t;
+            ShellPair &sp = t.sp;
+            const double *A = &B.xyz[3 * B.cen[a]], *Bc = &B.xyz[3 * B.cen[b]];
+            double ab2 = 0.0;
+            for (int x = 0; x < 3; ++x) {
+                sp.A[x] = A[x];
+                sp.AB[x] = A[x] - Bc[x];
+                ab2 += sp.AB[x] * sp.AB[x];
+            }
+            sp.Q = 0.0;
+            sp.offa = B.off[a]; sp.offb = B.off[b];
+            sp.sha = a; sp.shb = b;
+            sp.pairid = i * (i + 1) / 2 + j;
+            sp.pad = 0;
+            t.cls = pair_class_id(B.lv[a], B.lv[b]);
+            const bool same = (a == b);   // the reference's pointer test al1==al2 (TwoElectronInts.cpp:444)
+            for (int ia = 0; ia < B.npr[a]; ++ia) {
+                const double axp = B.alpha[B.poff[a] + ia], c1 = B.coef[B.poff[a] + ia];
+                const int jend = same ? ia + 1 : B.npr[b];
+                for (int ib = 0; ib < jend; ++ib) {
+                    const double bxp = B.alpha[B.poff[b] + ib], c2 = B.coef[B.poff[b] + ib];
+                    PrimPair pp;
+                    pp.p = axp + bxp;
+                    pp.ip = 1.0 / pp.p;
+                    const double s12 = std::exp(-axp * bxp * ab2 * pp.ip);
+                    for (int x = 0; x < 3; ++x) {
+                        pp.P[x] = (axp * A[x] + bxp * Bc[x]) * pp.ip;
+                        pp.PA[x] = pp.P[x] - A[x];
+                    }
+                    pp.u = s12 * pp.ip;
+                    pp.c = c1 * c2 * ((same && ia != ib) ? 2.0 : 1.0);
+                    if (pp.u > umax) umax = pp.u;
+                    t.pp.push_back(pp);
+                }
+            }
+            tmp.push_back(std::move(t));
+        }
+    // pass 2: exact prune.  A primitive quartet is skipped by the reference when
+    // sr = SR*u12*u34/sqrt(p+q) < prim_cut (TwoElectronInts.cpp:478-479); since u34 <= umax and
+    // sqrt(p+q) > sqrt(p12), a primitive pair with SR*u12*umax/sqrt(p12) < prim_cut can never survive.
+    long long nprim = 0, nkept = 0;
+    for (auto &t : tmp) {
+        std::vector<PrimPair> keep;
+        for (auto &pp : t.pp)
+            if (!(SR_TERM * pp.u * umax / std::sqrt(pp.p) * 1.0000001 < h->prim_cut)) keep.push_back(pp);
+        if (keep.empty()) continue;
+        t.sp.prim_off = (int)h->h_prims.size();
+        t.sp.nprim = (int)keep.size();
+        h->h_prims.insert(h->h_prims.end(), keep.begin(), keep.end());
+        h->cls[t.cls].pairs.push_back(t.sp);
+        nprim += keep.size();
+        ++nkept;
+    }
+    tmp.clear();
+    tmp.shrink_to_fit();
+    h->stats.n_shell_pairs = (long long)ns * (ns + 1) / 2;
+    h->stats.n_pairs_kept = nkept;
+    h->stats.n_prim_pairs = nprim;
+    if (nprim) {
+        CUDA_TRY(h, cudaMalloc(&h->d_prims, sizeof(PrimPair) * nprim));
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_prims, h->h_prims.data(), sizeof(PrimPair) * nprim, cudaMemcpyHostToDevice,
+                                    h->stream));
+    }
+    // Schwarz bounds: diagonal quartet (ab|ab) of every kept pair, on the GPU (MODE_SCHWARZ)
+    for (int c = 0; c < NPAIRCLASS; ++c) {
+        PairClassList &L = h->cls[c];
+        L.n = (int)L.pairs.size();
+        if (!L.n) continue;
+        CUDA_TRY(h, cudaMalloc(&L.d_pairs, sizeof(ShellPair) * L.n));
+        CUDA_TRY(h, cudaMemcpyAsync(L.d_pairs, L.pairs.data(), sizeof(ShellPair) * L.n, cudaMemcpyHostToDevice, h->stream));
+        std::vector<int2> tl(L.n);
+        for (int i = 0; i < L.n; ++i) tl[i] = make_int2(i, i);
+        int2 *d_tl = nullptr;
+        double *d_q = nullptr;
+        CUDA_TRY(h, cudaMalloc(&d_tl, sizeof(int2) * L.n));
+        CUDA_TRY(h, cudaMalloc(&d_q, sizeof(double) * L.n));
+        CUDA_TRY(h, cudaMemcpyAsync(d_tl, tl.data(), sizeof(int2) * L.n, cudaMemcpyHostToDevice, h->stream));
+        ClassTask task{};
+        task.bra = L.d_pairs; task.ket = L.d_pairs; task.prims = h->d_prims;
+        task.nbra = L.n; task.nket = L.n;
+        // no primitive cut here: the bound must hold for quartets whose partner pair is strong, where the
+        // reference's sr<1e-12 test passes although it would fail on the weak pair's own diagonal
+        task.prim_cut = 0.0;
+        task.task_list = d_tl; task.ntask = L.n; task.out = d_q;
+        const int groups = class_groups_per_cta(c, c);
+        const int grid = std::min((L.n + groups - 1) / groups, 148 * 16);
+        CUDA_TRY(h, launch_quartet_class(c, c, task, MODE_SCHWARZ, grid, h->stream));
+        std::vector<double> q(L.n);
+        CUDA_TRY(h, cudaMemcpyAsync(q.data(), d_q, sizeof(double) * L.n, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(d_tl);
+        cudaFree(d_q);
+        for (int i = 0; i < L.n; ++i) L.pairs[i].Q = q[i];
+        std::stable_sort(L.pairs.begin(), L.pairs.end(), [](const ShellPair &x, const ShellPair &y) { return x.Q > y.Q; });
+        CUDA_TRY(h, cudaMemcpyAsync(L.d_pairs, L.pairs.data(), sizeof(ShellPair) * L.n, cudaMemcpyHostToDevice, h->stream));
+        for (int i = 0; i < L.n; ++i) {
+            h->pair_cls[L.pairs[i].pairid] = c;
+            h->pair_pos[L.pairs[i].pairid] = i;
+        }
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    int rc = build_plans(h);
+    if (rc) return rc;
+    cudaEventRecord(h->ev3, h->stream);
+    cudaEventSynchronize(h->ev3);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev2, h->ev3);
+    h->stats.precompute_ms = ms;
+    h->pairs_ready = true;
+    return UNOMOL_OK;
+}
+
+// per (bra class >= ket class): prefix counts of kets passing Q_bra*Q_ket >= tau (kets sorted descending)
+static int build_plans(unomol_b200 *h) {
+    for (auto &p : h->plans)
+        if (p.d_ket_count) cudaFree(p.d_ket_count);
+    h->plans.clear();
+    long long total = 0;
+    for (int cb = 0; cb < NPAIRCLASS; ++cb)
+        for (int ck = 0; ck <= cb; ++ck) {
+            const PairClassList &Lb = h->cls[cb], &Lk = h->cls[ck];
+            if (!Lb.n || !Lk.n) continue;
+            ComboPlan plan;
+            plan.cb = cb; plan.ck = ck;
+            std::vector<int> kc(Lb.n, 0);
+            for (int i = 0; i < Lb.n; ++i) {
+                int cnt;
+                if (h->tau <= 0.0) cnt = Lk.n;
+                else {
+                    const double need = h->tau / Lb.pairs[i].Q;   // Q_ket >= need
+                    // first index with Q < need in a descending list
+                    int lo = 0, hi = Lk.n;
+                    while (lo < hi) {
+                        int mid = (lo + hi) / 2;
+                        if (Lk.pairs[mid].Q >= need) lo = mid + 1; else hi = mid;
+                    }
+                    cnt = lo;
+                }
+                if (cb == ck) cnt = std::min(cnt, i + 1);   // canonical: ket position <= bra position
+                kc[i] = cnt;
+                plan.nquartets += cnt;
+                if (cnt > 0) plan.nbra_eff = i + 1;
+            }
+            total += plan.nquartets;
+            if (plan.nbra_eff == 0) continue;
+            if (cudaMalloc(&plan.d_ket_count, sizeof(int) * Lb.n) != cudaSuccess) return UNOMOL_E_NOMEM;
+            cudaMemcpyAsync(plan.d_ket_count, kc.data(), sizeof(int) * Lb.n, cudaMemcpyHostToDevice, h->stream);
+            cudaStreamSynchronize(h->stream);
+            h->plans.push_back(plan);
+        }
+    const long long np = (long long)h->basis.nshell * (h->basis.nshell + 1) / 2;
+    h->stats.n_quartets_total = np * (np + 1) / 2;
+    (void)total;
+    if (h->d_counters) cudaFree(h->d_counters);
+    h->d_counters = nullptr;
+    if (cudaMalloc(&h->d_counters, sizeof(unsigned long long) * 2 * (h->plans.size() + 1)) != cudaSuccess) return UNOMOL_E_NOMEM;
+    return UNOMOL_OK;
+}
+
+// ---------------------------------------------------------------- Fock build
+static int ensure_buffers(unomol_b200 *h) {
+    if (h->d_PJ) return UNOMOL_OK;
+    const size_t n = h->basis.nbf, nn = n * n, no2 = n * (n + 1) / 2;
+    for (int s = 0; s < 2; ++s) {
+        CUDA_TRY(h, cudaMalloc(&h->d_Ppacked[s], sizeof(double) * no2));
+        CUDA_TRY(h, cudaMalloc(&h->d_Gpacked[s], sizeof(double) * no2));
+        CUDA_TRY(h, cudaMalloc(&h->d_PK[s], sizeof(double) * nn));
+        CUDA_TRY(h, cudaMalloc(&h->d_K[s], sizeof(double) * nn));
+    }
+    CUDA_TRY(h, cudaMalloc(&h->d_PJ, sizeof(double) * nn));
+    CUDA_TRY(h, cudaMalloc(&h->d_J, sizeof(double) * nn));
+    CUDA_TRY(h, cudaMallocHost(&h->h_pinned, sizeof(double) * no2 * 4));
+    return UNOMOL_OK;
+}
+
+typedef int (*nccl_allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+
+// device-resident core: packed dP[nspin] -> packed dG[nspin] (overwritten), on h->stream
+static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const double *dPB, double *dGA, double *dGB) {
+    if (!h->pairs_ready) {
+        int rc = build_pairs(h);
+        if (rc) return rc;
+    }
+    int rc = ensure_buffers(h);
+    if (rc) return rc;
+    const int n = h->basis.nbf;
+    const size_t nn = (size_t)n * n, no2 = (size_t)n * (n + 1) / 2;
+    cudaStream_t st = h->stream;
+    cudaEventRecord(h->ev0, st);
+    unpack_density_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(dPA, dPB, n, nspin, h->d_PJ, h->d_PK[0], h->d_PK[1]);
+    CUDA_TRY(h, cudaMemsetAsync(h->d_J, 0, sizeof(double) * nn, st));
+    for (int s = 0; s < nspin; ++s) CUDA_TRY(h, cudaMemsetAsync(h->d_K[s], 0, sizeof(double) * nn, st));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 2 * (h->plans.size() + 1), st));
+    cudaEventRecord(h->ev2, st);
+    int nlaunch = 2;
+    for (size_t ip = 0; ip < h->plans.size(); ++ip) {
+        const ComboPlan &pl = h->plans[ip];
+        ClassTask task{};
+        task.bra = h->cls[pl.cb].d_pairs; task.ket = h->cls[pl.ck].d_pairs; task.prims = h->d_prims;
+        task.ket_count = pl.d_ket_count;
+        task.nbra = pl.nbra_eff; task.nket = h->cls[pl.ck].n;
+        task.same_class = (pl.cb == pl.ck);
+        task.start_shell = h->start_shell;
+        task.rank = h->rank; task.nranks = h->nranks;
+        task.prim_cut = h->prim_cut;
+        task.nbf = n; task.nspin = nspin;
+        task.PJ = h->d_PJ; task.PK[0] = h->d_PK[0]; task.PK[1] = h->d_PK[1];
+        task.J = h->d_J; task.K[0] = h->d_K[0]; task.K[1] = h->d_K[1];
+        task.counters = h->d_counters + 2 * ip;
+        const int grid = std::min(pl.nbra_eff, 148 * 32);
+        CUDA_TRY(h, launch_quartet_class(pl.cb, pl.ck, task, MODE_DIGEST, grid, st));
+        ++nlaunch;
+    }
+    cudaEventRecord(h->ev3, st);
+    pack_fock_kernel<<<(unsigned)((no2 + 255) / 256), 256, 0, st>>>(h->d_J, h->d_K[0], h->d_K[1], n, nspin, dGA, dGB);
+    ++nlaunch;
+    CUDA_TRY(h, cudaGetLastError());
+    if (h->nccl_comm && h->nranks > 1) {
+        static nccl_allreduce_fn fn = nullptr;
+        if (!fn) fn = (nccl_allreduce_fn)dlsym(RTLD_DEFAULT, "ncclAllReduce");
+        if (!fn) { h->last_error = "ncclAllReduce not found in the process (load libnccl first)"; return UNOMOL_E_NCCL; }
+        // ncclDouble = 8, ncclSum = 0 (nccl.h)
+        if (fn(dGA, dGA, no2, 8, 0, h->nccl_comm, st) != 0) return UNOMOL_E_NCCL;
+        if (nspin == 2 && fn(dGB, dGB, no2, 8, 0, h->nccl_comm, st) != 0) return UNOMOL_E_NCCL;
+    }
+    cudaEventRecord(h->ev1, st);
+    h->stats.n_launches = nlaunch;
+    return UNOMOL_OK;
+}
+
+static int finish_stats(unomol_b200 *h) {
+    CUDA_TRY(h, cudaEventSynchronize(h->ev1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->stats.last_fock_ms = ms;
+    cudaEventElapsedTime(&ms, h->ev2, h->ev3);
+    h->stats.last_eri_kernel_ms = ms;
+    std::vector<unsigned long long> c(2 * (h->plans.size() + 1));
+    CUDA_TRY(h, cudaMemcpy(c.data(), h->d_counters, sizeof(unsigned long long) * c.size(), cudaMemcpyDeviceToHost));
+    long long nq = 0;
+    double fl = 0.0;
+    for (size_t ip = 0; ip < h->plans.size(); ++ip) {
+        int la, lb, lc, ld;
+        pair_class_l(h->plans[ip].cb, la, lb);
+        pair_class_l(h->plans[ip].ck, lc, ld);
+        nq += (long long)c[2 * ip];
+        fl += (double)c[2 * ip + 1] * model_flops_per_primitive_quartet(la, lb, lc, ld);
+    }
+    h->stats.n_quartets = nq;
+    h->stats.model_flops = fl;
+    return UNOMOL_OK;
+}
+
+// ---------------------------------------------------------------- C ABI
+extern "C" {
+
+const char *unomol_b200_version(void) { return "unomol_b200 0.1 (sm_100a)"; }
+
+const char *unomol_b200_strerror(int code) {
+    switch (code) {
+        case UNOMOL_OK: return "ok";
+        case UNOMOL_E_ARG: return "bad argument";
+        case UNOMOL_E_CUDA: return "CUDA failure or no CUDA device (there is no CPU fallback)";
+        case UNOMOL_E_UNSUPPORTED: return "angular momentum above d is not built into this library";
+        case UNOMOL_E_NOMEM: return "out of memory";
+        case UNOMOL_E_STATE: return "call order";
+        case UNOMOL_E_NCCL: return "NCCL failure";
+    }
+    return "unknown error";
+}
+
+int unomol_b200_create(const unomol_basis_desc *b, int start_shell, int device, int rank, int nranks,
+                       unomol_b200_t **out) {
+    if (!b || !out || b->nshell <= 0 || nranks < 1 || rank < 0 || rank >= nranks) return UNOMOL_E_ARG;
+    for (int s = 0; s < b->nshell; ++s)
+        if (b->lv[s] > MAXL) return UNOMOL_E_UNSUPPORTED;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) return UNOMOL_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return UNOMOL_E_CUDA;
+    unomol_b200 *h = new unomol_b200;
+    h->device = device; h->rank = rank; h->nranks = nranks; h->start_shell = start_shell;
+    HostBasis &B = h->basis;
+    B.nshell = b->nshell; B.nbf = b->nbf; B.ncen = b->ncen; B.maxl = b->maxl;
+    B.npr.assign(b->npr, b->npr + b->nshell);
+    B.lv.assign(b->lv, b->lv + b->nshell);
+    B.cen.assign(b->cen, b->cen + b->nshell);
+    B.off.assign(b->off, b->off + b->nshell);
+    B.poff.assign(b->poff, b->poff + b->nshell);
+    int nprim = 0;
+    for (int s = 0; s < b->nshell; ++s) nprim = std::max(nprim, b->poff[s] + b->npr[s]);
+    B.alpha.assign(b->alpha, b->alpha + nprim);
+    B.coef.assign(b->coef, b->coef + nprim);
+    B.xyz.assign(b->xyz, b->xyz + 3 * b->ncen);
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return UNOMOL_E_CUDA; }
+    cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
+    h->stats.nbf = B.nbf; h->stats.nshell = B.nshell; h->stats.rank = rank; h->stats.nranks = nranks;
+    int rc = build_pairs(h);
+    if (rc) { unomol_b200_destroy(h); return rc; }
+    *out = h;
+    return UNOMOL_OK;
+}
+
+void unomol_b200_destroy(unomol_b200_t *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    free_pairs(h);
+    for (int s = 0; s < 2; ++s) {
+        cudaFree(h->d_Ppacked[s]); cudaFree(h->d_Gpacked[s]); cudaFree(h->d_PK[s]); cudaFree(h->d_K[s]);
+    }
+    cudaFree(h->d_PJ); cudaFree(h->d_J); cudaFree(h->d_counters);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    unomol_scf_free(h);
+    if (h->ev0) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3); }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
+    if (!h || !name) return UNOMOL_E_ARG;
+    cudaSetDevice(h->device);
+    if (!strcmp(name, "schwarz_tau")) {
+        h->tau = value;
+        if (h->pairs_ready) return build_plans(h);
+        return UNOMOL_OK;
+    }
+    if (!strcmp(name, "prim_cut")) { h->prim_cut = value; h->pairs_ready = false; return UNOMOL_OK; }
+    if (!strcmp(name, "density_screen")) { h->density_screen = value != 0.0; return UNOMOL_OK; }
+    return UNOMOL_E_ARG;
+}
+
+int unomol_b200_set_geometry(unomol_b200_t *h, const double *xyz) {
+    if (!h || !xyz) return UNOMOL_E_ARG;
+    cudaSetDevice(h->device);
+    h->basis.xyz.assign(xyz, xyz + 3 * h->basis.ncen);
+    return build_pairs(h);
+}
+
+int unomol_b200_fock_rhf_device(unomol_b200_t *h, const double *dP, double *dG, int async) {
+    if (!h || !dP || !dG) return UNOMOL_E_ARG;
+    cudaSetDevice(h->device);
+    int rc = fock_device(h, 1, dP, nullptr, dG, nullptr);
+    if (rc || async) return rc;
+    return finish_stats(h);
+}
+
+int unomol_b200_fock_uhf_device(unomol_b200_t *h, const double *dPA, const double *dPB, double *dGA, double *dGB,
+                                int async) {
+    if (!h || !dPA || !dPB || !dGA || !dGB) return UNOMOL_E_ARG;
+    cudaSetDevice(h->device);
+    int rc = fock_device(h, 2, dPA, dPB, dGA, dGB);
+    if (rc || async) return rc;
+    return finish_stats(h);
+}
+
+static int fock_host(unomol_b200 *h, int nspin, const double *PA, const double *PB, double *GA, double *GB) {
+    cudaSetDevice(h->device);
+    int rc = ensure_buffers(h);
+    if (rc) return rc;
+    const size_t n = h->basis.nbf, no2 = n * (n + 1) / 2;
+    const double *Ph[2] = {PA, PB};
+    double *Gh[2] = {GA, GB};
+    for (int s = 0; s < nspin; ++s) {
+        memcpy(h->h_pinned + s * no2, Ph[s], sizeof(double) * no2);
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_Ppacked[s], h->h_pinned + s * no2, sizeof(double) * no2, cudaMemcpyHostToDevice,
+                                    h->stream));
+    }
+    rc = fock_device(h, nspin, h->d_Ppacked[0], h->d_Ppacked[1], h->d_Gpacked[0], h->d_Gpacked[1]);
+    if (rc) return rc;
+    for (int s = 0; s < nspin; ++s)
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_pinned + (2 + s) * no2, h->d_Gpacked[s], sizeof(double) * no2,
+                                    cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int s = 0; s < nspin; ++s) {
+        const double *src = h->h_pinned + (2 + s) * no2;
+        double *dst = Gh[s];
+        for (size_t i = 0; i < no2; ++i) dst[i] += src[i];   // the reference accumulates into G
+    }
+    return finish_stats(h);
+}
+
+int unomol_b200_fock_rhf(unomol_b200_t *h, const double *P, double *G) {
+    if (!h || !P || !G) return UNOMOL_E_ARG;
+    return fock_host(h, 1, P, nullptr, G, nullptr);
+}
+
+int unomol_b200_fock_uhf(unomol_b200_t *h, const double *PA, const double *PB, double *GA, double *GB) {
+    if (!h || !PA || !PB || !GA || !GB) return UNOMOL_E_ARG;
+    return fock_host(h, 2, PA, PB, GA, GB);
+}
+
+int unomol_b200_stats(unomol_b200_t *h, unomol_b200_stats_t *out) {
+    if (!h || !out) return UNOMOL_E_ARG;
+    *out = h->stats;
+    return UNOMOL_OK;
+}
+
+int unomol_b200_attach_nccl(unomol_b200_t *h, void *comm) {
+    if (!h) return UNOMOL_E_ARG;
+    h->nccl_comm = comm;
+    return UNOMOL_OK;
+}
+
+int unomol_b200_device_buffers(unomol_b200_t *h, void **stream, double **dP, double **dG) {
+    if (!h) return UNOMOL_E_ARG;
+    cudaSetDevice(h->device);
+    int rc = ensure_buffers(h);
+    if (rc) return rc;
+    if (stream) *stream = (void *)h->stream;
+    if (dP) { dP[0] = h->d_Ppacked[0]; dP[1] = h->d_Ppacked[1]; }
+    if (dG) { dG[0] = h->d_Gpacked[0]; dG[1] = h->d_Gpacked[1]; }
+    return UNOMOL_OK;
+}
+
+int unomol_b200_schwarz(unomol_b200_t *h, double *Q) {
+    if (!h || !Q) return UNOMOL_E_ARG;
+    if (!h->pairs_ready) { int rc = build_pairs(h); if (rc) return rc; }
+    const size_t np = (size_t)h->basis.nshell * (h->basis.nshell + 1) / 2;
+    for (size_t i = 0; i < np; ++i) Q[i] = 0.0;
+    for (int c = 0; c < NPAIRCLASS; ++c)
+        for (auto &sp : h->cls[c].pairs) Q[sp.pairid] = sp.Q;
+    return UNOMOL_OK;
+}
+
+// ---- test hooks -------------------------------------------------------------------------------------
+// locate the computed orientation of shell pair (i,j): class, position, and whether (i,j) is (a,b) or (b,a)
+static bool locate_pair(unomol_b200 *h, int i, int j, int &cls, int &pos, bool &swapped) {
+    int hi = std::max(i, j), lo = std::min(i, j);
+    int id = hi * (hi + 1) / 2 + lo;
+    cls = h->pair_cls[id];
+    pos = h->pair_pos[id];
+    if (pos < 0) return false;
+    const ShellPair &sp = h->cls[cls].pairs[pos];
+    swapped = (sp.sha != i);   // stored first shell differs from the caller's first shell
+    if (i == j) swapped = false;
+    return true;
+}
+
+int unomol_b200_eri_quartet(unomol_b200_t *h, int ish, int jsh, int ksh, int lsh, double *out) {
+    if (!h || !out) return UNOMOL_E_ARG;
+    const HostBasis &B = h->basis;
+    const int ns = B.nshell;
+    if (ish < 0 || jsh < 0 || ksh < 0 || lsh < 0 || ish >= ns || jsh >= ns || ksh >= ns || lsh >= ns) return UNOMOL_E_ARG;
+    cudaSetDevice(h->device);
+    if (!h->pairs_ready) { int rc = build_pairs(h); if (rc) return rc; }
+    auto nc = [&](int s) { return (B.lv[s] + 1) * (B.lv[s] + 2) / 2; };
+    const int n1 = nc(ish), n2 = nc(jsh), n3 = nc(ksh), n4 = nc(lsh);
+    const int ntot = n1 * n2 * n3 * n4;
+    for (int i = 0; i < ntot; ++i) out[i] = 0.0;
+    int c1, p1, c2, p2;
+    bool sw1, sw2;
+    if (!locate_pair(h, ish, jsh, c1, p1, sw1) || !locate_pair(h, ksh, lsh, c2, p2, sw2)) return UNOMOL_OK;  // exactly zero
+    const bool braket_swapped = c1 < c2;   // kernels exist for bra class >= ket class
+    const int cb = braket_swapped ? c2 : c1, ck = braket_swapped ? c1 : c2;
+    const int pb = braket_swapped ? p2 : p1, pk = braket_swapped ? p1 : p2;
+    int2 tl = make_int2(pb, pk);
+    long long off0 = 0;
+    int2 *d_tl; long long *d_off; double *d_out;
+    CUDA_TRY(h, cudaMalloc(&d_tl, sizeof(int2)));
+    CUDA_TRY(h, cudaMalloc(&d_off, sizeof(long long)));
+    CUDA_TRY(h, cudaMalloc(&d_out, sizeof(double) * ntot));
+    CUDA_TRY(h, cudaMemcpyAsync(d_tl, &tl, sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_off, &off0, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    ClassTask task{};
+    task.bra = h->cls[cb].d_pairs; task.ket = h->cls[ck].d_pairs; task.prims = h->d_prims;
+    task.nbra = h->cls[cb].n; task.nket = h->cls[ck].n;
+    task.prim_cut = h->prim_cut;
+    task.task_list = d_tl; task.task_out = d_off; task.ntask = 1; task.out = d_out;
+    CUDA_TRY(h, launch_quartet_class(cb, ck, task, MODE_DUMP, 1, h->stream));
+    std::vector<double> blk(ntot);
+    CUDA_TRY(h, cudaMemcpyAsync(blk.data(), d_out, sizeof(double) * ntot, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d_tl); cudaFree(d_off); cudaFree(d_out);
+    // block layout [a][b][c][d] in the kernel's orientation -> caller's [i][j][k][l]
+    // kernel bra pair = (A,B) shells, ket pair = (C,D)
+    const ShellPair &SB = h->cls[cb].pairs[pb], &SK = h->cls[ck].pairs[pk];
+    const int NA = nc(SB.sha), NB = nc(SB.shb), NC = nc(SK.sha), ND = nc(SK.shb);
+    (void)NA;
+    for (int i = 0; i < n1; ++i)
+        for (int j = 0; j < n2; ++j)
+            for (int k = 0; k < n3; ++k)
+                for (int l = 0; l < n4; ++l) {
+                    // components in the pair orientation of the caller's bra (ish,jsh) and ket (ksh,lsh)
+                    int b1 = sw1 ? j : i, b2 = sw1 ? i : j;   // (first,second) of pair (ish,jsh) as stored
+                    int k1 = sw2 ? l : k, k2 = sw2 ? k : l;
+                    int a, b, c, d;
+                    if (!braket_swapped) { a = b1; b = b2; c = k1; d = k2; }
+                    else { a = k1; b = k2; c = b1; d = b2; }
+                    out[((i * n2 + j) * n3 + k) * n4 + l] = blk[((a * NB + b) * NC + c) * ND + d];
+                }
+    return UNOMOL_OK;
+}
+
+int unomol_b200_dump_eris(unomol_b200_t *h, double thresh, unomol_twoint *buf, size_t cap, size_t *nout) {
+    if (!h || !nout) return UNOMOL_E_ARG;
+    cudaSetDevice(h->device);
+    if (!h->pairs_ready) { int rc = build_pairs(h); if (rc) return rc; }
+    const HostBasis &B = h->basis;
+    auto nc = [&](int s) { return (B.lv[s] + 1) * (B.lv[s] + 2) / 2; };
+    // every (bra,ket) combination of kept pairs, canonical orientation, dense offsets per combo
+    struct Combo { int cb, ck; long long base; int nint; };
+    std::vector<Combo> combos;
+    long long total = 0;
+    for (int cb = 0; cb < NPAIRCLASS; ++cb)
+        for (int ck = 0; ck <= cb; ++ck) {
+            const int nb = h->cls[cb].n, nk = h->cls[ck].n;
+            if (!nb || !nk) continue;
+            int la, lb, lc, ld;
+            pair_class_l(cb, la, lb); pair_class_l(ck, lc, ld);
+            const int nint = ((la + 1) * (la + 2) / 2) * ((lb + 1) * (lb + 2) / 2) * ((lc + 1) * (lc + 2) / 2) * ((ld + 1) * (ld + 2) / 2);
+            const long long ntask = (cb == ck) ? (long long)nb * (nb + 1) / 2 : (long long)nb * nk;
+            combos.push_back({cb, ck, total, nint});
+            total += ntask * nint;
+        }
+    if (total > (1LL << 28)) return UNOMOL_E_NOMEM;   // 2 GiB of doubles: this hook is for small systems
+    double *d_out = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d_out, sizeof(double) * std::max<long long>(total, 1)));
+    for (auto &cmb : combos) {
+        const int nb = h->cls[cmb.cb].n, nk = h->cls[cmb.ck].n;
+        std::vector<int2> tl;
+        std::vector<long long> off;
+        for (int i = 0; i < nb; ++i) {
+            const int jmax = (cmb.cb == cmb.ck) ? i + 1 : nk;
+            for (int j = 0; j < jmax; ++j) {
+                tl.push_back(make_int2(i, j));
+                const long long t = (cmb.cb == cmb.ck) ? (long long)i * (i + 1) / 2 + j : (long long)i * nk + j;
+                off.push_back(cmb.base + t * cmb.nint);
+            }
+        }
+        int2 *d_tl; long long *d_off;
+        CUDA_TRY(h, cudaMalloc(&d_tl, sizeof(int2) * tl.size()));
+        CUDA_TRY(h, cudaMalloc(&d_off, sizeof(long long) * off.size()));
+        CUDA_TRY(h, cudaMemcpyAsync(d_tl, tl.data(), sizeof(int2) * tl.size(), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(d_off, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice, h->stream));
+        ClassTask task{};
+        task.bra = h->cls[cmb.cb].d_pairs; task.ket = h->cls[cmb.ck].d_pairs; task.prims = h->d_prims;
+        task.nbra = nb; task.nket = nk; task.prim_cut = h->prim_cut;
+        task.task_list = d_tl; task.task_out = d_off; task.ntask = (int)tl.size(); task.out = d_out;
+        const int groups = class_groups_per_cta(cmb.cb, cmb.ck);
+        const int grid = std::min(((int)tl.size() + groups - 1) / groups, 148 * 16);
+        CUDA_TRY(h, launch_quartet_class(cmb.cb, cmb.ck, task, MODE_DUMP, grid, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        cudaFree(d_tl); cudaFree(d_off);
+    }
+    std::vector<double> all((size_t)std::max<long long>(total, 1));
+    CUDA_TRY(h, cudaMemcpy(all.data(), d_out, sizeof(double) * all.size(), cudaMemcpyDeviceToHost));
+    cudaFree(d_out);
+    auto combo_of = [&](int cb, int ck) -> const Combo * {
+        for (auto &c : combos) if (c.cb == cb && c.ck == ck) return &c;
+        return nullptr;
+    };
+    // the reference's loop order and canonical function filter (TwoElectronInts.cpp:541-653)
+    size_t cnt = 0;
+    const int ns = B.nshell;
+    for (int ish = h->start_shell; ish < ns; ++ish)
+        for (int jsh = 0; jsh <= ish; ++jsh) {
+            int c1, p1; bool sw1;
+            const bool have1 = locate_pair(h, ish, jsh, c1, p1, sw1);
+            for (int ksh = 0; ksh <= ish; ++ksh)
+                for (int lsh = 0; lsh <= ksh; ++lsh) {
+                    int c2, p2; bool sw2;
+                    const bool have2 = locate_pair(h, ksh, lsh, c2, p2, sw2);
+                    const double *blk = nullptr;
+                    bool bks = false;
+                    int NB = 1, NC = 1, ND = 1;
+                    if (have1 && have2) {
+                        bks = (c1 < c2) || (c1 == c2 && p1 < p2);
+                        const int cb = bks ? c2 : c1, ck = bks ? c1 : c2, pb = bks ? p2 : p1, pk = bks ? p1 : p2;
+                        const Combo *cmb = combo_of(cb, ck);
+                        const long long t = (cb == ck) ? (long long)pb * (pb + 1) / 2 + pk : (long long)pb * h->cls[ck].n + pk;
+                        blk = all.data() + cmb->base + t * cmb->nint;
+                        const ShellPair &SB = h->cls[cb].pairs[pb], &SK = h->cls[ck].pairs[pk];
+                        NB = nc(SB.shb); NC = nc(SK.sha); ND = nc(SK.shb);
+                    }
+                    for (int ils = 0; ils < nc(ish); ++ils) {
+                        const int ir = B.off[ish] + ils;
+                        for (int jls = 0; jls < nc(jsh); ++jls) {
+                            const int jr = B.off[jsh] + jls;
+                            if (jr > ir) break;
+                            for (int kls = 0; kls < nc(ksh); ++kls) {
+                                const int kr = B.off[ksh] + kls;
+                                if (kr > ir) break;
+                                for (int lls = 0; lls < nc(lsh); ++lls) {
+                                    const int lr = B.off[lsh] + lls;
+                                    if (lr > kr || (ir == kr && lr > jr)) break;
+                                    double v = 0.0;
+                                    if (blk) {
+                                        int b1 = sw1 ? jls : ils, b2 = sw1 ? ils : jls;
+                                        int k1 = sw2 ? lls : kls, k2 = sw2 ? kls : lls;
+                                        int a, b, c, d;
+                                        if (!bks) { a = b1; b = b2; c = k1; d = k2; }
+                                        else { a = k1; b = k2; c = b1; d = b2; }
+                                        v = blk[((a * NB + b) * NC + c) * ND + d];
+                                    }
+                                    if (std::fabs(v) > thresh) {
+                                        if (buf && cnt < cap) { buf[cnt].val = v; buf[cnt].i = ir; buf[cnt].j = jr; buf[cnt].k = kr; buf[cnt].l = lr; }
+                                        ++cnt;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+        }
+    *nout = cnt;
+    return UNOMOL_OK;
+}
+
+}  // extern "C"

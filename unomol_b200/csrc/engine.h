@@ -1,0 +1,76 @@
+// unomol_b200/csrc/engine.h -- host-side engine behind the C ABI (include/unomol_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "../../include/unomol_b200.h"
+#include "unomol_types.h"
+
+namespace ub200 {
+
+// launchers, one per quartet class, defined in eri_class_*.cu
+cudaError_t launch_quartet_class(int bra_class, int ket_class, const ClassTask &task, int mode, int grid,
+                                 cudaStream_t stream);
+int class_groups_per_cta(int bra_class, int ket_class);
+// SURVEY.md 8(d) flop model per primitive quartet of class (la lb | lc ld)
+double model_flops_per_primitive_quartet(int la, int lb, int lc, int ld);
+
+inline int pair_class_id(int la, int lb) { return la * (la + 1) / 2 + lb; }
+inline void pair_class_l(int cls, int &la, int &lb) {
+    static const int LA[NPAIRCLASS] = {0, 1, 1, 2, 2, 2}, LB[NPAIRCLASS] = {0, 0, 1, 0, 1, 2};
+    la = LA[cls];
+    lb = LB[cls];
+}
+
+struct HostBasis {
+    int nshell = 0, nbf = 0, ncen = 0, maxl = 0;
+    std::vector<int> npr, lv, cen, off, poff;
+    std::vector<double> alpha, coef, xyz;
+};
+
+struct PairClassList {
+    std::vector<ShellPair> pairs;   // sorted by Q descending after Schwarz
+    ShellPair *d_pairs = nullptr;
+    int n = 0;
+};
+
+struct ComboPlan {                  // one (bra class, ket class) launch
+    int cb = 0, ck = 0;
+    int nbra_eff = 0;               // leading bras that have at least one ket
+    long long nquartets = 0;        // sum of ket_count (all ranks, before start_shell filter)
+    int *d_ket_count = nullptr;
+};
+
+}  // namespace ub200
+
+struct unomol_b200 {
+    int device = 0, rank = 0, nranks = 1, start_shell = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    ub200::HostBasis basis;
+    double tau = 1e-12, prim_cut = 1e-12;
+    int density_screen = 0;
+    bool pairs_ready = false;
+    // pair data
+    ub200::PairClassList cls[ub200::NPAIRCLASS];
+    std::vector<ub200::PrimPair> h_prims;
+    ub200::PrimPair *d_prims = nullptr;
+    std::vector<int> pair_cls, pair_pos;      // per canonical shell pair id: class and position (-1 = pruned)
+    std::vector<ub200::ComboPlan> plans;
+    // density / Fock work buffers (device)
+    double *d_Ppacked[2] = {nullptr, nullptr}, *d_Gpacked[2] = {nullptr, nullptr};
+    double *d_PJ = nullptr, *d_PK[2] = {nullptr, nullptr}, *d_J = nullptr, *d_K[2] = {nullptr, nullptr};
+    double *h_pinned = nullptr;               // staging for host<->device copies (4 * no2 doubles)
+    unsigned long long *d_counters = nullptr; // 2 per combo
+    unomol_b200_stats_t stats{};
+    // SCF algebra
+    void *cusolver = nullptr, *cublas = nullptr;
+    double *d_X = nullptr, *d_F = nullptr, *d_W = nullptr, *d_T = nullptr, *d_evals = nullptr, *d_work = nullptr;
+    int *d_info = nullptr;
+    int lwork = 0;
+    // NCCL
+    void *nccl_comm = nullptr;
+    std::string last_error;
+};
+
+void unomol_scf_free(unomol_b200 *h);   // scf_device.cu

@@ -1,0 +1,62 @@
+// unomol_b200/csrc/unomol_types.h -- plain structs shared by host and device code.
+#pragma once
+#include <cstdint>
+
+namespace ub200 {
+
+constexpr int MAXL = 2;            // per-shell angular momentum handled by the built kernels (s, p, d)
+constexpr int NPAIRCLASS = 6;      // ss ps pp ds dp dd  (la >= lb; id = la*(la+1)/2 + lb)
+constexpr double SR_TERM = 34.9868366552497250;  // 2*pi^(5/2), reference TwoElectronInts.cpp:427
+
+// One primitive pair of a shell pair.  Replaces the per-quartet recomputation of p, P, P-A and
+// exp(-ab|AB|^2/p) in the reference's inner loops (TwoElectronInts.cpp:439-460).  80 B, 16-B aligned.
+struct __attribute__((aligned(16))) PrimPair {
+    double p;        // alpha_a + alpha_b
+    double ip;       // 1/p
+    double P[3];     // Gaussian product centre
+    double PA[3];    // P - A   (A = centre of the first, higher-l, shell)
+    double u;        // exp(-a b |AB|^2 / p) / p
+    double c;        // c_a c_b, doubled for off-diagonal primitive pairs of a same-shell pair (:444-450)
+};
+
+// One shell pair, first shell has l_a >= l_b.  96 B.
+struct __attribute__((aligned(16))) ShellPair {
+    double A[3];     // centre of shell a (needed for Q - C on the ket side via PA only; kept for dumps)
+    double AB[3];    // A - B
+    double Q;        // Schwarz bound sqrt(max |(ab|ab)|)
+    int offa, offb;  // first basis function of shell a / b
+    int prim_off;    // first PrimPair
+    int nprim;       // number of PrimPairs
+    int sha, shb;    // shell indices (a = higher l; ties keep the larger index first)
+    int pairid;      // canonical id  max(sh)*(max(sh)+1)/2 + min(sh)
+    int pad;
+};
+
+// Work descriptor of one (bra class, ket class) launch.
+struct ClassTask {
+    const ShellPair *bra;     // bra pairs of this class, sorted by Q descending
+    const ShellPair *ket;     // ket pairs
+    const PrimPair *prims;
+    const int *ket_count;     // per bra: number of leading kets to visit (Schwarz prefix, triangular cap)
+    int nbra, nket;
+    int same_class;           // bra and ket lists are the same list (triangular, diagonal gets 1/2)
+    int start_shell;          // quartet kept iff max shell index >= start_shell
+    int rank, nranks;         // bras are dealt round-robin to ranks
+    double prim_cut;          // reference's sr < 1e-12 cut
+    // digestion
+    int nbf, nspin;
+    const double *PJ;         // square nbf*nbf, pre-scaled density for the Coulomb term
+    const double *PK[2];      // square, per spin, exchange
+    double *J;                // square accumulators (upper/lower mixed; symmetrised afterwards)
+    double *K[2];
+    // dump / schwarz modes
+    const int2 *task_list;    // explicit (bra index, ket index) list
+    const long long *task_out;// output offset per task
+    int ntask;
+    double *out;              // dump: blocks; schwarz: one value per task
+    unsigned long long *counters;  // [0] quartets evaluated, [1] primitive quartets surviving the cut
+};
+
+enum Mode { MODE_DIGEST = 0, MODE_DUMP = 1, MODE_SCHWARZ = 2 };
+
+}  // namespace ub200
