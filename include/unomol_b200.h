@@ -136,6 +136,15 @@ int unomol_b200_scf_set_overlap(unomol_b200_t *h, const double *S);
  * P packed. */
 int unomol_b200_scf_diag(unomol_b200_t *h, const double *F, int nocc, double *evals, double *C, double *P);
 
+/* Bench support (no reference counterpart).
+ * sample_quartets: draws nsample shell quartets uniformly from the screened canonical quartet list the Fock
+ * build evaluates (all ranks), deterministic in seed; shells[4*q..] = (ish,jsh,ksh,lsh).  *ntotal receives the
+ * size of the list.  Used to time the reference on "the same screened quartet list" (SURVEY.md 8(d)).
+ * fp64_peak: measured DFMA throughput of the device in TFLOP/s (dependent-chain-free FMA loop on every SM). */
+int unomol_b200_sample_quartets(unomol_b200_t *h, long long nsample, unsigned long long seed, int *shells,
+                                long long *ntotal);
+int unomol_b200_fp64_peak(int device, double *tflops);
+
 const char *unomol_b200_strerror(int code);
 const char *unomol_b200_version(void);
 

@@ -49,7 +49,7 @@ EXPORTS = [
     "unomol_b200_fock_rhf", "unomol_b200_fock_uhf", "unomol_b200_fock_rhf_device", "unomol_b200_fock_uhf_device",
     "unomol_b200_eri_quartet", "unomol_b200_dump_eris", "unomol_b200_schwarz", "unomol_b200_stats",
     "unomol_b200_attach_nccl", "unomol_b200_device_buffers", "unomol_b200_scf_set_overlap", "unomol_b200_scf_diag",
-    "unomol_b200_strerror", "unomol_b200_version",
+    "unomol_b200_sample_quartets", "unomol_b200_fp64_peak", "unomol_b200_strerror", "unomol_b200_version",
 ]
 
 
@@ -74,6 +74,8 @@ def _load():
     L.unomol_b200_device_buffers.argtypes = [_P, ctypes.POINTER(_P), ctypes.POINTER(_P), ctypes.POINTER(_P)]
     L.unomol_b200_scf_set_overlap.argtypes = [_P, _pd]
     L.unomol_b200_scf_diag.argtypes = [_P, _pd, _I, _pd, _pd, _pd]
+    L.unomol_b200_sample_quartets.argtypes = [_P, ctypes.c_longlong, ctypes.c_ulonglong, _pi, ctypes.POINTER(ctypes.c_longlong)]
+    L.unomol_b200_fp64_peak.argtypes = [_I, _pd]
     L.unomol_b200_strerror.restype = ctypes.c_char_p; L.unomol_b200_strerror.argtypes = [_I]
     L.unomol_b200_version.restype = ctypes.c_char_p
     return L
@@ -186,6 +188,11 @@ class Handle:
         _chk(lib.unomol_b200_device_buffers(self.h, ctypes.byref(st), dP, dG), "device_buffers")
         return st.value, [dP[0], dP[1]], [dG[0], dG[1]]
 
+    def sample_quartets(self, nsample, seed=1):
+        sh = np.zeros((max(nsample, 1), 4), np.int32); tot = ctypes.c_longlong(0)
+        _chk(lib.unomol_b200_sample_quartets(self.h, nsample, seed, _ip(sh), ctypes.byref(tot)), "sample_quartets")
+        return sh[:nsample], tot.value
+
     def scf_set_overlap(self, S):
         S = np.ascontiguousarray(S, float)
         _chk(lib.unomol_b200_scf_set_overlap(self.h, _dp(S)), "scf_set_overlap")
@@ -196,3 +203,10 @@ class Handle:
         C = np.zeros((self.nbf, self.nbf)) if want_c else None
         _chk(lib.unomol_b200_scf_diag(self.h, _dp(F), nocc, _dp(ev), _dp(C) if want_c else None, _dp(P)), "scf_diag")
         return (ev, C, P) if want_c else (ev, P)
+
+
+def fp64_peak(device=0):
+    """measured DFMA throughput in TFLOP/s (the FP64 roofline denominator; not in MEASURED_PEAKS.json)"""
+    t = _D(0.0)
+    _chk(lib.unomol_b200_fp64_peak(device, ctypes.byref(t)), "fp64_peak")
+    return t.value

@@ -770,4 +770,88 @@ int unomol_b200_dump_eris(unomol_b200_t *h, double thresh, unomol_twoint *buf, s
     return UNOMOL_OK;
 }
 
+int unomol_b200_sample_quartets(unomol_b200_t *h, long long nsample, unsigned long long seed, int *shells,
+                                long long *ntotal) {
+    if (!h || nsample < 0 || (nsample > 0 && !shells)) return UNOMOL_E_ARG;
+    cudaSetDevice(h->device);
+    if (!h->pairs_ready) { int rc = build_pairs(h); if (rc) return rc; }
+    // cumulative quartet counts: per plan, per bra (recomputed on the host exactly like build_plans)
+    struct Row { int plan, bra; long long cum; };
+    std::vector<Row> rows;
+    long long total = 0;
+    std::vector<std::vector<int>> kcs(h->plans.size());
+    for (size_t ip = 0; ip < h->plans.size(); ++ip) {
+        const ComboPlan &pl = h->plans[ip];
+        const PairClassList &Lb = h->cls[pl.cb], &Lk = h->cls[pl.ck];
+        for (int i = 0; i < pl.nbra_eff; ++i) {
+            int cnt;
+            if (h->tau <= 0.0) cnt = Lk.n;
+            else {
+                const double need = h->tau / Lb.pairs[i].Q;
+                int lo = 0, hi = Lk.n;
+                while (lo < hi) { int mid = (lo + hi) / 2; if (Lk.pairs[mid].Q >= need) lo = mid + 1; else hi = mid; }
+                cnt = lo;
+            }
+            if (pl.cb == pl.ck) cnt = std::min(cnt, i + 1);
+            if (cnt <= 0) continue;
+            total += cnt;
+            rows.push_back({(int)ip, i, total});
+        }
+    }
+    if (ntotal) *ntotal = total;
+    if (total == 0) return UNOMOL_OK;
+    unsigned long long st = seed * 6364136223846793005ULL + 1442695040888963407ULL;
+    auto next = [&]() { st ^= st >> 12; st ^= st << 25; st ^= st >> 27; return st * 2685821657736338717ULL; };
+    for (long long q = 0; q < nsample; ++q) {
+        const long long r = (long long)(next() % (unsigned long long)total);
+        size_t lo = 0, hi = rows.size();
+        while (lo < hi) { size_t mid = (lo + hi) / 2; if (rows[mid].cum > r) hi = mid; else lo = mid + 1; }
+        const Row &row = rows[lo];
+        const long long before = lo ? rows[lo - 1].cum : 0;
+        const int ki = (int)(r - before);
+        const ComboPlan &pl = h->plans[row.plan];
+        const ShellPair &B = h->cls[pl.cb].pairs[row.bra], &K = h->cls[pl.ck].pairs[ki];
+        shells[4 * q + 0] = B.sha; shells[4 * q + 1] = B.shb; shells[4 * q + 2] = K.sha; shells[4 * q + 3] = K.shb;
+    }
+    return UNOMOL_OK;
+}
+
+namespace ub200 {
+__global__ void dfma_peak_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+}  // namespace ub200
+
+int unomol_b200_fp64_peak(int device, double *tflops) {
+    if (!tflops) return UNOMOL_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return UNOMOL_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return UNOMOL_E_CUDA;
+    const int blocks = prop.multiProcessorCount * 4, threads = 512, iters = 1 << 15;
+    double *d = nullptr;
+    if (cudaMalloc(&d, sizeof(double) * blocks * threads) != cudaSuccess) return UNOMOL_E_NOMEM;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        dfma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return UNOMOL_E_CUDA; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return UNOMOL_OK;
+}
+
 }  // extern "C"
