@@ -184,3 +184,18 @@ def test_schwarz_bounds_bound_the_integrals(capi, oracle):
         blk = oracle.quartet_block(ob, i, j, k, l)
         qa = Q[max(i, j) * (max(i, j) + 1) // 2 + min(i, j)]; qb = Q[max(k, l) * (max(k, l) + 1) // 2 + min(k, l)]
         assert np.max(np.abs(blk)) <= qa * qb * (1 + 1e-9) + 1e-13
+
+
+@pytest.mark.parametrize("name", ["631.nh3", "dh95.co2", "tz2p.sf6"])
+def test_register_kernels_agree_with_generic_kernel(capi, name):
+    """the register-resident class kernels (eri_reg.cuh) against the generic shared-memory kernel"""
+    b, h = _handle(capi, name)
+    rng = np.random.default_rng(21)
+    P = rng.standard_normal(b.no2); PB = rng.standard_normal(b.no2)
+    h.set_option("reg_kernels", 1)
+    G1 = h.fock_rhf(P); GA1, GB1 = h.fock_uhf(P, PB)
+    h.set_option("reg_kernels", 0)
+    G0 = h.fock_rhf(P); GA0, GB0 = h.fock_uhf(P, PB)
+    s = np.max(np.abs(G0))
+    assert np.max(np.abs(G1 - G0)) < 1e-13 * s
+    assert np.max(np.abs(GA1 - GA0)) < 1e-13 * s and np.max(np.abs(GB1 - GB0)) < 1e-13 * s

@@ -308,6 +308,9 @@ static int build_plans(unomol_b200 *h) {
             }
             total += plan.nquartets;
             if (plan.nbra_eff == 0) continue;
+            int maxbp = 0;
+            for (int i = 0; i < plan.nbra_eff; ++i) maxbp = std::max(maxbp, Lb.pairs[i].nprim);
+            plan.use_reg = h->use_reg_kernels && reg_class_available(cb, ck) && maxbp <= reg_max_bra_prims();
             if (cudaMalloc(&plan.d_ket_count, sizeof(int) * Lb.n) != cudaSuccess) return UNOMOL_E_NOMEM;
             cudaMemcpyAsync(plan.d_ket_count, kc.data(), sizeof(int) * Lb.n, cudaMemcpyHostToDevice, h->stream);
             cudaStreamSynchronize(h->stream);
@@ -372,8 +375,12 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         task.PJ = h->d_PJ; task.PK[0] = h->d_PK[0]; task.PK[1] = h->d_PK[1];
         task.J = h->d_J; task.K[0] = h->d_K[0]; task.K[1] = h->d_K[1];
         task.counters = h->d_counters + 2 * ip;
-        const int grid = std::min(pl.nbra_eff, 148 * 32);
-        CUDA_TRY(h, launch_quartet_class(pl.cb, pl.ck, task, MODE_DIGEST, grid, st));
+        const int nmine = (pl.nbra_eff - h->rank + h->nranks - 1) / h->nranks;
+        if (pl.use_reg) {
+            CUDA_TRY(h, launch_reg_class(pl.cb, pl.ck, task, std::min(nmine, 148 * 16), st));
+        } else {
+            CUDA_TRY(h, launch_quartet_class(pl.cb, pl.ck, task, MODE_DIGEST, std::min(nmine, 148 * 32), st));
+        }
         ++nlaunch;
     }
     cudaEventRecord(h->ev3, st);
@@ -490,6 +497,11 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
     }
     if (!strcmp(name, "prim_cut")) { h->prim_cut = value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "density_screen")) { h->density_screen = value != 0.0; return UNOMOL_OK; }
+    if (!strcmp(name, "reg_kernels")) {
+        h->use_reg_kernels = value != 0.0;
+        if (h->pairs_ready) return build_plans(h);
+        return UNOMOL_OK;
+    }
     return UNOMOL_E_ARG;
 }
 

@@ -12,6 +12,10 @@ namespace ub200 {
 cudaError_t launch_quartet_class(int bra_class, int ket_class, const ClassTask &task, int mode, int grid,
                                  cudaStream_t stream);
 int class_groups_per_cta(int bra_class, int ket_class);
+// register-resident kernels for the small classes (eri_reg_classes.cu)
+bool reg_class_available(int bra_class, int ket_class);
+int reg_max_bra_prims();
+cudaError_t launch_reg_class(int bra_class, int ket_class, const ClassTask &task, int grid, cudaStream_t stream);
 // SURVEY.md 8(d) flop model per primitive quartet of class (la lb | lc ld)
 double model_flops_per_primitive_quartet(int la, int lb, int lc, int ld);
 
@@ -39,6 +43,7 @@ struct ComboPlan {                  // one (bra class, ket class) launch
     int nbra_eff = 0;               // leading bras that have at least one ket
     long long nquartets = 0;        // sum of ket_count (all ranks, before start_shell filter)
     int *d_ket_count = nullptr;
+    bool use_reg = false;           // register-resident kernel (small class, bra contraction fits the stage)
 };
 
 }  // namespace ub200
@@ -50,6 +55,7 @@ struct unomol_b200 {
     ub200::HostBasis basis;
     double tau = 1e-12, prim_cut = 1e-12;
     int density_screen = 0;
+    int use_reg_kernels = 1;   // option "reg_kernels": 0 forces the generic kernel for every class
     bool pairs_ready = false;
     // pair data
     ub200::PairClassList cls[ub200::NPAIRCLASS];
