@@ -296,8 +296,26 @@ def analyse(ref_dir):
 
 
 # ---------------------------------------------------------------- emitters
+CONST_TABLE = None   # when a list, lit() appends the literal and returns a table reference (CUDA constant bank)
+
+
 def lit(s):
-    """decimal literal text -> C double literal"""
+    """decimal literal text -> C double literal (or a reference into the constant table for device code)"""
+    if CONST_TABLE is not None:
+        v = _lit(s)
+        import struct
+        if struct.unpack("<Q", struct.pack("<d", float(v)))[0] & 0xffffffff == 0:
+            return v          # fits the 32-bit FP64 immediate form (1.0, 0.5, 7.5, ...)
+        if v not in CONST_INDEX:
+            CONST_INDEX[v] = len(CONST_TABLE); CONST_TABLE.append(v)
+        return "RC(%d, %s)" % (CONST_INDEX[v], v)
+    return _lit(s)
+
+
+CONST_INDEX = {}
+
+
+def _lit(s):
     neg = s.startswith("-")
     if neg: s = s[1:]
     if s.startswith("."): s = "0" + s
@@ -418,18 +436,71 @@ def emit_c(res, path):
                 "    }\n}\n")
 
 
+def emit_f0f1_body(res, indent="    "):
+    """one-root variant returning w = F0 and f1 = w*t^2 = F1 without the root division (device hot path)"""
+    L = []
+    bands = res[1]
+    first = True
+    for b in bands:
+        cond = "x <= %s" % _lit(repr(b["hi"])) if b["hi"] != float("inf") else None
+        L.append(indent + (("if (%s) {" % cond) if first else (("else if (%s) {" % cond) if cond else "else {")))
+        first = False
+        if b["y0"] is not None: L.append(indent * 2 + "const double y = x - %s;" % lit(b["y0"]))
+        names = {"roots": "r", "weights": "w"}
+        have_f1 = any(name == "f1" for name, _, _ in b["rows"])
+        tail = []
+        sq = "%.17g" % (float(b["consts"].get("pie4", "0.785398163397448")) ** 0.5)
+        for name, ae, polys in b["rows"]:
+            ex = emit_expr(ae, polys, b["consts"], True, names).replace("w[0]", "w")
+            # cheaper, rounding-equivalent forms: 1/x and sqrt(pie4/x) from one rsqrt, no division by 2x
+            ex = re.sub(r"sqrt\(\((?:RC\(\d+, )?0\.785398163397448\)? \* xinv\)\)", "(%s * rx)" % lit(sq), ex)
+            ex = ex.replace("((w - g) / (x + x))", "(((w - g) * 0.5) * xinv)")
+            if name == "roots[0]":
+                if have_f1: continue
+                if ex.startswith("(0.5 / "):          # pure asymptotic band: t^2 = 0.5/x exactly
+                    tail.append(indent * 2 + "f1 = (w * 0.5) * xinv;")
+                else:
+                    tail.append(indent * 2 + "const double r0 = %s;" % ex)
+                    tail.append(indent * 2 + "f1 = w * (r0 / (1.0 + r0));")
+            elif name == "weights[0]": L.append(indent * 2 + "w = %s;" % ex)
+            elif name == "f1": L.append(indent * 2 + "f1 = %s;" % ex)
+            elif name == "xinv":
+                L.append(indent * 2 + "const double rx = ub_rsqrt(x);")
+                L.append(indent * 2 + "const double xinv = rx * rx;")
+            else: L.append(indent * 2 + "const double %s = %s;" % (name, ex))
+        L.extend(tail)
+        L.append(indent + "}")
+    return L
+
+
 def emit_cuda(res, path):
+    global CONST_TABLE
+    host_bodies = emit_function_bodies(res, fma=True, names={"roots": "r", "weights": "w"})
+    CONST_TABLE = []
+    CONST_INDEX.clear()
     bodies = emit_function_bodies(res, fma=True, names={"roots": "r", "weights": "w"})
+    f0f1 = emit_f0f1_body(res)
+    table = list(CONST_TABLE)
+    CONST_TABLE = None
     with open(path, "w") as f:
         f.write("// unomol_b200/csrc/rys_roots.cuh -- Rys quadrature roots and weights, 1..5 roots, FP64.\n/*\n" + HDR_NOTE +
                 " * Product code (host+device).  r[i] = t_i^2/(1-t_i^2), w[i] = weights, as in reference Rys.hpp:145-164.\n"
-                " * Horner steps are explicit fma() so the coefficients become FP64 immediates / constant-bank operands.\n */\n")
+                " * Horner steps are explicit fma(); in device code the coefficients come from a __constant__ table\n"
+                " * (RC(i, literal)) so they are constant-bank operands of the DFMA instead of UMOV-materialised\n"
+                " * immediates (ncu: 21 % of the issued instructions of the (ss|ss) kernel were UMOV before this).\n */\n")
         f.write("#pragma once\n#include <math.h>\n\n#ifdef __CUDACC__\n#define UNOMOL_HD __host__ __device__ __forceinline__\n#else\n#define UNOMOL_HD inline\n#endif\n\nnamespace ub200 {\n\n")
+        f.write("#ifdef __CUDACC__\nstatic __constant__ double rys_ctab[%d] = {\n" % len(table))
+        for i in range(0, len(table), 4):
+            f.write("    " + ", ".join(table[i:i + 4]) + ",\n")
+        f.write("};\n#endif\n#ifdef __CUDA_ARCH__\n#define RC(i, v) rys_ctab[i]\n#else\n#define RC(i, v) (v)\n#endif\n\n")
+        f.write("UNOMOL_HD double ub_rsqrt(double x) {\n#ifdef __CUDA_ARCH__\n    return rsqrt(x);\n#else\n    return 1.0 / sqrt(x);\n#endif\n}\n\n")
         f.write("template <int N> UNOMOL_HD void rys_roots(double x, double *r, double *w);\n\n")
         for n in sorted(bodies):
             f.write("template <> UNOMOL_HD void rys_roots<%d>(double x, double *r, double *w) {\n" % n)
             f.write("\n".join(drop_unused_locals(bodies[n])) + "\n}\n\n")
-        f.write("}  // namespace ub200\n")
+        f.write("// one root, division-free on the hot bands: w = F0(x), f1 = w*t^2 = F1(x) (same fit as rys_roots<1>)\n")
+        f.write("UNOMOL_HD void rys1_f0f1(double x, double &w, double &f1) {\n" + "\n".join(drop_unused_locals(f0f1)) + "\n}\n\n")
+        f.write("#undef RC\n}  // namespace ub200\n")
 
 
 def main():

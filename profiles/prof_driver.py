@@ -9,6 +9,9 @@ wl = sys.argv[1] if len(sys.argv) > 1 else "water154"
 nb = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 basis = bench.WORKLOADS[wl][1](B)
 h = capi.Handle(basis)
+import os
+if os.environ.get('UNOMOL_BUCKET_MIN'):
+    h.set_option('bucket_min_pairs', float(os.environ['UNOMOL_BUCKET_MIN']))
 P = bench.synthetic_density(basis)
 for _ in range(nb):
     G = h.fock_rhf(P)

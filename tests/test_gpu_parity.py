@@ -199,3 +199,18 @@ def test_register_kernels_agree_with_generic_kernel(capi, name):
     s = np.max(np.abs(G0))
     assert np.max(np.abs(G1 - G0)) < 1e-13 * s
     assert np.max(np.abs(GA1 - GA0)) < 1e-13 * s and np.max(np.abs(GB1 - GB0)) < 1e-13 * s
+
+
+def test_primitive_count_buckets_do_not_change_results(capi):
+    """pair lists split by primitive-pair count (used for large systems) against unsplit lists"""
+    b, h = _handle(capi, "dh95.co2")
+    rng = np.random.default_rng(33)
+    P = rng.standard_normal(b.no2)
+    G0 = h.fock_rhf(P)
+    h.set_option("bucket_min_pairs", 1)      # force bucketing on a small molecule
+    G1 = h.fock_rhf(P)
+    assert h.stats()["n_launches"] > 30
+    assert np.max(np.abs(G1 - G0)) < 1e-13 * np.max(np.abs(G0))
+    blk0 = h.eri_quartet(35, 2, 17, 30)
+    h.set_option("bucket_min_pairs", 10 ** 9)
+    assert np.max(np.abs(h.eri_quartet(35, 2, 17, 30) - blk0)) < 1e-14

@@ -128,7 +128,7 @@ __global__ void pack_fock_kernel(const double *__restrict__ J, const double *__r
 
 // ---------------------------------------------------------------- pair tables
 static void free_pairs(unomol_b200 *h) {
-    for (int c = 0; c < NPAIRCLASS; ++c) {
+    for (int c = 0; c < NGROUP; ++c) {
         if (h->cls[c].d_pairs) cudaFree(h->cls[c].d_pairs);
         h->cls[c].d_pairs = nullptr;
         h->cls[c].pairs.clear();
@@ -168,10 +168,10 @@ static int build_pairs(unomol_b200 *h) {
             const double *A = &B.xyz[3 * B.cen[a]], *Bc = &B.xyz[3 * B.cen[b]];
             double ab2 = 0.0;
             for (int x = 0; x < 3; ++x) {
-                sp.A[x] = A[x];
                 sp.AB[x] = A[x] - Bc[x];
                 ab2 += sp.AB[x] * sp.AB[x];
             }
+            sp.pmin = sp.umax = sp.spare = 0.0;
             sp.Q = 0.0;
             sp.offa = B.off[a]; sp.offb = B.off[b];
             sp.sha = a; sp.shb = b;
@@ -204,15 +204,25 @@ static int build_pairs(unomol_b200 *h) {
     // sr = SR*u12*u34/sqrt(p+q) < prim_cut (TwoElectronInts.cpp:478-479); since u34 <= umax and
     // sqrt(p+q) > sqrt(p12), a primitive pair with SR*u12*umax/sqrt(p12) < prim_cut can never survive.
     long long nprim = 0, nkept = 0;
+    const bool bucketed = (long long)tmp.size() >= h->bucket_min_pairs;
     for (auto &t : tmp) {
         std::vector<PrimPair> keep;
         for (auto &pp : t.pp)
             if (!(SR_TERM * pp.u * umax / std::sqrt(pp.p) * 1.0000001 < h->prim_cut)) keep.push_back(pp);
         if (keep.empty()) continue;
+        // primitive pairs sorted by u (descending) so the kernels can leave the primitive loops as soon as the
+        // bound SR*u_bra*u_ket/sqrt(pmin) drops below the cut
+        std::stable_sort(keep.begin(), keep.end(), [](const PrimPair &x, const PrimPair &y) { return x.u > y.u; });
+        t.sp.umax = keep.front().u;
+        t.sp.pmin = keep.front().p;
+        for (auto &pp : keep) t.sp.pmin = std::min(t.sp.pmin, pp.p);
         t.sp.prim_off = (int)h->h_prims.size();
         t.sp.nprim = (int)keep.size();
         h->h_prims.insert(h->h_prims.end(), keep.begin(), keep.end());
-        h->cls[t.cls].pairs.push_back(t.sp);
+        // lanes of a warp take different kets of one list: keep their primitive loop lengths similar
+        const int np = t.sp.nprim;
+        const int bucket = !bucketed ? 0 : (np <= 1 ? 0 : np <= 3 ? 1 : np <= 6 ? 2 : np <= 12 ? 3 : np <= 24 ? 4 : 5);
+        h->cls[t.cls * NBUCKET + bucket].pairs.push_back(t.sp);
         nprim += keep.size();
         ++nkept;
     }
@@ -227,7 +237,7 @@ static int build_pairs(unomol_b200 *h) {
                                     h->stream));
     }
     // Schwarz bounds: diagonal quartet (ab|ab) of every kept pair, on the GPU (MODE_SCHWARZ)
-    for (int c = 0; c < NPAIRCLASS; ++c) {
+    for (int c = 0; c < NGROUP; ++c) {
         PairClassList &L = h->cls[c];
         L.n = (int)L.pairs.size();
         if (!L.n) continue;
@@ -247,9 +257,9 @@ static int build_pairs(unomol_b200 *h) {
         // reference's sr<1e-12 test passes although it would fail on the weak pair's own diagonal
         task.prim_cut = 0.0;
         task.task_list = d_tl; task.ntask = L.n; task.out = d_q;
-        const int groups = class_groups_per_cta(c, c);
+        const int groups = class_groups_per_cta(c / NBUCKET, c / NBUCKET);
         const int grid = std::min((L.n + groups - 1) / groups, 148 * 16);
-        CUDA_TRY(h, launch_quartet_class(c, c, task, MODE_SCHWARZ, grid, h->stream));
+        CUDA_TRY(h, launch_quartet_class(c / NBUCKET, c / NBUCKET, task, MODE_SCHWARZ, grid, h->stream));
         std::vector<double> q(L.n);
         CUDA_TRY(h, cudaMemcpyAsync(q.data(), d_q, sizeof(double) * L.n, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -281,7 +291,7 @@ static int build_plans(unomol_b200 *h) {
         if (p.d_ket_count) cudaFree(p.d_ket_count);
     h->plans.clear();
     long long total = 0;
-    for (int cb = 0; cb < NPAIRCLASS; ++cb)
+    for (int cb = 0; cb < NGROUP; ++cb)
         for (int ck = 0; ck <= cb; ++ck) {
             const PairClassList &Lb = h->cls[cb], &Lk = h->cls[ck];
             if (!Lb.n || !Lk.n) continue;
@@ -310,7 +320,7 @@ static int build_plans(unomol_b200 *h) {
             if (plan.nbra_eff == 0) continue;
             int maxbp = 0;
             for (int i = 0; i < plan.nbra_eff; ++i) maxbp = std::max(maxbp, Lb.pairs[i].nprim);
-            plan.use_reg = h->use_reg_kernels && reg_class_available(cb, ck) && maxbp <= reg_max_bra_prims();
+            plan.use_reg = h->use_reg_kernels && reg_class_available(cb / NBUCKET, ck / NBUCKET) && maxbp <= reg_max_bra_prims();
             if (cudaMalloc(&plan.d_ket_count, sizeof(int) * Lb.n) != cudaSuccess) return UNOMOL_E_NOMEM;
             cudaMemcpyAsync(plan.d_ket_count, kc.data(), sizeof(int) * Lb.n, cudaMemcpyHostToDevice, h->stream);
             cudaStreamSynchronize(h->stream);
@@ -377,9 +387,9 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         task.counters = h->d_counters + 2 * ip;
         const int nmine = (pl.nbra_eff - h->rank + h->nranks - 1) / h->nranks;
         if (pl.use_reg) {
-            CUDA_TRY(h, launch_reg_class(pl.cb, pl.ck, task, std::min(nmine, 148 * 16), st));
+            CUDA_TRY(h, launch_reg_class(pl.cb / NBUCKET, pl.ck / NBUCKET, task, std::min(nmine, 148 * 16), st));
         } else {
-            CUDA_TRY(h, launch_quartet_class(pl.cb, pl.ck, task, MODE_DIGEST, std::min(nmine, 148 * 32), st));
+            CUDA_TRY(h, launch_quartet_class(pl.cb / NBUCKET, pl.ck / NBUCKET, task, MODE_DIGEST, std::min(nmine, 148 * 32), st));
         }
         ++nlaunch;
     }
@@ -413,8 +423,8 @@ static int finish_stats(unomol_b200 *h) {
     double fl = 0.0;
     for (size_t ip = 0; ip < h->plans.size(); ++ip) {
         int la, lb, lc, ld;
-        pair_class_l(h->plans[ip].cb, la, lb);
-        pair_class_l(h->plans[ip].ck, lc, ld);
+        pair_class_l(h->plans[ip].cb / NBUCKET, la, lb);
+        pair_class_l(h->plans[ip].ck / NBUCKET, lc, ld);
         nq += (long long)c[2 * ip];
         fl += (double)c[2 * ip + 1] * model_flops_per_primitive_quartet(la, lb, lc, ld);
     }
@@ -497,6 +507,7 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
     }
     if (!strcmp(name, "prim_cut")) { h->prim_cut = value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "density_screen")) { h->density_screen = value != 0.0; return UNOMOL_OK; }
+    if (!strcmp(name, "bucket_min_pairs")) { h->bucket_min_pairs = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "reg_kernels")) {
         h->use_reg_kernels = value != 0.0;
         if (h->pairs_ready) return build_plans(h);
@@ -593,7 +604,7 @@ int unomol_b200_schwarz(unomol_b200_t *h, double *Q) {
     if (!h->pairs_ready) { int rc = build_pairs(h); if (rc) return rc; }
     const size_t np = (size_t)h->basis.nshell * (h->basis.nshell + 1) / 2;
     for (size_t i = 0; i < np; ++i) Q[i] = 0.0;
-    for (int c = 0; c < NPAIRCLASS; ++c)
+    for (int c = 0; c < NGROUP; ++c)
         for (auto &sp : h->cls[c].pairs) Q[sp.pairid] = sp.Q;
     return UNOMOL_OK;
 }
@@ -642,7 +653,7 @@ int unomol_b200_eri_quartet(unomol_b200_t *h, int ish, int jsh, int ksh, int lsh
     task.nbra = h->cls[cb].n; task.nket = h->cls[ck].n;
     task.prim_cut = h->prim_cut;
     task.task_list = d_tl; task.task_out = d_off; task.ntask = 1; task.out = d_out;
-    CUDA_TRY(h, launch_quartet_class(cb, ck, task, MODE_DUMP, 1, h->stream));
+    CUDA_TRY(h, launch_quartet_class(cb / NBUCKET, ck / NBUCKET, task, MODE_DUMP, 1, h->stream));
     std::vector<double> blk(ntot);
     CUDA_TRY(h, cudaMemcpyAsync(blk.data(), d_out, sizeof(double) * ntot, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -677,12 +688,12 @@ int unomol_b200_dump_eris(unomol_b200_t *h, double thresh, unomol_twoint *buf, s
     struct Combo { int cb, ck; long long base; int nint; };
     std::vector<Combo> combos;
     long long total = 0;
-    for (int cb = 0; cb < NPAIRCLASS; ++cb)
+    for (int cb = 0; cb < NGROUP; ++cb)
         for (int ck = 0; ck <= cb; ++ck) {
             const int nb = h->cls[cb].n, nk = h->cls[ck].n;
             if (!nb || !nk) continue;
             int la, lb, lc, ld;
-            pair_class_l(cb, la, lb); pair_class_l(ck, lc, ld);
+            pair_class_l(cb / NBUCKET, la, lb); pair_class_l(ck / NBUCKET, lc, ld);
             const int nint = ((la + 1) * (la + 2) / 2) * ((lb + 1) * (lb + 2) / 2) * ((lc + 1) * (lc + 2) / 2) * ((ld + 1) * (ld + 2) / 2);
             const long long ntask = (cb == ck) ? (long long)nb * (nb + 1) / 2 : (long long)nb * nk;
             combos.push_back({cb, ck, total, nint});
@@ -712,9 +723,9 @@ int unomol_b200_dump_eris(unomol_b200_t *h, double thresh, unomol_twoint *buf, s
         task.bra = h->cls[cmb.cb].d_pairs; task.ket = h->cls[cmb.ck].d_pairs; task.prims = h->d_prims;
         task.nbra = nb; task.nket = nk; task.prim_cut = h->prim_cut;
         task.task_list = d_tl; task.task_out = d_off; task.ntask = (int)tl.size(); task.out = d_out;
-        const int groups = class_groups_per_cta(cmb.cb, cmb.ck);
+        const int groups = class_groups_per_cta(cmb.cb / NBUCKET, cmb.ck / NBUCKET);
         const int grid = std::min(((int)tl.size() + groups - 1) / groups, 148 * 16);
-        CUDA_TRY(h, launch_quartet_class(cmb.cb, cmb.ck, task, MODE_DUMP, grid, h->stream));
+        CUDA_TRY(h, launch_quartet_class(cmb.cb / NBUCKET, cmb.ck / NBUCKET, task, MODE_DUMP, grid, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         cudaFree(d_tl); cudaFree(d_off);
     }

@@ -55,10 +55,11 @@ struct unomol_b200 {
     ub200::HostBasis basis;
     double tau = 1e-12, prim_cut = 1e-12;
     int density_screen = 0;
-    int use_reg_kernels = 1;   // option "reg_kernels": 0 forces the generic kernel for every class
+    int use_reg_kernels = 1;
+    int bucket_min_pairs = 20000;   // primitive-count bucketing only pays off for large pair lists   // option "reg_kernels": 0 forces the generic kernel for every class
     bool pairs_ready = false;
     // pair data
-    ub200::PairClassList cls[ub200::NPAIRCLASS];
+    ub200::PairClassList cls[ub200::NGROUP];   // indexed by group id (class * NBUCKET + primitive-count bucket)
     std::vector<ub200::PrimPair> h_prims;
     ub200::PrimPair *d_prims = nullptr;
     std::vector<int> pair_cls, pair_pos;      // per canonical shell pair id: class and position (-1 = pruned)

@@ -153,14 +153,26 @@ eri_class_kernel(const ClassTask task) {
             for (int m = 0; m < C::NACC; ++m) acc[m] = 0.0;
             const PrimPair *bp = task.prims + bra.prim_off;
             const PrimPair *kp = task.prims + ket.prim_off;
+            // primitive cut with early exits: see eri_reg.cuh (lists sorted by u descending)
+            const double cut2 = task.prim_cut * task.prim_cut;
             for (int ib = 0; ib < bra.nprim; ++ib) {
                 const PrimPair b = bp[ib];
+                const double tb0 = SR_TERM * b.u;
+                {
+                    const double tq = tb0 * ket.umax;
+                    if (tq * tq < cut2 * ket.pmin) break;
+                    if (tq * tq < cut2 * (ket.pmin + b.p)) continue;
+                }
                 for (int ik = 0; ik < ket.nprim; ++ik) {
                     const PrimPair k = kp[ik];
                     const double txp = b.p + k.p;
+                    const double t = tb0 * k.u;
+                    if (t * t < cut2 * txp) {
+                        if (t * t < cut2 * (ket.pmin + b.p)) break;
+                        continue;
+                    }
                     const double itx = 1.0 / txp;
-                    double sr = SR_TERM * b.u * k.u * sqrt(itx);
-                    if (sr < task.prim_cut) continue;   // reference TwoElectronInts.cpp:479 (before coefficients)
+                    double sr = t * sqrt(itx);
                     sr *= b.c * k.c;
                     if (lig == 0) ++n_primq;
                     const double pq0 = b.P[0] - k.P[0], pq1 = b.P[1] - k.P[1], pq2 = b.P[2] - k.P[2];

@@ -6,6 +6,8 @@ namespace ub200 {
 
 constexpr int MAXL = 2;            // per-shell angular momentum handled by the built kernels (s, p, d)
 constexpr int NPAIRCLASS = 6;      // ss ps pp ds dp dd  (la >= lb; id = la*(la+1)/2 + lb)
+constexpr int NBUCKET = 6;         // pair lists are further split by primitive-pair count (1, 2-3, 4-6, 7-12, 13-24, 25+)
+constexpr int NGROUP = NPAIRCLASS * NBUCKET;   // group id = class * NBUCKET + bucket; one ERI launch per (bra group >= ket group)
 constexpr double SR_TERM = 34.9868366552497250;  // 2*pi^(5/2), reference TwoElectronInts.cpp:427
 
 // One primitive pair of a shell pair.  Replaces the per-quartet recomputation of p, P, P-A and
@@ -21,7 +23,9 @@ struct __attribute__((aligned(16))) PrimPair {
 
 // One shell pair, first shell has l_a >= l_b.  96 B.
 struct __attribute__((aligned(16))) ShellPair {
-    double A[3];     // centre of shell a (needed for Q - C on the ket side via PA only; kept for dumps)
+    double pmin;     // smallest primitive-pair exponent sum p of this pair (bound for the primitive cut)
+    double umax;     // largest u of this pair's primitive pairs (they are stored sorted by u, descending)
+    double spare;
     double AB[3];    // A - B
     double Q;        // Schwarz bound sqrt(max |(ab|ab)|)
     int offa, offb;  // first basis function of shell a / b
