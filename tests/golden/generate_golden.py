@@ -115,5 +115,22 @@ def main():
         json.dump(runs, open(path, "w"), indent=1)
 
 
+def cation_variants():
+    """BASELINE config 3 (UHF on the DZP molecules): the reference picks UHF only by the parity of nelec
+    (Unomol.cc:13), so the cation inputs are the shipped files with nelec lowered by one."""
+    runs = json.load(open(os.path.join(HERE, "ref_runs.json")))
+    global REFT
+    for name, ne in [("dh95.co2", 21), ("dh95.c2h2", 13)]:
+        lines = open(os.path.join(HERE, "inputs", "patin.dat." + name)).read().split("\n")
+        k = [i for i, l in enumerate(lines) if l.strip()][1]
+        f = lines[k].split(); lines[k] = "     %d    %s" % (ne, f[1])
+        open(os.path.join(HERE, "inputs", "patin.dat.%s.cation" % name), "w").write("\n".join(lines))
+    REFT = os.path.join(HERE, "inputs")
+    for n in ["dh95.co2.cation", "dh95.c2h2.cation"]:
+        runs[n] = run_unomol(n)
+    json.dump(runs, open(os.path.join(HERE, "ref_runs.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
     main()
+    cation_variants()

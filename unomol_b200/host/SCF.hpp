@@ -1,0 +1,310 @@
+// unomol_b200/host/SCF.hpp -- RestrictedHartreeFock / UnRestrictedHartreeFock drivers with the reference's call
+// surface and iteration logic (reference RHF.hpp:22-685, UHF.hpp:23-790), on top of the GPU two-electron engine.
+//
+// Mirrors, member for member where it matters for parity:
+//   update()         zero G -> tints.formGmatrix -> energy -> F = H + G -> diagonalise -> C -> P -> |dP|
+//                    (RHF.hpp:87-112, UHF.hpp:101-134)
+//   findEnergy()     nuclear repulsion, one-electron matrices, X = S^-1/2, core guess, two plain updates, then
+//                    scf_converger(); update(); is_converged()   (RHF.hpp:114-176, UHF.hpp:137-177)
+//   scf_converger()  shift history if the last dE < 0, else P <- (P + Pold)/2   (RHF.hpp:536-569; the
+//                    extrapolation branch is dead in the serial reference: extrap is never set)
+//   is_converged()   signed tests on ediff / pdiff per cflag   (RHF.hpp:390-402)
+//   final_output()   short.gs.out (E_iter0, E_final, dE) and scfout.gs.out energies + orbital energies
+//                    (RHF.hpp:404-459); PMATRIX.DAT checkpoint (RHF.hpp:172-174)
+// What changes: the packed EISPACK-style eigensolver / transforms (SymmPack.cpp:272-348) are replaced by
+// cuSOLVER / cuBLAS on the device through unomol_b200_scf_set_overlap / unomol_b200_scf_diag (no CPU fallback).
+// Moments, finite-field and polarisation-potential drivers are outside the hot-path scope.
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "Basis.hpp"
+#include "OneElectron.hpp"
+#include "TwoElectronInts.hpp"
+
+namespace unomol {
+
+namespace SymmPack {
+inline double TraceSymmPackProduct(const double *a, const double *b, int n) noexcept {   // SymmPack.cpp:7-18
+    double sum = 0.0;
+    int ij = 0;
+    for (int i = 0; i < n; ++ij, ++i) {
+        for (int j = 0; j < i; ++ij, ++j) sum += a[ij] * b[ij];
+        sum += 0.5 * a[ij] * b[ij];
+    }
+    return sum + sum;
+}
+inline double SymmPackDiffNorm(const double *a, const double *b, int n) noexcept {   // SymmPack.cpp:20-36
+    double sum = 0.0;
+    int ij = 0;
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < i; ++ij, ++j) { const double t = a[ij] - b[ij]; sum += t * t; }
+        const double t = a[ij] - b[ij];
+        sum += 0.5 * t * t;
+        ++ij;
+    }
+    sum = sum + sum;
+    return std::sqrt(sum) / n;
+}
+}  // namespace SymmPack
+
+inline double nuclear_repulsion_energy(int ncen, const Center *center) {   // RHF.hpp:273-290
+    double sum = 0.0;
+    for (int i = 0; i < ncen; ++i)
+        for (int j = i + 1; j < ncen; ++j) {
+            const double *r1 = center[i].r_vec(), *r2 = center[j].r_vec();
+            const double r12 = std::sqrt((r1[0] - r2[0]) * (r1[0] - r2[0]) + (r1[1] - r2[1]) * (r1[1] - r2[1]) + (r1[2] - r2[2]) * (r1[2] - r2[2]));
+            sum += center[i].charge() * center[j].charge() / r12;
+        }
+    return sum;
+}
+
+inline void scf_check(int rc, const char *what) {
+    if (rc != UNOMOL_OK) {
+        fprintf(stderr, "unomol_b200 %s: %s\n", what, unomol_b200_strerror(rc));
+        exit(EXIT_FAILURE);
+    }
+}
+
+class RestrictedHartreeFock {
+  public:
+    RestrictedHartreeFock() = delete;
+    RestrictedHartreeFock(Basis *b, TwoElectronInts *t) : basis(*b), tints(*t) {
+        no = basis.number_of_orbitals();
+        no2 = no * (no + 1) / 2;
+        ncen = basis.number_of_centers();
+        nocc = basis.number_of_electrons();
+        if (nocc % 2) fatal_error("Odd number of electrons in RHF");
+        nocc /= 2;
+        maxits = basis.maximum_iterations();
+        eps = basis.scf_eps();
+        scf_accel = basis.scf_flags(1);
+        cflag = basis.scf_flags(0);
+        for (auto *v : {&Pold2, &Pold, &Pmat, &Gmat, &Hmat, &Fock, &Tmat, &Smat}) v->assign(no2, 0.0);
+        Evals.assign(no, 0.0);
+        Cmat.assign((size_t)no * no, 0.0);
+    }
+
+    void update() noexcept {
+        for (int i = 0; i < no2; ++i) Gmat[i] = 0.0;
+        tints.formGmatrix(Pmat.data(), Gmat.data());
+        const double e1 = SymmPack::TraceSymmPackProduct(Pmat.data(), Hmat.data(), no) * 2.0;
+        const double e2 = SymmPack::TraceSymmPackProduct(Pmat.data(), Gmat.data(), no);
+        energy = e1 + e2;
+        ediff = energy - eold;
+        eold = energy;
+        for (int i = 0; i < no2; ++i) Fock[i] = Hmat[i] + Gmat[i];
+        if (scf_accel == 1) Pold2 = Pold;
+        Pold = Pmat;
+        scf_check(unomol_b200_scf_diag(tints.handle(), Fock.data(), nocc, Evals.data(), Cmat.data(), Pmat.data()), "scf_diag");
+        pdiff = SymmPack::SymmPackDiffNorm(Pmat.data(), Pold.data(), no);
+        ++iteration;
+    }
+
+    void findEnergy() noexcept {
+        nucrep = nuclear_repulsion_energy(ncen, basis.center_ptr());
+        OneElectronInts(basis, Smat.data(), Tmat.data(), Hmat.data());
+        scf_check(unomol_b200_scf_set_overlap(tints.handle(), Smat.data()), "scf_set_overlap");   // formXmatrix
+        if (basis.scf_flags(2)) {
+            FILE *in = fopen("PMATRIX.DAT", "r");
+            if (!in || fread(Pmat.data(), sizeof(double), no2, in) != (size_t)no2) fatal_error("Could not read PMATRIX.DAT");
+            fclose(in);
+        } else {
+            PmatrixGuess();
+        }
+        iteration = 0;
+        eold = 0.0;
+        update();
+        report();
+        init_energy = energy + nucrep;
+        iteration = 1;
+        update();
+        report();
+        iteration = 2;
+        while (iteration < maxits) {
+            scf_converger();
+            update();
+            if (is_converged()) break;
+            report();
+        }
+        FILE *fp = fopen("PMATRIX.DAT", "w");
+        if (fp) { fwrite(Pmat.data(), sizeof(double), no2, fp); fclose(fp); }
+        final_output(init_energy);
+    }
+
+    void PmatrixGuess() {   // core-Hamiltonian guess, RHF.hpp:205-211
+        scf_check(unomol_b200_scf_diag(tints.handle(), Hmat.data(), nocc, Evals.data(), Cmat.data(), Pmat.data()), "scf_diag");
+    }
+
+    bool is_converged() const noexcept {
+        switch (cflag) {
+            case 0: return ediff < eps;
+            case 1: return pdiff < eps;
+            default: return pdiff < eps && ediff < eps;
+        }
+    }
+
+    void scf_converger() {
+        if (ediff < 0.0) {
+            Pold2 = Pold;
+            Pold = Pmat;
+            return;
+        }
+        for (int i = 0; i < no2; ++i) Pmat[i] = (Pmat[i] + Pold[i]) * 0.5;
+    }
+
+    void final_output(double e0) {
+        FILE *out = fopen("short.gs.out", "w");
+        fprintf(out, "%25.16le\n%25.16le\n%25.16le\n", e0, energy + nucrep, ediff);
+        fclose(out);
+        out = fopen("scfout.gs.out", "w");
+        const double trace_t = 2.0 * SymmPack::TraceSymmPackProduct(Pmat.data(), Tmat.data(), no);
+        const double virial = std::fabs((energy + nucrep - trace_t) / (trace_t) / 2.0);
+        if (maxits <= iteration) fprintf(out, "WARNING CONVERGENCE _NOT_ REACHED!\n");
+        fprintf(out, "Final Iteration              = %12u\n", iteration);
+        fprintf(out, "Hartree Fock Energy          = %25.15le Hartree\n", energy + nucrep);
+        fprintf(out, "Electronic Energy            = %25.15le Hartree\n", energy);
+        fprintf(out, "Nuclear Rep. Energy          = %25.15le Hartree\n", nucrep);
+        fprintf(out, "Kinetic Energy               = %25.15le Hartree\n", trace_t);
+        fprintf(out, "Difference in Final Energies = %25.16le Hartree\n", ediff);
+        fprintf(out, "Pmatrix diff norm            = %25.16le\n", pdiff);
+        fprintf(out, "virial                       = %25.16le\n", virial);
+        fprintf(out, "xxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxx\n               Orbital Energies\nOrbital Energy          Occupancy\n");
+        for (int i = 0; i < no; i++) fprintf(out, "%7u %25.16le %12u\n", i + 1, Evals[i], i < nocc ? 2 : 0);
+        fprintf(out, "xxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxx\n");
+        fclose(out);
+    }
+
+    double total_energy() const { return energy + nucrep; }
+    int iterations() const { return iteration; }
+
+  private:
+    void report() const {
+        fprintf(stderr, "Iteration     =  %6d\nEnergy        =  %25.16le\nDelta Energy  =  %25.15le\nDelta Density =  %25.15le\n\n", iteration,
+                eold + nucrep, ediff, pdiff);
+    }
+    Basis &basis;
+    TwoElectronInts &tints;
+    int no = 0, no2 = 0, ncen = 0, nocc = 0, maxits = 0, scf_accel = 0, cflag = 0, iteration = 0;
+    double eps = 0, ediff = 10.0, pdiff = 10.0, eold = 0, nucrep = 0, energy = 0, init_energy = 0;
+    std::vector<double> Pold2, Pold, Pmat, Gmat, Hmat, Fock, Tmat, Smat, Evals, Cmat;
+};
+
+class UnRestrictedHartreeFock {
+  public:
+    UnRestrictedHartreeFock() = delete;
+    UnRestrictedHartreeFock(Basis *b, TwoElectronInts *t) : basis(*b), tints(*t) {
+        no = basis.number_of_orbitals();
+        no2 = no * (no + 1) / 2;
+        ncen = basis.number_of_centers();
+        noccB = basis.number_of_electrons();
+        noccA = noccB - noccB / 2;   // UHF.hpp:38-40
+        noccB /= 2;
+        maxits = basis.maximum_iterations();
+        eps = basis.scf_eps();
+        scf_accel = basis.scf_flags(1);
+        cflag = basis.scf_flags(0);
+        for (auto *v : {&Pold2A, &PoldA, &PmatA, &GmatA, &Pold2B, &PoldB, &PmatB, &GmatB, &Hmat, &Fock, &Tmat, &Smat}) v->assign(no2, 0.0);
+        EvalsA.assign(no, 0.0);
+        EvalsB.assign(no, 0.0);
+    }
+
+    void update() noexcept {   // UHF.hpp:101-134
+        for (int i = 0; i < no2; ++i) GmatA[i] = GmatB[i] = 0.0;
+        tints.formGmatrix(PmatA.data(), PmatB.data(), GmatA.data(), GmatB.data());
+        energy = SymmPack::TraceSymmPackProduct(PmatA.data(), Hmat.data(), no) + SymmPack::TraceSymmPackProduct(PmatB.data(), Hmat.data(), no) +
+                 0.5 * (SymmPack::TraceSymmPackProduct(PmatA.data(), GmatA.data(), no) + SymmPack::TraceSymmPackProduct(PmatB.data(), GmatB.data(), no));
+        ediff = energy - eold;
+        eold = energy;
+        for (int i = 0; i < no2; ++i) Fock[i] = Hmat[i] + GmatA[i];
+        if (scf_accel == 1) Pold2A = PoldA;
+        PoldA = PmatA;
+        scf_check(unomol_b200_scf_diag(tints.handle(), Fock.data(), noccA, EvalsA.data(), nullptr, PmatA.data()), "scf_diag");
+        pdiff = SymmPack::SymmPackDiffNorm(PmatA.data(), PoldA.data(), no);
+        for (int i = 0; i < no2; ++i) Fock[i] = Hmat[i] + GmatB[i];
+        if (scf_accel == 1) Pold2B = PoldB;
+        PoldB = PmatB;
+        scf_check(unomol_b200_scf_diag(tints.handle(), Fock.data(), noccB, EvalsB.data(), nullptr, PmatB.data()), "scf_diag");
+        pdiff += SymmPack::SymmPackDiffNorm(PmatB.data(), PoldB.data(), no);
+        ++iteration;
+    }
+
+    void findEnergy() noexcept {   // UHF.hpp:137-177
+        nucrep = nuclear_repulsion_energy(ncen, basis.center_ptr());
+        OneElectronInts(basis, Smat.data(), Tmat.data(), Hmat.data());
+        scf_check(unomol_b200_scf_set_overlap(tints.handle(), Smat.data()), "scf_set_overlap");
+        if (basis.scf_flags(2)) {
+            FILE *in = fopen("PMATRIX.DAT", "r");
+            if (!in || fread(PmatA.data(), sizeof(double), no2, in) != (size_t)no2 || fread(PmatB.data(), sizeof(double), no2, in) != (size_t)no2)
+                fatal_error("Could not read PMATRIX.DAT");
+            fclose(in);
+        } else {   // PmatrixGuess, UHF.hpp:206-215: both spins from the core Hamiltonian
+            scf_check(unomol_b200_scf_diag(tints.handle(), Hmat.data(), noccA, EvalsA.data(), nullptr, PmatA.data()), "scf_diag");
+            scf_check(unomol_b200_scf_diag(tints.handle(), Hmat.data(), noccB, EvalsB.data(), nullptr, PmatB.data()), "scf_diag");
+        }
+        iteration = 0;
+        eold = 0.0;
+        update();
+        const double init_energy = energy + nucrep;
+        iteration = 1;
+        eold = 0.0;   // the reference resets eold here (UHF.hpp:152-154)
+        update();
+        while (iteration < maxits) {
+            scf_converger();
+            update();
+            if (is_converged()) break;
+            fprintf(stderr, "Iteration    =     %5d\nDelta Energy =  %25.15le\n", iteration, ediff);
+        }
+        FILE *fp = fopen("PMATRIX.DAT", "w");
+        if (fp) { fwrite(PmatA.data(), sizeof(double), no2, fp); fwrite(PmatB.data(), sizeof(double), no2, fp); fclose(fp); }
+        FILE *out = fopen("short.gs.out", "w");
+        fprintf(out, "%25.16le\n%25.16le\n%25.16le\n", init_energy, energy + nucrep, ediff);
+        fclose(out);
+        out = fopen("scfout.gs.out", "w");
+        if (maxits <= iteration) fprintf(out, "WARNING CONVERGENCE _NOT_ REACHED!\n");
+        fprintf(out, "Final Iteration              = %12u\n", iteration);
+        fprintf(out, "Hartree Fock Energy          = %25.15le Hartree\n", energy + nucrep);
+        fprintf(out, "Electronic Energy            = %25.15le Hartree\n", energy);
+        fprintf(out, "Nuclear Rep. Energy          = %25.15le Hartree\n", nucrep);
+        fprintf(out, "Difference in Final Energies = %25.16le Hartree\n", ediff);
+        fprintf(out, "Pmatrix diff norm            = %25.16le\n", pdiff);
+        fprintf(out, "               Alpha Orbital Energies\n");
+        for (int i = 0; i < no; i++) fprintf(out, "%7u %25.16le %12u\n", i + 1, EvalsA[i], i < noccA ? 1 : 0);
+        fprintf(out, "               Beta Orbital Energies\n");
+        for (int i = 0; i < no; i++) fprintf(out, "%7u %25.16le %12u\n", i + 1, EvalsB[i], i < noccB ? 1 : 0);
+        fclose(out);
+    }
+
+    bool is_converged() const noexcept {
+        switch (cflag) {
+            case 0: return ediff < eps;
+            case 1: return pdiff < eps;
+            default: return pdiff < eps && ediff < eps;
+        }
+    }
+
+    void scf_converger() {   // UHF.hpp:690-740, serial path (extrap never set)
+        if (ediff < 0.0) {
+            Pold2A = PoldA; PoldA = PmatA;
+            Pold2B = PoldB; PoldB = PmatB;
+            return;
+        }
+        for (int i = 0; i < no2; ++i) {
+            PmatA[i] = (PmatA[i] + PoldA[i]) * 0.5;
+            PmatB[i] = (PmatB[i] + PoldB[i]) * 0.5;
+        }
+    }
+
+    double total_energy() const { return energy + nucrep; }
+    int iterations() const { return iteration; }
+
+  private:
+    Basis &basis;
+    TwoElectronInts &tints;
+    int no = 0, no2 = 0, ncen = 0, noccA = 0, noccB = 0, maxits = 0, scf_accel = 0, cflag = 0, iteration = 0;
+    double eps = 0, ediff = 10.0, pdiff = 10.0, eold = 0, nucrep = 0, energy = 0;
+    std::vector<double> Pold2A, PoldA, PmatA, GmatA, Pold2B, PoldB, PmatB, GmatB, Hmat, Fock, Tmat, Smat, EvalsA, EvalsB;
+};
+
+}  // namespace unomol

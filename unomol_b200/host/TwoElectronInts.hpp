@@ -1,0 +1,94 @@
+// unomol_b200/host/TwoElectronInts.hpp -- drop-in for the reference class unomol::TwoElectronInts
+// (reference TwoElectronInts.hpp:79-110): same constructor and public methods, forwarding to the C ABI of
+// libunomol_b200.so (include/unomol_b200.h).  Works with the reference's own Basis as well as with
+// unomol_b200/host/Basis.hpp: it only uses the accessors both provide.
+//
+//   TwoElectronInts(const Basis&, int start_shell, const std::string& base_str)   reference :83-88
+//   calculate / recalculate(const Basis&)                                         reference :94-98
+//   formGmatrix(P, G)               G += 2J - K        reference TwoElectronInts.cpp:822-844
+//   formGmatrix(PA, PB, GA, GB)     G^s += J - K^s     reference TwoElectronInts.cpp:846-869
+//   directFormGMatrix(P, G, basis)  integral-direct RHF, reference :871-1055 (here every build is direct)
+// base_str named the MINTS.DAT integral cache file (reference Unomol.cc:9); there is no cache any more, the
+// argument is accepted and ignored.  Errors terminate the process like the reference's fatal_error
+// (Util.cpp:5-8), after printing unomol_b200_strerror().
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include "../../include/unomol_b200.h"
+
+namespace unomol {
+
+class TwoElectronInts {
+  public:
+    TwoElectronInts() = delete;
+    TwoElectronInts(const TwoElectronInts &) = delete;
+
+    template <class BasisT>
+    TwoElectronInts(const BasisT &basis, int start_shell, const std::string &base_str) : start(start_shell) {
+        (void)base_str;
+        const char *dev = getenv("UNOMOL_DEVICE");
+        device = dev ? atoi(dev) : 0;
+        calculate(basis);
+    }
+
+    ~TwoElectronInts() { unomol_b200_destroy(h); }
+
+    template <class BasisT>
+    void calculate(const BasisT &basis) {
+        // flatten Basis/Shell/Center (reference Basis.hpp) into the C-ABI descriptor
+        const int ns = basis.number_of_shells(), nc = basis.number_of_centers();
+        std::vector<int> npr(ns), lv(ns), cen(ns), off(ns), poff(ns);
+        std::vector<double> alpha, coef, xyz(3 * nc);
+        for (int s = 0; s < ns; ++s) {
+            const auto &sh = basis.shell_ptr()[s];
+            npr[s] = sh.number_of_prims(); lv[s] = sh.Lvalue(); cen[s] = sh.center();
+            off[s] = basis.offset(s); poff[s] = (int)alpha.size();
+            for (int k = 0; k < npr[s]; ++k) { alpha.push_back(sh.alf(k)); coef.push_back(sh.cof(k)); }
+        }
+        for (int c = 0; c < nc; ++c)
+            for (int x = 0; x < 3; ++x) xyz[3 * c + x] = basis.center_ptr()[c].position(x);
+        if (h) {   // same basis, new geometry: recalculate()
+            check(unomol_b200_set_geometry(h, xyz.data()), "set_geometry");
+            return;
+        }
+        unomol_basis_desc d;
+        d.nshell = ns; d.nbf = basis.number_of_orbitals(); d.ncen = nc; d.maxl = basis.maxLvalue();
+        d.npr = npr.data(); d.lv = lv.data(); d.cen = cen.data(); d.off = off.data(); d.poff = poff.data();
+        d.alpha = alpha.data(); d.coef = coef.data(); d.xyz = xyz.data();
+        check(unomol_b200_create(&d, start, device, 0, 1, &h), "create");
+        const char *tau = getenv("UNOMOL_SCHWARZ_TAU");
+        if (tau) check(unomol_b200_set_option(h, "schwarz_tau", atof(tau)), "set_option");
+        unomol_b200_stats_t st;
+        unomol_b200_stats(h, &st);
+        fprintf(stderr, "unomol_b200: %lld shell pairs kept of %lld, %lld primitive pairs, set-up %.3f ms\n", st.n_pairs_kept,
+                st.n_shell_pairs, st.n_prim_pairs, st.precompute_ms);
+    }
+
+    template <class BasisT>
+    void recalculate(const BasisT &basis) { calculate(basis); }
+
+    void formGmatrix(const double *Pmat, double *Gmat) { check(unomol_b200_fock_rhf(h, Pmat, Gmat), "fock_rhf"); }
+
+    void formGmatrix(const double *PmatA, const double *PmatB, double *GmatA, double *GmatB) {
+        check(unomol_b200_fock_uhf(h, PmatA, PmatB, GmatA, GmatB), "fock_uhf");
+    }
+
+    template <class BasisT>
+    void directFormGMatrix(const double *Pmat, double *Gmat, const BasisT &) { formGmatrix(Pmat, Gmat); }
+
+    unomol_b200_t *handle() const noexcept { return h; }
+
+  private:
+    static void check(int rc, const char *what) {
+        if (rc != UNOMOL_OK) {
+            fprintf(stderr, "unomol_b200 %s: %s\n", what, unomol_b200_strerror(rc));
+            exit(EXIT_FAILURE);
+        }
+    }
+    unomol_b200_t *h = nullptr;
+    int start = 0, device = 0;
+};
+
+}  // namespace unomol
