@@ -144,6 +144,9 @@ int unomol_b200_scf_diag(unomol_b200_t *h, const double *F, int nocc, double *ev
 int unomol_b200_sample_quartets(unomol_b200_t *h, long long nsample, unsigned long long seed, int *shells,
                                 long long *ntotal);
 int unomol_b200_fp64_peak(int device, double *tflops);
+/* algorithmic FLOPs of the reference's Rys algorithm per PRIMITIVE quartet of class (la lb|lc ld);
+ * this is the per-unit figure behind stats.model_flops and bench.py's roofline.achieved.  Host only. */
+double unomol_b200_model_flops(int la, int lb, int lc, int ld);
 
 const char *unomol_b200_strerror(int code);
 const char *unomol_b200_version(void);

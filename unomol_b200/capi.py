@@ -49,7 +49,7 @@ EXPORTS = [
     "unomol_b200_fock_rhf", "unomol_b200_fock_uhf", "unomol_b200_fock_rhf_device", "unomol_b200_fock_uhf_device",
     "unomol_b200_eri_quartet", "unomol_b200_dump_eris", "unomol_b200_schwarz", "unomol_b200_stats",
     "unomol_b200_attach_nccl", "unomol_b200_device_buffers", "unomol_b200_scf_set_overlap", "unomol_b200_scf_diag",
-    "unomol_b200_sample_quartets", "unomol_b200_fp64_peak", "unomol_b200_strerror", "unomol_b200_version",
+    "unomol_b200_sample_quartets", "unomol_b200_fp64_peak", "unomol_b200_model_flops", "unomol_b200_strerror", "unomol_b200_version",
 ]
 
 
@@ -76,6 +76,7 @@ def _load():
     L.unomol_b200_scf_diag.argtypes = [_P, _pd, _I, _pd, _pd, _pd]
     L.unomol_b200_sample_quartets.argtypes = [_P, ctypes.c_longlong, ctypes.c_ulonglong, _pi, ctypes.POINTER(ctypes.c_longlong)]
     L.unomol_b200_fp64_peak.argtypes = [_I, _pd]
+    L.unomol_b200_model_flops.restype = _D; L.unomol_b200_model_flops.argtypes = [_I, _I, _I, _I]
     L.unomol_b200_strerror.restype = ctypes.c_char_p; L.unomol_b200_strerror.argtypes = [_I]
     L.unomol_b200_version.restype = ctypes.c_char_p
     return L

@@ -850,6 +850,8 @@ __global__ void dfma_peak_kernel(double *out, int iters, double a, double b) {
 }
 }  // namespace ub200
 
+double unomol_b200_model_flops(int la, int lb, int lc, int ld) { return model_flops_per_primitive_quartet(la, lb, lc, ld); }
+
 int unomol_b200_fp64_peak(int device, double *tflops) {
     if (!tflops) return UNOMOL_E_ARG;
     if (cudaSetDevice(device) != cudaSuccess) return UNOMOL_E_CUDA;
