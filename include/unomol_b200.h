@@ -66,6 +66,8 @@ typedef struct unomol_b200_stats_t {
     double precompute_ms;         /* pair data + Schwarz bounds of the last create/set_geometry */
     int n_launches;               /* kernels launched by the last Fock build */
     int nbf, nshell, rank, nranks;
+    long long n_prim_quartets;    /* primitive quartets that passed the reference's sr cut in the last build */
+    long long n_prim_candidates;  /* primitive quartets tested against the cut (register kernels only) */
 } unomol_b200_stats_t;
 
 /* Replaces the TwoElectronInts constructor (TwoElectronInts.hpp:83-88) + calculate() set-up

@@ -38,7 +38,8 @@ class Stats(ctypes.Structure):
                 ("n_prim_pairs", ctypes.c_longlong), ("n_quartets", ctypes.c_longlong),
                 ("n_quartets_total", ctypes.c_longlong), ("model_flops", _D), ("last_fock_ms", _D),
                 ("last_eri_kernel_ms", _D), ("precompute_ms", _D), ("n_launches", _I), ("nbf", _I),
-                ("nshell", _I), ("rank", _I), ("nranks", _I)]
+                ("nshell", _I), ("rank", _I), ("nranks", _I),
+                ("n_prim_quartets", ctypes.c_longlong), ("n_prim_candidates", ctypes.c_longlong)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -385,6 +385,8 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         task.PJ = h->d_PJ; task.PK[0] = h->d_PK[0]; task.PK[1] = h->d_PK[1];
         task.J = h->d_J; task.K[0] = h->d_K[0]; task.K[1] = h->d_K[1];
         task.counters = h->d_counters + 2 * ip;
+        task.debug_flags = h->debug_flags;
+        task.cand_counter = h->d_counters + 2 * h->plans.size();
         const int nmine = (pl.nbra_eff - h->rank + h->nranks - 1) / h->nranks;
         if (pl.use_reg) {
             CUDA_TRY(h, launch_reg_class(pl.cb / NBUCKET, pl.ck / NBUCKET, task, std::min(nmine, 148 * 16), st));
@@ -430,6 +432,9 @@ static int finish_stats(unomol_b200 *h) {
     }
     h->stats.n_quartets = nq;
     h->stats.model_flops = fl;
+    h->stats.n_prim_candidates = (long long)c[2 * h->plans.size()];
+    h->stats.n_prim_quartets = 0;
+    for (size_t ip = 0; ip < h->plans.size(); ++ip) h->stats.n_prim_quartets += (long long)c[2 * ip + 1];
     return UNOMOL_OK;
 }
 
@@ -508,6 +513,7 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
     if (!strcmp(name, "prim_cut")) { h->prim_cut = value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "density_screen")) { h->density_screen = value != 0.0; return UNOMOL_OK; }
     if (!strcmp(name, "bucket_min_pairs")) { h->bucket_min_pairs = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
+    if (!strcmp(name, "debug_flags")) { h->debug_flags = (int)value; return UNOMOL_OK; }
     if (!strcmp(name, "reg_kernels")) {
         h->use_reg_kernels = value != 0.0;
         if (h->pairs_ready) return build_plans(h);

@@ -56,6 +56,7 @@ struct unomol_b200 {
     double tau = 1e-12, prim_cut = 1e-12;
     int density_screen = 0;
     int use_reg_kernels = 1;
+    int debug_flags = 0;            // option "debug_flags" (profiling experiments; see ClassTask)
     int bucket_min_pairs = 20000;   // primitive-count bucketing only pays off for large pair lists   // option "reg_kernels": 0 forces the generic kernel for every class
     bool pairs_ready = false;
     // pair data

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const ClassTask ta
     unsigned phase[2] = {0u, 0u};
     int s = 0;
     if (bi < task.nbra && tid == 0) issue(bi, 0);
-    unsigned long long n_quart = 0, n_primq = 0;
+    unsigned long long n_quart = 0, n_primq = 0, n_cand = 0;
 
     while (bi < task.nbra) {
         jb += gridDim.x;
@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const ClassTask ta
                     }
                     while (ib < nbp) {
                         const double t = tk * bp[ib].u;
+                        ++n_cand;
                         if (t * t >= cut2 * (bp[ib].p + k.p)) { found = true; break; }
                         if (t * t < cut2 * (pminb + k.p)) { ib = nbp; break; }
                         ++ib;
@@ -195,13 +196,13 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const ClassTask ta
                     const double pq0 = bp[ib].P[0] - k.P[0], pq1 = bp[ib].P[1] - k.P[1], pq2 = bp[ib].P[2] - k.P[2];
                     const double X = bpv * k.p * itx * (pq0 * pq0 + pq1 * pq1 + pq2 * pq2);
                     if constexpr (NR == 1 && GI * GJ == 1) {
-                        double w, f1;
-                        rys1_f0f1(X, w, f1);
+                        double w = 1.0, f1 = 0.0;
+                        if (!(task.debug_flags & 2)) rys1_f0f1(X, w, f1);
                         acc[0] = fma(sr, w, acc[0]);
                     } else if constexpr (NR == 1) {
                         // (ps|ss): one root, G[1][0] = C per axis: sr*w*C = sr*(PA*w - q/(p+q)*PQ*F1)
-                        double w, f1;
-                        rys1_f0f1(X, w, f1);
+                        double w = 1.0, f1 = 0.0;
+                        if (!(task.debug_flags & 2)) rys1_f0f1(X, w, f1);
                         const double a = sr * w, bq = sr * f1 * k.p * itx;
                         acc[0] = fma(a, bp[ib].PA[0], fma(-bq, pq0, acc[0]));
                         acc[1] = fma(a, bp[ib].PA[1], fma(-bq, pq1, acc[1]));
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const ClassTask ta
             // ---- J/K digestion (reference TwoElectronInts.cpp:699-820, shell-block form)
             const int n = task.nbf;
             const int oa = bra.offa, ob = bra.offb, oc = ket.offa, od = ket.offb;
-            {
+            if (!(task.debug_flags & 4)) {
                 // J[a,b] += sum_cd V PJ[c,d]   (kept in registers across this bra's kets)
                 double pcd[NCD];
 #pragma unroll
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const ClassTask ta
                     atomicAdd(task.J + (size_t)(oc + cd / ND) * n + od + cd % ND, sacc);
                 }
             }
-            for (int sp = 0; sp < task.nspin; ++sp) {
+            for (int sp = 0; sp < ((task.debug_flags & 5) ? 0 : task.nspin); ++sp) {
                 const double *P = task.PK[sp];
                 double *K = task.K[sp];
                 // K[a,c] += sum_bd V P[b,d] ; K[a,d] += sum_bc V P[b,c]
@@ -440,8 +441,10 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const ClassTask ta
         for (int o = 16; o > 0; o >>= 1) {
             n_quart += __shfl_xor_sync(0xffffffffu, n_quart, o);
             n_primq += __shfl_xor_sync(0xffffffffu, n_primq, o);
+            n_cand += __shfl_xor_sync(0xffffffffu, n_cand, o);
         }
         if (lane == 0) {
+            if (task.cand_counter) atomicAdd(task.cand_counter, n_cand);
             atomicAdd(task.counters, n_quart);
             atomicAdd(task.counters + 1, n_primq);
         }

@@ -59,6 +59,8 @@ struct ClassTask {
     int ntask;
     double *out;              // dump: blocks; schwarz: one value per task
     unsigned long long *counters;  // [0] quartets evaluated, [1] primitive quartets surviving the cut
+    unsigned long long *cand_counter;  // primitive-quartet candidates tested against the cut (all launches)
+    int debug_flags;               // profiling experiments only (results invalid): 1 skip exchange digestion, 2 skip root evaluation, 4 skip all digestion
 };
 
 enum Mode { MODE_DIGEST = 0, MODE_DUMP = 1, MODE_SCHWARZ = 2 };
