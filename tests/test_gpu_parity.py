@@ -214,3 +214,64 @@ def test_primitive_count_buckets_do_not_change_results(capi):
     blk0 = h.eri_quartet(35, 2, 17, 30)
     h.set_option("bucket_min_pairs", 10 ** 9)
     assert np.max(np.abs(h.eri_quartet(35, 2, 17, 30) - blk0)) < 1e-14
+
+
+# ---------------------------------------------------------------- edge cases
+def test_h2_minimal_basis_two_functions(capi, oracle):
+    """smallest input of the reference's test set: 2 basis functions, 6 unique integrals"""
+    b, h = _handle(capi, "3g.h2")
+    ob = oracle.basis(golden_input("3g.h2"))
+    vals, ijkl, ncalc = oracle.unique_eris(ob)
+    assert ncalc == 6
+    gv, gi = h.dump_eris(1e-14)
+    assert np.array_equal(gi, ijkl) and np.max(np.abs(gv - vals)) < ERI_TOL
+    P = np.array([0.3, -0.2, 0.7])
+    assert np.max(np.abs(h.fock_rhf(P) - oracle.form_g_rhf(vals, ijkl, P))) < 1e-13
+
+
+def test_start_shell_past_the_end_gives_zero(capi):
+    from unomol_b200.basis import Basis
+    b = Basis.from_patin(golden_input("631.nh3"))
+    h = capi.Handle(b, start_shell=b.nshell)
+    G = h.fock_rhf(np.ones(b.no2))
+    assert np.all(G == 0.0)
+    assert h.stats()["n_quartets"] == 0
+
+
+def test_everything_screened_out_gives_zero(capi):
+    b, h = _handle(capi, "631.nh3")
+    h.set_option("schwarz_tau", 1e30)
+    assert np.all(h.fock_rhf(np.ones(b.no2)) == 0.0)
+
+
+def test_zero_density_and_single_spin(capi):
+    b, h = _handle(capi, "dh95.c2h2")
+    Z = np.zeros(b.no2)
+    assert np.all(h.fock_rhf(Z) == 0.0)
+    rng = np.random.default_rng(8)
+    PA = rng.standard_normal(b.no2)
+    GA, GB = h.fock_uhf(PA, Z)
+    # beta sees only the Coulomb field of alpha: GB = J[PA]; GA = J[PA] - K[PA]; RHF(PA) = 2J - K
+    G = h.fock_rhf(PA)
+    assert np.max(np.abs((GA + GB) - G)) < 1e-12 * np.max(np.abs(G))
+
+
+def test_bad_arguments_fail_loudly(capi):
+    from unomol_b200.basis import Basis
+    b = Basis.from_patin(golden_input("3g.h2o"))
+    with pytest.raises(capi.UnomolError):
+        capi.Handle(b, rank=2, nranks=2)
+    h = capi.Handle(b)
+    with pytest.raises(capi.UnomolError):
+        h.set_option("no_such_option", 1.0)
+    import ctypes
+    assert capi.lib.unomol_b200_eri_quartet(h.h, 0, 0, 0, 99, None) != 0
+
+
+def test_f_shells_are_rejected_not_silently_wrong(capi):
+    """l > 2 is outside the built kernels: create must fail with UNOMOL_E_UNSUPPORTED (-3), never fall back"""
+    from unomol_b200.basis import Basis
+    b = Basis.from_patin(golden_input("3g.h2o"))
+    b.lv = b.lv.copy(); b.lv[0] = 3
+    with pytest.raises(capi.UnomolError, match="-3"):
+        capi.Handle(b)

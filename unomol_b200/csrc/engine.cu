@@ -318,6 +318,12 @@ static int build_plans(unomol_b200 *h) {
             }
             total += plan.nquartets;
             if (plan.nbra_eff == 0) continue;
+            {
+                int la, lb, lc, ld;
+                pair_class_l(cb / NBUCKET, la, lb);
+                pair_class_l(ck / NBUCKET, lc, ld);
+                plan.cost = (double)plan.nquartets * model_flops_per_primitive_quartet(la, lb, lc, ld);
+            }
             int maxbp = 0;
             for (int i = 0; i < plan.nbra_eff; ++i) maxbp = std::max(maxbp, Lb.pairs[i].nprim);
             plan.use_reg = h->use_reg_kernels && reg_class_available(cb / NBUCKET, ck / NBUCKET) && maxbp <= reg_max_bra_prims();
@@ -371,7 +377,24 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
     CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 2 * (h->plans.size() + 1), st));
     cudaEventRecord(h->ev2, st);
     int nlaunch = 2;
-    for (size_t ip = 0; ip < h->plans.size(); ++ip) {
+    // The class launches are independent (they only meet in the FP64 reds on J/K): spread them over a few streams,
+    // largest first, so that the small launches of small molecules (SF6: 24 launches of a few hundred CTAs)
+    // overlap instead of each leaving most SMs idle.
+    if (!h->aux[0]) {
+        for (int a = 0; a < unomol_b200::NAUX; ++a) {
+            CUDA_TRY(h, cudaStreamCreateWithFlags(&h->aux[a], cudaStreamNonBlocking));
+            CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join[a], cudaEventDisableTiming));
+        }
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
+    for (int a = 0; a < unomol_b200::NAUX; ++a) CUDA_TRY(h, cudaStreamWaitEvent(h->aux[a], h->ev_fork, 0));
+    std::vector<size_t> order(h->plans.size());
+    std::iota(order.begin(), order.end(), (size_t)0);
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return h->plans[x].cost > h->plans[y].cost; });
+    for (size_t io = 0; io < order.size(); ++io) {
+        const size_t ip = order[io];
+        cudaStream_t st = h->aux[io % unomol_b200::NAUX];
         const ComboPlan &pl = h->plans[ip];
         ClassTask task{};
         task.bra = h->cls[pl.cb].d_pairs; task.ket = h->cls[pl.ck].d_pairs; task.prims = h->d_prims;
@@ -394,6 +417,10 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
             CUDA_TRY(h, launch_quartet_class(pl.cb / NBUCKET, pl.ck / NBUCKET, task, MODE_DIGEST, std::min(nmine, 148 * 32), st));
         }
         ++nlaunch;
+    }
+    for (int a = 0; a < unomol_b200::NAUX; ++a) {
+        CUDA_TRY(h, cudaEventRecord(h->ev_join[a], h->aux[a]));
+        CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join[a], 0));
     }
     cudaEventRecord(h->ev3, st);
     pack_fock_kernel<<<(unsigned)((no2 + 255) / 256), 256, 0, st>>>(h->d_J, h->d_K[0], h->d_K[1], n, nspin, dGA, dGB);
@@ -498,6 +525,11 @@ void unomol_b200_destroy(unomol_b200_t *h) {
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     unomol_scf_free(h);
     if (h->ev0) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3); }
+    for (int a = 0; a < unomol_b200::NAUX; ++a) {
+        if (h->aux[a]) cudaStreamDestroy(h->aux[a]);
+        if (h->ev_join[a]) cudaEventDestroy(h->ev_join[a]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }

@@ -43,6 +43,7 @@ struct ComboPlan {                  // one (bra class, ket class) launch
     int nbra_eff = 0;               // leading bras that have at least one ket
     long long nquartets = 0;        // sum of ket_count (all ranks, before start_shell filter)
     int *d_ket_count = nullptr;
+    double cost = 0.0;              // quartets x model flops: launch order (largest first)
     bool use_reg = false;           // register-resident kernel (small class, bra contraction fits the stage)
 };
 
@@ -52,6 +53,9 @@ struct unomol_b200 {
     int device = 0, rank = 0, nranks = 1, start_shell = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    static constexpr int NAUX = 4;            // class launches of one build are spread over these streams
+    cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr, nullptr, nullptr};
     ub200::HostBasis basis;
     double tau = 1e-12, prim_cut = 1e-12;
     int density_screen = 0;
