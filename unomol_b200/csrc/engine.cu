@@ -404,6 +404,7 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         task.start_shell = h->start_shell;
         task.rank = h->rank; task.nranks = h->nranks;
         task.prim_cut = h->prim_cut;
+        task.value_cut = h->value_cut;
         task.nbf = n; task.nspin = nspin;
         task.PJ = h->d_PJ; task.PK[0] = h->d_PK[0]; task.PK[1] = h->d_PK[1];
         task.J = h->d_J; task.K[0] = h->d_K[0]; task.K[1] = h->d_K[1];
@@ -545,6 +546,7 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
     if (!strcmp(name, "prim_cut")) { h->prim_cut = value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "density_screen")) { h->density_screen = value != 0.0; return UNOMOL_OK; }
     if (!strcmp(name, "bucket_min_pairs")) { h->bucket_min_pairs = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
+    if (!strcmp(name, "value_cut")) { h->value_cut = value; return UNOMOL_OK; }
     if (!strcmp(name, "debug_flags")) { h->debug_flags = (int)value; return UNOMOL_OK; }
     if (!strcmp(name, "reg_kernels")) {
         h->use_reg_kernels = value != 0.0;

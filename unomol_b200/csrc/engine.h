@@ -57,7 +57,7 @@ struct unomol_b200 {
     cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr, nullptr, nullptr};
     ub200::HostBasis basis;
-    double tau = 1e-12, prim_cut = 1e-12;
+    double tau = 1e-12, prim_cut = 1e-12, value_cut = 1e-14;
     int density_screen = 0;
     int use_reg_kernels = 1;
     int debug_flags = 0;            // option "debug_flags" (profiling experiments; see ClassTask)

@@ -326,6 +326,13 @@ eri_class_kernel(const ClassTask task) {
                 for (int s = T / 2; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(gmask, mx, s));
                 if (lig == 0) task.out[t] = sqrt(mx);
             } else {
+                // blocks entirely below the reference's storage threshold |val| <= 1e-14 never reach its G (see eri_reg.cuh)
+                {
+                    double mx = 0.0;
+                    for (int o = lig; o < C::NINT; o += T) mx = fmax(mx, fabs(SG(OFF_A + o)));
+                    for (int s = T / 2; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(gmask, mx, s));
+                    if (mx <= task.value_cut * sym) continue;
+                }
                 // ---------------- J/K digestion (reference TwoElectronInts.cpp:699-820, shell-block form)
                 // V at OFF_A: [a][b][c][d].  Outputs are dealt to the lanes of the group.
                 const int n = task.nbf;

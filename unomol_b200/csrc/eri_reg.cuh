@@ -195,7 +195,9 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const ClassTask ta
                     ++n_primq;
                     const double pq0 = bp[ib].P[0] - k.P[0], pq1 = bp[ib].P[1] - k.P[1], pq2 = bp[ib].P[2] - k.P[2];
                     const double X = bpv * k.p * itx * (pq0 * pq0 + pq1 * pq1 + pq2 * pq2);
-                    if constexpr (NR == 1 && GI * GJ == 1) {
+                    if (task.debug_flags & 8) {
+                        acc[0] += sr * X;   // timing experiment: no integral evaluation at all
+                    } else if constexpr (NR == 1 && GI * GJ == 1) {
                         double w = 1.0, f1 = 0.0;
                         if (!(task.debug_flags & 2)) rys1_f0f1(X, w, f1);
                         acc[0] = fma(sr, w, acc[0]);
@@ -318,6 +320,16 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const ClassTask ta
                 constexpr double nrm = c_norm(LA, a) * c_norm(LB, b) * c_norm(LC, c) * c_norm(LD, d);
                 V[O] = v * (nrm * sym);
             });
+            // The reference never stores an integral with |val| <= 1e-14 (TwoElectronInts.cpp:513,667-671), so such
+            // integrals never reach its G.  A quartet whose whole block is below that threshold is therefore skipped
+            // here before any gather / red (most Schwarz survivors of a large cluster are of this kind: the bound
+            // Q_ab*Q_cd >= tau says nothing about the 1/R decay between distant charge distributions).
+            {
+                double vmax = 0.0;
+#pragma unroll
+                for (int o = 0; o < NINT; ++o) vmax = fmax(vmax, fabs(V[o]));
+                if (vmax <= task.value_cut * sym) continue;
+            }
             // ---- J/K digestion (reference TwoElectronInts.cpp:699-820, shell-block form)
             const int n = task.nbf;
             const int oa = bra.offa, ob = bra.offb, oc = ket.offa, od = ket.offb;

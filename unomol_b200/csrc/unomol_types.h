@@ -47,6 +47,7 @@ struct ClassTask {
     int start_shell;          // quartet kept iff max shell index >= start_shell
     int rank, nranks;         // bras are dealt round-robin to ranks
     double prim_cut;          // reference's sr < 1e-12 cut
+    double value_cut;         // reference's |val| > 1e-14 storage threshold (TwoElectronInts.cpp:513)
     // digestion
     int nbf, nspin;
     const double *PJ;         // square nbf*nbf, pre-scaled density for the Coulomb term
