@@ -11,6 +11,8 @@
 // No CPU fallback: every compute entry point needs a CUDA device.
 #include <algorithm>
 #include <array>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -153,32 +155,44 @@ static int build_pairs(unomol_b200 *h) {
     h->pair_cls.assign((size_t)ns * (ns + 1) / 2, -1);
     h->pair_pos.assign((size_t)ns * (ns + 1) / 2, -1);
     h->h_prims.clear();
-    // pass 1: every primitive pair of every shell pair; track the global maximum of u for the exact prune
-    struct TmpPair { ShellPair sp; std::vector<PrimPair> pp; int cls; };
-    std::vector<TmpPair> tmp;
-    tmp.reserve((size_t)ns * (ns + 1) / 2);
+    // Exact prune.  A primitive quartet is skipped by the reference when sr = SR*u12*u34/sqrt(p+q) < prim_cut
+    // (TwoElectronInts.cpp:478-479).  u34 <= umax and sqrt(p+q) > sqrt(p12), so a primitive pair with
+    // SR*u12*umax/sqrt(p12) < prim_cut can never survive against any partner and is dropped; umax = 1/(2 alpha_min)
+    // is attained by the most diffuse shell paired with itself.  A whole shell pair is rejected before any exp()
+    // when even its most diffuse primitive pair fails that test (u, 1/p and 1/sqrt(p) are all largest there).
+    // Rows of the (i >= j) pair triangle are processed by a few host threads; the result is concatenated in (i, j)
+    // order so the tables do not depend on the thread count.
+    std::vector<double> amin(ns);
     double umax = 0.0;
-    for (int i = 0; i < ns; ++i)
+    for (int s = 0; s < ns; ++s) {
+        amin[s] = B.alpha[B.poff[s]];
+        for (int k = 1; k < B.npr[s]; ++k) amin[s] = std::min(amin[s], B.alpha[B.poff[s] + k]);
+        umax = std::max(umax, 0.5 / amin[s]);
+    }
+    struct OutPair { ShellPair sp; int cls; int first, count; };
+    struct RowOut { std::vector<OutPair> pairs; std::vector<PrimPair> prims; };
+    std::vector<RowOut> rows(ns);
+    const double prim_cut = h->prim_cut;
+    auto do_row = [&](int i) {
+        RowOut &R = rows[i];
+        std::vector<PrimPair> keep;
         for (int j = 0; j <= i; ++j) {
             // first shell = higher l (reference swaps so that l1 >= l2, TwoElectronInts.cpp:563-580)
             int a = i, b = j;
             if (B.lv[i] < B.lv[j]) { a = j; b = i; }
-            TmpPair t;
-            ShellPair &sp = t.sp;
             const double *A = &B.xyz[3 * B.cen[a]], *Bc = &B.xyz[3 * B.cen[b]];
+            ShellPair sp;
             double ab2 = 0.0;
             for (int x = 0; x < 3; ++x) {
                 sp.AB[x] = A[x] - Bc[x];
                 ab2 += sp.AB[x] * sp.AB[x];
             }
-            sp.pmin = sp.umax = sp.spare = 0.0;
-            sp.Q = 0.0;
-            sp.offa = B.off[a]; sp.offb = B.off[b];
-            sp.sha = a; sp.shb = b;
-            sp.pairid = i * (i + 1) / 2 + j;
-            sp.pad = 0;
-            t.cls = pair_class_id(B.lv[a], B.lv[b]);
+            {
+                const double pm = amin[a] + amin[b], mu = amin[a] * amin[b] / pm;
+                if (SR_TERM * std::exp(-mu * ab2) / pm * umax / std::sqrt(pm) * 1.0000001 < prim_cut) continue;
+            }
             const bool same = (a == b);   // the reference's pointer test al1==al2 (TwoElectronInts.cpp:444)
+            keep.clear();
             for (int ia = 0; ia < B.npr[a]; ++ia) {
                 const double axp = B.alpha[B.poff[a] + ia], c1 = B.coef[B.poff[a] + ia];
                 const int jend = same ? ia + 1 : B.npr[b];
@@ -187,47 +201,63 @@ static int build_pairs(unomol_b200 *h) {
                     PrimPair pp;
                     pp.p = axp + bxp;
                     pp.ip = 1.0 / pp.p;
-                    const double s12 = std::exp(-axp * bxp * ab2 * pp.ip);
+                    pp.u = std::exp(-axp * bxp * ab2 * pp.ip) * pp.ip;
+                    if (SR_TERM * pp.u * umax / std::sqrt(pp.p) * 1.0000001 < prim_cut) continue;
                     for (int x = 0; x < 3; ++x) {
                         pp.P[x] = (axp * A[x] + bxp * Bc[x]) * pp.ip;
                         pp.PA[x] = pp.P[x] - A[x];
                     }
-                    pp.u = s12 * pp.ip;
                     pp.c = c1 * c2 * ((same && ia != ib) ? 2.0 : 1.0);
-                    if (pp.u > umax) umax = pp.u;
-                    t.pp.push_back(pp);
+                    keep.push_back(pp);
                 }
             }
-            tmp.push_back(std::move(t));
+            if (keep.empty()) continue;
+            // primitive pairs sorted by u (descending) so the kernels can leave the primitive loops as soon as the
+            // bound SR*u_bra*u_ket/sqrt(pmin) drops below the cut
+            std::stable_sort(keep.begin(), keep.end(), [](const PrimPair &x, const PrimPair &y) { return x.u > y.u; });
+            sp.umax = keep.front().u;
+            sp.pmin = keep.front().p;
+            for (auto &pp : keep) sp.pmin = std::min(sp.pmin, pp.p);
+            sp.spare = 0.0;
+            sp.Q = 0.0;
+            sp.offa = B.off[a]; sp.offb = B.off[b];
+            sp.sha = a; sp.shb = b;
+            sp.pairid = i * (i + 1) / 2 + j;
+            sp.pad = 0;
+            sp.prim_off = 0;
+            sp.nprim = (int)keep.size();
+            R.pairs.push_back({sp, pair_class_id(B.lv[a], B.lv[b]), (int)R.prims.size(), (int)keep.size()});
+            R.prims.insert(R.prims.end(), keep.begin(), keep.end());
         }
-    // pass 2: exact prune.  A primitive quartet is skipped by the reference when
-    // sr = SR*u12*u34/sqrt(p+q) < prim_cut (TwoElectronInts.cpp:478-479); since u34 <= umax and
-    // sqrt(p+q) > sqrt(p12), a primitive pair with SR*u12*umax/sqrt(p12) < prim_cut can never survive.
-    long long nprim = 0, nkept = 0;
-    const bool bucketed = (long long)tmp.size() >= h->bucket_min_pairs;
-    for (auto &t : tmp) {
-        std::vector<PrimPair> keep;
-        for (auto &pp : t.pp)
-            if (!(SR_TERM * pp.u * umax / std::sqrt(pp.p) * 1.0000001 < h->prim_cut)) keep.push_back(pp);
-        if (keep.empty()) continue;
-        // primitive pairs sorted by u (descending) so the kernels can leave the primitive loops as soon as the
-        // bound SR*u_bra*u_ket/sqrt(pmin) drops below the cut
-        std::stable_sort(keep.begin(), keep.end(), [](const PrimPair &x, const PrimPair &y) { return x.u > y.u; });
-        t.sp.umax = keep.front().u;
-        t.sp.pmin = keep.front().p;
-        for (auto &pp : keep) t.sp.pmin = std::min(t.sp.pmin, pp.p);
-        t.sp.prim_off = (int)h->h_prims.size();
-        t.sp.nprim = (int)keep.size();
-        h->h_prims.insert(h->h_prims.end(), keep.begin(), keep.end());
-        // lanes of a warp take different kets of one list: keep their primitive loop lengths similar
-        const int np = t.sp.nprim;
-        const int bucket = !bucketed ? 0 : (np <= 1 ? 0 : np <= 3 ? 1 : np <= 6 ? 2 : np <= 12 ? 3 : np <= 24 ? 4 : 5);
-        h->cls[t.cls * NBUCKET + bucket].pairs.push_back(t.sp);
-        nprim += keep.size();
-        ++nkept;
+    };
+    {
+        const int nthr = std::max(1, std::min<int>(16, std::min<int>((int)std::thread::hardware_concurrency(), ns / 64)));
+        if (nthr <= 1) {
+            for (int i = 0; i < ns; ++i) do_row(i);
+        } else {
+            std::atomic<int> next(0);
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nthr; ++t)
+                pool.emplace_back([&]() { for (int i = next.fetch_add(1); i < ns; i = next.fetch_add(1)) do_row(ns - 1 - i); });
+            for (auto &t : pool) t.join();
+        }
     }
-    tmp.clear();
-    tmp.shrink_to_fit();
+    long long nprim = 0, nkept = 0;
+    const bool bucketed = (long long)ns * (ns + 1) / 2 >= h->bucket_min_pairs;
+    for (int i = 0; i < ns; ++i) {
+        for (auto &o : rows[i].pairs) {
+            o.sp.prim_off = (int)h->h_prims.size();
+            h->h_prims.insert(h->h_prims.end(), rows[i].prims.begin() + o.first, rows[i].prims.begin() + o.first + o.count);
+            // lanes of a warp take different kets of one list: keep their primitive loop lengths similar
+            const int np = o.count;
+            const int bucket = !bucketed ? 0 : (np <= 1 ? 0 : np <= 3 ? 1 : np <= 6 ? 2 : np <= 12 ? 3 : np <= 24 ? 4 : 5);
+            h->cls[o.cls * NBUCKET + bucket].pairs.push_back(o.sp);
+            nprim += np;
+            ++nkept;
+        }
+        RowOut().pairs.swap(rows[i].pairs);
+        std::vector<PrimPair>().swap(rows[i].prims);
+    }
     h->stats.n_shell_pairs = (long long)ns * (ns + 1) / 2;
     h->stats.n_pairs_kept = nkept;
     h->stats.n_prim_pairs = nprim;
