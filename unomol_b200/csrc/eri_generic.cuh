@@ -52,7 +52,9 @@ struct QC {
     static constexpr int THREADS = (T == 1) ? 64 : 128;
     static constexpr int GPW = 32 / T;                    // groups per warp
     static constexpr int GROUPS = THREADS / T;            // groups per CTA
-    static constexpr size_t SMEM = sizeof(double) * GROUP_DOUBLES * GROUPS + sizeof(int) * NEF;
+    // + element table (NEF ints) + horizontal-transfer term tables (4 packed terms per ket / bra function pair)
+    //   + per-pair Cartesian norm products
+    static constexpr size_t SMEM = sizeof(double) * (GROUP_DOUBLES * GROUPS + NAB + NCD) + sizeof(int) * (NEF + 4 * NCD + 4 * NAB);
 };
 
 // Cartesian components, AuxFunctions order (lx = L..0, ly = L-lx..0), packed lx | ly<<4 | lz<<8
@@ -104,7 +106,11 @@ eri_class_kernel(const ClassTask task) {
     constexpr int T = C::T, NR = C::NR, GI = C::GI, GJ = C::GJ, GSZ = C::GSZ, GPW = C::GPW;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *smem = reinterpret_cast<double *>(smem_raw);
-    int *elem_tab = reinterpret_cast<int *>(smem + (size_t)C::GROUP_DOUBLES * C::GROUPS);
+    double *nrm_ab = smem + (size_t)C::GROUP_DOUBLES * C::GROUPS;
+    double *nrm_cd = nrm_ab + C::NAB;
+    int *elem_tab = reinterpret_cast<int *>(nrm_cd + C::NCD);
+    int *ket_terms = elem_tab + C::NEF;      // [NCD][4]: source f index | jx<<8 | jy<<10 | jz<<12 | binom<<14 ; -1 = unused
+    int *bra_terms = ket_terms + 4 * C::NCD; // [NAB][4]: source e index | ix<<8 | ...
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lig = lane & (T - 1);               // lane in group
@@ -122,6 +128,38 @@ eri_class_kernel(const ClassTask task) {
         int ox = (pe & 15) * GJ + (pf & 15), oy = ((pe >> 4) & 15) * GJ + ((pf >> 4) & 15),
             oz = ((pe >> 8) & 15) * GJ + ((pf >> 8) & 15);
         elem_tab[k] = ox | (oy << 10) | (oz << 20);
+    }
+    // horizontal-transfer plans, built once per CTA (reference Rys.hpp:173-192: shift from the second shell of a
+    // pair onto the first): target pair (c,d) = sum over j <= d of binom(d,j) CD^j [f = c + d - j]
+    for (int cd = tid; cd < C::NCD; cd += blockDim.x) {
+        const int c = cd / C::ND, d = cd - c * C::ND;
+        const int pc = cart_pack(LC, c), pd = cart_pack(LD, d);
+        const int cx = pc & 15, cy = (pc >> 4) & 15, cz = pc >> 8, dx = pd & 15, dy = (pd >> 4) & 15, dz = pd >> 8;
+        int nt = 0;
+        for (int jx = 0; jx <= dx; ++jx)
+            for (int jy = 0; jy <= dy; ++jy)
+                for (int jz = 0; jz <= dz; ++jz) {
+                    const int f = range_index<LC>(cx + dx - jx, cy + dy - jy, cz + dz - jz);
+                    const int bn = (int)(binom_small(dx, jx) * binom_small(dy, jy) * binom_small(dz, jz));
+                    ket_terms[cd * 4 + nt++] = f | (jx << 8) | (jy << 10) | (jz << 12) | (bn << 14);
+                }
+        for (; nt < 4; ++nt) ket_terms[cd * 4 + nt] = -1;
+        nrm_cd[cd] = cart_norm(pc) * cart_norm(pd);
+    }
+    for (int ab = tid; ab < C::NAB; ab += blockDim.x) {
+        const int a = ab / C::NB, b = ab - a * C::NB;
+        const int pa = cart_pack(LA, a), pb = cart_pack(LB, b);
+        const int ax = pa & 15, ay = (pa >> 4) & 15, az = pa >> 8, bx = pb & 15, by = (pb >> 4) & 15, bz = pb >> 8;
+        int nt = 0;
+        for (int ix = 0; ix <= bx; ++ix)
+            for (int iy = 0; iy <= by; ++iy)
+                for (int iz = 0; iz <= bz; ++iz) {
+                    const int e = range_index<LA>(ax + bx - ix, ay + by - iy, az + bz - iz);
+                    const int bn = (int)(binom_small(bx, ix) * binom_small(by, iy) * binom_small(bz, iz));
+                    bra_terms[ab * 4 + nt++] = e | (ix << 8) | (iy << 10) | (iz << 12) | (bn << 14);
+                }
+        for (; nt < 4; ++nt) bra_terms[ab * 4 + nt] = -1;
+        nrm_ab[ab] = cart_norm(pa) * cart_norm(pb);
     }
     __syncthreads();
 
@@ -251,28 +289,21 @@ eri_class_kernel(const ClassTask task) {
                 if (C::NEF % T == 0 || kel < C::NEF) SG(OFF_A + kel) = acc[m];
             }
             if (T > 1) __syncwarp(gmask);
-            // step 1: H1[e][c,d] = sum_j binom(d,j) CD^j E[e][f(c+d-j)]
+            // step 1: H1[e][c,d] = sum_j binom(d,j) CD^j E[e][f(c+d-j)]   (term plans from shared memory)
             for (int o = lig; o < C::NE * C::NCD; o += T) {
                 const int e = o / C::NCD, cd = o - e * C::NCD;
                 double v;
                 if (LD == 0) {
                     v = SG(OFF_A + e * C::NF + cd);       // f == c, no shift
                 } else {
-                    const int c = cd / C::ND, d = cd - c * C::ND;
-                    const int pc = cart_pack(LC, c), pd = cart_pack(LD, d);
-                    const int cx = pc & 15, cy = (pc >> 4) & 15, cz = pc >> 8;
-                    const int dx = pd & 15, dy = (pd >> 4) & 15, dz = pd >> 8;
                     v = 0.0;
-                    for (int jx = 0; jx <= dx; ++jx) {
-                        const double fx = binom_small(dx, jx) * ipow_small(ket.AB[0], jx);
-                        for (int jy = 0; jy <= dy; ++jy) {
-                            const double fy = fx * binom_small(dy, jy) * ipow_small(ket.AB[1], jy);
-                            for (int jz = 0; jz <= dz; ++jz) {
-                                const double fz = fy * binom_small(dz, jz) * ipow_small(ket.AB[2], jz);
-                                const int f = range_index<LC>(cx + dx - jx, cy + dy - jy, cz + dz - jz);
-                                v = fma(fz, SG(OFF_A + e * C::NF + f), v);
-                            }
-                        }
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int tm = ket_terms[cd * 4 + t];
+                        if (tm < 0) break;
+                        const double cf = (double)(tm >> 14) * ipow_small(ket.AB[0], (tm >> 8) & 3) * ipow_small(ket.AB[1], (tm >> 10) & 3) *
+                                          ipow_small(ket.AB[2], (tm >> 12) & 3);
+                        v = fma(cf, SG(OFF_A + e * C::NF + (tm & 255)), v);
                     }
                 }
                 SG(OFF_B + o) = v;
@@ -288,30 +319,21 @@ eri_class_kernel(const ClassTask task) {
             // step 2: V[a,b][c,d] = norm * sum_i binom(b,i) AB^i H1[e(a+b-i)][cd]
             for (int o = lig; o < C::NINT; o += T) {
                 const int ab = o / C::NCD, cd = o - ab * C::NCD;
-                const int a = ab / C::NB, bq = ab - a * C::NB;
-                const int pa = cart_pack(LA, a), pb = cart_pack(LB, bq);
                 double v;
                 if (LB == 0) {
-                    v = SG(OFF_B + a * C::NCD + cd);
+                    v = SG(OFF_B + ab * C::NCD + cd);     // NB == 1: e == a
                 } else {
-                    const int ax = pa & 15, ay = (pa >> 4) & 15, az = pa >> 8;
-                    const int bx = pb & 15, by = (pb >> 4) & 15, bz = pb >> 8;
                     v = 0.0;
-                    for (int ix = 0; ix <= bx; ++ix) {
-                        const double fx = binom_small(bx, ix) * ipow_small(bra.AB[0], ix);
-                        for (int iy = 0; iy <= by; ++iy) {
-                            const double fy = fx * binom_small(by, iy) * ipow_small(bra.AB[1], iy);
-                            for (int iz = 0; iz <= bz; ++iz) {
-                                const double fz = fy * binom_small(bz, iz) * ipow_small(bra.AB[2], iz);
-                                const int e = range_index<LA>(ax + bx - ix, ay + by - iy, az + bz - iz);
-                                v = fma(fz, SG(OFF_B + e * C::NCD + cd), v);
-                            }
-                        }
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int tm = bra_terms[ab * 4 + t];
+                        if (tm < 0) break;
+                        const double cf = (double)(tm >> 14) * ipow_small(bra.AB[0], (tm >> 8) & 3) * ipow_small(bra.AB[1], (tm >> 10) & 3) *
+                                          ipow_small(bra.AB[2], (tm >> 12) & 3);
+                        v = fma(cf, SG(OFF_B + (tm & 255) * C::NCD + cd), v);
                     }
                 }
-                const int c = cd / C::ND, d = cd - c * C::ND;
-                const double nrm = cart_norm(pa) * cart_norm(pb) * cart_norm(cart_pack(LC, c)) * cart_norm(cart_pack(LD, d));
-                SG(OFF_A + o) = v * nrm * sym;
+                SG(OFF_A + o) = v * (nrm_ab[ab] * nrm_cd[cd] * sym);
             }
             if (T > 1) __syncwarp(gmask);
 
