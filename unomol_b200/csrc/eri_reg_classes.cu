@@ -7,7 +7,7 @@ namespace ub200 {
 
 template <int LA, int LB, int LC, int LD>
 static cudaError_t launch_reg(const ClassTask &task, int grid, cudaStream_t stream) {
-    static_assert(QC<LA, LB, LC, LD>::NEF <= 81, "register kernel is for small classes");
+    static_assert(QC<LA, LB, LC, LD>::NEF <= 144, "register kernel is for small classes");
     if (grid <= 0) return cudaSuccess;
     eri_reg_kernel<LA, LB, LC, LD><<<grid, REG_THREADS, 0, stream>>>(task);
     return cudaGetLastError();
@@ -18,6 +18,7 @@ bool reg_class_available(int cb, int ck) {
         case 0 * 8 + 0: case 1 * 8 + 0: case 1 * 8 + 1: case 2 * 8 + 0: case 2 * 8 + 1:
         case 3 * 8 + 0: case 3 * 8 + 1: case 4 * 8 + 0: case 5 * 8 + 0:
         case 2 * 8 + 2: case 3 * 8 + 2: case 3 * 8 + 3: case 4 * 8 + 1:
+        case 4 * 8 + 3: case 5 * 8 + 1: case 4 * 8 + 2:
             return true;
     }
     return false;
@@ -40,6 +41,9 @@ cudaError_t launch_reg_class(int cb, int ck, const ClassTask &task, int grid, cu
         case 3 * 8 + 2: return launch_reg<2, 0, 1, 1>(task, grid, stream);
         case 3 * 8 + 3: return launch_reg<2, 0, 2, 0>(task, grid, stream);
         case 4 * 8 + 1: return launch_reg<2, 1, 1, 0>(task, grid, stream);
+        case 4 * 8 + 3: return launch_reg<2, 1, 2, 0>(task, grid, stream);
+        case 5 * 8 + 1: return launch_reg<2, 2, 1, 0>(task, grid, stream);
+        case 4 * 8 + 2: return launch_reg<2, 1, 1, 1>(task, grid, stream);
     }
     return cudaErrorNotSupported;
 }
