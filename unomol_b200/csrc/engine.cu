@@ -132,7 +132,9 @@ __global__ void pack_fock_kernel(const double *__restrict__ J, const double *__r
 static void free_pairs(unomol_b200 *h) {
     for (int c = 0; c < NGROUP; ++c) {
         if (h->cls[c].d_pairs) cudaFree(h->cls[c].d_pairs);
+        if (h->cls[c].d_hot) cudaFree(h->cls[c].d_hot);
         h->cls[c].d_pairs = nullptr;
+        h->cls[c].d_hot = nullptr;
         h->cls[c].pairs.clear();
         h->cls[c].n = 0;
     }
@@ -298,6 +300,15 @@ static int build_pairs(unomol_b200 *h) {
         for (int i = 0; i < L.n; ++i) L.pairs[i].Q = q[i];
         std::stable_sort(L.pairs.begin(), L.pairs.end(), [](const ShellPair &x, const ShellPair &y) { return x.Q > y.Q; });
         CUDA_TRY(h, cudaMemcpyAsync(L.d_pairs, L.pairs.data(), sizeof(ShellPair) * L.n, cudaMemcpyHostToDevice, h->stream));
+        {
+            std::vector<KetHot> hot(L.n);
+            for (int i = 0; i < L.n; ++i) {
+                const ShellPair &sp = L.pairs[i];
+                hot[i] = KetHot{sp.offa, sp.offb, sp.prim_off, sp.nprim, sp.sha, sp.shb, sp.pairid, 0};
+            }
+            CUDA_TRY(h, cudaMalloc(&L.d_hot, sizeof(KetHot) * L.n));
+            CUDA_TRY(h, cudaMemcpy(L.d_hot, hot.data(), sizeof(KetHot) * L.n, cudaMemcpyHostToDevice));
+        }
         for (int i = 0; i < L.n; ++i) {
             h->pair_cls[L.pairs[i].pairid] = c;
             h->pair_pos[L.pairs[i].pairid] = i;
@@ -428,6 +439,7 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         const ComboPlan &pl = h->plans[ip];
         ClassTask task{};
         task.bra = h->cls[pl.cb].d_pairs; task.ket = h->cls[pl.ck].d_pairs; task.prims = h->d_prims;
+        task.ket_hot = h->cls[pl.ck].d_hot;
         task.ket_count = pl.d_ket_count;
         task.nbra = pl.nbra_eff; task.nket = h->cls[pl.ck].n;
         task.same_class = (pl.cb == pl.ck);

@@ -35,6 +35,7 @@ struct HostBasis {
 struct PairClassList {
     std::vector<ShellPair> pairs;   // sorted by Q descending after Schwarz
     ShellPair *d_pairs = nullptr;
+    KetHot *d_hot = nullptr;        // hot-field mirror of d_pairs
     int n = 0;
 };
 

@@ -76,6 +76,20 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phas
     }
 }
 
+// streaming (evict-first) 16-byte loads for data every thread reads exactly once per quartet (ket records, ket
+// primitives): keeps L1 for the rows of P that the whole CTA gathers from (ncu: L1 hit rate 22 %, L2 at 73-85 % of
+// its throughput on the large launches)
+template <class T>
+__device__ __forceinline__ T load_streaming(const T *p) {
+    static_assert(sizeof(T) % 16 == 0, "16-byte multiples only");
+    T out;
+    const int4 *src = reinterpret_cast<const int4 *>(p);
+    int4 *dst = reinterpret_cast<int4 *>(&out);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); ++i) dst[i] = __ldcs(src + i);
+    return out;
+}
+
 constexpr int REG_MAX_BRA_PRIMS = 36;   // 6 x 6 primitives; larger contractions fall back to the generic kernel
 constexpr int REG_THREADS = 128;
 
@@ -139,7 +153,7 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const ClassTask ta
         for (int i = 0; i < NAB; ++i) jab[i] = 0.0;
 
         for (int ki = tid; ki < kcount; ki += REG_THREADS) {
-            const ShellPair ket = task.ket[ki];
+            const KetHot ket = load_streaming(task.ket_hot + ki);   // 32 B per thread, coalesced
             {
                 const int imax = max(max(bra.sha, bra.shb), max(ket.sha, ket.shb));
                 if (imax < task.start_shell) continue;
@@ -165,13 +179,26 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const ClassTask ta
                 bool found = false;
                 while (ik < nkp) {
                     if (!have_k) {
-                        k = kp[ik];
+                        {   // scan fields only (first 16 bytes of the record)
+                            const double2 up = *reinterpret_cast<const double2 *>(kp + ik);
+                            k.u = up.x; k.p = up.y;
+                        }
                         tk = SR_TERM * k.u;
                         const double tb = tk * bumax;
                         if (tb * tb < cut2 * pminb) { ik = nkp; break; }
                         if (tb * tb < cut2 * (pminb + k.p)) { ++ik; continue; }
                         have_k = true;
                         ib = 0;
+                        {   // this ket primitive has at least a chance: fetch the rest of its hot 48 bytes, and the cold
+                            // 32 bytes only when the ket carries angular momentum (P-C and 1/q are unused otherwise)
+                            const double2 *src = reinterpret_cast<const double2 *>(kp + ik);
+                            const double2 c1 = src[1], c2 = src[2];
+                            k.c = c1.x; k.P[0] = c1.y; k.P[1] = c2.x; k.P[2] = c2.y;
+                            if constexpr (GJ > 1) {
+                                const double2 c3 = src[3], c4 = src[4];
+                                k.ip = c3.x; k.PA[0] = c3.y; k.PA[1] = c4.x; k.PA[2] = c4.y;
+                            }
+                        }
                     }
                     while (ib < nbp) {
                         const double t = tk * bp[ib].u;
@@ -258,7 +285,11 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const ClassTask ta
             }
             ++n_quart;
             // ---- horizontal transfer in registers: ket, then bra (reference Rys.hpp:173-192, once per quartet)
-            const double cdx = ket.AB[0], cdy = ket.AB[1], cdz = ket.AB[2];
+            double cdx = 0.0, cdy = 0.0, cdz = 0.0;
+            if constexpr (LD > 0) {
+                const ShellPair *kfull = task.ket + ki;
+                cdx = kfull->AB[0]; cdy = kfull->AB[1]; cdz = kfull->AB[2];
+            }
             double h1[NE * NCD];
             static_for<NE * NCD>([&](auto oo) {
                 constexpr int O = decltype(oo)::value;

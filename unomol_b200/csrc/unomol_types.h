@@ -13,12 +13,25 @@ constexpr double SR_TERM = 34.9868366552497250;  // 2*pi^(5/2), reference TwoEle
 // One primitive pair of a shell pair.  Replaces the per-quartet recomputation of p, P, P-A and
 // exp(-ab|AB|^2/p) in the reference's inner loops (TwoElectronInts.cpp:439-460).  80 B, 16-B aligned.
 struct __attribute__((aligned(16))) PrimPair {
-    double p;        // alpha_a + alpha_b
-    double ip;       // 1/p
-    double P[3];     // Gaussian product centre
-    double PA[3];    // P - A   (A = centre of the first, higher-l, shell)
+    // hot 48 bytes (all a ket of s functions ever needs): scan fields first
     double u;        // exp(-a b |AB|^2 / p) / p
+    double p;        // alpha_a + alpha_b
     double c;        // c_a c_b, doubled for off-diagonal primitive pairs of a same-shell pair (:444-450)
+    double P[3];     // Gaussian product centre
+    // cold 32 bytes: only when the pair carries angular momentum / more than one root
+    double ip;       // 1/p
+    double PA[3];    // P - A   (A = centre of the first, higher-l, shell)
+};
+
+// The 32 bytes of a shell pair that the ket side of a quartet reads per thread (one sector, coalesced across
+// the lanes of a warp); the full ShellPair record is what the bra side stages through TMA.
+struct __attribute__((aligned(16))) KetHot {
+    int offa, offb;  // first basis function of shell a / b
+    int prim_off;    // first PrimPair
+    int nprim;
+    int sha, shb;    // shell indices
+    int pairid;      // canonical id
+    int pad;
 };
 
 // One shell pair, first shell has l_a >= l_b.  96 B.
@@ -40,6 +53,7 @@ struct __attribute__((aligned(16))) ShellPair {
 struct ClassTask {
     const ShellPair *bra;     // bra pairs of this class, sorted by Q descending
     const ShellPair *ket;     // ket pairs
+    const KetHot *ket_hot;    // the same list, hot fields only
     const PrimPair *prims;
     const int *ket_count;     // per bra: number of leading kets to visit (Schwarz prefix, triangular cap)
     int nbra, nket;
