@@ -87,30 +87,31 @@ double model_flops_per_primitive_quartet(int la, int lb, int lc, int ld) {
 }
 
 // ---------------------------------------------------------------- small utility kernels
-__global__ void unpack_density_kernel(const double *__restrict__ PA, const double *__restrict__ PB, int n, int nspin,
+__global__ void unpack_density_kernel(const double *__restrict__ PA, const double *__restrict__ PB, int n, int ld, int nspin,
                                       double *__restrict__ PJ, double *__restrict__ PK0, double *__restrict__ PK1) {
-    // packed lower-triangular -> square symmetric.  RHF: PJ = 4P (G = 2J-K with J,K symmetrised from half
-    // accumulators), UHF: PJ = 2(PA+PB).
+    // packed lower-triangular -> square symmetric with leading dimension ld (even, so that every row is 16-byte
+    // aligned for TMA row copies).  RHF: PJ = 4P (G = 2J-K with J,K symmetrised from half accumulators),
+    // UHF: PJ = 2(PA+PB).
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t nn = (size_t)n * n;
-    if (idx >= nn) return;
+    if (idx >= (size_t)n * n) return;
     int i = (int)(idx / n), j = (int)(idx % n);
     int a = i > j ? i : j, b = i > j ? j : i;
     size_t p = (size_t)a * (a + 1) / 2 + b;
+    size_t o = (size_t)i * ld + j;
     double pa = PA[p];
     if (nspin == 1) {
-        PJ[idx] = 4.0 * pa;
-        PK0[idx] = pa;
+        PJ[o] = 4.0 * pa;
+        PK0[o] = pa;
     } else {
         double pb = PB[p];
-        PJ[idx] = 2.0 * (pa + pb);
-        PK0[idx] = pa;
-        PK1[idx] = pb;
+        PJ[o] = 2.0 * (pa + pb);
+        PK0[o] = pa;
+        PK1[o] = pb;
     }
 }
 
 __global__ void pack_fock_kernel(const double *__restrict__ J, const double *__restrict__ K0,
-                                 const double *__restrict__ K1, int n, int nspin, double *__restrict__ G0,
+                                 const double *__restrict__ K1, int n, int ld, int nspin, double *__restrict__ G0,
                                  double *__restrict__ G1) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t no2 = (size_t)n * (n + 1) / 2;
@@ -120,7 +121,7 @@ __global__ void pack_fock_kernel(const double *__restrict__ J, const double *__r
     while ((size_t)i * (i + 1) / 2 > idx) --i;
     while ((size_t)(i + 1) * (i + 2) / 2 <= idx) ++i;
     int j = (int)(idx - (size_t)i * (i + 1) / 2);
-    size_t ij = (size_t)i * n + j, ji = (size_t)j * n + i;
+    size_t ij = (size_t)i * ld + j, ji = (size_t)j * ld + i;
     double jj = J[ij] + J[ji];
     G0[idx] = jj - (K0[ij] + K0[ji]);
     if (nspin == 2) G1[idx] = jj - (K1[ij] + K1[ji]);
@@ -385,7 +386,7 @@ static int build_plans(unomol_b200 *h) {
 // ---------------------------------------------------------------- Fock build
 static int ensure_buffers(unomol_b200 *h) {
     if (h->d_PJ) return UNOMOL_OK;
-    const size_t n = h->basis.nbf, nn = n * n, no2 = n * (n + 1) / 2;
+    const size_t n = h->basis.nbf, ld = (n + 1) & ~(size_t)1, nn = ld * ld, no2 = n * (n + 1) / 2;
     for (int s = 0; s < 2; ++s) {
         CUDA_TRY(h, cudaMalloc(&h->d_Ppacked[s], sizeof(double) * no2));
         CUDA_TRY(h, cudaMalloc(&h->d_Gpacked[s], sizeof(double) * no2));
@@ -408,11 +409,11 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
     }
     int rc = ensure_buffers(h);
     if (rc) return rc;
-    const int n = h->basis.nbf;
-    const size_t nn = (size_t)n * n, no2 = (size_t)n * (n + 1) / 2;
+    const int n = h->basis.nbf, ld = (n + 1) & ~1;
+    const size_t nn = (size_t)ld * ld, no2 = (size_t)n * (n + 1) / 2;
     cudaStream_t st = h->stream;
     cudaEventRecord(h->ev0, st);
-    unpack_density_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(dPA, dPB, n, nspin, h->d_PJ, h->d_PK[0], h->d_PK[1]);
+    unpack_density_kernel<<<(unsigned)(((size_t)n * n + 255) / 256), 256, 0, st>>>(dPA, dPB, n, ld, nspin, h->d_PJ, h->d_PK[0], h->d_PK[1]);
     CUDA_TRY(h, cudaMemsetAsync(h->d_J, 0, sizeof(double) * nn, st));
     for (int s = 0; s < nspin; ++s) CUDA_TRY(h, cudaMemsetAsync(h->d_K[s], 0, sizeof(double) * nn, st));
     CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 2 * (h->plans.size() + 1), st));
@@ -447,7 +448,7 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         task.rank = h->rank; task.nranks = h->nranks;
         task.prim_cut = h->prim_cut;
         task.value_cut = h->value_cut;
-        task.nbf = n; task.nspin = nspin;
+        task.nbf = ld; task.nspin = nspin;   // kernels use nbf only as the leading dimension of the square matrices
         task.PJ = h->d_PJ; task.PK[0] = h->d_PK[0]; task.PK[1] = h->d_PK[1];
         task.J = h->d_J; task.K[0] = h->d_K[0]; task.K[1] = h->d_K[1];
         task.counters = h->d_counters + 2 * ip;
@@ -455,7 +456,7 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         task.cand_counter = h->d_counters + 2 * h->plans.size();
         const int nmine = (pl.nbra_eff - h->rank + h->nranks - 1) / h->nranks;
         if (pl.use_reg) {
-            CUDA_TRY(h, launch_reg_class(pl.cb / NBUCKET, pl.ck / NBUCKET, task, std::min(nmine, 148 * 16), st));
+            CUDA_TRY(h, launch_reg_class(pl.cb / NBUCKET, pl.ck / NBUCKET, task, std::min(nmine, 148 * 16), st, h->stage_rows != 0));
         } else {
             CUDA_TRY(h, launch_quartet_class(pl.cb / NBUCKET, pl.ck / NBUCKET, task, MODE_DIGEST, std::min(nmine, 148 * 32), st));
         }
@@ -466,7 +467,7 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join[a], 0));
     }
     cudaEventRecord(h->ev3, st);
-    pack_fock_kernel<<<(unsigned)((no2 + 255) / 256), 256, 0, st>>>(h->d_J, h->d_K[0], h->d_K[1], n, nspin, dGA, dGB);
+    pack_fock_kernel<<<(unsigned)((no2 + 255) / 256), 256, 0, st>>>(h->d_J, h->d_K[0], h->d_K[1], n, ld, nspin, dGA, dGB);
     ++nlaunch;
     CUDA_TRY(h, cudaGetLastError());
     if (h->nccl_comm && h->nranks > 1) {
@@ -588,6 +589,7 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
     if (!strcmp(name, "prim_cut")) { h->prim_cut = value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "density_screen")) { h->density_screen = value != 0.0; return UNOMOL_OK; }
     if (!strcmp(name, "bucket_min_pairs")) { h->bucket_min_pairs = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
+    if (!strcmp(name, "stage_rows")) { h->stage_rows = (int)value; return UNOMOL_OK; }
     if (!strcmp(name, "value_cut")) { h->value_cut = value; return UNOMOL_OK; }
     if (!strcmp(name, "debug_flags")) { h->debug_flags = (int)value; return UNOMOL_OK; }
     if (!strcmp(name, "reg_kernels")) {

@@ -15,7 +15,7 @@ int class_groups_per_cta(int bra_class, int ket_class);
 // register-resident kernels for the small classes (eri_reg_classes.cu)
 bool reg_class_available(int bra_class, int ket_class);
 int reg_max_bra_prims();
-cudaError_t launch_reg_class(int bra_class, int ket_class, const ClassTask &task, int grid, cudaStream_t stream);
+cudaError_t launch_reg_class(int bra_class, int ket_class, const ClassTask &task, int grid, cudaStream_t stream, bool allow_rows);
 // SURVEY.md 8(d) flop model per primitive quartet of class (la lb | lc ld)
 double model_flops_per_primitive_quartet(int la, int lb, int lc, int ld);
 
@@ -61,6 +61,7 @@ struct unomol_b200 {
     double tau = 1e-12, prim_cut = 1e-12, value_cut = 1e-14;
     int density_screen = 0;
     int use_reg_kernels = 1;
+    int stage_rows = 1;             // option "stage_rows": stage the bra's rows of P in shared memory (TMA) when they fit
     int debug_flags = 0;            // option "debug_flags" (profiling experiments; see ClassTask)
     int bucket_min_pairs = 20000;   // primitive-count bucketing only pays off for large pair lists   // option "reg_kernels": 0 forces the generic kernel for every class
     bool pairs_ready = false;

@@ -91,26 +91,39 @@ __device__ __forceinline__ T load_streaming(const T *p) {
 }
 
 constexpr int REG_MAX_BRA_PRIMS = 36;   // 6 x 6 primitives; larger contractions fall back to the generic kernel
-constexpr int REG_THREADS = 128;
+constexpr int REG_THREADS = 128;           // CTA size without row staging
+constexpr int REG_THREADS_ROWS = 256;      // with the bra's P rows staged in shared memory (shared by twice the threads)
+constexpr int REG_ROWS_MIN_KETS = 512;     // stage rows only for bras with at least this many kets (else gather from L2)
+constexpr size_t REG_ROWS_MAX_BYTES = 66 * 1024;   // rows of shells a and b: (NA+NB) * ld * 8 bytes must fit this
 
 struct __align__(16) BraStage {
     ShellPair pair;
     PrimPair prims[REG_MAX_BRA_PRIMS];
 };
 
-template <int LA, int LB, int LC, int LD>
-__global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const ClassTask task) {
+// ROWS: the NA+NB rows of the exchange density P that belong to the bra's two shells are staged once per bra in
+// dynamic shared memory by one TMA bulk copy each (rows are contiguous in the square matrix), so the four exchange
+// gathers of every quartet (P_bd, P_bc, P_ad, P_ac) become shared-memory reads instead of L2 sectors.  ncu on the
+// largest launches of (H2O)_154 showed L2 at 73-85 % of its throughput with 22-25 % L1 hit rate: those gathers and
+// the exchange reds are most of the traffic.  RHF only (one spin), and only when the rows fit REG_ROWS_MAX_BYTES.
+template <int LA, int LB, int LC, int LD, bool ROWS>
+__global__ void __launch_bounds__(ROWS ? REG_THREADS_ROWS : REG_THREADS) eri_reg_kernel(const ClassTask task) {
     using C = QC<LA, LB, LC, LD>;
     constexpr int NR = C::NR, GI = C::GI, GJ = C::GJ, NE = C::NE, NF = C::NF, NEF = C::NEF;
     constexpr int NA = C::NA, NB = C::NB, NC = C::NC, ND = C::ND, NAB = C::NAB, NCD = C::NCD, NINT = C::NINT;
     __shared__ BraStage stage[2];
     __shared__ __align__(8) unsigned long long bars[2];
-    __shared__ double jab_red[REG_THREADS / 32][NAB];
+    __shared__ double jab_red[REG_THREADS_ROWS / 32][NAB];
+    __shared__ __align__(8) unsigned long long row_bar;
+    extern __shared__ __align__(16) double srows[];   // [(NA+NB) * ld] when ROWS
+    const int nthreads = ROWS ? REG_THREADS_ROWS : REG_THREADS;
+    unsigned row_phase = 0u;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
+        mbar_init(&row_bar, 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -146,13 +159,22 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const ClassTask ta
         const int kcount = task.ket_count[bi];
         const double abx = bra.AB[0], aby = bra.AB[1], abz = bra.AB[2];
         const double bumax = bra.umax, pminb = bra.pmin;
+        // stage the rows P[a-shell][:] and P[b-shell][:] for this bra (CTA-uniform decision)
+        const bool use_rows = ROWS && kcount >= REG_ROWS_MIN_KETS;
+        bool rows_ready = !use_rows;
+        if (ROWS && use_rows && tid == 0) {
+            const unsigned bytes_a = (unsigned)(sizeof(double) * NA * task.nbf), bytes_b = (unsigned)(sizeof(double) * NB * task.nbf);
+            mbar_expect_tx(&row_bar, bytes_a + bytes_b);
+            tma_bulk_g2s(srows, task.PK[0] + (size_t)bra.offa * task.nbf, bytes_a, &row_bar);
+            tma_bulk_g2s(srows + (size_t)NA * task.nbf, task.PK[0] + (size_t)bra.offb * task.nbf, bytes_b, &row_bar);
+        }
         const double cut2 = task.prim_cut * task.prim_cut;
 
         double jab[NAB];
 #pragma unroll
         for (int i = 0; i < NAB; ++i) jab[i] = 0.0;
 
-        for (int ki = tid; ki < kcount; ki += REG_THREADS) {
+        for (int ki = tid; ki < kcount; ki += nthreads) {
             const KetHot ket = load_streaming(task.ket_hot + ki);   // 32 B per thread, coalesced
             {
                 const int imax = max(max(bra.sha, bra.shb), max(ket.sha, ket.shb));
@@ -392,17 +414,24 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const ClassTask ta
                     atomicAdd(task.J + (size_t)(oc + cd / ND) * n + od + cd % ND, sacc);
                 }
             }
+            if (ROWS && !rows_ready) {
+                mbar_wait(&row_bar, row_phase);
+                rows_ready = true;
+            }
             for (int sp = 0; sp < ((task.debug_flags & 5) ? 0 : task.nspin); ++sp) {
                 const double *P = task.PK[sp];
                 double *K = task.K[sp];
+                // row bases of the two bra shells: shared memory when staged, the square matrix in global otherwise
+                const double *Pa = (ROWS && use_rows) ? srows : P + (size_t)oa * n;
+                const double *Pb = (ROWS && use_rows) ? srows + (size_t)NA * n : P + (size_t)ob * n;
                 // K[a,c] += sum_bd V P[b,d] ; K[a,d] += sum_bc V P[b,c]
                 double pbd[NB * ND], pbc[NB * NC];
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
 #pragma unroll
-                    for (int d = 0; d < ND; ++d) pbd[b * ND + d] = P[(size_t)(ob + b) * n + od + d];
+                    for (int d = 0; d < ND; ++d) pbd[b * ND + d] = Pb[(size_t)b * n + od + d];
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) pbc[b * NC + c] = P[(size_t)(ob + b) * n + oc + c];
+                    for (int c = 0; c < NC; ++c) pbc[b * NC + c] = Pb[(size_t)b * n + oc + c];
                 }
 #pragma unroll
                 for (int a = 0; a < NA; ++a) {
@@ -430,9 +459,9 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const ClassTask ta
 #pragma unroll
                 for (int a = 0; a < NA; ++a) {
 #pragma unroll
-                    for (int d = 0; d < ND; ++d) pad[a * ND + d] = P[(size_t)(oa + a) * n + od + d];
+                    for (int d = 0; d < ND; ++d) pad[a * ND + d] = Pa[(size_t)a * n + od + d];
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) pac[a * NC + c] = P[(size_t)(oa + a) * n + oc + c];
+                    for (int c = 0; c < NC; ++c) pac[a * NC + c] = Pa[(size_t)a * n + oc + c];
                 }
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
@@ -471,11 +500,12 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const ClassTask ta
             if (tid < NAB) {
                 double v = 0.0;
 #pragma unroll
-                for (int w = 0; w < REG_THREADS / 32; ++w) v += jab_red[w][tid];
+                for (int w = 0; w < nthreads / 32; ++w) v += jab_red[w][tid];
                 if (v != 0.0) atomicAdd(task.J + (size_t)(bra.offa + tid / NB) * n + bra.offb + tid % NB, v);
             }
         }
-        __syncthreads();   // everyone is done with stage[s] and jab_red before they are overwritten
+        __syncthreads();   // everyone is done with stage[s], the staged rows and jab_red before they are overwritten
+        if (ROWS && use_rows) row_phase ^= 1u;
         bi = bn;
         s ^= 1;
     }
