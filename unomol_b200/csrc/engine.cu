@@ -90,8 +90,8 @@ double model_flops_per_primitive_quartet(int la, int lb, int lc, int ld) {
 __global__ void unpack_density_kernel(const double *__restrict__ PA, const double *__restrict__ PB, int n, int ld, int nspin,
                                       double *__restrict__ PJ, double *__restrict__ PK0, double *__restrict__ PK1) {
     // packed lower-triangular -> square symmetric with leading dimension ld (even, so that every row is 16-byte
-    // aligned for TMA row copies).  RHF: PJ = 4P (G = 2J-K with J,K symmetrised from half accumulators),
-    // UHF: PJ = 2(PA+PB).
+    // aligned for TMA row copies).  The Coulomb scale (4 for RHF: G = 2J-K with J,K symmetrised from half
+    // accumulators; 2 for UHF with PJ = PA+PB) is applied by the kernels when J is flushed (ClassTask::jscale).
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)n * n) return;
     int i = (int)(idx / n), j = (int)(idx % n);
@@ -100,11 +100,10 @@ __global__ void unpack_density_kernel(const double *__restrict__ PA, const doubl
     size_t o = (size_t)i * ld + j;
     double pa = PA[p];
     if (nspin == 1) {
-        PJ[o] = 4.0 * pa;
-        PK0[o] = pa;
+        PK0[o] = pa;          // RHF: the Coulomb term reads the same array (one N^2 matrix less in L2)
     } else {
         double pb = PB[p];
-        PJ[o] = 2.0 * (pa + pb);
+        PJ[o] = pa + pb;
         PK0[o] = pa;
         PK1[o] = pb;
     }
@@ -449,7 +448,8 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         task.prim_cut = h->prim_cut;
         task.value_cut = h->value_cut;
         task.nbf = ld; task.nspin = nspin;   // kernels use nbf only as the leading dimension of the square matrices
-        task.PJ = h->d_PJ; task.PK[0] = h->d_PK[0]; task.PK[1] = h->d_PK[1];
+        task.PJ = (nspin == 1) ? h->d_PK[0] : h->d_PJ; task.PK[0] = h->d_PK[0]; task.PK[1] = h->d_PK[1];
+        task.jscale = (nspin == 1) ? 4.0 : 2.0;
         task.J = h->d_J; task.K[0] = h->d_K[0]; task.K[1] = h->d_K[1];
         task.counters = h->d_counters + 2 * ip;
         task.debug_flags = h->debug_flags;

@@ -370,14 +370,14 @@ eri_class_kernel(const ClassTask task) {
                         for (int c = 0; c < NC; ++c)
                             for (int d = 0; d < ND; ++d)
                                 s = fma(SG(OFF_A + o * C::NCD + c * ND + d), task.PJ[(size_t)(oc + c) * n + od + d], s);
-                        atomicAdd(task.J + (size_t)(oa + a) * n + ob + b, s);
+                        atomicAdd(task.J + (size_t)(oa + a) * n + ob + b, task.jscale * s);
                     } else if (o < N_JAB + N_JCD) {
                         const int cd = o - N_JAB, c = cd / ND, d = cd - c * ND;
                         double s = 0.0;
                         for (int a = 0; a < NA; ++a)
                             for (int b = 0; b < NB; ++b)
                                 s = fma(SG(OFF_A + (a * NB + b) * C::NCD + cd), task.PJ[(size_t)(oa + a) * n + ob + b], s);
-                        atomicAdd(task.J + (size_t)(oc + c) * n + od + d, s);
+                        atomicAdd(task.J + (size_t)(oc + c) * n + od + d, task.jscale * s);
                     } else {
                         int r = o - N_JAB - N_JCD;
                         const int sp = r / N_K;

@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(ROWS ? REG_THREADS_ROWS : REG_THREADS) eri_reg
                     double sacc = 0.0;
 #pragma unroll
                     for (int ab = 0; ab < NAB; ++ab) sacc = fma(V[ab * NCD + cd], pab[ab], sacc);
-                    atomicAdd(task.J + (size_t)(oc + cd / ND) * n + od + cd % ND, sacc);
+                    atomicAdd(task.J + (size_t)(oc + cd / ND) * n + od + cd % ND, task.jscale * sacc);
                 }
             }
             if (ROWS && !rows_ready) {
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(ROWS ? REG_THREADS_ROWS : REG_THREADS) eri_reg
                 double v = 0.0;
 #pragma unroll
                 for (int w = 0; w < nthreads / 32; ++w) v += jab_red[w][tid];
-                if (v != 0.0) atomicAdd(task.J + (size_t)(bra.offa + tid / NB) * n + bra.offb + tid % NB, v);
+                if (v != 0.0) atomicAdd(task.J + (size_t)(bra.offa + tid / NB) * n + bra.offb + tid % NB, task.jscale * v);
             }
         }
         __syncthreads();   // everyone is done with stage[s], the staged rows and jab_red before they are overwritten

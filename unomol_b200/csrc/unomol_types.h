@@ -64,7 +64,8 @@ struct ClassTask {
     double value_cut;         // reference's |val| > 1e-14 storage threshold (TwoElectronInts.cpp:513)
     // digestion
     int nbf, nspin;
-    const double *PJ;         // square nbf*nbf, pre-scaled density for the Coulomb term
+    const double *PJ;         // square density for the Coulomb term: P itself (RHF, same array as PK[0]) or PA+PB (UHF)
+    double jscale;            // 4 (RHF: G = 2J-K from half accumulators) or 2 (UHF), applied when J is flushed
     const double *PK[2];      // square, per spin, exchange
     double *J;                // square accumulators (upper/lower mixed; symmetrised afterwards)
     double *K[2];
