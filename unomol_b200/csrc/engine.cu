@@ -246,6 +246,14 @@ static int build_pairs(unomol_b200 *h) {
     }
     long long nprim = 0, nkept = 0;
     const bool bucketed = (long long)ns * (ns + 1) / 2 >= h->bucket_min_pairs;
+    // column/row blocking: keep (rows of a bra block) x (columns of a ket block) x 8 B x ~2.5 matrices within ~48 MB of L2
+    int nblock = h->col_blocks;
+    if (nblock <= 0) {
+        // measured (profiles/exp_blocks.py): N=2002 (80 MB) is fastest unblocked, N=4004 (320 MB) 1.56x faster with 3 blocks
+        const double foot = 2.5 * 8.0 * (double)B.nbf * (double)B.nbf;
+        nblock = foot <= 100e6 ? 1 : (int)std::ceil(std::sqrt(foot / 48e6));
+    }
+    nblock = std::max(1, std::min(nblock, NBLOCK));
     for (int i = 0; i < ns; ++i) {
         for (auto &o : rows[i].pairs) {
             o.sp.prim_off = (int)h->h_prims.size();
@@ -253,7 +261,9 @@ static int build_pairs(unomol_b200 *h) {
             // lanes of a warp take different kets of one list: keep their primitive loop lengths similar
             const int np = o.count;
             const int bucket = !bucketed ? 0 : (np <= 1 ? 0 : np <= 3 ? 1 : np <= 6 ? 2 : np <= 12 ? 3 : np <= 24 ? 4 : 5);
-            h->cls[o.cls * NBUCKET + bucket].pairs.push_back(o.sp);
+            // spatial block = slab of shell indices of the pair's larger shell (inputs list atoms, hence shells, in spatial order)
+            const int block = std::min(nblock - 1, (int)((long long)std::max(o.sp.sha, o.sp.shb) * nblock / ns));
+            h->cls[o.cls * NSUB + bucket * NBLOCK + block].pairs.push_back(o.sp);
             nprim += np;
             ++nkept;
         }
@@ -289,9 +299,9 @@ static int build_pairs(unomol_b200 *h) {
         // reference's sr<1e-12 test passes although it would fail on the weak pair's own diagonal
         task.prim_cut = 0.0;
         task.task_list = d_tl; task.ntask = L.n; task.out = d_q;
-        const int groups = class_groups_per_cta(c / NBUCKET, c / NBUCKET);
+        const int groups = class_groups_per_cta(c / NSUB, c / NSUB);
         const int grid = std::min((L.n + groups - 1) / groups, 148 * 16);
-        CUDA_TRY(h, launch_quartet_class(c / NBUCKET, c / NBUCKET, task, MODE_SCHWARZ, grid, h->stream));
+        CUDA_TRY(h, launch_quartet_class(c / NSUB, c / NSUB, task, MODE_SCHWARZ, grid, h->stream));
         std::vector<double> q(L.n);
         CUDA_TRY(h, cudaMemcpyAsync(q.data(), d_q, sizeof(double) * L.n, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -361,13 +371,13 @@ static int build_plans(unomol_b200 *h) {
             if (plan.nbra_eff == 0) continue;
             {
                 int la, lb, lc, ld;
-                pair_class_l(cb / NBUCKET, la, lb);
-                pair_class_l(ck / NBUCKET, lc, ld);
+                pair_class_l(cb / NSUB, la, lb);
+                pair_class_l(ck / NSUB, lc, ld);
                 plan.cost = (double)plan.nquartets * model_flops_per_primitive_quartet(la, lb, lc, ld);
             }
             int maxbp = 0;
             for (int i = 0; i < plan.nbra_eff; ++i) maxbp = std::max(maxbp, Lb.pairs[i].nprim);
-            plan.use_reg = h->use_reg_kernels && reg_class_available(cb / NBUCKET, ck / NBUCKET) && maxbp <= reg_max_bra_prims();
+            plan.use_reg = h->use_reg_kernels && reg_class_available(cb / NSUB, ck / NSUB) && maxbp <= reg_max_bra_prims();
             if (cudaMalloc(&plan.d_ket_count, sizeof(int) * Lb.n) != cudaSuccess) return UNOMOL_E_NOMEM;
             cudaMemcpyAsync(plan.d_ket_count, kc.data(), sizeof(int) * Lb.n, cudaMemcpyHostToDevice, h->stream);
             cudaStreamSynchronize(h->stream);
@@ -456,9 +466,9 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         task.cand_counter = h->d_counters + 2 * h->plans.size();
         const int nmine = (pl.nbra_eff - h->rank + h->nranks - 1) / h->nranks;
         if (pl.use_reg) {
-            CUDA_TRY(h, launch_reg_class(pl.cb / NBUCKET, pl.ck / NBUCKET, task, std::min(nmine, 148 * 16), st, h->stage_rows != 0));
+            CUDA_TRY(h, launch_reg_class(pl.cb / NSUB, pl.ck / NSUB, task, std::min(nmine, 148 * 16), st, h->stage_rows != 0));
         } else {
-            CUDA_TRY(h, launch_quartet_class(pl.cb / NBUCKET, pl.ck / NBUCKET, task, MODE_DIGEST, std::min(nmine, 148 * 32), st));
+            CUDA_TRY(h, launch_quartet_class(pl.cb / NSUB, pl.ck / NSUB, task, MODE_DIGEST, std::min(nmine, 148 * 32), st));
         }
         ++nlaunch;
     }
@@ -496,8 +506,8 @@ static int finish_stats(unomol_b200 *h) {
     double fl = 0.0;
     for (size_t ip = 0; ip < h->plans.size(); ++ip) {
         int la, lb, lc, ld;
-        pair_class_l(h->plans[ip].cb / NBUCKET, la, lb);
-        pair_class_l(h->plans[ip].ck / NBUCKET, lc, ld);
+        pair_class_l(h->plans[ip].cb / NSUB, la, lb);
+        pair_class_l(h->plans[ip].ck / NSUB, lc, ld);
         nq += (long long)c[2 * ip];
         fl += (double)c[2 * ip + 1] * model_flops_per_primitive_quartet(la, lb, lc, ld);
     }
@@ -589,6 +599,7 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
     if (!strcmp(name, "prim_cut")) { h->prim_cut = value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "density_screen")) { h->density_screen = value != 0.0; return UNOMOL_OK; }
     if (!strcmp(name, "bucket_min_pairs")) { h->bucket_min_pairs = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
+    if (!strcmp(name, "col_blocks")) { h->col_blocks = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "stage_rows")) { h->stage_rows = (int)value; return UNOMOL_OK; }
     if (!strcmp(name, "value_cut")) { h->value_cut = value; return UNOMOL_OK; }
     if (!strcmp(name, "debug_flags")) { h->debug_flags = (int)value; return UNOMOL_OK; }
@@ -737,7 +748,7 @@ int unomol_b200_eri_quartet(unomol_b200_t *h, int ish, int jsh, int ksh, int lsh
     task.nbra = h->cls[cb].n; task.nket = h->cls[ck].n;
     task.prim_cut = h->prim_cut;
     task.task_list = d_tl; task.task_out = d_off; task.ntask = 1; task.out = d_out;
-    CUDA_TRY(h, launch_quartet_class(cb / NBUCKET, ck / NBUCKET, task, MODE_DUMP, 1, h->stream));
+    CUDA_TRY(h, launch_quartet_class(cb / NSUB, ck / NSUB, task, MODE_DUMP, 1, h->stream));
     std::vector<double> blk(ntot);
     CUDA_TRY(h, cudaMemcpyAsync(blk.data(), d_out, sizeof(double) * ntot, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -777,7 +788,7 @@ int unomol_b200_dump_eris(unomol_b200_t *h, double thresh, unomol_twoint *buf, s
             const int nb = h->cls[cb].n, nk = h->cls[ck].n;
             if (!nb || !nk) continue;
             int la, lb, lc, ld;
-            pair_class_l(cb / NBUCKET, la, lb); pair_class_l(ck / NBUCKET, lc, ld);
+            pair_class_l(cb / NSUB, la, lb); pair_class_l(ck / NSUB, lc, ld);
             const int nint = ((la + 1) * (la + 2) / 2) * ((lb + 1) * (lb + 2) / 2) * ((lc + 1) * (lc + 2) / 2) * ((ld + 1) * (ld + 2) / 2);
             const long long ntask = (cb == ck) ? (long long)nb * (nb + 1) / 2 : (long long)nb * nk;
             combos.push_back({cb, ck, total, nint});
@@ -807,9 +818,9 @@ int unomol_b200_dump_eris(unomol_b200_t *h, double thresh, unomol_twoint *buf, s
         task.bra = h->cls[cmb.cb].d_pairs; task.ket = h->cls[cmb.ck].d_pairs; task.prims = h->d_prims;
         task.nbra = nb; task.nket = nk; task.prim_cut = h->prim_cut;
         task.task_list = d_tl; task.task_out = d_off; task.ntask = (int)tl.size(); task.out = d_out;
-        const int groups = class_groups_per_cta(cmb.cb / NBUCKET, cmb.ck / NBUCKET);
+        const int groups = class_groups_per_cta(cmb.cb / NSUB, cmb.ck / NSUB);
         const int grid = std::min(((int)tl.size() + groups - 1) / groups, 148 * 16);
-        CUDA_TRY(h, launch_quartet_class(cmb.cb / NBUCKET, cmb.ck / NBUCKET, task, MODE_DUMP, grid, h->stream));
+        CUDA_TRY(h, launch_quartet_class(cmb.cb / NSUB, cmb.ck / NSUB, task, MODE_DUMP, grid, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         cudaFree(d_tl); cudaFree(d_off);
     }

@@ -61,12 +61,13 @@ struct unomol_b200 {
     double tau = 1e-12, prim_cut = 1e-12, value_cut = 1e-14;
     int density_screen = 0;
     int use_reg_kernels = 1;
+    int col_blocks = 0;             // option "col_blocks": spatial blocks per pair list (0 = choose from N so a launch fits L2)
     int stage_rows = 1;             // option "stage_rows": stage the bra's rows of P in shared memory (TMA) when they fit
     int debug_flags = 0;            // option "debug_flags" (profiling experiments; see ClassTask)
     int bucket_min_pairs = 20000;   // primitive-count bucketing only pays off for large pair lists   // option "reg_kernels": 0 forces the generic kernel for every class
     bool pairs_ready = false;
     // pair data
-    ub200::PairClassList cls[ub200::NGROUP];   // indexed by group id (class * NBUCKET + primitive-count bucket)
+    ub200::PairClassList cls[ub200::NGROUP];   // indexed by group id (class * NSUB + bucket * NBLOCK + spatial block)
     std::vector<ub200::PrimPair> h_prims;
     ub200::PrimPair *d_prims = nullptr;
     std::vector<int> pair_cls, pair_pos;      // per canonical shell pair id: class and position (-1 = pruned)

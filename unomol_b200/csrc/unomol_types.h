@@ -7,7 +7,10 @@ namespace ub200 {
 constexpr int MAXL = 2;            // per-shell angular momentum handled by the built kernels (s, p, d)
 constexpr int NPAIRCLASS = 6;      // ss ps pp ds dp dd  (la >= lb; id = la*(la+1)/2 + lb)
 constexpr int NBUCKET = 6;         // pair lists are further split by primitive-pair count (1, 2-3, 4-6, 7-12, 13-24, 25+)
-constexpr int NGROUP = NPAIRCLASS * NBUCKET;   // group id = class * NBUCKET + bucket; one ERI launch per (bra group >= ket group)
+constexpr int NBLOCK = 4;          // ... and by spatial block (slab of shell indices) so that for large N a launch's rows x columns
+                                   // footprint in the square P/J/K matrices stays L2-resident
+constexpr int NSUB = NBUCKET * NBLOCK;
+constexpr int NGROUP = NPAIRCLASS * NSUB;   // group id = class * NSUB + bucket * NBLOCK + block; one launch per (bra group >= ket group)
 constexpr double SR_TERM = 34.9868366552497250;  // 2*pi^(5/2), reference TwoElectronInts.cpp:427
 
 // One primitive pair of a shell pair.  Replaces the per-quartet recomputation of p, P, P-A and
