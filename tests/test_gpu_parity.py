@@ -275,3 +275,19 @@ def test_f_shells_are_rejected_not_silently_wrong(capi):
     b.lv = b.lv.copy(); b.lv[0] = 3
     with pytest.raises(capi.UnomolError, match="-3"):
         capi.Handle(b)
+
+
+def test_spatial_blocks_do_not_change_results(capi):
+    """pair lists split into spatial blocks (used for N > ~2500 to keep a launch's P/J/K footprint in L2)"""
+    b, h = _handle(capi, "tz2p.sf6")
+    rng = np.random.default_rng(44)
+    P = rng.standard_normal(b.no2)
+    G0 = h.fock_rhf(P)
+    h.set_option("col_blocks", 3)
+    G1 = h.fock_rhf(P)
+    assert h.stats()["n_launches"] > 60
+    assert np.max(np.abs(G1 - G0)) < 1e-13 * np.max(np.abs(G0))
+    GA, GB = h.fock_uhf(P, 0.5 * P)
+    h.set_option("col_blocks", 1)
+    GA0, GB0 = h.fock_uhf(P, 0.5 * P)
+    assert np.max(np.abs(GA - GA0)) < 1e-13 * np.max(np.abs(GA0)) and np.max(np.abs(GB - GB0)) < 1e-13 * np.max(np.abs(GA0))
