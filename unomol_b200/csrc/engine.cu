@@ -464,7 +464,7 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         task.counters = h->d_counters + 2 * ip;
         task.debug_flags = h->debug_flags;
         task.cand_counter = h->d_counters + 2 * h->plans.size();
-        const int nmine = (pl.nbra_eff - h->rank + h->nranks - 1) / h->nranks;
+        const int nmine = (pl.nbra_eff + h->nranks - 1) / h->nranks;
         if (pl.use_reg) {
             CUDA_TRY(h, launch_reg_class(pl.cb / NSUB, pl.ck / NSUB, task, std::min(nmine, 148 * 16), st, h->stage_rows != 0));
         } else {

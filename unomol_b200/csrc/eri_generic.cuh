@@ -167,13 +167,16 @@ eri_class_kernel(const ClassTask task) {
 
     // DIGEST: outer = bra index (CTA-uniform), groups stride over that bra's Schwarz-surviving kets.
     // DUMP / SCHWARZ: outer = chunk of GROUPS explicit (bra,ket) tasks, one per group.
-    // bras are dealt round-robin to ranks: this rank owns bra = rank + nranks*outer
-    const int nouter = (MODE == MODE_DIGEST) ? (task.nbra - task.rank + task.nranks - 1) / task.nranks
+    // bras are dealt to ranks in snake order: this rank owns one bra of every block of nranks
+    const int nouter = (MODE == MODE_DIGEST) ? (task.nbra + task.nranks - 1) / task.nranks
                                              : (task.ntask + C::GROUPS - 1) / C::GROUPS;
     for (int outer = blockIdx.x; outer < nouter; outer += gridDim.x) {
         int bi = 0, kfirst = 0, kcount = 0, kstep = 1;
         if (MODE == MODE_DIGEST) {
-            bi = task.rank + task.nranks * outer; kfirst = group; kcount = task.ket_count[bi]; kstep = C::GROUPS;
+            // snake order over ranks (see eri_reg.cuh)
+            bi = task.nranks * outer + ((outer & 1) ? task.nranks - 1 - task.rank : task.rank);
+            if (bi >= task.nbra) continue;
+            kfirst = group; kcount = task.ket_count[bi]; kstep = C::GROUPS;
         } else {
             const int t = outer * C::GROUPS + group;
             if (t < task.ntask) { bi = task.task_list[t].x; kfirst = task.task_list[t].y; kcount = kfirst + 1; }

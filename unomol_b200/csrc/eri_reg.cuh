@@ -129,7 +129,9 @@ __global__ void __launch_bounds__(ROWS ? REG_THREADS_ROWS : REG_THREADS) eri_reg
     __syncthreads();
 
     // this rank owns bras rank, rank+nranks, ...; this CTA walks them with stride gridDim.x
-    auto bra_of = [&](int j) { return task.rank + task.nranks * j; };
+    // Bras are dealt to ranks in blocks of nranks, alternating direction (snake order): the lists are sorted by
+    // Schwarz bound, so plain round-robin would hand rank 0 the heavier bra of every block.
+    auto bra_of = [&](int j) { return task.nranks * j + ((j & 1) ? task.nranks - 1 - task.rank : task.rank); };
     auto issue = [&](int b, int s) {
         // thread 0: TMA the bra's pair record and its primitive pairs
         const ShellPair *gp = task.bra + b;

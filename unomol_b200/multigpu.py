@@ -15,8 +15,9 @@ def env_rank():
 
 
 def owner_of(index, nranks):
-    """rank that owns position `index` of a Schwarz-sorted bra list (round-robin, as the kernels deal them)"""
-    return index % nranks
+    """rank that owns position `index` of a Schwarz-sorted bra list (blocks of nranks in snake order, as the kernels deal them)"""
+    block, pos = divmod(index, nranks)
+    return pos if block % 2 == 0 else nranks - 1 - pos
 
 
 def allreduce_packed(G, group=None):
