@@ -66,3 +66,32 @@ def test_orbital_energies_h2o(tmp_path):
     ref = RUNS["631.h2o"]["orbital_energies"]
     assert len(ev) == len(ref) == 25
     assert max(abs(a - b) for a, b in zip(ev, ref)) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "631.co", "431.nh3"])
+def test_scfout_matches_reference_golden_file(name, tmp_path):
+    """scfout.gs.out against the reference's checked-in test/scfout.dat.*: energies, orbital energies, Mulliken
+    populations and atomic charges (iteration count and the last dE / dP lines excluded: the goldens predate the
+    reference's current damping)."""
+    import re
+    e0, e1, de, out = run_scf(name, tmp_path)
+    gold = open(os.path.join(GOLDEN, "scfout", "scfout.dat." + name)).read()
+
+    def field(txt, label):
+        return float(re.search(re.escape(label) + r"\s*=\s*([-+\d.eE]+)", txt).group(1))
+
+    for label, tol in [("Hartree Fock Energy", 1e-9), ("Electronic Energy", 1e-9), ("Nuclear Rep. Energy", 1e-10), ("Kinetic Energy", 1e-6),
+                       ("virial", 1e-7)]:
+        assert abs(field(out, label) - field(gold, label)) < tol, label
+
+    def table(txt, header):
+        blk = txt.split(header, 1)[1].split("xxxx", 1)[0]
+        return [[float(x) for x in ln.split()] for ln in blk.strip().splitlines() if re.match(r"^\s*\d+\s", ln)]
+
+    ev, evg = table(out, "Orbital Energy          Occupancy"), table(gold, "Orbital Energy          Occupancy")
+    assert len(ev) == len(evg)
+    assert max(abs(a[1] - b[1]) for a, b in zip(ev, evg)) < 1e-6 and all(a[2] == b[2] for a, b in zip(ev, evg))
+    mp, mpg = table(out, "Orbital  Net Population"), table(gold, "Orbital  Net Population")
+    assert max(abs(a[1] - b[1]) for a, b in zip(mp, mpg)) < 1e-6
+    ch, chg = table(out, "Orbital   Nuclear Charge   Net Charge"), table(gold, "Orbital   Nuclear Charge   Net Charge")
+    assert max(abs(a[2] - b[2]) for a, b in zip(ch, chg)) < 1e-6

@@ -173,7 +173,29 @@ class RestrictedHartreeFock {
         fprintf(out, "xxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxx\n               Orbital Energies\nOrbital Energy          Occupancy\n");
         for (int i = 0; i < no; i++) fprintf(out, "%7u %25.16le %12u\n", i + 1, Evals[i], i < nocc ? 2 : 0);
         fprintf(out, "xxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxx\n");
+        PopulationAnalysis(out);
         fclose(out);
+    }
+
+    // Mulliken populations (2 P S)_ii and atomic charges, same layout as the reference (RHF.hpp:571-660)
+    void PopulationAnalysis(FILE *out) const {
+        auto at = [&](const std::vector<double> &m, int i, int j) { return i >= j ? m[(size_t)i * (i + 1) / 2 + j] : m[(size_t)j * (j + 1) / 2 + i]; };
+        std::vector<double> pop(no, 0.0), net(ncen);
+        for (int i = 0; i < no; ++i) {
+            double sum = 0.0;
+            for (int k = 0; k < no; ++k) sum += at(Pmat, i, k) * at(Smat, k, i);
+            pop[i] = sum + sum;
+        }
+        for (int c = 0; c < ncen; ++c) net[c] = basis.center_ptr()[c].charge();
+        int ir = 0;
+        for (int s = 0; s < basis.number_of_shells(); ++s) {
+            const int lv = basis.shell_ptr()[s].Lvalue(), cn = basis.shell_ptr()[s].center();
+            for (int k = 0; k < (lv + 1) * (lv + 2) / 2; ++k, ++ir) net[cn] -= pop[ir];
+        }
+        fprintf(out, "xxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxx\n           Mulliken Populations \nOrbital  Net Population\n");
+        for (int i = 0; i < no; ++i) fprintf(out, "%7u %25.16le\n", i + 1, pop[i]);
+        fprintf(out, "xxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxx\nMulliken Atomic Charges \nOrbital   Nuclear Charge   Net Charge \n");
+        for (int c = 0; c < ncen; ++c) fprintf(out, "%7u %15.10lf %15.10lf \n", c + 1, basis.center_ptr()[c].charge(), net[c]);
     }
 
     double total_energy() const { return energy + nucrep; }
