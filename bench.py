@@ -153,26 +153,28 @@ def screened_sample_cpu(basis, nsample, tau, seed):
             O = Oracle(); ob = O.basis(path)
             blk = lambda i, j: O.quartet_block(ob, i, j, i, j)
         nc = lambda s: (int(basis.lv[s]) + 1) * (int(basis.lv[s]) + 2) // 2
-        npairs = max(2000, int(4 * np.sqrt(nsample) * 30))
+        npairs = 20000
         pi = rng.integers(0, ns, npairs); pj = rng.integers(0, ns, npairs)
         pi, pj = np.maximum(pi, pj), np.minimum(pi, pj)
         Q = np.zeros(npairs)
         cen = basis.xyz[basis.cen]
-        for k in range(npairs):
+        far = np.sum((cen[pi] - cen[pj]) ** 2, axis=1) > 600.0     # > 24.5 bohr: negligible for these exponents
+        for k in np.nonzero(~far)[0]:
             i, j = int(pi[k]), int(pj[k])
-            if np.sum((cen[i] - cen[j]) ** 2) > 600.0:     # > 24.5 bohr: negligible for these exponents
-                continue
             b = blk(i, j)
             n1, n2 = nc(i), nc(j)
             Q[k] = np.sqrt(np.max(np.abs(b.reshape(n1 * n2, n1 * n2).diagonal())))
-    out = []
+    # vectorised rejection sampling of (pair, pair) with Q_ab*Q_cd >= tau
+    out = np.zeros((0, 4), np.int32)
     tries = 0
-    while len(out) < nsample and tries < 200 * nsample:
-        a, b = rng.integers(0, npairs, 2); tries += 1
-        if Q[a] * Q[b] >= tau and Q[a] * Q[b] > 0:
-            out.append((pi[a], pj[a], pi[b], pj[b]))
-    frac = len(out) / max(tries, 1)
-    return np.array(out, np.int32), frac
+    while len(out) < nsample and tries < 400:
+        a = rng.integers(0, npairs, 1 << 20); b2 = rng.integers(0, npairs, 1 << 20); tries += 1
+        ok = (Q[a] * Q[b2] >= tau) & (Q[a] * Q[b2] > 0)
+        a, b2 = a[ok], b2[ok]
+        out = np.concatenate([out, np.stack([pi[a], pj[a], pi[b2], pj[b2]], axis=1).astype(np.int32)])
+    out = out[:nsample]
+    frac = float(np.mean((Q[:, None] * Q[None, :2000] >= tau))) if npairs else 0.0
+    return out, frac
 
 
 def main():
@@ -201,7 +203,7 @@ def main():
         import multiprocessing as mp
         cores = os.cpu_count() or 1
         from oracle.oracle import Reference
-        per_step = 50000 * cores if basis.nbf > 300 else 20000 * cores
+        per_step = 200000 * cores if basis.nbf > 300 else 50000 * cores
         shells, frac = screened_sample_cpu(basis, per_step, args.tau, 7)
         d = tempfile.mkdtemp(); path = os.path.join(d, "patin.dat"); basis.write_patin(path)
         chunks = [shells[i::cores] for i in range(cores)]
