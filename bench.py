@@ -241,6 +241,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     h = capi.Handle(basis, device=local, rank=rank, nranks=world)
     h.set_option("schwarz_tau", args.tau)
+    stealing = False
+    if world > 1 and not os.environ.get("UNOMOL_NO_STEAL"):
+        from unomol_b200.multigpu import enable_work_stealing
+        stealing = enable_work_stealing(h)
+        if not stealing:
+            h.set_option("work_stealing", 0)     # CUDA IPC unavailable: every rank falls back to the static split
+    config["multi_gpu_split"] = ("dynamic: shared work counters over NVLink (work stealing)" if stealing else
+                                 ("static snake-order split" if world > 1 else "single GPU, dynamic CTA scheduling"))
     no2 = basis.no2
     P_host = torch.from_numpy(synthetic_density(basis)).pin_memory()
     G_host = torch.zeros(no2, dtype=torch.float64).pin_memory()

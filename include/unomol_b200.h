@@ -124,6 +124,16 @@ int unomol_b200_stats(unomol_b200_t *h, unomol_b200_stats_t *out);
  * (reference RHF_MPI.hpp:108).  The symbol is resolved from the already-loaded libnccl at run time. */
 int unomol_b200_attach_nccl(unomol_b200_t *h, void *nccl_comm);
 
+/* Work stealing across the GPUs of one box (north star: "static-plus-work-stealing split of screened quartets").
+ * Rank 0 calls steal_export: it allocates the per-launch work counters on its GPU and returns a 64-byte CUDA IPC
+ * handle; the caller ships the 64 bytes to the other ranks (torch.distributed broadcast, MPI_Bcast ...), each of
+ * which calls steal_import.  From then on every CTA of every rank claims bras of the Schwarz-sorted lists from the
+ * same counters with system-scope atomics over NVLink, heaviest first, so no GPU idles while another still has
+ * work.  CONTRACT: every rank performs every Fock build, and a collective over all ranks (the all-reduce of G)
+ * separates consecutive builds.  Without these calls a multi-rank handle uses the static snake-order split. */
+int unomol_b200_steal_export(unomol_b200_t *h, void *handle64);
+int unomol_b200_steal_import(unomol_b200_t *h, const void *handle64);
+
 /* Device pointers of the square density / partial-G work buffers and the stream the library launches on
  * (for callers that keep the SCF on the device or time with their own events). */
 int unomol_b200_device_buffers(unomol_b200_t *h, void **stream, double **dP_packed, double **dG_packed);

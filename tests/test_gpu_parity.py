@@ -291,3 +291,18 @@ def test_spatial_blocks_do_not_change_results(capi):
     h.set_option("col_blocks", 1)
     GA0, GB0 = h.fock_uhf(P, 0.5 * P)
     assert np.max(np.abs(GA - GA0)) < 1e-13 * np.max(np.abs(GA0)) and np.max(np.abs(GB - GB0)) < 1e-13 * np.max(np.abs(GA0))
+
+
+def test_multi_gpu_work_stealing_and_static_split():
+    """needs >= 2 GPUs on the box: torchrun with one rank per GPU, partial G's all-reduced over NCCL"""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("single-GPU box")
+    from conftest import ROOT
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)),
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "multigpu_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "OK" in p.stdout, (p.stdout[-1500:], p.stderr[-1500:])

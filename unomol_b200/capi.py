@@ -49,7 +49,7 @@ EXPORTS = [
     "unomol_b200_create", "unomol_b200_destroy", "unomol_b200_set_option", "unomol_b200_set_geometry",
     "unomol_b200_fock_rhf", "unomol_b200_fock_uhf", "unomol_b200_fock_rhf_device", "unomol_b200_fock_uhf_device",
     "unomol_b200_eri_quartet", "unomol_b200_dump_eris", "unomol_b200_schwarz", "unomol_b200_stats",
-    "unomol_b200_attach_nccl", "unomol_b200_device_buffers", "unomol_b200_scf_set_overlap", "unomol_b200_scf_diag",
+    "unomol_b200_attach_nccl", "unomol_b200_steal_export", "unomol_b200_steal_import", "unomol_b200_device_buffers", "unomol_b200_scf_set_overlap", "unomol_b200_scf_diag",
     "unomol_b200_sample_quartets", "unomol_b200_fp64_peak", "unomol_b200_model_flops", "unomol_b200_strerror", "unomol_b200_version",
 ]
 
@@ -72,6 +72,8 @@ def _load():
     L.unomol_b200_schwarz.argtypes = [_P, _pd]
     L.unomol_b200_stats.argtypes = [_P, ctypes.POINTER(Stats)]
     L.unomol_b200_attach_nccl.argtypes = [_P, _P]
+    L.unomol_b200_steal_export.argtypes = [_P, ctypes.c_char_p]
+    L.unomol_b200_steal_import.argtypes = [_P, ctypes.c_char_p]
     L.unomol_b200_device_buffers.argtypes = [_P, ctypes.POINTER(_P), ctypes.POINTER(_P), ctypes.POINTER(_P)]
     L.unomol_b200_scf_set_overlap.argtypes = [_P, _pd]
     L.unomol_b200_scf_diag.argtypes = [_P, _pd, _I, _pd, _pd, _pd]
@@ -184,6 +186,14 @@ class Handle:
 
     def attach_nccl(self, comm_ptr):
         _chk(lib.unomol_b200_attach_nccl(self.h, _P(comm_ptr)), "attach_nccl")
+
+    def steal_export(self):
+        buf = ctypes.create_string_buffer(64)
+        _chk(lib.unomol_b200_steal_export(self.h, buf), "steal_export")
+        return buf.raw
+
+    def steal_import(self, handle64):
+        _chk(lib.unomol_b200_steal_import(self.h, ctypes.create_string_buffer(handle64, 64)), "steal_import")
 
     def device_buffers(self):
         st = _P(); dP = (_P * 2)(); dG = (_P * 2)()

@@ -428,6 +428,20 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
     CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 2 * (h->plans.size() + 1), st));
     cudaEventRecord(h->ev2, st);
     int nlaunch = 2;
+    // work counters of this build (see engine.h)
+    unsigned long long *work = nullptr;
+    if (h->d_work_shared && h->steal_enabled) {
+        const int par = (int)(h->build_count & 1);
+        work = h->d_work_shared + (size_t)par * unomol_b200::MAXPLAN;
+        if (h->work_owner)   // reset the other set; it is next used after the collective that ends this build
+            CUDA_TRY(h, cudaMemsetAsync(h->d_work_shared + (size_t)(par ^ 1) * unomol_b200::MAXPLAN, 0,
+                                        sizeof(unsigned long long) * unomol_b200::MAXPLAN, st));
+    } else if (h->nranks == 1) {
+        if (!h->d_work_local) CUDA_TRY(h, cudaMalloc(&h->d_work_local, sizeof(unsigned long long) * unomol_b200::MAXPLAN));
+        CUDA_TRY(h, cudaMemsetAsync(h->d_work_local, 0, sizeof(unsigned long long) * std::max<size_t>(1, h->plans.size()), st));
+        work = h->d_work_local;
+    }
+    ++h->build_count;
     // The class launches are independent (they only meet in the FP64 reds on J/K): spread them over a few streams,
     // largest first, so that the small launches of small molecules (SF6: 24 launches of a few hundred CTAs)
     // overlap instead of each leaving most SMs idle.
@@ -463,8 +477,10 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         task.J = h->d_J; task.K[0] = h->d_K[0]; task.K[1] = h->d_K[1];
         task.counters = h->d_counters + 2 * ip;
         task.debug_flags = h->debug_flags;
+        task.work_counter = work ? work + ip : nullptr;
         task.cand_counter = h->d_counters + 2 * h->plans.size();
-        const int nmine = (pl.nbra_eff + h->nranks - 1) / h->nranks;
+        const int nmine = work ? pl.nbra_eff : (pl.nbra_eff + h->nranks - 1) / h->nranks;
+        task.chunk = std::max(1, std::min(8, pl.nbra_eff / (148 * 16 * 8 * h->nranks)));
         if (pl.use_reg) {
             CUDA_TRY(h, launch_reg_class(pl.cb / NSUB, pl.ck / NSUB, task, std::min(nmine, 148 * 16), st, h->stage_rows != 0));
         } else {
@@ -576,6 +592,8 @@ void unomol_b200_destroy(unomol_b200_t *h) {
         cudaFree(h->d_Ppacked[s]); cudaFree(h->d_Gpacked[s]); cudaFree(h->d_PK[s]); cudaFree(h->d_K[s]);
     }
     cudaFree(h->d_PJ); cudaFree(h->d_J); cudaFree(h->d_counters);
+    cudaFree(h->d_work_local);
+    if (h->d_work_shared) { if (h->work_owner) cudaFree(h->d_work_shared); else cudaIpcCloseMemHandle(h->d_work_shared); }
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     unomol_scf_free(h);
     if (h->ev0) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3); }
@@ -599,6 +617,7 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
     if (!strcmp(name, "prim_cut")) { h->prim_cut = value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "density_screen")) { h->density_screen = value != 0.0; return UNOMOL_OK; }
     if (!strcmp(name, "bucket_min_pairs")) { h->bucket_min_pairs = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
+    if (!strcmp(name, "work_stealing")) { h->steal_enabled = value != 0.0; h->build_count = 0; return UNOMOL_OK; }
     if (!strcmp(name, "col_blocks")) { h->col_blocks = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "stage_rows")) { h->stage_rows = (int)value; return UNOMOL_OK; }
     if (!strcmp(name, "value_cut")) { h->value_cut = value; return UNOMOL_OK; }
@@ -674,6 +693,37 @@ int unomol_b200_fock_uhf(unomol_b200_t *h, const double *PA, const double *PB, d
 int unomol_b200_stats(unomol_b200_t *h, unomol_b200_stats_t *out) {
     if (!h || !out) return UNOMOL_E_ARG;
     *out = h->stats;
+    return UNOMOL_OK;
+}
+
+int unomol_b200_steal_export(unomol_b200_t *h, void *handle64) {
+    if (!h || !handle64) return UNOMOL_E_ARG;
+    cudaSetDevice(h->device);
+    if (!h->d_work_shared) {
+        CUDA_TRY(h, cudaMalloc(&h->d_work_shared, sizeof(unsigned long long) * 2 * unomol_b200::MAXPLAN));
+        CUDA_TRY(h, cudaMemset(h->d_work_shared, 0, sizeof(unsigned long long) * 2 * unomol_b200::MAXPLAN));
+        h->work_owner = true;
+    }
+    cudaIpcMemHandle_t ipc;
+    CUDA_TRY(h, cudaIpcGetMemHandle(&ipc, h->d_work_shared));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+    memcpy(handle64, &ipc, 64);
+    h->build_count = 0;
+    return UNOMOL_OK;
+}
+
+int unomol_b200_steal_import(unomol_b200_t *h, const void *handle64) {
+    if (!h || !handle64) return UNOMOL_E_ARG;
+    cudaSetDevice(h->device);
+    if (h->d_work_shared) return UNOMOL_E_STATE;
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, handle64, 64);
+    void *p = nullptr;
+    CUDA_TRY(h, cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+    h->d_work_shared = (unsigned long long *)p;
+    h->work_owner = false;
+    h->work_imported = true;
+    h->build_count = 0;
     return UNOMOL_OK;
 }
 

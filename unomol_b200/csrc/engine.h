@@ -77,6 +77,13 @@ struct unomol_b200 {
     double *d_PJ = nullptr, *d_PK[2] = {nullptr, nullptr}, *d_J = nullptr, *d_K[2] = {nullptr, nullptr};
     double *h_pinned = nullptr;               // staging for host<->device copies (4 * no2 doubles)
     unsigned long long *d_counters = nullptr; // 2 per combo
+    // dynamic bra scheduling: one work counter per launch.  Local (single rank) or shared: allocated on rank 0's GPU,
+    // exported as a CUDA IPC handle and mapped by every other rank (system-scope atomics over NVLink); two sets,
+    // alternating per build, so that the owner can reset one while the other is in use.
+    static constexpr int MAXPLAN = ub200::NGROUP * (ub200::NGROUP + 1) / 2;
+    unsigned long long *d_work_local = nullptr, *d_work_shared = nullptr;
+    bool work_owner = false, work_imported = false, steal_enabled = true;   // option "work_stealing"
+    long long build_count = 0;
     unomol_b200_stats_t stats{};
     // SCF algebra
     void *cusolver = nullptr, *cublas = nullptr;

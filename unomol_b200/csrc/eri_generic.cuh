@@ -165,19 +165,27 @@ eri_class_kernel(const ClassTask task) {
 
     unsigned long long n_quart = 0, n_primq = 0;
 
-    // DIGEST: outer = bra index (CTA-uniform), groups stride over that bra's Schwarz-surviving kets.
+    // DIGEST: every WARP takes bras one at a time -- from the shared work counter when there is one (dynamic
+    // self-scheduling, heaviest bras first; across ranks when the counter is IPC-mapped peer memory), else in the
+    // static snake order over ranks -- and its groups stride over that bra's Schwarz-surviving kets.
     // DUMP / SCHWARZ: outer = chunk of GROUPS explicit (bra,ket) tasks, one per group.
-    // bras are dealt to ranks in snake order: this rank owns one bra of every block of nranks
-    const int nouter = (MODE == MODE_DIGEST) ? (task.nbra + task.nranks - 1) / task.nranks
-                                             : (task.ntask + C::GROUPS - 1) / C::GROUPS;
-    for (int outer = blockIdx.x; outer < nouter; outer += gridDim.x) {
+    const int warps_per_cta = C::THREADS / 32;
+    const int nouter = (MODE == MODE_DIGEST) ? task.nbra : (task.ntask + C::GROUPS - 1) / C::GROUPS;
+    int wseq = blockIdx.x * warps_per_cta + warp;   // static sequence position of this warp
+    for (int outer = (MODE == MODE_DIGEST) ? 0 : blockIdx.x;; outer += (MODE == MODE_DIGEST) ? 1 : gridDim.x) {
         int bi = 0, kfirst = 0, kcount = 0, kstep = 1;
         if (MODE == MODE_DIGEST) {
-            // snake order over ranks (see eri_reg.cuh)
-            bi = task.nranks * outer + ((outer & 1) ? task.nranks - 1 - task.rank : task.rank);
-            if (bi >= task.nbra) continue;
-            kfirst = group; kcount = task.ket_count[bi]; kstep = C::GROUPS;
+            if (task.work_counter) {
+                if (lane == 0) bi = (int)atomicAdd_system(task.work_counter, 1ULL);
+                bi = __shfl_sync(0xffffffffu, bi, 0);
+            } else {
+                bi = task.nranks * wseq + ((wseq & 1) ? task.nranks - 1 - task.rank : task.rank);
+                wseq += gridDim.x * warps_per_cta;
+            }
+            if (bi >= task.nbra) break;
+            kfirst = gw; kcount = task.ket_count[bi]; kstep = GPW;
         } else {
+            if (outer >= nouter) break;
             const int t = outer * C::GROUPS + group;
             if (t < task.ntask) { bi = task.task_list[t].x; kfirst = task.task_list[t].y; kcount = kfirst + 1; }
         }

@@ -142,17 +142,42 @@ __global__ void __launch_bounds__(ROWS ? REG_THREADS_ROWS : REG_THREADS) eri_reg
         tma_bulk_g2s(&stage[s].prims[0], task.prims + gp->prim_off, (unsigned)(sizeof(PrimPair) * np), &bars[s]);
     };
 
-    int jb = blockIdx.x;
-    int bi = bra_of(jb);
+    // Bra sequence of this CTA.  Dynamic (work_counter != null): thread 0 claims chunks of consecutive bras with a
+    // system-scope atomic on a counter shared by every CTA of every rank (the lists are sorted by Schwarz bound, so
+    // work is handed out heaviest first and whoever is free takes the next chunk: work stealing inside a GPU and,
+    // when the counter lives in IPC-mapped peer memory, across the GPUs of the box).  Static fallback: snake order.
+    __shared__ int s_next;
+    int jb = blockIdx.x, cpos = 0, cend = 0;   // thread 0's sequencer state
+    auto advance = [&]() -> int {             // thread 0 only
+        if (task.work_counter) {
+            if (cpos >= cend) {
+                cpos = (int)atomicAdd_system(task.work_counter, (unsigned long long)task.chunk);
+                cend = cpos + task.chunk;
+            }
+            return cpos < task.nbra ? cpos++ : task.nbra;
+        }
+        const int b = bra_of(jb);
+        jb += gridDim.x;
+        return b < task.nbra ? b : task.nbra;
+    };
     unsigned phase[2] = {0u, 0u};
     int s = 0;
-    if (bi < task.nbra && tid == 0) issue(bi, 0);
+    if (tid == 0) {
+        const int b0 = advance();
+        s_next = b0;
+        if (b0 < task.nbra) issue(b0, 0);
+    }
+    __syncthreads();
+    int bi = s_next;
+    __syncthreads();
     unsigned long long n_quart = 0, n_primq = 0, n_cand = 0;
 
     while (bi < task.nbra) {
-        jb += gridDim.x;
-        const int bn = bra_of(jb);
-        if (bn < task.nbra && tid == 0) issue(bn, s ^ 1);     // prefetch the next bra while this one is computed
+        if (tid == 0) {
+            const int b1 = advance();
+            s_next = b1;
+            if (b1 < task.nbra) issue(b1, s ^ 1);     // prefetch the next bra while this one is computed
+        }
         mbar_wait(&bars[s], phase[s]);
         phase[s] ^= 1u;
         const ShellPair &bra = stage[s].pair;
@@ -489,6 +514,7 @@ __global__ void __launch_bounds__(ROWS ? REG_THREADS_ROWS : REG_THREADS) eri_reg
             }
         }
         // ---- J_ab: one reduction per bra (warp shuffle, then one red per warp)
+        int bnext;
         {
             const int n = task.nbf;
 #pragma unroll
@@ -499,6 +525,7 @@ __global__ void __launch_bounds__(ROWS ? REG_THREADS_ROWS : REG_THREADS) eri_reg
                 if (lane == 0) jab_red[warp][ab] = v;
             }
             __syncthreads();
+            bnext = s_next;   // written by thread 0 at the top of this iteration; re-written only after the barrier below
             if (tid < NAB) {
                 double v = 0.0;
 #pragma unroll
@@ -508,7 +535,7 @@ __global__ void __launch_bounds__(ROWS ? REG_THREADS_ROWS : REG_THREADS) eri_reg
         }
         __syncthreads();   // everyone is done with stage[s], the staged rows and jab_red before they are overwritten
         if (ROWS && use_rows) row_phase ^= 1u;
-        bi = bn;
+        bi = bnext;
         s ^= 1;
     }
     if (task.counters) {

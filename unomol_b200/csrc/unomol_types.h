@@ -62,7 +62,10 @@ struct ClassTask {
     int nbra, nket;
     int same_class;           // bra and ket lists are the same list (triangular, diagonal gets 1/2)
     int start_shell;          // quartet kept iff max shell index >= start_shell
-    int rank, nranks;         // bras are dealt round-robin to ranks
+    int rank, nranks;         // static fallback: bras are dealt to ranks in snake order
+    unsigned long long *work_counter;  // dynamic self-scheduling: next unclaimed bra of this launch (device-local, or on rank 0's
+                              // GPU and IPC/NVLink-mapped into every rank: work stealing across the GPUs of the box); null = static
+    int chunk;                // bras claimed per atomic
     double prim_cut;          // reference's sr < 1e-12 cut
     double value_cut;         // reference's |val| > 1e-14 storage threshold (TwoElectronInts.cpp:513)
     // digestion

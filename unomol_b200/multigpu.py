@@ -34,6 +34,34 @@ def allreduce_packed(G, group=None):
     return G
 
 
+def enable_work_stealing(handle):
+    """share rank 0's work counters with every rank (CUDA IPC handle broadcast); returns False when IPC is unavailable"""
+    import torch.distributed as dist
+    from . import capi
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return True
+    box = [None]
+    ok = True
+    try:
+        if dist.get_rank() == 0:
+            box[0] = handle.steal_export()
+    except capi.UnomolError:
+        box[0] = b""
+    dist.broadcast_object_list(box, src=0)
+    if dist.get_rank() != 0:
+        if not box[0]:
+            ok = False
+        else:
+            try:
+                handle.steal_import(box[0])
+            except capi.UnomolError:
+                ok = False
+    flag = [ok]
+    gathered = [None] * dist.get_world_size()
+    dist.all_gather_object(gathered, ok)
+    return all(gathered)
+
+
 class DistributedFock:
     """RHF/UHF Fock build over all ranks: the Python-side equivalent of RHF_MPI::update's Bcast/Reduce bracket."""
 
@@ -45,6 +73,9 @@ class DistributedFock:
         self.h = capi.Handle(basis, start_shell=start_shell, device=self.local, rank=self.rank, nranks=self.world)
         if tau is not None:
             self.h.set_option("schwarz_tau", tau)
+        self.stealing = enable_work_stealing(self.h) if self.world > 1 else False
+        if self.world > 1 and not self.stealing:
+            self.h.set_option("work_stealing", 0)
         self.no2 = basis.no2
         self.dP = torch.zeros(self.no2, dtype=torch.float64, device="cuda")
         self.dG = torch.zeros(self.no2, dtype=torch.float64, device="cuda")
