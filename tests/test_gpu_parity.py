@@ -306,3 +306,17 @@ def test_multi_gpu_work_stealing_and_static_split():
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "multigpu_check.py")],
                        capture_output=True, text=True, timeout=900)
     assert p.returncode == 0 and "OK" in p.stdout, (p.stdout[-1500:], p.stderr[-1500:])
+
+
+def test_device_pair_tables_match_host_pair_tables(capi):
+    """pair tables built on the GPU (pair_device.cu) against the threaded host path (engine.cu)"""
+    for name in ("631.nh3", "tz2p.sf6"):
+        b, h = _handle(capi, name)
+        rng = np.random.default_rng(3)
+        P = rng.standard_normal(b.no2)
+        G1 = h.fock_rhf(P); Q1 = h.schwarz(); s1 = h.stats()
+        h.set_option("device_pairs", 0)
+        G0 = h.fock_rhf(P); Q0 = h.schwarz(); s0 = h.stats()
+        assert s0["n_pairs_kept"] == s1["n_pairs_kept"] and s0["n_prim_pairs"] == s1["n_prim_pairs"]
+        assert np.max(np.abs(Q1 - Q0)) < 1e-13 * np.max(Q0)
+        assert np.max(np.abs(G1 - G0)) < 1e-13 * np.max(np.abs(G0))

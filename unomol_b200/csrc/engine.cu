@@ -164,6 +164,33 @@ static int build_pairs(unomol_b200 *h) {
     // when even its most diffuse primitive pair fails that test (u, 1/p and 1/sqrt(p) are all largest there).
     // Rows of the (i >= j) pair triangle are processed by a few host threads; the result is concatenated in (i, j)
     // order so the tables do not depend on the thread count.
+    long long nprim = 0, nkept = 0;
+    const bool bucketed = (long long)ns * (ns + 1) / 2 >= h->bucket_min_pairs;
+    // column/row blocking: keep (rows of a bra block) x (columns of a ket block) x 8 B x ~2.5 matrices within ~48 MB of L2
+    int nblock = h->col_blocks;
+    if (nblock <= 0) {
+        // measured (profiles/exp_blocks.py): N=2002 (80 MB) is fastest unblocked, N=4004 (320 MB) 1.56x faster with 3 blocks
+        const double foot = 2.5 * 8.0 * (double)B.nbf * (double)B.nbf;
+        nblock = foot <= 100e6 ? 1 : (int)std::ceil(std::sqrt(foot / 48e6));
+    }
+    nblock = std::max(1, std::min(nblock, NBLOCK));
+    auto group_of = [&](const ShellPair &sp, int cls) {
+        // lanes of a warp take different kets of one list: keep their primitive loop lengths similar (bucket);
+        // spatial block = slab of shell indices of the pair's larger shell (inputs list atoms, hence shells, in spatial order)
+        const int np = sp.nprim;
+        const int bucket = !bucketed ? 0 : (np <= 1 ? 0 : np <= 3 ? 1 : np <= 6 ? 2 : np <= 12 ? 3 : np <= 24 ? 4 : 5);
+        const int block = std::min(nblock - 1, (int)((long long)std::max(sp.sha, sp.shb) * nblock / ns));
+        return cls * NSUB + bucket * NBLOCK + block;
+    };
+    if (h->device_pairs) {
+        // primitive-pair generation, exact prune and per-pair sort on the GPU (pair_device.cu); the host only groups
+        std::vector<ShellPair> kept;
+        std::vector<int> kcls;
+        int rc = build_pair_tables_device(h, kept, kcls, &h->d_prims, &nprim);
+        if (rc) return rc;
+        nkept = (long long)kept.size();
+        for (size_t i = 0; i < kept.size(); ++i) h->cls[group_of(kept[i], kcls[i])].pairs.push_back(kept[i]);
+    } else {
     std::vector<double> amin(ns);
     double umax = 0.0;
     for (int s = 0; s < ns; ++s) {
@@ -244,40 +271,26 @@ static int build_pairs(unomol_b200 *h) {
             for (auto &t : pool) t.join();
         }
     }
-    long long nprim = 0, nkept = 0;
-    const bool bucketed = (long long)ns * (ns + 1) / 2 >= h->bucket_min_pairs;
-    // column/row blocking: keep (rows of a bra block) x (columns of a ket block) x 8 B x ~2.5 matrices within ~48 MB of L2
-    int nblock = h->col_blocks;
-    if (nblock <= 0) {
-        // measured (profiles/exp_blocks.py): N=2002 (80 MB) is fastest unblocked, N=4004 (320 MB) 1.56x faster with 3 blocks
-        const double foot = 2.5 * 8.0 * (double)B.nbf * (double)B.nbf;
-        nblock = foot <= 100e6 ? 1 : (int)std::ceil(std::sqrt(foot / 48e6));
-    }
-    nblock = std::max(1, std::min(nblock, NBLOCK));
     for (int i = 0; i < ns; ++i) {
         for (auto &o : rows[i].pairs) {
             o.sp.prim_off = (int)h->h_prims.size();
             h->h_prims.insert(h->h_prims.end(), rows[i].prims.begin() + o.first, rows[i].prims.begin() + o.first + o.count);
-            // lanes of a warp take different kets of one list: keep their primitive loop lengths similar
-            const int np = o.count;
-            const int bucket = !bucketed ? 0 : (np <= 1 ? 0 : np <= 3 ? 1 : np <= 6 ? 2 : np <= 12 ? 3 : np <= 24 ? 4 : 5);
-            // spatial block = slab of shell indices of the pair's larger shell (inputs list atoms, hence shells, in spatial order)
-            const int block = std::min(nblock - 1, (int)((long long)std::max(o.sp.sha, o.sp.shb) * nblock / ns));
-            h->cls[o.cls * NSUB + bucket * NBLOCK + block].pairs.push_back(o.sp);
-            nprim += np;
+            h->cls[group_of(o.sp, o.cls)].pairs.push_back(o.sp);
+            nprim += o.count;
             ++nkept;
         }
         RowOut().pairs.swap(rows[i].pairs);
         std::vector<PrimPair>().swap(rows[i].prims);
     }
-    h->stats.n_shell_pairs = (long long)ns * (ns + 1) / 2;
-    h->stats.n_pairs_kept = nkept;
-    h->stats.n_prim_pairs = nprim;
     if (nprim) {
         CUDA_TRY(h, cudaMalloc(&h->d_prims, sizeof(PrimPair) * nprim));
         CUDA_TRY(h, cudaMemcpyAsync(h->d_prims, h->h_prims.data(), sizeof(PrimPair) * nprim, cudaMemcpyHostToDevice,
                                     h->stream));
     }
+    }   // host path
+    h->stats.n_shell_pairs = (long long)ns * (ns + 1) / 2;
+    h->stats.n_pairs_kept = nkept;
+    h->stats.n_prim_pairs = nprim;
     // Schwarz bounds: diagonal quartet (ab|ab) of every kept pair, on the GPU (MODE_SCHWARZ)
     for (int c = 0; c < NGROUP; ++c) {
         PairClassList &L = h->cls[c];
@@ -618,6 +631,7 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
     if (!strcmp(name, "density_screen")) { h->density_screen = value != 0.0; return UNOMOL_OK; }
     if (!strcmp(name, "bucket_min_pairs")) { h->bucket_min_pairs = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "work_stealing")) { h->steal_enabled = value != 0.0; h->build_count = 0; return UNOMOL_OK; }
+    if (!strcmp(name, "device_pairs")) { h->device_pairs = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "col_blocks")) { h->col_blocks = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "stage_rows")) { h->stage_rows = (int)value; return UNOMOL_OK; }
     if (!strcmp(name, "value_cut")) { h->value_cut = value; return UNOMOL_OK; }

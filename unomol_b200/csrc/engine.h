@@ -6,6 +6,8 @@
 #include "../../include/unomol_b200.h"
 #include "unomol_types.h"
 
+struct unomol_b200;
+
 namespace ub200 {
 
 // launchers, one per quartet class, defined in eri_class_*.cu
@@ -15,6 +17,9 @@ int class_groups_per_cta(int bra_class, int ket_class);
 // register-resident kernels for the small classes (eri_reg_classes.cu)
 bool reg_class_available(int bra_class, int ket_class);
 int reg_max_bra_prims();
+// device-side shell-pair / primitive-pair tables (pair_device.cu)
+int build_pair_tables_device(unomol_b200 *h, std::vector<ShellPair> &kept, std::vector<int> &cls, PrimPair **d_prims_out,
+                             long long *nprim_out);
 cudaError_t launch_reg_class(int bra_class, int ket_class, const ClassTask &task, int grid, cudaStream_t stream, bool allow_rows);
 // SURVEY.md 8(d) flop model per primitive quartet of class (la lb | lc ld)
 double model_flops_per_primitive_quartet(int la, int lb, int lc, int ld);
@@ -61,6 +66,7 @@ struct unomol_b200 {
     double tau = 1e-12, prim_cut = 1e-12, value_cut = 1e-14;
     int density_screen = 0;
     int use_reg_kernels = 1;
+    int device_pairs = 1;           // option "device_pairs": build the pair tables on the GPU (0 = threaded host path)
     int col_blocks = 0;             // option "col_blocks": spatial blocks per pair list (0 = choose from N so a launch fits L2)
     int stage_rows = 1;             // option "stage_rows": stage the bra's rows of P in shared memory (TMA) when they fit
     int debug_flags = 0;            // option "debug_flags" (profiling experiments; see ClassTask)
