@@ -349,6 +349,13 @@ def main():
         peak = capi.fp64_peak(local)
         achieved = model_flops / (kernel_ms * 1e-3) / 1e12 / max(world, 1) if kernel_ms > 0 else 0.0
         # per-GPU roofline: model flops of all ranks / world over the slowest rank's kernel time
+        # DRAM / L2 bytes of one build from the committed ncu pass of the same workload (profiles/r1_traffic_*.json;
+        # `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum`), not measured live
+        traffic = l2_bytes = None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic_%s.json" % args.workload)
+        if os.path.exists(tpath) and world == 1:
+            tj = json.load(open(tpath))["total"]
+            traffic, l2_bytes = tj["dram_bytes"], tj["l2_bytes"]
         line = {"metric": "eri_shell_quartets_per_s", "value": value, "unit": "quartets/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -361,7 +368,7 @@ def main():
                 "e2e": {"value": e2e_val, "unit": "quartets/s", "h2d_bytes_per_step": int(no2 * 8),
                         "d2h_bytes_per_step": int(no2 * 8), "s_per_step": e2e_s / args.steps},
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                             "frac": achieved / peak if peak else None, "traffic": None,
+                             "frac": achieved / peak if peak else None, "traffic": traffic, "l2_bytes": l2_bytes,
                              "kernel": "eri_class_kernel<*> (fused ERI + J/K digestion, all class launches of one build)",
                              "kernel_ms_per_build": kernel_ms, "model_gflop_per_build": model_flops / 1e9,
                              "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)"}}
