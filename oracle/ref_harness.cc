@@ -10,7 +10,9 @@
 //   ref_rys_roots        -> Rys::calculate_roots            (Rys.hpp:145-164, Rys.cpp:314-2197)
 //   ref_basis_*          -> Basis::Basis(patin.dat)          (Basis.hpp:181-255)
 //   ref_quartet_block    -> calc_two_electron_ints_rys       (TwoElectronInts.cpp:420-509) on one ordered
-//                           shell quartet, all Cartesian components (no canonical filter)
+//                           shell quartet, all Cartesian components (no canonical filter); for l_tot > 8
+//                           calc_two_electron_ints_md (TwoElectronInts.cpp:269-418), the reference's own
+//                           dispatch rule (TwoElectronInts.cpp:661-665)
 //   ref_tints_*          -> TwoElectronInts ctor/calculate, formGmatrix x2 (TwoElectronInts.cpp:511-869)
 //   ref_one_electron     -> OneElectronInts                  (OneElectronInts.cpp:127-202)
 #include <cstdio>
@@ -27,6 +29,7 @@
 namespace unomol {
 // exported by the reference's TwoElectronInts.o (external linkage, not declared in its header)
 void calc_two_electron_ints_rys(const ShellQuartet& sq, const AuxFunctions& aux, Rys& rys, TwoInts* sints);
+void calc_two_electron_ints_md(const ShellQuartet& sq, const AuxFunctions& aux, MDInts& mds, TwoInts* sints);
 }
 
 using namespace unomol;
@@ -99,7 +102,7 @@ int ref_quartet_block(void* bp, int ish, int jsh, int ksh, int lsh, double* out)
         lv[t] = (shell + sh[t])->Lvalue();
         nls[t] = aux.number_of_lstates(lv[t]);
     }
-    if (lv[0] + lv[1] + lv[2] + lv[3] > 8) return -1;
+    const bool use_md = lv[0] + lv[1] + lv[2] + lv[3] > 8;   // TwoElectronInts.cpp:661-665
     bool sw12 = lv[0] < lv[1], sw34 = lv[2] < lv[3];
     int s1 = sw12 ? jsh : ish, s2 = sw12 ? ish : jsh, s3 = sw34 ? lsh : ksh, s4 = sw34 ? ksh : lsh;
     const Shell *p1 = shell + s1, *p2 = shell + s2, *p3 = shell + s3, *p4 = shell + s4;
@@ -129,7 +132,13 @@ int ref_quartet_block(void* bp, int ish, int jsh, int ksh, int lsh, double* out)
                     ++knt;
                 }
     sq.len = knt;
-    calc_two_electron_ints_rys(sq, aux, *rys, sints.data());
+    if (use_md) {
+        static MDInts* mds = nullptr;
+        if (!mds) mds = new MDInts(4);
+        calc_two_electron_ints_md(sq, aux, *mds, sints.data());
+    } else {
+        calc_two_electron_ints_rys(sq, aux, *rys, sints.data());
+    }
     for (int i = 0; i < n; ++i) out[i] = sints[i].val;
     return n;
 }

@@ -162,6 +162,7 @@ void oracle_basis_set_center(oracle_basis *b, int icen, double x, double y, doub
  * Rys 2-D recurrence and transfer (Rys.hpp:113-143,194-212 and :85-111,173-192).
  * ---------------------------------------------------------------------------------------------- */
 #define GDIM 10 /* l12, l34 <= 8 */
+#define ORACLE_MAXFUNC 50625 /* 15^4: (gg|gg) */
 typedef struct {
     double G[3][5][GDIM][GDIM]; /* [axis][root][i][j] */
     double w[5];
@@ -246,8 +247,8 @@ static double rys_shift(rys_tables *T, const double *ab, const double *cd, const
 typedef struct {
     int s1, s2, s3, s4;  /* shell ids after the l-ordering swaps */
     int len;
-    int comp[1296][4];   /* component ids (for shells s1..s4, i.e. after swap) */
-    double norm[1296];
+    int comp[ORACLE_MAXFUNC][4];   /* component ids (for shells s1..s4, i.e. after swap) */
+    double norm[ORACLE_MAXFUNC];
 } quartet_view;
 
 /* calc_two_electron_ints_rys, TwoElectronInts.cpp:420-509 */
@@ -315,6 +316,173 @@ static void eri_quartet_rys(const oracle_basis *b, const quartet_view *q, double
     }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * McMurchie-Davidson path for l_tot > 8 (f/g shells): calc_two_electron_ints_md and its one-/two-centre
+ * variants (TwoElectronInts.cpp:9-418), MD_Dfunction::eval (MD_Dfunction.hpp:39-72), MD_Rfunction::eval
+ * -> Fgamma + loop_eval (MD_Rfunction.hpp:49-70, 2185-2319).  The one- and two-centre variants are the
+ * general routine with P-A = P-B = 0 (and P-Q taken from the centres); they are restated by setting
+ * those differences to exactly zero when both shells of a pair sit on the same centre (the reference
+ * tests pointer equality of the centre vectors, TwoElectronInts.cpp:274-275).  No primitive threshold on
+ * this path.  Fgamma keeps the reference's semantics on purpose: power series + downward recursion for
+ * t <= 20, bare asymptotic value + upward recursion for t > 20 (relative error up to 2.5e-10 just above 20).
+ * ---------------------------------------------------------------------------------------------- */
+#define MD_LDIM 5   /* l per shell <= 4 */
+#define MD_TDIM 9   /* hermite index <= 8 per pair */
+#define MD_RDIM 17  /* l_tot <= 16 */
+
+/* MD_Rfunction::Fgamma, MD_Rfunction.hpp:2185-2206 */
+static void md_fgamma(double *fm, double t, int m) {
+    const double tcrit = 20.0, sqrtpi = 0.88622692545275801365, eps = 1.e-12;
+    if (t > tcrit) {
+        fm[0] = sqrtpi / sqrt(t);
+        for (int i = 1; i <= m; i++) fm[i] = fm[i - 1] * (i - 0.5) / t;
+        return;
+    }
+    double mphalf = m + 0.5, term = 0.5 / mphalf, sum = term;
+    for (int i = 1; i <= 200; i++) {
+        term *= (t / (mphalf + i));
+        sum += term;
+        if (term < eps) break;
+    }
+    double twot = 2.0 * t, expt = exp(-t);
+    fm[m] = sum * expt;
+    for (int i = m - 1; i >= 0; i--) fm[i] = (fm[i + 1] * twot + expt) / (i + i + 1.0);
+}
+
+/* MD_Dfunction::eval, MD_Dfunction.hpp:39-72: E[i][j][n], i <= l1 (first shell), j <= l2, n <= i+j */
+static void md_ecoef(double (*E)[MD_LDIM][MD_TDIM], double abi, double ax, double bx, int l1, int l2) {
+    for (int i = 0; i <= l1; i++)
+        for (int j = 0; j <= l2; j++)
+            for (int k = 0; k < MD_TDIM; k++) E[i][j][k] = 0.0;
+    E[0][0][0] = 1.0;
+    for (int j = 1; j <= l2; j++) {
+        E[0][j][0] = bx * E[0][j - 1][0] + E[0][j - 1][1];
+        for (int n = 1; n < j; n++) E[0][j][n] = abi * E[0][j - 1][n - 1] + bx * E[0][j - 1][n] + (n + 1) * E[0][j - 1][n + 1];
+        E[0][j][j] = abi * E[0][j - 1][j - 1];
+    }
+    for (int i = 1; i <= l1; i++)
+        for (int j = 0; j <= l2; j++) {
+            int ipj = i + j;
+            E[i][j][0] = ax * E[i - 1][j][0] + E[i - 1][j][1];
+            for (int n = 1; n < ipj; n++) E[i][j][n] = abi * E[i - 1][j][n - 1] + ax * E[i - 1][j][n] + (n + 1) * E[i - 1][j][n + 1];
+            E[i][j][ipj] = abi * E[i - 1][j][ipj - 1];
+        }
+}
+
+/* MD_Rfunction::eval + loop_eval, MD_Rfunction.hpp:49-70, 2208-2319: R[lx][ly][lz] for lx+ly+lz <= ltot.
+ * Same recurrences (z first, then y, then x; coefficient (l-1) on the l-2 term), written with one loop per
+ * axis instead of the reference's unrolled l = 1, 2 cases. */
+static double g_rz[MD_RDIM][MD_RDIM][MD_RDIM][MD_RDIM + 1];
+static void md_rtensor(double (*R)[MD_RDIM][MD_RDIM], double sr, double t, double w, const double *pq, int ltot) {
+    double *r0 = g_rz[0][0][0];
+    md_fgamma(r0, t, ltot);
+    double term = -(w + w), sterm = sr;
+    for (int m = 0; m <= ltot; ++m) {
+        r0[m] = sterm * r0[m];
+        sterm *= term;
+    }
+    const double x = pq[0], y = pq[1], z = pq[2];
+    for (int lz = 1; lz <= ltot; ++lz)
+        for (int m = 0; m <= ltot - lz; ++m)
+            g_rz[0][0][lz][m] = z * g_rz[0][0][lz - 1][m + 1] + (lz > 1 ? (lz - 1) * g_rz[0][0][lz - 2][m + 1] : 0.0);
+    for (int ly = 1; ly <= ltot; ++ly)
+        for (int lz = 0; lz <= ltot - ly; ++lz)
+            for (int m = 0; m <= ltot - ly - lz; ++m)
+                g_rz[0][ly][lz][m] = y * g_rz[0][ly - 1][lz][m + 1] + (ly > 1 ? (ly - 1) * g_rz[0][ly - 2][lz][m + 1] : 0.0);
+    for (int lx = 1; lx <= ltot; ++lx)
+        for (int ly = 0; ly <= ltot - lx; ++ly)
+            for (int lz = 0; lz <= ltot - lx - ly; ++lz)
+                for (int m = 0; m <= ltot - lx - ly - lz; ++m)
+                    g_rz[lx][ly][lz][m] = x * g_rz[lx - 1][ly][lz][m + 1] + (lx > 1 ? (lx - 1) * g_rz[lx - 2][ly][lz][m + 1] : 0.0);
+    for (int lx = 0; lx <= ltot; ++lx)
+        for (int ly = 0; ly <= ltot - lx; ++ly)
+            for (int lz = 0; lz <= ltot - lx - ly; ++lz) R[lx][ly][lz] = g_rz[lx][ly][lz][0];
+}
+
+/* calc_two_electron_ints_md, TwoElectronInts.cpp:269-418 */
+static void eri_quartet_md(const oracle_basis *b, const quartet_view *q, double *vals, long *nprimq) {
+    const double SRterm = 34.9868366552497250;
+    const int s1 = q->s1, s2 = q->s2, s3 = q->s3, s4 = q->s4;
+    const double *A = b->xyz + 3 * b->cen[s1], *B = b->xyz + 3 * b->cen[s2];
+    const double *C = b->xyz + 3 * b->cen[s3], *D = b->xyz + 3 * b->cen[s4];
+    const double *al1 = b->alpha + b->poff[s1], *co1 = b->coef + b->poff[s1];
+    const double *al2 = b->alpha + b->poff[s2], *co2 = b->coef + b->poff[s2];
+    const double *al3 = b->alpha + b->poff[s3], *co3 = b->coef + b->poff[s3];
+    const double *al4 = b->alpha + b->poff[s4], *co4 = b->coef + b->poff[s4];
+    const int lv1 = b->lv[s1], lv2 = b->lv[s2], lv3 = b->lv[s3], lv4 = b->lv[s4];
+    const int lvt = lv1 + lv2 + lv3 + lv4;
+    double ab2 = 0.0, cd2 = 0.0;
+    for (int t = 0; t < 3; ++t) {
+        ab2 += (A[t] - B[t]) * (A[t] - B[t]);
+        cd2 += (C[t] - D[t]) * (C[t] - D[t]);
+    }
+    const int one12 = (b->cen[s1] == b->cen[s2]), one34 = (b->cen[s3] == b->cen[s4]);
+    const int same12 = (s1 == s2), same34 = (s3 == s4);
+    static double E12[3][MD_LDIM][MD_LDIM][MD_TDIM], E34[3][MD_LDIM][MD_LDIM][MD_TDIM], R[MD_RDIM][MD_RDIM][MD_RDIM];
+    for (int k = 0; k < q->len; ++k) vals[k] = 0.0;
+    for (int i = 0; i < b->npr[s1]; ++i) {
+        double axp = al1[i], c1 = co1[i], f12 = 1.0;
+        int jend = b->npr[s2];
+        if (same12) { f12 = 2.0; jend = i + 1; }
+        for (int j = 0; j < jend; ++j) {
+            if (i == j) f12 = 1.0;
+            double c12 = c1 * f12 * co2[j];
+            double bxp = al2[j], pxp = axp + bxp, abi = 1.0 / pxp;
+            double s12 = c12 * exp(-axp * bxp * ab2 * abi);
+            double p[3];
+            for (int t = 0; t < 3; ++t) p[t] = one12 ? A[t] : (axp * A[t] + bxp * B[t]) * abi;
+            abi *= 0.5;
+            for (int t = 0; t < 3; ++t) md_ecoef(E12[t], abi, p[t] - A[t], p[t] - B[t], lv1, lv2);
+            for (int k = 0; k < b->npr[s3]; ++k) {
+                double cxp = al3[k], c3 = co3[k], f34 = 1.0;
+                int lend = b->npr[s4];
+                if (same34) { f34 = 2.0; lend = k + 1; }
+                for (int l = 0; l < lend; ++l) {
+                    if (k == l) f34 = 1.0;
+                    double c34 = c3 * f34 * co4[l];
+                    double dxp = al4[l], qxp = cxp + dxp, cdi = 1.0 / qxp;
+                    double s34 = c34 * exp(-cxp * dxp * cd2 * cdi);
+                    double txp = pxp + qxp;
+                    double sr = SRterm * s12 * s34 * 2. * abi * cdi / sqrt(txp);
+                    double qq[3], pq[3];
+                    for (int t = 0; t < 3; ++t) qq[t] = one34 ? C[t] : (cxp * C[t] + dxp * D[t]) * cdi;
+                    cdi *= 0.5;
+                    for (int t = 0; t < 3; ++t) md_ecoef(E34[t], cdi, qq[t] - C[t], qq[t] - D[t], lv3, lv4);
+                    for (int t = 0; t < 3; ++t) pq[t] = p[t] - qq[t];
+                    double pq2 = pq[0] * pq[0] + pq[1] * pq[1] + pq[2] * pq[2];
+                    double w = pxp * qxp / txp, tt = w * pq2;
+                    if (nprimq) ++*nprimq;
+                    md_rtensor(R, sr, tt, w, pq, lvt);
+                    for (int kc = 0; kc < q->len; ++kc) {
+                        const int *c = q->comp[kc];
+                        const int *v1 = g_cart[lv1][c[0]], *v2 = g_cart[lv2][c[1]], *v3 = g_cart[lv3][c[2]], *v4 = g_cart[lv4][c[3]];
+                        const int l12 = v1[0] + v2[0], m12 = v1[1] + v2[1], n12 = v1[2] + v2[2];
+                        const int l34 = v3[0] + v4[0], m34 = v3[1] + v4[1], n34 = v3[2] + v4[2];
+                        double sum = 0;
+                        for (int ix12 = 0; ix12 <= l12; ++ix12)
+                            for (int iy12 = 0; iy12 <= m12; ++iy12)
+                                for (int iz12 = 0; iz12 <= n12; ++iz12) {
+                                    double v12 = E12[0][v1[0]][v2[0]][ix12] * E12[1][v1[1]][v2[1]][iy12] * E12[2][v1[2]][v2[2]][iz12];
+                                    for (int ix34 = 0; ix34 <= l34; ++ix34)
+                                        for (int iy34 = 0; iy34 <= m34; ++iy34) {
+                                            const double v34 = v12 * E34[0][v3[0]][v4[0]][ix34] * E34[1][v3[1]][v4[1]][iy34];
+                                            const double *rzp = R[ix12 + ix34][iy12 + iy34] + iz12;
+                                            const double *dzp = E34[2][v3[2]][v4[2]];
+                                            int sx = ((ix34 + iy34) % 2) ? -1 : 1;
+                                            for (int iz34 = 0; iz34 <= n34; ++iz34) {
+                                                sum += sx * v34 * dzp[iz34] * rzp[iz34];
+                                                sx = -sx;
+                                            }
+                                        }
+                                }
+                        vals[kc] += sum * q->norm[kc];
+                    }
+                }
+            }
+        }
+    }
+}
+
 int oracle_quartet_block(const oracle_basis *b, int ish, int jsh, int ksh, int lsh, double *out) {
     init_tables();
     int sh[4] = {ish, jsh, ksh, lsh}, lv[4], n[4];
@@ -322,7 +490,6 @@ int oracle_quartet_block(const oracle_basis *b, int ish, int jsh, int ksh, int l
         lv[t] = b->lv[sh[t]];
         n[t] = oracle_ncart(lv[t]);
     }
-    if (lv[0] + lv[1] + lv[2] + lv[3] > 8) return -1;
     int sw12 = lv[0] < lv[1], sw34 = lv[2] < lv[3]; /* TwoElectronInts.cpp:563,604 */
     static quartet_view q;
     q.s1 = sw12 ? jsh : ish; q.s2 = sw12 ? ish : jsh;
@@ -338,7 +505,8 @@ int oracle_quartet_block(const oracle_basis *b, int ish, int jsh, int ksh, int l
                     ++knt;
                 }
     q.len = knt;
-    eri_quartet_rys(b, &q, out, NULL);
+    if (lv[0] + lv[1] + lv[2] + lv[3] > 8) eri_quartet_md(b, &q, out, NULL); /* dispatch: TwoElectronInts.cpp:661-665 */
+    else eri_quartet_rys(b, &q, out, NULL);
     return knt;
 }
 
@@ -349,8 +517,8 @@ static long walk_quartets(const oracle_basis *b, int start, long sample_mod, lon
                           void *ctx, long *ncalc, long *nprimq) {
     init_tables();
     static quartet_view q;
-    static int ijkl[1296][4];
-    static double vals[1296];
+    static int ijkl[ORACLE_MAXFUNC][4];
+    static double vals[ORACLE_MAXFUNC];
     long nq = 0, running = 0;
     for (int ish = start; ish < b->nshell; ++ish)
         for (int jsh = 0; jsh <= ish; ++jsh)
@@ -382,12 +550,12 @@ static long walk_quartets(const oracle_basis *b, int start, long sample_mod, lon
                     }
                     if (!knt) continue;
                     if (sample_mod > 1 && (running++ % sample_mod) != sample_rem) continue;
-                    if (lv1 + lv2 + lv3 + lv4 > 8) continue; /* MD path (l_tot>8) is not restated; dormant at maxl<=2 */
                     q.s1 = sw12 ? jsh : ish; q.s2 = sw12 ? ish : jsh;
                     q.s3 = sw34 ? lsh : ksh; q.s4 = sw34 ? ksh : lsh;
                     q.len = knt;
                     if (ncalc) *ncalc += knt;
-                    eri_quartet_rys(b, &q, vals, nprimq);
+                    if (lv1 + lv2 + lv3 + lv4 > 8) eri_quartet_md(b, &q, vals, nprimq); /* :661-665 */
+                    else eri_quartet_rys(b, &q, vals, nprimq);
                     sink(ctx, &q, ijkl, vals);
                     ++nq;
                 }

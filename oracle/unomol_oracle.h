@@ -48,7 +48,8 @@ double oracle_cart_norm(int l, int comp);
 int oracle_rys_roots(int nroots, double x, double *r, double *w);
 
 /* One ordered shell quartet, every Cartesian component, out[((a*n2+b)*n3+c)*n4+d]
- * (TwoElectronInts.cpp:420-509 + Rys.hpp:85-212).  Returns the number of values, <0 if l_tot>8. */
+ * (TwoElectronInts.cpp:420-509 + Rys.hpp:85-212; for l_tot > 8 the McMurchie-Davidson routine,
+ * TwoElectronInts.cpp:9-418, by the reference's dispatch rule :661-665).  Returns the number of values. */
 int oracle_quartet_block(const oracle_basis *b, int ish, int jsh, int ksh, int lsh, double *out);
 
 /* The unique-integral list of TwoElectronInts::calculate (TwoElectronInts.cpp:511-697): same loop order,

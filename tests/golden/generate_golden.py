@@ -12,6 +12,7 @@ Writes, next to this script:
   eri_631_nh3.npz, eri_631_co.npz   ditto (108 345 computed each)
   g_<input>.npz           reference formGmatrix for seeded random P (RHF and UHF), several inputs
   quartets_<input>.npz    reference calc_two_electron_ints_rys blocks for seeded random ordered shell quartets
+  *_fg_h2o.npz            the same for OUR f/g-shell input inputs/patin.dat.fg.h2o (see highl_input)
 """
 import json, os, re, shutil, subprocess, sys, tempfile
 import numpy as np
@@ -131,6 +132,50 @@ def cation_variants():
     json.dump(runs, open(os.path.join(HERE, "ref_runs.json"), "w"), indent=1)
 
 
+def highl_input():
+    """f/g shells: none of the reference's shipped inputs has l > 2, so inputs/patin.dat.fg.h2o is OURS
+    (a water-like 3-centre system with s..g shells on O, s p f / s d f on the hydrogens, 67 functions, exponents chosen so
+    that one-, two- and multi-centre quartets with l_tot > 8 occur and some reach t > 20 in the reference's Fgamma).
+    Fixtures come from the unmodified reference: stored-list G matrices, shell-quartet blocks through
+    calc_two_electron_ints_rys (l_tot <= 8) / calc_two_electron_ints_md (l_tot > 8), and a full SCF run."""
+    global REFT
+    R = Reference()
+    n = "fg.h2o"
+    path = os.path.join(HERE, "inputs", "patin.dat." + n)
+    h = R.basis(path)
+    nbf = R.lib.ref_basis_norb(h); no2 = nbf * (nbf + 1) // 2
+    rng = np.random.default_rng(12345)
+    P = rng.standard_normal(no2); PB = rng.standard_normal(no2)
+    t = R.tints(h)
+    G, _ = R.form_g_rhf(t, P)
+    GA, GB, _ = R.form_g_uhf(t, P, PB)
+    S, T, H = R.one_electron(h)
+    np.savez_compressed(os.path.join(HERE, "g_fg_h2o.npz"), P=P, PB=PB, G=G, GA=GA, GB=GB, S=S, T=T, H=H)
+    R.tints_destroy(t)
+    shells = R.basis_shells(h)
+    ns = len(shells)
+    nc = lambda s: (shells[s][1] + 1) * (shells[s][1] + 2) // 2
+    quart = [(5, 4, 3, 3), (5, 4, 8, 8), (8, 8, 11, 11), (5, 5, 11, 11), (8, 5, 11, 4), (4, 8, 5, 11), (11, 5, 8, 3),
+             (5, 0, 0, 0), (4, 4, 0, 0), (5, 3, 2, 1), (8, 2, 11, 10), (5, 5, 2, 2), (4, 4, 4, 4), (3, 5, 4, 2), (5, 5, 5, 4)]
+    for q in rng.integers(0, ns, size=(400, 4)):
+        q = tuple(int(x) for x in q)
+        if max(shells[s][1] for s in q) >= 3 and nc(q[0]) * nc(q[1]) * nc(q[2]) * nc(q[3]) <= 6000 and len(quart) < 75:
+            quart.append(q)
+    blocks = [R.quartet_block(h, (nc(i), nc(j), nc(k), nc(l)), i, j, k, l).ravel() for (i, j, k, l) in quart]
+    np.savez_compressed(os.path.join(HERE, "quartets_fg_h2o.npz"), quartets=np.array(quart),
+                        offsets=np.cumsum([0] + [len(b) for b in blocks]), values=np.concatenate(blocks))
+    R.basis_close(h)
+    runs = json.load(open(os.path.join(HERE, "ref_runs.json")))
+    REFT = os.path.join(HERE, "inputs")
+    runs[n] = run_unomol(n)
+    print(n, runs[n]["e_final"], runs[n]["iterations"], flush=True)
+    json.dump(runs, open(os.path.join(HERE, "ref_runs.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
+    if "--highl-only" in sys.argv:
+        highl_input()
+        sys.exit(0)
     main()
     cation_variants()
+    highl_input()

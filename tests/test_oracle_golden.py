@@ -41,7 +41,7 @@ def test_unique_integral_list_matches_reference_cache(oracle, name):
     assert ncalc == {"3g.h2o": 406, "631.nh3": 108345, "631.co": 108345}[name]
 
 
-@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "631.co", "b.dhdz", "dh95.co2"])
+@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "631.co", "b.dhdz", "dh95.co2", "fg.h2o"])
 def test_g_matrices_match_reference(oracle, name):
     g = np.load(os.path.join(GOLDEN, "g_%s.npz" % name.replace(".", "_")))
     b = oracle.basis(golden_input(name))
@@ -54,7 +54,7 @@ def test_g_matrices_match_reference(oracle, name):
     assert np.max(np.abs(GB - g["GB"])) < 1e-12 * scale
 
 
-@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "b.dhdz", "dh95.co2", "dh95.c2h2"])
+@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "b.dhdz", "dh95.co2", "dh95.c2h2", "fg.h2o"])
 def test_quartet_blocks_match_reference(oracle, name):
     g = np.load(os.path.join(GOLDEN, "quartets_%s.npz" % name.replace(".", "_")))
     b = oracle.basis(golden_input(name))
@@ -62,6 +62,18 @@ def test_quartet_blocks_match_reference(oracle, name):
         ref = g["values"][g["offsets"][q]:g["offsets"][q + 1]]
         blk = oracle.quartet_block(b, int(i), int(j), int(k), int(l)).ravel()
         assert np.max(np.abs(blk - ref)) < 1e-13
+
+
+def test_high_l_fixture_covers_both_reference_algorithms(oracle):
+    """fg.h2o (ours; f and g shells): the fixture holds blocks of both the Rys path (l_tot <= 8) and the
+    McMurchie-Davidson path (l_tot > 8, reference TwoElectronInts.cpp:661-665), one-, two- and multi-centre."""
+    g = np.load(os.path.join(GOLDEN, "quartets_fg_h2o.npz"))
+    b = oracle.basis(golden_input("fg.h2o"))
+    assert b.maxl == 4
+    ltot = [sum(int(b.lv[s]) for s in q) for q in g["quartets"]]
+    ncen = [len({int(b.cen[s]) for s in q}) for q in g["quartets"]]
+    assert min(ltot) <= 8 < max(ltot)
+    assert {1, 2, 3} <= {n for n, lt in zip(ncen, ltot) if lt > 8}
 
 
 def test_direct_g_equals_stored_g(oracle):
