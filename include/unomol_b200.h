@@ -25,7 +25,7 @@ extern "C" {
 #define UNOMOL_OK 0
 #define UNOMOL_E_ARG (-1)      /* bad argument (null pointer, index out of range, ...) */
 #define UNOMOL_E_CUDA (-2)     /* CUDA runtime / cuSOLVER / cuBLAS failure, or no device */
-#define UNOMOL_E_UNSUPPORTED (-3) /* angular momentum outside the built kernels (l > 2 per shell) */
+#define UNOMOL_E_UNSUPPORTED (-3) /* angular momentum above g (l > 4 per shell; reference Basis.hpp:222) */
 #define UNOMOL_E_NOMEM (-4)
 #define UNOMOL_E_STATE (-5)    /* call order (e.g. fock before create) */
 #define UNOMOL_E_NCCL (-6)

@@ -25,7 +25,7 @@ def _handle(capi, name, **kw):
     return b, capi.Handle(b, **kw)
 
 
-@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "b.dhdz", "dh95.co2", "dh95.c2h2", "tz2p.sf6"])
+@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "b.dhdz", "dh95.co2", "dh95.c2h2", "tz2p.sf6", "fg.h2o"])
 def test_quartet_blocks_vs_reference_fixture(capi, name):
     path = os.path.join(GOLDEN, "quartets_%s.npz" % name.replace(".", "_"))
     g = np.load(path)
@@ -90,7 +90,7 @@ def test_unique_integral_list_vs_reference_cache(capi, name):
     assert not extra or max(extra) < 1e-14 + ERI_TOL
 
 
-@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "631.co", "b.dhdz", "dh95.co2", "dh95.c2h2", "tz2p.sf6"])
+@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "631.co", "b.dhdz", "dh95.co2", "dh95.c2h2", "tz2p.sf6", "fg.h2o"])
 def test_g_matrices_vs_reference_fixture(capi, name):
     g = np.load(os.path.join(GOLDEN, "g_%s.npz" % name.replace(".", "_")))
     b, h = _handle(capi, name)
@@ -268,13 +268,70 @@ def test_bad_arguments_fail_loudly(capi):
     assert capi.lib.unomol_b200_eri_quartet(h.h, 0, 0, 0, 99, None) != 0
 
 
-def test_f_shells_are_rejected_not_silently_wrong(capi):
-    """l > 2 is outside the built kernels: create must fail with UNOMOL_E_UNSUPPORTED (-3), never fall back"""
+def test_h_shells_are_rejected_not_silently_wrong(capi):
+    """l > 4 is outside the reference's own range (Basis.hpp:222): create must fail with UNOMOL_E_UNSUPPORTED (-3)"""
     from unomol_b200.basis import Basis
     b = Basis.from_patin(golden_input("3g.h2o"))
-    b.lv = b.lv.copy(); b.lv[0] = 3
+    b.lv = b.lv.copy(); b.lv[0] = 5
     with pytest.raises(capi.UnomolError, match="-3"):
         capi.Handle(b)
+
+
+# ---------------------------------------------------------------- f / g shells (SURVEY 8 row a9)
+def test_high_l_quartets_vs_oracle_both_algorithms(capi, oracle):
+    """fg.h2o: shells up to g.  Quartets with l_tot <= 8 follow the reference's Rys routine, l_tot > 8 its
+    McMurchie-Davidson routine incl. the Fgamma t > 20 asymptotic branch (TwoElectronInts.cpp:661-665); one-, two- and
+    multi-centre cases, every ordering of the four shells, plus the largest block (gg|gg) = 50 625 integrals."""
+    b, h = _handle(capi, "fg.h2o")
+    ob = oracle.basis(golden_input("fg.h2o"))
+    rng = np.random.default_rng(17)
+    cases = [(5, 5, 5, 5), (5, 4, 8, 8), (8, 8, 11, 11), (11, 11, 8, 8), (4, 5, 11, 8), (0, 5, 0, 0), (2, 11, 8, 3), (3, 3, 5, 5)]
+    cases += [tuple(int(x) for x in rng.integers(0, b.nshell, 4)) for _ in range(60)]
+    worst_rys = worst_md = 0.0
+    for (i, j, k, l) in cases:
+        d = float(np.max(np.abs(h.eri_quartet(i, j, k, l) - oracle.quartet_block(ob, i, j, k, l))))
+        if b.lv[i] + b.lv[j] + b.lv[k] + b.lv[l] > 8:
+            worst_md = max(worst_md, d)
+        else:
+            worst_rys = max(worst_rys, d)
+    assert worst_rys < ERI_TOL and worst_md < ERI_TOL, (worst_rys, worst_md)
+
+
+def test_high_l_unique_integral_list_vs_oracle(capi, oracle):
+    """all 2.6 million function quartets of fg.h2o (2.3 million above the reference's 1e-14 storage threshold)"""
+    b, h = _handle(capi, "fg.h2o")
+    ob = oracle.basis(golden_input("fg.h2o"))
+    vals, ijkl, ncalc = oracle.unique_eris(ob, thresh=-1.0)      # every computed record, reference loop order
+    gv, gi = h.dump_eris(-1.0)
+    assert len(gv) == ncalc == len(vals) and np.array_equal(gi, ijkl)
+    assert np.max(np.abs(gv - vals)) < ERI_TOL
+
+
+def test_high_l_start_shell_multirank_and_schwarz(capi, oracle):
+    b, h = _handle(capi, "fg.h2o")
+    ob = oracle.basis(golden_input("fg.h2o"))
+    rng = np.random.default_rng(23)
+    P = rng.standard_normal(b.no2)
+    h.set_option("schwarz_tau", 0.0)
+    full = h.fock_rhf(P)
+    parts = []
+    for r in range(2):
+        hr = capi.Handle(b, rank=r, nranks=2)
+        hr.set_option("schwarz_tau", 0.0)
+        parts.append(hr.fock_rhf(P))
+    assert np.max(np.abs(parts[0] + parts[1] - full)) < 1e-12 * np.max(np.abs(full))
+    start = b.nshell - 2
+    hs = capi.Handle(b, start_shell=start)
+    hs.set_option("schwarz_tau", 0.0)
+    vals, ijkl, _ = oracle.unique_eris(ob, start_shell=start)
+    Gref = oracle.form_g_rhf(vals, ijkl, P)
+    assert np.max(np.abs(hs.fock_rhf(P) - Gref)) < 1e-12 * max(1.0, np.max(np.abs(Gref)))
+    Q = h.schwarz()
+    for _ in range(25):
+        i, j, k, l = (int(x) for x in rng.integers(0, b.nshell, 4))
+        blk = oracle.quartet_block(ob, i, j, k, l)
+        qa = Q[max(i, j) * (max(i, j) + 1) // 2 + min(i, j)]; qb = Q[max(k, l) * (max(k, l) + 1) // 2 + min(k, l)]
+        assert np.max(np.abs(blk)) <= qa * qb * (1 + 1e-9) + 1e-13
 
 
 def test_spatial_blocks_do_not_change_results(capi):

@@ -44,6 +44,14 @@ def test_rhf_energy_dzp_vs_fresh_reference_run(name, tmp_path):
     assert abs(e0 - RUNS[name]["e_init"]) < E_TOL
 
 
+def test_rhf_with_f_and_g_shells(tmp_path):
+    """fg.h2o (ours): s..g shells, Rys for l_tot <= 8 and McMurchie-Davidson above, as the reference dispatches"""
+    e0, e1, de, out = run_scf("fg.h2o", tmp_path)
+    assert RUNS["fg.h2o"]["converged"] and "NOT_ REACHED" not in out
+    assert abs(e1 - RUNS["fg.h2o"]["e_final"]) < E_TOL, (e1, RUNS["fg.h2o"]["e_final"])
+    assert abs(e0 - RUNS["fg.h2o"]["e_init"]) < E_TOL
+
+
 def test_rhf_sf6_tz2p(tmp_path):
     """BASELINE config 4: 190 basis functions, d shells, 4-5 Rys roots"""
     e0, e1, de, out = run_scf("tz2p.sf6", tmp_path)

@@ -1,0 +1,74 @@
+"""CPU: the runtime-L kernel body for f/g shells (unomol_b200/csrc/eri_highl.cuh) compiled as plain single-threaded
+C++ by tests/host_emul/highl_emul.cpp (HL_NT = 1) and checked against the reference fixtures and the oracle.  This
+checks the ARITHMETIC of the device code on machines without a GPU (both the Rys branch, l_tot <= 8, and the
+McMurchie-Davidson branch, l_tot > 8, plus the J/K digestion); the CUDA build of the same header is what
+tests/test_gpu_parity.py runs through the C ABI.  Test infrastructure only -- nothing here is a product path."""
+import ctypes
+import os
+import subprocess
+import numpy as np
+import pytest
+from conftest import GOLDEN, ROOT, golden_input
+
+_I = ctypes.c_int
+_D = ctypes.c_double
+_ip = lambda a: a.ctypes.data_as(ctypes.POINTER(_I))
+_dp = lambda a: a.ctypes.data_as(ctypes.POINTER(_D))
+
+
+@pytest.fixture(scope="module")
+def emul():
+    d = os.path.join(ROOT, "tests", "host_emul")
+    so = os.path.join(d, "libhighl_emul.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, os.path.join(d, "highl_emul.cpp")])
+    L = ctypes.CDLL(so)
+    L.hl_emul_quartet.argtypes = [_I, _I] + [ctypes.POINTER(_I)] * 5 + [ctypes.POINTER(_D)] * 3 + [_D, _I, _I, _I, _I, ctypes.POINTER(_D)]
+    L.hl_emul_fock.argtypes = [_I, _I] + [ctypes.POINTER(_I)] * 5 + [ctypes.POINTER(_D)] * 3 + [_D, _D, _I] + [ctypes.POINTER(_D)] * 4 + [_I]
+    return L
+
+
+def _basis_args(b):
+    return (b.nshell, b.nbf, _ip(b.npr), _ip(b.lv), _ip(b.cen), _ip(b.off), _ip(b.poff), _dp(b.alpha), _dp(b.coef),
+            _dp(np.ascontiguousarray(b.xyz)))
+
+
+def _block(emul, b, i, j, k, l):
+    nc = lambda s: (b.lv[s] + 1) * (b.lv[s] + 2) // 2
+    out = np.zeros((nc(i), nc(j), nc(k), nc(l)))
+    emul.hl_emul_quartet(*_basis_args(b), 1e-12, i, j, k, l, _dp(out))
+    return out
+
+
+def test_kernel_body_blocks_vs_reference_fixture(emul, oracle):
+    g = np.load(os.path.join(GOLDEN, "quartets_fg_h2o.npz"))
+    b = oracle.basis(golden_input("fg.h2o"))
+    worst = 0.0
+    for q, (i, j, k, l) in enumerate(g["quartets"]):
+        ref = g["values"][g["offsets"][q]:g["offsets"][q + 1]]
+        worst = max(worst, float(np.max(np.abs(_block(emul, b, int(i), int(j), int(k), int(l)).ravel() - ref))))
+    assert worst < 1e-12, worst
+
+
+@pytest.mark.parametrize("name", ["dh95.co2", "631.nh3"])
+def test_kernel_body_also_reproduces_spd_classes(emul, oracle, name):
+    """the runtime-L body is general in l: s/p/d quartets (which the product gives to the class kernels) agree too,
+    including the primitive cut sr < 1e-12 on contracted shells"""
+    b = oracle.basis(golden_input(name))
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for _ in range(80):
+        q = [int(x) for x in rng.integers(0, b.nshell, 4)]
+        worst = max(worst, float(np.max(np.abs(_block(emul, b, *q) - oracle.quartet_block(b, *q)))))
+    assert worst < 1e-12, worst
+
+
+def test_kernel_body_fock_build_vs_reference_fixture(emul, oracle):
+    g = np.load(os.path.join(GOLDEN, "g_fg_h2o.npz"))
+    b = oracle.basis(golden_input("fg.h2o"))
+    P, PB = np.ascontiguousarray(g["P"]), np.ascontiguousarray(g["PB"])
+    G = np.zeros_like(P); GA = np.zeros_like(P); GB = np.zeros_like(P)
+    emul.hl_emul_fock(*_basis_args(b), 1e-12, 1e-14, 1, _dp(P), _dp(PB), _dp(G), _dp(GB), 0)
+    emul.hl_emul_fock(*_basis_args(b), 1e-12, 1e-14, 2, _dp(P), _dp(PB), _dp(GA), _dp(GB), 0)
+    scale = np.max(np.abs(g["G"]))
+    assert np.max(np.abs(G - g["G"])) < 1e-12 * scale
+    assert np.max(np.abs(GA - g["GA"])) < 1e-12 * scale and np.max(np.abs(GB - g["GB"])) < 1e-12 * scale

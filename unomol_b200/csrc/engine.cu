@@ -19,6 +19,7 @@
 #include <dlfcn.h>
 #include <numeric>
 #include "engine.h"
+#include "eri_highl.cuh"
 
 using namespace ub200;
 
@@ -63,6 +64,27 @@ int class_groups_per_cta(int cb, int ck) {
     }
     return 1;
 }
+
+// Any (bra pair class, ket pair class): class-templated kernels for s/p/d, the runtime-L kernel as soon as one shell is f or g.
+static cudaError_t ensure_hl_scratch(unomol_b200 *h) {
+    if (h->d_hl_scratch) return cudaSuccess;
+    const long long nc = (h->basis.maxl + 1) * (h->basis.maxl + 2) / 2;
+    h->hl_slab = nc * nc * nc * nc;
+    return cudaMalloc(&h->d_hl_scratch, sizeof(double) * (size_t)h->hl_slab * unomol_b200::HL_GRID);
+}
+static inline bool is_highl(int cb, int ck) { return cb >= NSPDCLASS || ck >= NSPDCLASS; }
+cudaError_t launch_any_class(unomol_b200 *h, int cb, int ck, const ClassTask &task, int mode, int grid, cudaStream_t s) {
+    if (!is_highl(cb, ck)) return launch_quartet_class(cb, ck, task, mode, grid, s);
+    cudaError_t e = ensure_hl_scratch(h);
+    if (e != cudaSuccess) return e;
+    HighLArgs hl;
+    pair_class_l(cb, hl.la, hl.lb);
+    pair_class_l(ck, hl.lc, hl.ld);
+    hl.scratch = h->d_hl_scratch;
+    hl.slab = h->hl_slab;
+    return launch_highl(task, hl, mode, std::min(grid, unomol_b200::HL_GRID), s);
+}
+static int any_groups_per_cta(int cb, int ck) { return is_highl(cb, ck) ? 1 : class_groups_per_cta(cb, ck); }
 
 // algorithmic FLOPs of the reference's Rys algorithm per PRIMITIVE quartet.
 double model_flops_per_primitive_quartet(int la, int lb, int lc, int ld) {
@@ -165,6 +187,11 @@ static int build_pairs(unomol_b200 *h) {
     // Rows of the (i >= j) pair triangle are processed by a few host threads; the result is concatenated in (i, j)
     // order so the tables do not depend on the thread count.
     long long nprim = 0, nkept = 0;
+    // The McMurchie-Davidson path (l_tot > 8) has NO primitive cut in the reference (TwoElectronInts.cpp:269-418), so
+    // with f/g shells in the basis nothing may be pruned up front; the Rys classes apply the cut per primitive quartet.
+    h->has_highl = false;
+    for (int s = 0; s < ns; ++s) h->has_highl |= (B.lv[s] > 2);
+    const double prune_cut = h->has_highl ? 0.0 : h->prim_cut;
     const bool bucketed = (long long)ns * (ns + 1) / 2 >= h->bucket_min_pairs;
     // column/row blocking: keep (rows of a bra block) x (columns of a ket block) x 8 B x ~2.5 matrices within ~48 MB of L2
     int nblock = h->col_blocks;
@@ -186,7 +213,7 @@ static int build_pairs(unomol_b200 *h) {
         // primitive-pair generation, exact prune and per-pair sort on the GPU (pair_device.cu); the host only groups
         std::vector<ShellPair> kept;
         std::vector<int> kcls;
-        int rc = build_pair_tables_device(h, kept, kcls, &h->d_prims, &nprim);
+        int rc = build_pair_tables_device(h, prune_cut, kept, kcls, &h->d_prims, &nprim);
         if (rc) return rc;
         nkept = (long long)kept.size();
         for (size_t i = 0; i < kept.size(); ++i) h->cls[group_of(kept[i], kcls[i])].pairs.push_back(kept[i]);
@@ -201,7 +228,7 @@ static int build_pairs(unomol_b200 *h) {
     struct OutPair { ShellPair sp; int cls; int first, count; };
     struct RowOut { std::vector<OutPair> pairs; std::vector<PrimPair> prims; };
     std::vector<RowOut> rows(ns);
-    const double prim_cut = h->prim_cut;
+    const double prim_cut = prune_cut;
     auto do_row = [&](int i) {
         RowOut &R = rows[i];
         std::vector<PrimPair> keep;
@@ -312,9 +339,9 @@ static int build_pairs(unomol_b200 *h) {
         // reference's sr<1e-12 test passes although it would fail on the weak pair's own diagonal
         task.prim_cut = 0.0;
         task.task_list = d_tl; task.ntask = L.n; task.out = d_q;
-        const int groups = class_groups_per_cta(c / NSUB, c / NSUB);
+        const int groups = any_groups_per_cta(c / NSUB, c / NSUB);
         const int grid = std::min((L.n + groups - 1) / groups, 148 * 16);
-        CUDA_TRY(h, launch_quartet_class(c / NSUB, c / NSUB, task, MODE_SCHWARZ, grid, h->stream));
+        CUDA_TRY(h, launch_any_class(h, c / NSUB, c / NSUB, task, MODE_SCHWARZ, grid, h->stream));
         std::vector<double> q(L.n);
         CUDA_TRY(h, cudaMemcpyAsync(q.data(), d_q, sizeof(double) * L.n, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -390,7 +417,8 @@ static int build_plans(unomol_b200 *h) {
             }
             int maxbp = 0;
             for (int i = 0; i < plan.nbra_eff; ++i) maxbp = std::max(maxbp, Lb.pairs[i].nprim);
-            plan.use_reg = h->use_reg_kernels && reg_class_available(cb / NSUB, ck / NSUB) && maxbp <= reg_max_bra_prims();
+            plan.highl = is_highl(cb / NSUB, ck / NSUB);
+            plan.use_reg = !plan.highl && h->use_reg_kernels && reg_class_available(cb / NSUB, ck / NSUB) && maxbp <= reg_max_bra_prims();
             if (cudaMalloc(&plan.d_ket_count, sizeof(int) * Lb.n) != cudaSuccess) return UNOMOL_E_NOMEM;
             cudaMemcpyAsync(plan.d_ket_count, kc.data(), sizeof(int) * Lb.n, cudaMemcpyHostToDevice, h->stream);
             cudaStreamSynchronize(h->stream);
@@ -472,8 +500,9 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
     std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return h->plans[x].cost > h->plans[y].cost; });
     for (size_t io = 0; io < order.size(); ++io) {
         const size_t ip = order[io];
-        cudaStream_t st = h->aux[io % unomol_b200::NAUX];
         const ComboPlan &pl = h->plans[ip];
+        // the runtime-L launches share one scratch area: keep them on one stream
+        cudaStream_t st = pl.highl ? h->aux[0] : h->aux[io % unomol_b200::NAUX];
         ClassTask task{};
         task.bra = h->cls[pl.cb].d_pairs; task.ket = h->cls[pl.ck].d_pairs; task.prims = h->d_prims;
         task.ket_hot = h->cls[pl.ck].d_hot;
@@ -494,7 +523,9 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         task.cand_counter = h->d_counters + 2 * h->plans.size();
         const int nmine = work ? pl.nbra_eff : (pl.nbra_eff + h->nranks - 1) / h->nranks;
         task.chunk = std::max(1, std::min(8, pl.nbra_eff / (148 * 16 * 8 * h->nranks)));
-        if (pl.use_reg) {
+        if (pl.highl) {
+            CUDA_TRY(h, launch_any_class(h, pl.cb / NSUB, pl.ck / NSUB, task, MODE_DIGEST, nmine, st));
+        } else if (pl.use_reg) {
             CUDA_TRY(h, launch_reg_class(pl.cb / NSUB, pl.ck / NSUB, task, std::min(nmine, 148 * 16), st, h->stage_rows != 0));
         } else {
             CUDA_TRY(h, launch_quartet_class(pl.cb / NSUB, pl.ck / NSUB, task, MODE_DIGEST, std::min(nmine, 148 * 32), st));
@@ -558,7 +589,7 @@ const char *unomol_b200_strerror(int code) {
         case UNOMOL_OK: return "ok";
         case UNOMOL_E_ARG: return "bad argument";
         case UNOMOL_E_CUDA: return "CUDA failure or no CUDA device (there is no CPU fallback)";
-        case UNOMOL_E_UNSUPPORTED: return "angular momentum above d is not built into this library";
+        case UNOMOL_E_UNSUPPORTED: return "angular momentum above g (l > 4) is not supported (as in the reference, Basis.hpp:222)";
         case UNOMOL_E_NOMEM: return "out of memory";
         case UNOMOL_E_STATE: return "call order";
         case UNOMOL_E_NCCL: return "NCCL failure";
@@ -604,7 +635,7 @@ void unomol_b200_destroy(unomol_b200_t *h) {
     for (int s = 0; s < 2; ++s) {
         cudaFree(h->d_Ppacked[s]); cudaFree(h->d_Gpacked[s]); cudaFree(h->d_PK[s]); cudaFree(h->d_K[s]);
     }
-    cudaFree(h->d_PJ); cudaFree(h->d_J); cudaFree(h->d_counters);
+    cudaFree(h->d_PJ); cudaFree(h->d_J); cudaFree(h->d_counters); cudaFree(h->d_hl_scratch);
     cudaFree(h->d_work_local);
     if (h->d_work_shared) { if (h->work_owner) cudaFree(h->d_work_shared); else cudaIpcCloseMemHandle(h->d_work_shared); }
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -812,7 +843,7 @@ int unomol_b200_eri_quartet(unomol_b200_t *h, int ish, int jsh, int ksh, int lsh
     task.nbra = h->cls[cb].n; task.nket = h->cls[ck].n;
     task.prim_cut = h->prim_cut;
     task.task_list = d_tl; task.task_out = d_off; task.ntask = 1; task.out = d_out;
-    CUDA_TRY(h, launch_quartet_class(cb / NSUB, ck / NSUB, task, MODE_DUMP, 1, h->stream));
+    CUDA_TRY(h, launch_any_class(h, cb / NSUB, ck / NSUB, task, MODE_DUMP, 1, h->stream));
     std::vector<double> blk(ntot);
     CUDA_TRY(h, cudaMemcpyAsync(blk.data(), d_out, sizeof(double) * ntot, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -882,9 +913,9 @@ int unomol_b200_dump_eris(unomol_b200_t *h, double thresh, unomol_twoint *buf, s
         task.bra = h->cls[cmb.cb].d_pairs; task.ket = h->cls[cmb.ck].d_pairs; task.prims = h->d_prims;
         task.nbra = nb; task.nket = nk; task.prim_cut = h->prim_cut;
         task.task_list = d_tl; task.task_out = d_off; task.ntask = (int)tl.size(); task.out = d_out;
-        const int groups = class_groups_per_cta(cmb.cb / NSUB, cmb.ck / NSUB);
+        const int groups = any_groups_per_cta(cmb.cb / NSUB, cmb.ck / NSUB);
         const int grid = std::min(((int)tl.size() + groups - 1) / groups, 148 * 16);
-        CUDA_TRY(h, launch_quartet_class(cmb.cb / NSUB, cmb.ck / NSUB, task, MODE_DUMP, grid, h->stream));
+        CUDA_TRY(h, launch_any_class(h, cmb.cb / NSUB, cmb.ck / NSUB, task, MODE_DUMP, grid, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         cudaFree(d_tl); cudaFree(d_off);
     }

@@ -18,7 +18,7 @@ int class_groups_per_cta(int bra_class, int ket_class);
 bool reg_class_available(int bra_class, int ket_class);
 int reg_max_bra_prims();
 // device-side shell-pair / primitive-pair tables (pair_device.cu)
-int build_pair_tables_device(unomol_b200 *h, std::vector<ShellPair> &kept, std::vector<int> &cls, PrimPair **d_prims_out,
+int build_pair_tables_device(unomol_b200 *h, double prune_cut, std::vector<ShellPair> &kept, std::vector<int> &cls, PrimPair **d_prims_out,
                              long long *nprim_out);
 cudaError_t launch_reg_class(int bra_class, int ket_class, const ClassTask &task, int grid, cudaStream_t stream, bool allow_rows);
 // SURVEY.md 8(d) flop model per primitive quartet of class (la lb | lc ld)
@@ -26,10 +26,13 @@ double model_flops_per_primitive_quartet(int la, int lb, int lc, int ld);
 
 inline int pair_class_id(int la, int lb) { return la * (la + 1) / 2 + lb; }
 inline void pair_class_l(int cls, int &la, int &lb) {
-    static const int LA[NPAIRCLASS] = {0, 1, 1, 2, 2, 2}, LB[NPAIRCLASS] = {0, 0, 1, 0, 1, 2};
-    la = LA[cls];
-    lb = LB[cls];
+    la = 0;
+    while ((la + 1) * (la + 2) / 2 <= cls) ++la;
+    lb = cls - la * (la + 1) / 2;
 }
+// runtime-L kernel for quartets with f/g shells (eri_highl.cu)
+struct HighLArgs;
+cudaError_t launch_highl(const ClassTask &task, const HighLArgs &hl, int mode, int grid, cudaStream_t stream);
 
 struct HostBasis {
     int nshell = 0, nbf = 0, ncen = 0, maxl = 0;
@@ -51,6 +54,7 @@ struct ComboPlan {                  // one (bra class, ket class) launch
     int *d_ket_count = nullptr;
     double cost = 0.0;              // quartets x model flops: launch order (largest first)
     bool use_reg = false;           // register-resident kernel (small class, bra contraction fits the stage)
+    bool highl = false;             // contains an f or g shell: runtime-L kernel
 };
 
 }  // namespace ub200
@@ -83,6 +87,11 @@ struct unomol_b200 {
     double *d_PJ = nullptr, *d_PK[2] = {nullptr, nullptr}, *d_J = nullptr, *d_K[2] = {nullptr, nullptr};
     double *h_pinned = nullptr;               // staging for host<->device copies (4 * no2 doubles)
     unsigned long long *d_counters = nullptr; // 2 per combo
+    // runtime-L kernel (f/g shells): per-CTA slabs for the Cartesian block of a quartet; its launches share one stream
+    double *d_hl_scratch = nullptr;
+    long long hl_slab = 0;
+    static constexpr int HL_GRID = 148 * 2;
+    bool has_highl = false;
     // dynamic bra scheduling: one work counter per launch.  Local (single rank) or shared: allocated on rank 0's GPU,
     // exported as a CUDA IPC handle and mapped by every other rank (system-scope atomics over NVLink); two sets,
     // alternating per build, so that the owner can reset one while the other is in use.

@@ -106,7 +106,7 @@ __global__ void flag_kernel(const int *__restrict__ count, int *__restrict__ fla
 
 // Builds the tables on h->stream.  kept / cls: the kept shell pairs in canonical (i,j) order with prim_off, nprim,
 // pmin, umax filled; *d_prims_out: device array of all primitive pairs (ownership passes to the caller).
-int build_pair_tables_device(unomol_b200 *h, std::vector<ShellPair> &kept, std::vector<int> &cls, PrimPair **d_prims_out,
+int build_pair_tables_device(unomol_b200 *h, double prune_cut, std::vector<ShellPair> &kept, std::vector<int> &cls, PrimPair **d_prims_out,
                              long long *nprim_out) {
     const HostBasis &HB = h->basis;
     const int ns = HB.nshell;
@@ -145,7 +145,7 @@ int build_pair_tables_device(unomol_b200 *h, std::vector<ShellPair> &kept, std::
     PD_TRY(cudaMemcpyAsync(d_d + 2 * nprim_basis + 3 * HB.ncen, amin.data(), sizeof(double) * ns, cudaMemcpyHostToDevice, st));
     B.npr = d_i; B.lv = d_i + ns; B.cen = d_i + 2 * ns; B.off = d_i + 3 * ns; B.poff = d_i + 4 * ns;
     B.alpha = d_d; B.coef = d_d + nprim_basis; B.xyz = d_d + 2 * nprim_basis; B.amin = d_d + 2 * nprim_basis + 3 * HB.ncen;
-    B.ns = ns; B.umax = umax; B.prim_cut = h->prim_cut;
+    B.ns = ns; B.umax = umax; B.prim_cut = prune_cut;   // 0 with f/g shells: the reference's MD path has no primitive cut
     PD_TRY(cudaMalloc(&d_count, sizeof(int) * np));
     PD_TRY(cudaMalloc(&d_off, sizeof(int) * np));
     PD_TRY(cudaMalloc(&d_flag, sizeof(int) * np));

@@ -4,8 +4,10 @@
 
 namespace ub200 {
 
-constexpr int MAXL = 2;            // per-shell angular momentum handled by the built kernels (s, p, d)
-constexpr int NPAIRCLASS = 6;      // ss ps pp ds dp dd  (la >= lb; id = la*(la+1)/2 + lb)
+constexpr int MAXL = 4;            // per-shell angular momentum handled (s..g; reference Basis.hpp:222)
+constexpr int NPAIRCLASS = 15;     // ss ps pp ds dp dd fs fp fd ff gs gp gd gf gg  (la >= lb; id = la*(la+1)/2 + lb)
+constexpr int NSPDCLASS = 6;       // pair classes below this id (l <= 2) have class-templated kernels; a quartet with an f or g
+                                   // shell goes to the runtime-L kernel (eri_highl.cuh)
 constexpr int NBUCKET = 6;         // pair lists are further split by primitive-pair count (1, 2-3, 4-6, 7-12, 13-24, 25+)
 constexpr int NBLOCK = 4;          // ... and by spatial block (slab of shell indices) so that for large N a launch's rows x columns
                                    // footprint in the square P/J/K matrices stays L2-resident
