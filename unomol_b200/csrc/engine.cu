@@ -162,8 +162,10 @@ static void free_pairs(unomol_b200 *h) {
     }
     if (h->d_prims) cudaFree(h->d_prims);
     h->d_prims = nullptr;
-    for (auto &p : h->plans)
+    for (auto &p : h->plans) {
         if (p.d_ket_count) cudaFree(p.d_ket_count);
+        if (p.d_ket_prefix) cudaFree(p.d_ket_prefix);
+    }
     h->plans.clear();
     h->pairs_ready = false;
 }
@@ -378,8 +380,10 @@ static int build_pairs(unomol_b200 *h) {
 
 // per (bra class >= ket class): prefix counts of kets passing Q_bra*Q_ket >= tau (kets sorted descending)
 static int build_plans(unomol_b200 *h) {
-    for (auto &p : h->plans)
+    for (auto &p : h->plans) {
         if (p.d_ket_count) cudaFree(p.d_ket_count);
+        if (p.d_ket_prefix) cudaFree(p.d_ket_prefix);
+    }
     h->plans.clear();
     long long total = 0;
     for (int cb = 0; cb < NGROUP; ++cb)
@@ -407,6 +411,7 @@ static int build_plans(unomol_b200 *h) {
                 plan.nquartets += cnt;
                 if (cnt > 0) plan.nbra_eff = i + 1;
             }
+            plan.nquartets_eff = plan.nquartets;
             total += plan.nquartets;
             if (plan.nbra_eff == 0) continue;
             {
@@ -421,6 +426,13 @@ static int build_plans(unomol_b200 *h) {
             plan.use_reg = !plan.highl && h->use_reg_kernels && reg_class_available(cb / NSUB, ck / NSUB) && maxbp <= reg_max_bra_prims();
             if (cudaMalloc(&plan.d_ket_count, sizeof(int) * Lb.n) != cudaSuccess) return UNOMOL_E_NOMEM;
             cudaMemcpyAsync(plan.d_ket_count, kc.data(), sizeof(int) * Lb.n, cudaMemcpyHostToDevice, h->stream);
+            std::vector<long long> pre;
+            if (plan.highl) {
+                pre.assign(plan.nbra_eff + 1, 0);
+                for (int i = 0; i < plan.nbra_eff; ++i) pre[i + 1] = pre[i] + kc[i];
+                if (cudaMalloc(&plan.d_ket_prefix, sizeof(long long) * pre.size()) != cudaSuccess) return UNOMOL_E_NOMEM;
+                cudaMemcpyAsync(plan.d_ket_prefix, pre.data(), sizeof(long long) * pre.size(), cudaMemcpyHostToDevice, h->stream);
+            }
             cudaStreamSynchronize(h->stream);
             h->plans.push_back(plan);
         }
@@ -507,6 +519,7 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         task.bra = h->cls[pl.cb].d_pairs; task.ket = h->cls[pl.ck].d_pairs; task.prims = h->d_prims;
         task.ket_hot = h->cls[pl.ck].d_hot;
         task.ket_count = pl.d_ket_count;
+        task.ket_prefix = pl.d_ket_prefix;
         task.nbra = pl.nbra_eff; task.nket = h->cls[pl.ck].n;
         task.same_class = (pl.cb == pl.ck);
         task.start_shell = h->start_shell;
@@ -524,7 +537,9 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         const int nmine = work ? pl.nbra_eff : (pl.nbra_eff + h->nranks - 1) / h->nranks;
         task.chunk = std::max(1, std::min(8, pl.nbra_eff / (148 * 16 * 8 * h->nranks)));
         if (pl.highl) {
-            CUDA_TRY(h, launch_any_class(h, pl.cb / NSUB, pl.ck / NSUB, task, MODE_DIGEST, nmine, st));
+            // work items of the runtime-L kernel are single quartets
+            const long long nq = work ? pl.nquartets_eff : (pl.nquartets_eff + h->nranks - 1) / h->nranks;
+            CUDA_TRY(h, launch_any_class(h, pl.cb / NSUB, pl.ck / NSUB, task, MODE_DIGEST, (int)std::min<long long>(nq, 1 << 20), st));
         } else if (pl.use_reg) {
             CUDA_TRY(h, launch_reg_class(pl.cb / NSUB, pl.ck / NSUB, task, std::min(nmine, 148 * 16), st, h->stage_rows != 0));
         } else {

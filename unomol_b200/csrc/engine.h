@@ -51,7 +51,9 @@ struct ComboPlan {                  // one (bra class, ket class) launch
     int cb = 0, ck = 0;
     int nbra_eff = 0;               // leading bras that have at least one ket
     long long nquartets = 0;        // sum of ket_count (all ranks, before start_shell filter)
+    long long nquartets_eff = 0;
     int *d_ket_count = nullptr;
+    long long *d_ket_prefix = nullptr;   // runtime-L plans: exclusive prefix sum of the ket counts [nbra_eff + 1]
     double cost = 0.0;              // quartets x model flops: launch order (largest first)
     bool use_reg = false;           // register-resident kernel (small class, bra contraction fits the stage)
     bool highl = false;             // contains an f or g shell: runtime-L kernel

@@ -9,29 +9,39 @@ template <int MODE>
 __global__ void __launch_bounds__(HL_THREADS) eri_highl_kernel(const ClassTask task, const HighLArgs hl) {
     extern __shared__ __align__(16) unsigned char hl_smem_raw[];
     double *sm = reinterpret_cast<double *>(hl_smem_raw);
-    __shared__ int s_bi;
+    __shared__ long long s_q;
     hl_init_tables(hl, sm);
     double *V = hl.scratch + (size_t)blockIdx.x * hl.slab;
     const int NAB = hl_ncart(hl.la) * hl_ncart(hl.lb), NCD = hl_ncart(hl.lc) * hl_ncart(hl.ld), NINT = NAB * NCD;
     double *red = sm + HL_OFF_RED;
     unsigned long long n_quart = 0, n_primq = 0;
-    int seq = blockIdx.x;
+    long long seq = blockIdx.x;
     for (int outer = blockIdx.x;; outer += gridDim.x) {
         int bi = 0, kfirst = 0, kcount = 0;
         if (MODE == MODE_DIGEST) {
-            // bras one at a time: from the launch's work counter (dynamic, heaviest first; shared across ranks when
-            // the counter is IPC-mapped peer memory), else static snake order over ranks -- as eri_generic.cuh
+            // quartets one at a time: from the launch's work counter (dynamic, heaviest bras first; shared across ranks
+            // when the counter is IPC-mapped peer memory), else static snake order over ranks -- as eri_generic.cuh,
+            // but per quartet: a block can be 50 625 integrals and a launch may have fewer bras than the GPU has SMs
+            const long long total = task.ket_prefix[task.nbra];
+            long long q;
             if (task.work_counter) {
                 __syncthreads();
-                if (threadIdx.x == 0) s_bi = (int)atomicAdd_system(task.work_counter, 1ULL);
+                if (threadIdx.x == 0) s_q = (long long)atomicAdd_system(task.work_counter, 1ULL);
                 __syncthreads();
-                bi = s_bi;
+                q = s_q;
             } else {
-                bi = task.nranks * seq + ((seq & 1) ? task.nranks - 1 - task.rank : task.rank);
+                q = (long long)task.nranks * seq + ((seq & 1) ? task.nranks - 1 - task.rank : task.rank);
                 seq += gridDim.x;
             }
-            if (bi >= task.nbra) break;
-            kcount = task.ket_count[bi];
+            if (q >= total) break;
+            int lo = 0, hi = task.nbra;      // largest bi with ket_prefix[bi] <= q
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (task.ket_prefix[mid] <= q) lo = mid; else hi = mid;
+            }
+            bi = lo;
+            kfirst = (int)(q - task.ket_prefix[bi]);
+            kcount = kfirst + 1;
         } else {
             if (outer >= task.ntask) break;
             bi = task.task_list[outer].x;

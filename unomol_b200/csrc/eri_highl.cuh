@@ -11,8 +11,8 @@
 //                with the reference to 1e-12 per integral is the contract, and an exact Boys function would miss it.
 // Both branches live in one kernel so that a launch is defined by its (bra list, ket list) like every other launch.
 //
-// Work decomposition: one CTA per contracted shell quartet at a time (a CTA claims a bra pair from the launch's work
-// counter and walks that bra's Schwarz-surviving kets).  All per-primitive tables (2-D Rys tables and their shifted
+// Work decomposition: one CTA per contracted shell quartet at a time (a CTA claims single quartets of the launch's
+// Schwarz-screened (bra, ket) list from the launch's work counter).  All per-primitive tables (2-D Rys tables and their shifted
 // per-axis integrals; Hermite E coefficients and the R_tuv tensor) live in shared memory; the Cartesian block
 // V[a][b][c][d] (up to 15^4 = 50 625 doubles for (gg|gg)) lives in a per-CTA global scratch slab, each thread
 // owning a fixed strided subset so that no atomics are needed.  f/g shells are rare and almost always uncontracted;
@@ -328,40 +328,63 @@ HL_FN unsigned long long hl_quartet_block(const HighLArgs &hl, const ShellPair &
                     }
                 }
                 HL_SYNC();
-                // six-index contraction per function quartet (:388-411)
-                for (int o = tid; o < NINT; o += nt) {
-                    int r = o;
-                    const int d = r % ND; r /= ND;
-                    const int c = r % NC; r /= NC;
-                    const int bb = r % NB;
-                    const int a = r / NB;
-                    const int pa = cexp[a], pb = cexp[HL_NC + bb], pc = cexp[2 * HL_NC + c], pd = cexp[3 * HL_NC + d];
-                    const int l1 = pa & 15, m1 = (pa >> 4) & 15, n1 = (pa >> 8) & 15;
-                    const int l2 = pb & 15, m2 = (pb >> 4) & 15, n2 = (pb >> 8) & 15;
-                    const int l3 = pc & 15, m3 = (pc >> 4) & 15, n3 = (pc >> 8) & 15;
-                    const int l4 = pd & 15, m4 = (pd >> 4) & 15, n4 = (pd >> 8) & 15;
-                    const double *ex12 = E12 + (l1 * HL_LD + l2) * HL_TD, *ey12 = E12 + ESZ + (m1 * HL_LD + m2) * HL_TD,
-                                 *ez12 = E12 + 2 * ESZ + (n1 * HL_LD + n2) * HL_TD;
-                    const double *ex34 = E34 + (l3 * HL_LD + l4) * HL_TD, *ey34 = E34 + ESZ + (m3 * HL_LD + m4) * HL_TD,
-                                 *ez34 = E34 + 2 * ESZ + (n3 * HL_LD + n4) * HL_TD;
-                    const int l12 = l1 + l2, m12 = m1 + m2, n12 = n1 + n2, l34 = l3 + l4, m34 = m3 + m4, n34 = n3 + n4;
-                    double sum = 0.0;
-                    for (int ix12 = 0; ix12 <= l12; ++ix12)
-                        for (int iy12 = 0; iy12 <= m12; ++iy12)
-                            for (int iz12 = 0; iz12 <= n12; ++iz12) {
-                                const double v12 = ex12[ix12] * ey12[iy12] * ez12[iz12];
-                                for (int ix34 = 0; ix34 <= l34; ++ix34)
-                                    for (int iy34 = 0; iy34 <= m34; ++iy34) {
-                                        const double v34 = v12 * ex34[ix34] * ey34[iy34];
-                                        const double *rzp = &RR(ix12 + ix34, iy12 + iy34, iz12);
-                                        double sx = ((ix34 + iy34) & 1) ? -1.0 : 1.0;
-                                        for (int iz34 = 0; iz34 <= n34; ++iz34) {
-                                            sum += sx * v34 * ez34[iz34] * rzp[iz34];
-                                            sx = -sx;
-                                        }
+                // Six-index contraction (:388-411), factorised: the ket pair's Hermite expansion is folded into R first,
+                //   W[cd][tuv] = sum_{t'u'v'} (-1)^{t'+u'+v'} E34x[t'] E34y[u'] E34z[v'] R[t+t'][u+u'][v+v'],
+                // then the bra pair's: V[ab][cd] += sum_{tuv} E12x[t] E12y[u] E12z[v] W[cd][tuv].  Same terms as the
+                // reference's nested loops, summed in a different order (~50x fewer operations for (gg|gg)).  W is built
+                // for a chunk of ket function pairs at a time in the shared memory that held the y-stage table.
+                {
+                    const int D = La + 1, NHd = D * D * D, NAB = NA * NB, NCD = NC * ND;
+                    const int CH = (HL_RD * HL_RD * (HL_RD + 1)) / NHd;   // >= 7
+                    double *W = Ay;
+                    for (int cd0 = 0; cd0 < NCD; cd0 += CH) {
+                        const int cha = (NCD - cd0 < CH) ? NCD - cd0 : CH;
+                        for (int o = tid; o < cha * NHd; o += nt) {
+                            const int cdl = o / NHd, h = o - cdl * NHd;
+                            const int t = h / (D * D), u = (h / D) % D, v = h % D;
+                            if (t + u + v > La) continue;
+                            const int cd = cd0 + cdl, c = cd / ND, d = cd - c * ND;
+                            const int pc = cexp[2 * HL_NC + c], pd = cexp[3 * HL_NC + d];
+                            const int l3 = pc & 15, m3 = (pc >> 4) & 15, n3 = (pc >> 8) & 15;
+                            const int l4 = pd & 15, m4 = (pd >> 4) & 15, n4 = (pd >> 8) & 15;
+                            const double *ex34 = E34 + (l3 * HL_LD + l4) * HL_TD, *ey34 = E34 + ESZ + (m3 * HL_LD + m4) * HL_TD,
+                                         *ez34 = E34 + 2 * ESZ + (n3 * HL_LD + n4) * HL_TD;
+                            const int l34 = l3 + l4, m34 = m3 + m4, n34 = n3 + n4;
+                            double sum = 0.0;
+                            for (int ix = 0; ix <= l34; ++ix)
+                                for (int iy = 0; iy <= m34; ++iy) {
+                                    const double v34 = ex34[ix] * ey34[iy];
+                                    const double *rzp = &RR(t + ix, u + iy, v);
+                                    double sx = ((ix + iy) & 1) ? -1.0 : 1.0;
+                                    for (int iz = 0; iz <= n34; ++iz) {
+                                        sum += sx * v34 * ez34[iz] * rzp[iz];
+                                        sx = -sx;
                                     }
-                            }
-                    V[o] += sum;
+                                }
+                            W[o] = sum;
+                        }
+                        HL_SYNC();
+                        for (int o = tid; o < NAB * cha; o += nt) {
+                            const int ab = o / cha, cdl = o - ab * cha;
+                            const int a = ab / NB, bb = ab - a * NB;
+                            const int pa = cexp[a], pb = cexp[HL_NC + bb];
+                            const int l1 = pa & 15, m1 = (pa >> 4) & 15, n1 = (pa >> 8) & 15;
+                            const int l2 = pb & 15, m2 = (pb >> 4) & 15, n2 = (pb >> 8) & 15;
+                            const double *ex12 = E12 + (l1 * HL_LD + l2) * HL_TD, *ey12 = E12 + ESZ + (m1 * HL_LD + m2) * HL_TD,
+                                         *ez12 = E12 + 2 * ESZ + (n1 * HL_LD + n2) * HL_TD;
+                            const int l12 = l1 + l2, m12 = m1 + m2, n12 = n1 + n2;
+                            const double *Wc = W + cdl * NHd;
+                            double sum = 0.0;
+                            for (int t = 0; t <= l12; ++t)
+                                for (int u = 0; u <= m12; ++u) {
+                                    const double v12 = ex12[t] * ey12[u];
+                                    const double *wz = Wc + (t * D + u) * D;
+                                    for (int v = 0; v <= n12; ++v) sum += v12 * ez12[v] * wz[v];
+                                }
+                            V[ab * NCD + cd0 + cdl] += sum;
+                        }
+                        HL_SYNC();
+                    }
                 }
             }
             HL_SYNC();   // E12 is rewritten by the next bra primitive

@@ -61,6 +61,8 @@ struct ClassTask {
     const KetHot *ket_hot;    // the same list, hot fields only
     const PrimPair *prims;
     const int *ket_count;     // per bra: number of leading kets to visit (Schwarz prefix, triangular cap)
+    const long long *ket_prefix;  // runtime-L kernel only: exclusive prefix sum of ket_count over the bras [nbra + 1]; its work
+                              // items are single shell quartets (a (gg|gg) block is 50 625 integrals), not bras
     int nbra, nket;
     int same_class;           // bra and ket lists are the same list (triangular, diagonal gets 1/2)
     int start_shell;          // quartet kept iff max shell index >= start_shell
