@@ -13,6 +13,8 @@ Writes, next to this script:
   g_<input>.npz           reference formGmatrix for seeded random P (RHF and UHF), several inputs
   quartets_<input>.npz    reference calc_two_electron_ints_rys blocks for seeded random ordered shell quartets
   *_fg_h2o.npz            the same for OUR f/g-shell input inputs/patin.dat.fg.h2o (see highl_input)
+  moments/moments.out.*   moments.out of fresh reference runs; moments/moments.dat.* the reference's checked-in goldens
+  momints_<input>.npz     the reference's raw dipole/quadrupole integrals (RMOM.DAT)
 """
 import json, os, re, shutil, subprocess, sys, tempfile
 import numpy as np
@@ -172,10 +174,40 @@ def highl_input():
     json.dump(runs, open(os.path.join(HERE, "ref_runs.json"), "w"), indent=1)
 
 
+def moments_fixtures():
+    """moments.out of fresh runs of the unmodified reference (the checked-in test/moments.dat.* carry a stale electronic
+    qyy) and the reference's raw moment integrals (RMOM.DAT records, Structs.hpp:17-20)."""
+    os.makedirs(os.path.join(HERE, "moments"), exist_ok=True)
+    for n in ["3g.h2o", "631.h2o", "631.nh3", "631.co", "dh95.co2", "b.dhdz", "dh95.co2.cation", "fg.h2o"]:
+        d = tempfile.mkdtemp()
+        try:
+            txt = open(os.path.join(HERE, "inputs", "patin.dat." + n)).read().split("\n")
+            k = [i for i, l in enumerate(txt) if l.strip()][3]
+            txt[k] = " 0 0"
+            open(os.path.join(d, "patin.dat"), "w").write("\n".join(txt))
+            subprocess.run([Reference.UNOMOL], cwd=d, capture_output=True, text=True, timeout=3600)
+            shutil.copyfile(os.path.join(d, "moments.out"), os.path.join(HERE, "moments", "moments.out." + n))
+            if n in ("631.nh3", "dh95.co2", "fg.h2o"):
+                rec = np.fromfile(os.path.join(d, "RMOM.DAT"), dtype=np.dtype([("v", "f8", 9), ("ijr", "u4"), ("pad", "u4")]))
+                m = np.zeros((9, len(rec))); m[:, rec["ijr"]] = rec["v"].T
+                np.savez_compressed(os.path.join(HERE, "momints_%s.npz" % n.replace(".", "_")), m=m)
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+    for f in sorted(os.listdir(REFT0)):
+        if f.startswith("moments.dat."):
+            shutil.copyfile(os.path.join(REFT0, f), os.path.join(HERE, "moments", f))
+
+
+REFT0 = "/root/reference/test"
+
 if __name__ == "__main__":
+    if "--moments-only" in sys.argv:
+        moments_fixtures()
+        sys.exit(0)
     if "--highl-only" in sys.argv:
         highl_input()
         sys.exit(0)
     main()
     cation_variants()
     highl_input()
+    moments_fixtures()

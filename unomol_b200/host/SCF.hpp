@@ -13,7 +13,8 @@
 //                    (RHF.hpp:404-459); PMATRIX.DAT checkpoint (RHF.hpp:172-174)
 // What changes: the packed EISPACK-style eigensolver / transforms (SymmPack.cpp:272-348) are replaced by
 // cuSOLVER / cuBLAS on the device through unomol_b200_scf_set_overlap / unomol_b200_scf_diag (no CPU fallback).
-// Moments, finite-field and polarisation-potential drivers are outside the hot-path scope.
+//                    moments.out / mol_dipmom.out through host/Moments.hpp (reference RHF.hpp:457-458, UHF.hpp:483)
+// Finite-field and polarisation-potential drivers are outside the hot-path scope.
 #pragma once
 #include <cmath>
 #include <cstdio>
@@ -21,6 +22,7 @@
 #include <vector>
 #include "Basis.hpp"
 #include "OneElectron.hpp"
+#include "Moments.hpp"
 #include "TwoElectronInts.hpp"
 
 namespace unomol {
@@ -175,6 +177,16 @@ class RestrictedHartreeFock {
         fprintf(out, "xxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxx\n");
         PopulationAnalysis(out);
         fclose(out);
+        // reference RHF.hpp:457-458
+        MomentMatrices mom;
+        MomentInts(basis, mom);
+        AnalyzeMoments(mom, Pmat.data(), (const double *)nullptr, basis.center_ptr(), ncen, no);
+        out = fopen("mol_dipmom.out", "w");
+        if (out) {
+            fprintf(out, " MULTIPOLE MOMENT ANALYSIS \n units in bohr - hartree atomic units \n\n");
+            AnalyzeMOMoments(mom, Cmat.data(), no, out, "MO TRANSISITION DIPOLE MOMENTS");
+            fclose(out);
+        }
     }
 
     // Mulliken populations (2 P S)_ii and atomic charges, same layout as the reference (RHF.hpp:571-660)
@@ -296,6 +308,11 @@ class UnRestrictedHartreeFock {
         fprintf(out, "               Beta Orbital Energies\n");
         for (int i = 0; i < no; i++) fprintf(out, "%7u %25.16le %12u\n", i + 1, EvalsB[i], i < noccB ? 1 : 0);
         fclose(out);
+        // reference UHF.hpp:483 (moments.out from (PA + PB)/2; the MO transition dipoles need the eigenvectors, which this
+        // driver does not bring back from the device for UHF)
+        MomentMatrices mom;
+        MomentInts(basis, mom);
+        AnalyzeMoments(mom, PmatA.data(), PmatB.data(), basis.center_ptr(), ncen, no);
     }
 
     bool is_converged() const noexcept {
