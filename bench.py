@@ -186,6 +186,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("UNOMOL_BENCH_WORKLOAD", "water154"))
     ap.add_argument("--tau", type=float, default=1e-12)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--set", action="append", default=[], metavar="OPTION=VALUE",
+                    help="engine option for experiments (unomol_b200_set_option), e.g. --set ket_runs=0")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -241,6 +243,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     h = capi.Handle(basis, device=local, rank=rank, nranks=world)
     h.set_option("schwarz_tau", args.tau)
+    for kv in args.set:
+        k, v = kv.split("=")
+        h.set_option(k, float(v))
+        config.setdefault("options", {})[k] = float(v)
     stealing = False
     if world > 1 and not os.environ.get("UNOMOL_NO_STEAL"):
         from unomol_b200.multigpu import enable_work_stealing
