@@ -18,6 +18,7 @@
 #pragma once
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "Basis.hpp"
@@ -181,7 +182,9 @@ class RestrictedHartreeFock {
         MomentMatrices mom;
         MomentInts(basis, mom);
         AnalyzeMoments(mom, Pmat.data(), (const double *)nullptr, basis.center_ptr(), ncen, no);
-        out = fopen("mol_dipmom.out", "w");
+        // O(N^3) on the host and N(N+1)/2 text lines: written like the reference up to 1000 functions, beyond that only on
+        // request (UNOMOL_MOL_DIPMOM=1) -- at 2002 functions it is a 100 MB file and a minute of host time
+        out = (no <= 1000 || std::getenv("UNOMOL_MOL_DIPMOM")) ? fopen("mol_dipmom.out", "w") : nullptr;
         if (out) {
             fprintf(out, " MULTIPOLE MOMENT ANALYSIS \n units in bohr - hartree atomic units \n\n");
             AnalyzeMOMoments(mom, Cmat.data(), no, out, "MO TRANSISITION DIPOLE MOMENTS");
