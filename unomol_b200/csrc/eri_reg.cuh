@@ -533,6 +533,9 @@ __global__ void __launch_bounds__(ROWS ? REG_THREADS_ROWS : REG_THREADS) eri_reg
                 if (v != 0.0) atomicAdd(task.J + (size_t)(bra.offa + tid / NB) * n + bra.offb + tid % NB, task.jscale * v);
             }
         }
+        // The issuing thread makes sure this bra's row copy has landed even if none of its own quartets reached the exchange
+        // step (all skipped by start_shell / the value cut): the next bra's copy reuses the buffer and the barrier phase.
+        if (ROWS && use_rows && tid == 0 && !rows_ready) mbar_wait(&row_bar, row_phase);
         __syncthreads();   // everyone is done with stage[s], the staged rows and jab_red before they are overwritten
         if (ROWS && use_rows) row_phase ^= 1u;
         bi = bnext;
