@@ -141,9 +141,10 @@ def _random_rotation(rng):
                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
 
 
-def water_cluster(n, seed=20261017, spacing=5.8, jitter=0.3):
+def water_cluster(n, seed=20261017, spacing=5.8, jitter=0.3, frames=None):
     """(H2O)_n / 6-31G: water geometry of test/patin.dat.631.h2o on a simple cubic lattice of the given
-    spacing (bohr), each molecule rotated by a random unit quaternion and jittered."""
+    spacing (bohr), each molecule rotated by a random unit quaternion and jittered.
+    frames: optional list that receives each molecule's rotation matrix (for superposition_density)."""
     rng = np.random.default_rng(seed)
     side = int(np.ceil(n ** (1.0 / 3.0) - 1e-9))
     sites = [(i, j, k) for i in range(side) for j in range(side) for k in range(side)][:n]
@@ -153,6 +154,8 @@ def water_cluster(n, seed=20261017, spacing=5.8, jitter=0.3):
     shells = []
     for m, site in enumerate(sites):
         R = _random_rotation(rng)
+        if frames is not None:
+            frames.append(R)
         origin = spacing * np.array(site, float) + rng.uniform(-jitter, jitter, 3)
         pos = WATER_GEOM @ R.T + origin
         for a in range(3):
@@ -168,6 +171,45 @@ def water_cluster(n, seed=20261017, spacing=5.8, jitter=0.3):
     b.int_flag = [0, 0]; b.scf_flag = [2, 1, 0]; b.prt_flag = [0, 0, 0]
     b._set_shells(shells)
     return b
+
+
+def water_monomer():
+    """one water molecule in the reference orientation (identity rotation, no jitter), same shells as water_cluster"""
+    b = Basis()
+    b.ncen = 3
+    b.charge = np.array([8.0, 1.0, 1.0]); b.xyz = WATER_GEOM.copy()
+    shells = []
+    for a in range(3):
+        for (l, al, co) in (O_631G if a == 0 else H_631G):
+            shells.append((l, a, np.array(al, float), np.array(co, float)))
+    b.maxl = 1
+    b.nelec = 10
+    b.maxits = 299
+    b.eps = 1e-10
+    b.int_flag = [0, 0]; b.scf_flag = [2, 1, 0]; b.prt_flag = [0, 0, 0]
+    b._set_shells(shells)
+    return b
+
+
+def superposition_density(P_monomer, frames):
+    """Packed block-diagonal starting density of a water cluster from the converged density of water_monomer():
+    a molecule rotated by R carries P' = D P D^T with D = 1 on s functions and D = R on each (x, y, z) p triple
+    (Cartesian functions are lab-frame; s and p shells only).  For PMATRIX.DAT restarts (reference RHF.hpp:120-123)."""
+    mono = water_monomer()
+    nb = mono.nbf
+    Pm = np.zeros((nb, nb))
+    Pm[np.tril_indices(nb)] = P_monomer
+    Pm = Pm + Pm.T - np.diag(np.diag(Pm))
+    n = len(frames)
+    P = np.zeros((n * nb, n * nb))
+    for m, R in enumerate(frames):
+        D = np.eye(nb)
+        for s in range(mono.nshell):
+            if mono.lv[s] == 1:
+                o = int(mono.off[s])
+                D[o:o + 3, o:o + 3] = R
+        P[m * nb:(m + 1) * nb, m * nb:(m + 1) * nb] = D @ Pm @ D.T
+    return P[np.tril_indices(n * nb)]
 
 
 def test_input(name):
