@@ -318,9 +318,10 @@ def main():
             Gn[:] = 0.0
             h.fock_rhf(Pn, Gn)
         else:
-            dP.copy_(P_host, non_blocking=True)
-            device_step()
-            G_host.copy_(dG, non_blocking=True)
+            with torch.cuda.stream(ext):      # copies, build and all-reduce ordered on the library's stream
+                dP.copy_(P_host, non_blocking=True)
+                device_step()
+                G_host.copy_(dG, non_blocking=True)
             ext.synchronize()
 
     e2e_step()
@@ -338,21 +339,25 @@ def main():
     # X^T F X -> eigen-decomposition -> C -> P on cuSOLVER/cuBLAS (reference RHF.hpp:87-112).  H and S are synthetic
     # (identity-like overlap): the O(N^3) algebra does not depend on their values.
     scf_ms = None
-    if world == 1 and basis.nbf <= 6000:
+    if basis.nbf <= 6000:
+        # N > 1: every rank holds the all-reduced G and runs the (replicated) device algebra on its own GPU, the
+        # counterpart of RHF_MPI::update where rank 0 does the algebra and broadcasts P (reference RHF_MPI.hpp:101-131)
         n = basis.nbf
         Sd = np.zeros(no2); Sd[np.cumsum(np.arange(1, n + 1)) - 1] = 1.0
         h.scf_set_overlap(Sd)
         nocc = max(1, getattr(basis, "nelec", 2) // 2)
         Hn = -np.abs(Pn)
-        Gn[:] = 0.0
-        h.fock_rhf(Pn, Gn)
+        e2e_step()
         h.scf_diag(Hn + Gn, nocc)          # warm-up: cuSOLVER handle, workspace query and allocation
-        t0 = time.perf_counter()
+        sync_all(); t0 = time.perf_counter()
         for _ in range(2):
-            Gn[:] = 0.0
-            h.fock_rhf(Pn, Gn)
+            e2e_step()
             ev, Pnew = h.scf_diag(Hn + Gn, nocc)
-        scf_ms = (time.perf_counter() - t0) / 2 * 1e3
+        sync_all()
+        t = torch.tensor([(time.perf_counter() - t0) / 2 * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        scf_ms = float(t.item())
 
     if rank == 0:
         peak = capi.fp64_peak(local)
