@@ -82,7 +82,10 @@ void unomol_b200_destroy(unomol_b200_t *h);
 /* Options (before the next set_geometry/fock call).  Names:
  *   "schwarz_tau"   quartet kept iff Q_ab*Q_cd >= tau (default 1e-12; 0 keeps every quartet)
  *   "prim_cut"      the reference's primitive-quartet cut sr < cut (TwoElectronInts.cpp:479; default 1e-12)
- *   "density_screen" 0/1: weight the Schwarz test with max|P| over the six digestion blocks (default 0) */
+ *   "value_cut"     shell-quartet blocks whose largest |integral| is <= value_cut are not digested (default 1e-14, the
+ *                   reference's storage threshold, TwoElectronInts.cpp:513,667-671; 0 digests everything)
+ * plus tuning/experiment switches documented in unomol_b200/csrc/engine.h (reg_kernels, stage_rows, col_blocks,
+ * bucket_min_pairs, device_pairs, work_stealing, debug_flags).  Unknown names return UNOMOL_E_ARG. */
 int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value);
 
 /* Replaces recalculate() (TwoElectronInts.hpp:96-98) after the caller moved centres

@@ -674,7 +674,6 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
         return UNOMOL_OK;
     }
     if (!strcmp(name, "prim_cut")) { h->prim_cut = value; h->pairs_ready = false; return UNOMOL_OK; }
-    if (!strcmp(name, "density_screen")) { h->density_screen = value != 0.0; return UNOMOL_OK; }
     if (!strcmp(name, "bucket_min_pairs")) { h->bucket_min_pairs = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "work_stealing")) { h->steal_enabled = value != 0.0; h->build_count = 0; return UNOMOL_OK; }
     if (!strcmp(name, "device_pairs")) { h->device_pairs = (int)value; h->pairs_ready = false; return UNOMOL_OK; }

@@ -70,7 +70,6 @@ struct unomol_b200 {
     cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr, nullptr, nullptr};
     ub200::HostBasis basis;
     double tau = 1e-12, prim_cut = 1e-12, value_cut = 1e-14;
-    int density_screen = 0;
     int use_reg_kernels = 1;
     int device_pairs = 1;           // option "device_pairs": build the pair tables on the GPU (0 = threaded host path)
     int col_blocks = 0;             // option "col_blocks": spatial blocks per pair list (0 = choose from N so a launch fits L2)
