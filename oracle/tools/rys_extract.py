@@ -473,6 +473,29 @@ def emit_f0f1_body(res, indent="    "):
     return L
 
 
+def hoist_common(lines, indent="    "):
+    """Device code: the bands of one fit repeat exp(-x), 1/x, sqrt(pie4/x) (and rsqrt(x) in the one-root variant).  On the
+    GPU the lanes of a warp fall into different bands, so every copy runs with the few lanes of its band (ncu, (ss|ss)
+    kernel: 47 % of the issued warp instructions had <= 3 active lanes).  Evaluating these once before the band dispatch
+    costs the lanes that do not need them nothing they would not have waited for anyway, and is bit-identical."""
+    body = "\n".join(lines)
+    top = []
+    if "exp((-x))" in body:
+        top.append(indent + "const double ub_g = exp((-x));")
+        body = body.replace("exp((-x))", "ub_g")
+    if "double xinv = (1.0 / x);" in body:
+        top.append(indent + "const double ub_xinv = (1.0 / x);")
+        body = body.replace("double xinv = (1.0 / x);", "double xinv = ub_xinv;")
+        m = re.search(r"sqrt\(\((RC\(\d+, 0\.785398163397448\)) \* xinv\)\)", body)
+        if m:
+            top.append(indent + "const double ub_sq = sqrt((%s * ub_xinv));" % m.group(1))
+            body = body.replace(m.group(0), "ub_sq")
+    if "const double rx = ub_rsqrt(x);" in body:
+        top.append(indent + "const double ub_rx = ub_rsqrt(x);")
+        body = body.replace("const double rx = ub_rsqrt(x);", "const double rx = ub_rx;")
+    return top + body.split("\n")
+
+
 def emit_cuda(res, path):
     global CONST_TABLE
     host_bodies = emit_function_bodies(res, fma=True, names={"roots": "r", "weights": "w"})
@@ -487,7 +510,9 @@ def emit_cuda(res, path):
                 " * Product code (host+device).  r[i] = t_i^2/(1-t_i^2), w[i] = weights, as in reference Rys.hpp:145-164.\n"
                 " * Horner steps are explicit fma(); in device code the coefficients come from a __constant__ table\n"
                 " * (RC(i, literal)) so they are constant-bank operands of the DFMA instead of UMOV-materialised\n"
-                " * immediates (ncu: 21 % of the issued instructions of the (ss|ss) kernel were UMOV before this).\n */\n")
+                " * immediates (ncu: 21 % of the issued instructions of the (ss|ss) kernel were UMOV before this).\n"
+                " * exp(-x), 1/x, sqrt(pie4/x) and rsqrt(x) are evaluated once before the band dispatch (hoist_common in the\n"
+                " * generator): the lanes of a warp land in different bands, and per-band copies ran with a few lanes each.\n */\n")
         f.write("#pragma once\n#include <math.h>\n\n#ifdef __CUDACC__\n#define UNOMOL_HD __host__ __device__ __forceinline__\n#else\n#define UNOMOL_HD inline\n#endif\n\nnamespace ub200 {\n\n")
         f.write("#ifdef __CUDACC__\nstatic __constant__ double rys_ctab[%d] = {\n" % len(table))
         for i in range(0, len(table), 4):
@@ -497,9 +522,9 @@ def emit_cuda(res, path):
         f.write("template <int N> UNOMOL_HD void rys_roots(double x, double *r, double *w);\n\n")
         for n in sorted(bodies):
             f.write("template <> UNOMOL_HD void rys_roots<%d>(double x, double *r, double *w) {\n" % n)
-            f.write("\n".join(drop_unused_locals(bodies[n])) + "\n}\n\n")
+            f.write("\n".join(hoist_common(drop_unused_locals(bodies[n]))) + "\n}\n\n")
         f.write("// one root, division-free on the hot bands: w = F0(x), f1 = w*t^2 = F1(x) (same fit as rys_roots<1>)\n")
-        f.write("UNOMOL_HD void rys1_f0f1(double x, double &w, double &f1) {\n" + "\n".join(drop_unused_locals(f0f1)) + "\n}\n\n")
+        f.write("UNOMOL_HD void rys1_f0f1(double x, double &w, double &f1) {\n" + "\n".join(hoist_common(drop_unused_locals(f0f1))) + "\n}\n\n")
         f.write("#undef RC\n}  // namespace ub200\n")
 
 
