@@ -142,35 +142,40 @@ def highl_input():
     calc_two_electron_ints_rys (l_tot <= 8) / calc_two_electron_ints_md (l_tot > 8), and a full SCF run."""
     global REFT
     R = Reference()
-    n = "fg.h2o"
-    path = os.path.join(HERE, "inputs", "patin.dat." + n)
-    h = R.basis(path)
-    nbf = R.lib.ref_basis_norb(h); no2 = nbf * (nbf + 1) // 2
-    rng = np.random.default_rng(12345)
-    P = rng.standard_normal(no2); PB = rng.standard_normal(no2)
-    t = R.tints(h)
-    G, _ = R.form_g_rhf(t, P)
-    GA, GB, _ = R.form_g_uhf(t, P, PB)
-    S, T, H = R.one_electron(h)
-    np.savez_compressed(os.path.join(HERE, "g_fg_h2o.npz"), P=P, PB=PB, G=G, GA=GA, GB=GB, S=S, T=T, H=H)
-    R.tints_destroy(t)
-    shells = R.basis_shells(h)
-    ns = len(shells)
-    nc = lambda s: (shells[s][1] + 1) * (shells[s][1] + 2) // 2
-    quart = [(5, 4, 3, 3), (5, 4, 8, 8), (8, 8, 11, 11), (5, 5, 11, 11), (8, 5, 11, 4), (4, 8, 5, 11), (11, 5, 8, 3),
-             (5, 0, 0, 0), (4, 4, 0, 0), (5, 3, 2, 1), (8, 2, 11, 10), (5, 5, 2, 2), (4, 4, 4, 4), (3, 5, 4, 2), (5, 5, 5, 4)]
-    for q in rng.integers(0, ns, size=(400, 4)):
-        q = tuple(int(x) for x in q)
-        if max(shells[s][1] for s in q) >= 3 and nc(q[0]) * nc(q[1]) * nc(q[2]) * nc(q[3]) <= 6000 and len(quart) < 75:
-            quart.append(q)
-    blocks = [R.quartet_block(h, (nc(i), nc(j), nc(k), nc(l)), i, j, k, l).ravel() for (i, j, k, l) in quart]
-    np.savez_compressed(os.path.join(HERE, "quartets_fg_h2o.npz"), quartets=np.array(quart),
-                        offsets=np.cumsum([0] + [len(b) for b in blocks]), values=np.concatenate(blocks))
-    R.basis_close(h)
     runs = json.load(open(os.path.join(HERE, "ref_runs.json")))
     REFT = os.path.join(HERE, "inputs")
-    runs[n] = run_unomol(n)
-    print(n, runs[n]["e_final"], runs[n]["iterations"], flush=True)
+    fixed = {"fg.h2o": [(5, 4, 3, 3), (5, 4, 8, 8), (8, 8, 11, 11), (5, 5, 11, 11), (8, 5, 11, 4), (4, 8, 5, 11), (11, 5, 8, 3),
+                        (5, 0, 0, 0), (4, 4, 0, 0), (5, 3, 2, 1), (8, 2, 11, 10), (5, 5, 2, 2), (4, 4, 4, 4), (3, 5, 4, 2), (5, 5, 5, 4)],
+             # fg2.hf (ours): CONTRACTED f and g shells, so the same-shell primitive triangle with doubled off-diagonal
+             # coefficients (TwoElectronInts.cpp:293-299) and primitive sums are exercised on the McMurchie-Davidson path
+             "fg2.hf": [(3, 3, 3, 3), (4, 4, 7, 7), (4, 3, 3, 2), (7, 7, 7, 7), (4, 3, 7, 7), (7, 4, 3, 7), (3, 3, 2, 2),
+                        (4, 0, 0, 0), (3, 1, 2, 0), (7, 5, 6, 5), (4, 4, 4, 3)]}
+    for n in ["fg.h2o", "fg2.hf"]:
+        path = os.path.join(HERE, "inputs", "patin.dat." + n)
+        h = R.basis(path)
+        nbf = R.lib.ref_basis_norb(h); no2 = nbf * (nbf + 1) // 2
+        rng = np.random.default_rng(12345)
+        P = rng.standard_normal(no2); PB = rng.standard_normal(no2)
+        t = R.tints(h)
+        G, _ = R.form_g_rhf(t, P)
+        GA, GB, _ = R.form_g_uhf(t, P, PB)
+        S, T, H = R.one_electron(h)
+        np.savez_compressed(os.path.join(HERE, "g_%s.npz" % n.replace(".", "_")), P=P, PB=PB, G=G, GA=GA, GB=GB, S=S, T=T, H=H)
+        R.tints_destroy(t)
+        shells = R.basis_shells(h)
+        ns = len(shells)
+        nc = lambda s: (shells[s][1] + 1) * (shells[s][1] + 2) // 2
+        quart = list(fixed[n])
+        for q in rng.integers(0, ns, size=(400, 4)):
+            q = tuple(int(x) for x in q)
+            if max(shells[s][1] for s in q) >= 3 and nc(q[0]) * nc(q[1]) * nc(q[2]) * nc(q[3]) <= 6000 and len(quart) < (75 if n == "fg.h2o" else 45):
+                quart.append(q)
+        blocks = [R.quartet_block(h, (nc(i), nc(j), nc(k), nc(l)), i, j, k, l).ravel() for (i, j, k, l) in quart]
+        np.savez_compressed(os.path.join(HERE, "quartets_%s.npz" % n.replace(".", "_")), quartets=np.array(quart),
+                            offsets=np.cumsum([0] + [len(b) for b in blocks]), values=np.concatenate(blocks))
+        R.basis_close(h)
+        runs[n] = run_unomol(n)
+        print(n, runs[n]["e_final"], runs[n]["iterations"], flush=True)
     json.dump(runs, open(os.path.join(HERE, "ref_runs.json"), "w"), indent=1)
 
 
@@ -178,7 +183,7 @@ def moments_fixtures():
     """moments.out of fresh runs of the unmodified reference (the checked-in test/moments.dat.* carry a stale electronic
     qyy) and the reference's raw moment integrals (RMOM.DAT records, Structs.hpp:17-20)."""
     os.makedirs(os.path.join(HERE, "moments"), exist_ok=True)
-    for n in ["3g.h2o", "631.h2o", "631.nh3", "631.co", "dh95.co2", "b.dhdz", "dh95.co2.cation", "fg.h2o"]:
+    for n in ["3g.h2o", "631.h2o", "631.nh3", "631.co", "dh95.co2", "b.dhdz", "dh95.co2.cation", "fg.h2o", "fg2.hf"]:
         d = tempfile.mkdtemp()
         try:
             txt = open(os.path.join(HERE, "inputs", "patin.dat." + n)).read().split("\n")
@@ -187,7 +192,7 @@ def moments_fixtures():
             open(os.path.join(d, "patin.dat"), "w").write("\n".join(txt))
             subprocess.run([Reference.UNOMOL], cwd=d, capture_output=True, text=True, timeout=3600)
             shutil.copyfile(os.path.join(d, "moments.out"), os.path.join(HERE, "moments", "moments.out." + n))
-            if n in ("631.nh3", "dh95.co2", "fg.h2o"):
+            if n in ("631.nh3", "dh95.co2", "fg.h2o", "fg2.hf"):
                 rec = np.fromfile(os.path.join(d, "RMOM.DAT"), dtype=np.dtype([("v", "f8", 9), ("ijr", "u4"), ("pad", "u4")]))
                 m = np.zeros((9, len(rec))); m[:, rec["ijr"]] = rec["v"].T
                 np.savez_compressed(os.path.join(HERE, "momints_%s.npz" % n.replace(".", "_")), m=m)

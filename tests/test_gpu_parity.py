@@ -25,7 +25,7 @@ def _handle(capi, name, **kw):
     return b, capi.Handle(b, **kw)
 
 
-@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "b.dhdz", "dh95.co2", "dh95.c2h2", "tz2p.sf6", "fg.h2o"])
+@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "b.dhdz", "dh95.co2", "dh95.c2h2", "tz2p.sf6", "fg.h2o", "fg2.hf"])
 def test_quartet_blocks_vs_reference_fixture(capi, name):
     path = os.path.join(GOLDEN, "quartets_%s.npz" % name.replace(".", "_"))
     g = np.load(path)
@@ -90,7 +90,7 @@ def test_unique_integral_list_vs_reference_cache(capi, name):
     assert not extra or max(extra) < 1e-14 + ERI_TOL
 
 
-@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "631.co", "b.dhdz", "dh95.co2", "dh95.c2h2", "tz2p.sf6", "fg.h2o"])
+@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "631.co", "b.dhdz", "dh95.co2", "dh95.c2h2", "tz2p.sf6", "fg.h2o", "fg2.hf"])
 def test_g_matrices_vs_reference_fixture(capi, name):
     g = np.load(os.path.join(GOLDEN, "g_%s.npz" % name.replace(".", "_")))
     b, h = _handle(capi, name)

@@ -44,12 +44,13 @@ def test_rhf_energy_dzp_vs_fresh_reference_run(name, tmp_path):
     assert abs(e0 - RUNS[name]["e_init"]) < E_TOL
 
 
-def test_rhf_with_f_and_g_shells(tmp_path):
-    """fg.h2o (ours): s..g shells, Rys for l_tot <= 8 and McMurchie-Davidson above, as the reference dispatches"""
-    e0, e1, de, out = run_scf("fg.h2o", tmp_path)
-    assert RUNS["fg.h2o"]["converged"] and "NOT_ REACHED" not in out
-    assert abs(e1 - RUNS["fg.h2o"]["e_final"]) < E_TOL, (e1, RUNS["fg.h2o"]["e_final"])
-    assert abs(e0 - RUNS["fg.h2o"]["e_init"]) < E_TOL
+@pytest.mark.parametrize("name", ["fg.h2o", "fg2.hf"])
+def test_rhf_with_f_and_g_shells(name, tmp_path):
+    """ours: s..g shells (fg2.hf: contracted f and g), Rys for l_tot <= 8 and McMurchie-Davidson above, as the reference dispatches"""
+    e0, e1, de, out = run_scf(name, tmp_path)
+    assert RUNS[name]["converged"] and "NOT_ REACHED" not in out
+    assert abs(e1 - RUNS[name]["e_final"]) < E_TOL, (e1, RUNS[name]["e_final"])
+    assert abs(e0 - RUNS[name]["e_init"]) < E_TOL
 
 
 def test_rhf_sf6_tz2p(tmp_path):
@@ -138,7 +139,7 @@ def test_uhf_moments_out_invariants_vs_fresh_reference_run(name, tmp_path):
         assert abs(d_o - d_r) < 5e-6 * max(1.0, d_r)
 
 
-@pytest.mark.parametrize("name", ["3g.h2o", "631.h2o", "631.nh3", "631.co", "dh95.co2", "fg.h2o"])
+@pytest.mark.parametrize("name", ["3g.h2o", "631.h2o", "631.nh3", "631.co", "dh95.co2", "fg.h2o", "fg2.hf"])
 def test_moments_out_matches_fresh_reference_run(name, tmp_path):
     """moments.out (dipole and quadrupole moments: total, electronic, nuclear) against a fresh run of the unmodified
     reference, RHF and UHF (reference Moments.cpp:189-363).  7 significant digits are printed; the density is converged

@@ -39,9 +39,11 @@ def _block(emul, b, i, j, k, l):
     return out
 
 
-def test_kernel_body_blocks_vs_reference_fixture(emul, oracle):
-    g = np.load(os.path.join(GOLDEN, "quartets_fg_h2o.npz"))
-    b = oracle.basis(golden_input("fg.h2o"))
+@pytest.mark.parametrize("name", ["fg.h2o", "fg2.hf"])
+def test_kernel_body_blocks_vs_reference_fixture(emul, oracle, name):
+    """fg2.hf has CONTRACTED f and g shells: primitive sums and the same-shell primitive triangle on the MD branch"""
+    g = np.load(os.path.join(GOLDEN, "quartets_%s.npz" % name.replace(".", "_")))
+    b = oracle.basis(golden_input(name))
     worst = 0.0
     for q, (i, j, k, l) in enumerate(g["quartets"]):
         ref = g["values"][g["offsets"][q]:g["offsets"][q + 1]]

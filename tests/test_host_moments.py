@@ -16,7 +16,7 @@ def moments_check(tmp_path_factory):
     return exe
 
 
-@pytest.mark.parametrize("name", ["631.nh3", "dh95.co2", "fg.h2o"])
+@pytest.mark.parametrize("name", ["631.nh3", "dh95.co2", "fg.h2o", "fg2.hf"])
 def test_moment_integrals_match_reference(moments_check, tmp_path, name):
     ref = np.load(os.path.join(GOLDEN, "momints_%s.npz" % name.replace(".", "_")))["m"]
     out = tmp_path / "m.bin"
@@ -33,7 +33,7 @@ def onee_check(tmp_path_factory):
     return exe
 
 
-@pytest.mark.parametrize("name", ["631.nh3", "dh95.co2", "tz2p.sf6", "fg.h2o"])
+@pytest.mark.parametrize("name", ["631.nh3", "dh95.co2", "tz2p.sf6", "fg.h2o", "fg2.hf"])
 @pytest.mark.parametrize("threads", ["1", "4"])
 def test_one_electron_matrices_match_reference(onee_check, tmp_path, name, threads):
     """overlap, kinetic and core-Hamiltonian matrices of the host driver (threaded over shell-pair rows) against the

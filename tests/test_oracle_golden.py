@@ -54,7 +54,7 @@ def test_g_matrices_match_reference(oracle, name):
     assert np.max(np.abs(GB - g["GB"])) < 1e-12 * scale
 
 
-@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "b.dhdz", "dh95.co2", "dh95.c2h2", "fg.h2o"])
+@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "b.dhdz", "dh95.co2", "dh95.c2h2", "fg.h2o", "fg2.hf"])
 def test_quartet_blocks_match_reference(oracle, name):
     g = np.load(os.path.join(GOLDEN, "quartets_%s.npz" % name.replace(".", "_")))
     b = oracle.basis(golden_input(name))
