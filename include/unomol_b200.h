@@ -136,6 +136,11 @@ int unomol_b200_attach_nccl(unomol_b200_t *h, void *nccl_comm);
  * separates consecutive builds.  Without these calls a multi-rank handle uses the static snake-order split. */
 int unomol_b200_steal_export(unomol_b200_t *h, void *handle64);
 int unomol_b200_steal_import(unomol_b200_t *h, const void *handle64);
+/* The same for handles that live in ONE process (one host thread per GPU, as unomol_b200/host/TwoElectronInts.hpp does
+ * with UNOMOL_GPUS=N): CUDA IPC cannot re-open a handle inside its own process, so `peer` maps `owner`'s work counters
+ * through CUDA peer access instead.  Same contract: every handle performs every build; the builds of all handles are
+ * joined before the next one starts.  Returns UNOMOL_E_CUDA when the two devices cannot access each other. */
+int unomol_b200_steal_share(unomol_b200_t *owner, unomol_b200_t *peer);
 
 /* Device pointers of the square density / partial-G work buffers and the stream the library launches on
  * (for callers that keep the SCF on the device or time with their own events). */

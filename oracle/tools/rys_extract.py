@@ -493,7 +493,7 @@ def hoist_common(lines, indent="    "):
     if "const double rx = ub_rsqrt(x);" in body:
         top.append(indent + "const double ub_rx = ub_rsqrt(x);")
         body = body.replace("const double rx = ub_rsqrt(x);", "const double rx = ub_rx;")
-    return top + body.split("\n")
+    return top + drop_unused_locals(body.split("\n"))   # e.g. xinv when its only use became ub_sq
 
 
 def emit_cuda(res, path):

@@ -365,6 +365,37 @@ def test_multi_gpu_work_stealing_and_static_split():
     assert p.returncode == 0 and "OK" in p.stdout, (p.stdout[-1500:], p.stderr[-1500:])
 
 
+@pytest.mark.parametrize("two_devices", [False, True])
+def test_in_process_handles_share_work_counters(capi, two_devices):
+    """unomol_b200_steal_share: two handles of ONE process (rank 0/2 and 1/2, one host thread each) claim bras from the
+    same work counters; their partial G's add up to the 1-rank G over repeated builds.  On one device the two handles
+    simply run concurrently; with two devices the counters are reached through NVLink peer access (what the C++ shim does
+    with UNOMOL_GPUS=N)."""
+    import threading
+    import torch
+    if two_devices and torch.cuda.device_count() < 2:
+        pytest.skip("single-GPU box")
+    from unomol_b200.basis import Basis
+    b = Basis.from_patin(golden_input("tz2p.sf6"))
+    rng = np.random.default_rng(61)
+    P = rng.standard_normal(b.no2)
+    full = capi.Handle(b).fock_rhf(P)
+    h0 = capi.Handle(b, device=0, rank=0, nranks=2)
+    h1 = capi.Handle(b, device=1 if two_devices else 0, rank=1, nranks=2)
+    h0.steal_share(h1)
+    for rep in range(4):                     # alternating counter sets
+        parts = [None, None]
+
+        def run(i, h):
+            parts[i] = h.fock_rhf(P)
+        t = threading.Thread(target=run, args=(1, h1))
+        t.start(); run(0, h0); t.join()
+        assert np.max(np.abs(parts[0] + parts[1] - full)) < 1e-12 * np.max(np.abs(full)), rep
+    n0, n1 = h0.stats()["n_quartets"], h1.stats()["n_quartets"]
+    hf = capi.Handle(b); hf.fock_rhf(P)
+    assert n0 > 0 and n1 > 0 and n0 + n1 == hf.stats()["n_quartets"]
+
+
 def test_device_pair_tables_match_host_pair_tables(capi):
     """pair tables built on the GPU (pair_device.cu) against the threaded host path (engine.cu)"""
     for name in ("631.nh3", "tz2p.sf6"):

@@ -19,9 +19,10 @@ RUNS = json.load(open(os.path.join(GOLDEN, "ref_runs.json")))
 E_TOL = 1e-9
 
 
-def run_scf(name, tmp_path):
+def run_scf(name, tmp_path, env=None):
     shutil.copyfile(golden_input(name), tmp_path / "patin.dat")
-    p = subprocess.run([BIN], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    p = subprocess.run([BIN], cwd=tmp_path, capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, **env) if env else None)
     assert p.returncode == 0, p.stderr[-2000:]
     e0, e1, de = [float(x) for x in open(tmp_path / "short.gs.out").read().split()]
     out = open(tmp_path / "scfout.gs.out").read()
@@ -51,6 +52,17 @@ def test_rhf_with_f_and_g_shells(name, tmp_path):
     assert RUNS[name]["converged"] and "NOT_ REACHED" not in out
     assert abs(e1 - RUNS[name]["e_final"]) < E_TOL, (e1, RUNS[name]["e_final"])
     assert abs(e0 - RUNS[name]["e_init"]) < E_TOL
+
+
+@pytest.mark.parametrize("name", ["dh95.co2", "dh95.co2.cation"])
+def test_scf_driver_on_all_gpus_of_the_box(name, tmp_path):
+    """UNOMOL_GPUS=N: the C++ TwoElectronInts shim drives N GPUs from one process (RHF and UHF); needs >= 2 GPUs"""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("single-GPU box")
+    e0, e1, de, out = run_scf(name, tmp_path, env={"UNOMOL_GPUS": str(min(n, 4))})
+    assert abs(e1 - RUNS[name]["e_final"]) < 5e-9, (e1, RUNS[name]["e_final"])
 
 
 def test_rhf_sf6_tz2p(tmp_path):

@@ -49,7 +49,7 @@ EXPORTS = [
     "unomol_b200_create", "unomol_b200_destroy", "unomol_b200_set_option", "unomol_b200_set_geometry",
     "unomol_b200_fock_rhf", "unomol_b200_fock_uhf", "unomol_b200_fock_rhf_device", "unomol_b200_fock_uhf_device",
     "unomol_b200_eri_quartet", "unomol_b200_dump_eris", "unomol_b200_schwarz", "unomol_b200_stats",
-    "unomol_b200_attach_nccl", "unomol_b200_steal_export", "unomol_b200_steal_import", "unomol_b200_device_buffers", "unomol_b200_scf_set_overlap", "unomol_b200_scf_diag",
+    "unomol_b200_attach_nccl", "unomol_b200_steal_export", "unomol_b200_steal_import", "unomol_b200_steal_share", "unomol_b200_device_buffers", "unomol_b200_scf_set_overlap", "unomol_b200_scf_diag",
     "unomol_b200_sample_quartets", "unomol_b200_fp64_peak", "unomol_b200_model_flops", "unomol_b200_strerror", "unomol_b200_version",
 ]
 
@@ -74,6 +74,7 @@ def _load():
     L.unomol_b200_attach_nccl.argtypes = [_P, _P]
     L.unomol_b200_steal_export.argtypes = [_P, ctypes.c_char_p]
     L.unomol_b200_steal_import.argtypes = [_P, ctypes.c_char_p]
+    L.unomol_b200_steal_share.argtypes = [_P, _P]
     L.unomol_b200_device_buffers.argtypes = [_P, ctypes.POINTER(_P), ctypes.POINTER(_P), ctypes.POINTER(_P)]
     L.unomol_b200_scf_set_overlap.argtypes = [_P, _pd]
     L.unomol_b200_scf_diag.argtypes = [_P, _pd, _I, _pd, _pd, _pd]
@@ -191,6 +192,10 @@ class Handle:
         buf = ctypes.create_string_buffer(64)
         _chk(lib.unomol_b200_steal_export(self.h, buf), "steal_export")
         return buf.raw
+
+    def steal_share(self, peer):
+        """in-process variant: `peer` (another Handle of this process) claims work from this handle's counters"""
+        _chk(lib.unomol_b200_steal_share(self.h, peer.h), "steal_share")
 
     def steal_import(self, handle64):
         _chk(lib.unomol_b200_steal_import(self.h, ctypes.create_string_buffer(handle64, 64)), "steal_import")

@@ -652,7 +652,7 @@ void unomol_b200_destroy(unomol_b200_t *h) {
     }
     cudaFree(h->d_PJ); cudaFree(h->d_J); cudaFree(h->d_counters); cudaFree(h->d_hl_scratch);
     cudaFree(h->d_work_local);
-    if (h->d_work_shared) { if (h->work_owner) cudaFree(h->d_work_shared); else cudaIpcCloseMemHandle(h->d_work_shared); }
+    if (h->d_work_shared && !h->work_borrowed) { if (h->work_owner) cudaFree(h->d_work_shared); else cudaIpcCloseMemHandle(h->d_work_shared); }
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     unomol_scf_free(h);
     if (h->ev0) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3); }
@@ -783,6 +783,32 @@ int unomol_b200_steal_import(unomol_b200_t *h, const void *handle64) {
     h->work_owner = false;
     h->work_imported = true;
     h->build_count = 0;
+    return UNOMOL_OK;
+}
+
+int unomol_b200_steal_share(unomol_b200_t *owner, unomol_b200_t *peer) {
+    if (!owner || !peer || owner == peer) return UNOMOL_E_ARG;
+    if (peer->d_work_shared) return UNOMOL_E_STATE;
+    cudaSetDevice(owner->device);
+    if (!owner->d_work_shared) {
+        CUDA_TRY(owner, cudaMalloc(&owner->d_work_shared, sizeof(unsigned long long) * 2 * unomol_b200::MAXPLAN));
+        CUDA_TRY(owner, cudaMemset(owner->d_work_shared, 0, sizeof(unsigned long long) * 2 * unomol_b200::MAXPLAN));
+        owner->work_owner = true;
+        owner->build_count = 0;
+    }
+    cudaSetDevice(peer->device);
+    if (peer->device != owner->device) {
+        int can = 0;
+        CUDA_TRY(peer, cudaDeviceCanAccessPeer(&can, peer->device, owner->device));
+        if (!can) { peer->last_error = "no peer access between the two devices"; return UNOMOL_E_CUDA; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(owner->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return UNOMOL_E_CUDA; }
+        cudaGetLastError();
+    }
+    peer->d_work_shared = owner->d_work_shared;
+    peer->work_owner = false;
+    peer->work_borrowed = true;
+    peer->build_count = owner->build_count;
     return UNOMOL_OK;
 }
 

@@ -455,7 +455,10 @@ cudaError_t launch_class(const ClassTask &task, int mode, int grid, cudaStream_t
     template <>                                                                                                    \
     cudaError_t launch_class<LA, LB, LC, LD>(const ClassTask &task, int mode, int grid, cudaStream_t stream) {      \
         using C = QC<LA, LB, LC, LD>;                                                                              \
-        static bool attr_done = false;                                                                             \
+        static bool attr_done_dev[64] = {}; /* per device: one process may drive several GPUs */                   \
+        int attr_dev = 0;                                                                                          \
+        cudaGetDevice(&attr_dev);                                                                                  \
+        bool &attr_done = attr_done_dev[attr_dev & 63];                                                            \
         if (!attr_done) {                                                                                          \
             cudaFuncSetAttribute(eri_class_kernel<LA, LB, LC, LD, MODE_DIGEST>,                                    \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);                       \
