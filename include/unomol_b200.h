@@ -156,6 +156,23 @@ int unomol_b200_scf_set_overlap(unomol_b200_t *h, const double *S);
  * P packed. */
 int unomol_b200_scf_diag(unomol_b200_t *h, const double *F, int nocc, double *evals, double *C, double *P);
 
+/* Device-resident RHF iteration = RestrictedHartreeFock::scf_converger + update (reference RHF.hpp:536-569, 87-112) with the
+ * density, G, F and the core Hamiltonian kept on the GPU: per iteration only two scalars cross the bus.
+ *   scf_load           after scf_set_overlap: packed core Hamiltonian H and starting density P (host pointers).
+ *   scf_iterate_rhf    damp != 0 first replaces P by (P + P_previous)/2 (scf_converger's mixing branch; the caller
+ *                      decides from the sign of the last energy change like the reference), then G = 2J-K[P],
+ *                      *e_elec = 2 tr(PH) + tr(PG), F = H + G, F' = X^T F X, eigen-decomposition, C = X W,
+ *                      P <- C_occ C_occ^T, *pdiff = ||P - P_previous||_F / nbf (SymmPackDiffNorm).
+ *   ..._begin/_finish  the same in two halves for multi-rank callers: _begin enqueues the mixing and this rank's partial
+ *                      Fock build into the packed device G (unomol_b200_device_buffers), the caller all-reduces that
+ *                      buffer on the library stream (or attaches NCCL and lets the library do it), _finish does the rest.
+ *   scf_fetch          current P (packed), orbital energies, C (row-major, eigenvectors in columns); any may be NULL. */
+int unomol_b200_scf_load(unomol_b200_t *h, const double *H, const double *P);
+int unomol_b200_scf_iterate_rhf(unomol_b200_t *h, int nocc, int damp, double *e_elec, double *pdiff);
+int unomol_b200_scf_iterate_rhf_begin(unomol_b200_t *h, int damp);
+int unomol_b200_scf_iterate_rhf_finish(unomol_b200_t *h, int nocc, double *e_elec, double *pdiff);
+int unomol_b200_scf_fetch(unomol_b200_t *h, double *P, double *evals, double *C);
+
 /* Bench support (no reference counterpart).
  * sample_quartets: draws nsample shell quartets uniformly from the screened canonical quartet list the Fock
  * build evaluates (all ranks), deterministic in seed; shells[4*q..] = (ish,jsh,ksh,lsh).  *ntotal receives the

@@ -65,6 +65,52 @@ def test_scf_driver_on_all_gpus_of_the_box(name, tmp_path):
     assert abs(e1 - RUNS[name]["e_final"]) < 5e-9, (e1, RUNS[name]["e_final"])
 
 
+def test_host_side_scf_bookkeeping_gives_the_same_energy(tmp_path):
+    """UNOMOL_HOST_SCF=1: P/G cross the bus every iteration and the traces / mixing run on the host like the reference's
+    update(); the default keeps them on the device (unomol_b200_scf_iterate_rhf)"""
+    e0, e1, de, out = run_scf("631.nh3", tmp_path, env={"UNOMOL_HOST_SCF": "1"})
+    assert abs(e1 - SHORT["631.nh3"][1]) < E_TOL and abs(e0 - SHORT["631.nh3"][0]) < E_TOL
+
+
+def test_device_resident_iteration_matches_host_algebra():
+    """unomol_b200_scf_iterate_rhf against the same iteration assembled on the host from fock_rhf + scf_diag, with and
+    without the mixing step, and in its begin/finish form"""
+    import numpy as np
+    from unomol_b200 import capi
+    from unomol_b200.basis import Basis
+    g = np.load(os.path.join(GOLDEN, "g_dh95_co2.npz"))
+    b = Basis.from_patin(golden_input("dh95.co2"))
+    S, H = g["S"], g["H"]
+    n, nocc = b.nbf, b.nelec // 2
+    tri = np.tril_indices(n)
+    w = np.where(tri[0] == tri[1], 1.0, 2.0)
+    hd = capi.Handle(b); hd.set_option("schwarz_tau", 0.0); hd.scf_set_overlap(S)
+    hh = capi.Handle(b); hh.set_option("schwarz_tau", 0.0); hh.scf_set_overlap(S)
+    ev, P = hh.scf_diag(H, nocc)                       # core guess
+    hd.scf_load(H, P)
+    Pold = P.copy()
+    for it, damp in enumerate([False, False, True, False, True]):
+        if damp:
+            P = 0.5 * (P + Pold)
+        G = hh.fock_rhf(P)
+        e_ref = float(np.sum(w * P * (2.0 * H + G)))
+        Pold = P.copy()
+        ev, P = hh.scf_diag(H + G, nocc)
+        d = P - Pold
+        pd_ref = float(np.sqrt(np.sum(w * d * d)) / n)
+        if it % 2:
+            hd.scf_iterate_rhf_begin(damp); e, pd = hd.scf_iterate_rhf_finish(nocc)
+        else:
+            e, pd = hd.scf_iterate_rhf(nocc, damp)
+        assert abs(e - e_ref) < 1e-9 * abs(e_ref), (it, e, e_ref)
+        assert abs(pd - pd_ref) < 1e-9, (it, pd, pd_ref)
+    Pd, evd, Cd = hd.scf_fetch(want_c=True)
+    assert np.max(np.abs(Pd - P)) < 1e-9 and np.max(np.abs(evd - ev)) < 1e-9
+    Cocc = Cd[:, :nocc]
+    Pc = Cocc @ Cocc.T
+    assert np.max(np.abs(Pc[tri] - Pd)) < 1e-10
+
+
 def test_rhf_sf6_tz2p(tmp_path):
     """BASELINE config 4: 190 basis functions, d shells, 4-5 Rys roots"""
     e0, e1, de, out = run_scf("tz2p.sf6", tmp_path)

@@ -50,6 +50,7 @@ EXPORTS = [
     "unomol_b200_fock_rhf", "unomol_b200_fock_uhf", "unomol_b200_fock_rhf_device", "unomol_b200_fock_uhf_device",
     "unomol_b200_eri_quartet", "unomol_b200_dump_eris", "unomol_b200_schwarz", "unomol_b200_stats",
     "unomol_b200_attach_nccl", "unomol_b200_steal_export", "unomol_b200_steal_import", "unomol_b200_steal_share", "unomol_b200_device_buffers", "unomol_b200_scf_set_overlap", "unomol_b200_scf_diag",
+    "unomol_b200_scf_load", "unomol_b200_scf_iterate_rhf", "unomol_b200_scf_iterate_rhf_begin", "unomol_b200_scf_iterate_rhf_finish", "unomol_b200_scf_fetch",
     "unomol_b200_sample_quartets", "unomol_b200_fp64_peak", "unomol_b200_model_flops", "unomol_b200_strerror", "unomol_b200_version",
 ]
 
@@ -78,6 +79,11 @@ def _load():
     L.unomol_b200_device_buffers.argtypes = [_P, ctypes.POINTER(_P), ctypes.POINTER(_P), ctypes.POINTER(_P)]
     L.unomol_b200_scf_set_overlap.argtypes = [_P, _pd]
     L.unomol_b200_scf_diag.argtypes = [_P, _pd, _I, _pd, _pd, _pd]
+    L.unomol_b200_scf_load.argtypes = [_P, _pd, _pd]
+    L.unomol_b200_scf_iterate_rhf.argtypes = [_P, _I, _I, _pd, _pd]
+    L.unomol_b200_scf_iterate_rhf_begin.argtypes = [_P, _I]
+    L.unomol_b200_scf_iterate_rhf_finish.argtypes = [_P, _I, _pd, _pd]
+    L.unomol_b200_scf_fetch.argtypes = [_P, _pd, _pd, _pd]
     L.unomol_b200_sample_quartets.argtypes = [_P, ctypes.c_longlong, ctypes.c_ulonglong, _pi, ctypes.POINTER(ctypes.c_longlong)]
     L.unomol_b200_fp64_peak.argtypes = [_I, _pd]
     L.unomol_b200_model_flops.restype = _D; L.unomol_b200_model_flops.argtypes = [_I, _I, _I, _I]
@@ -213,6 +219,28 @@ class Handle:
     def scf_set_overlap(self, S):
         S = np.ascontiguousarray(S, float)
         _chk(lib.unomol_b200_scf_set_overlap(self.h, _dp(S)), "scf_set_overlap")
+
+    def scf_load(self, H, P):
+        _chk(lib.unomol_b200_scf_load(self.h, _dp(np.ascontiguousarray(H, float)), _dp(np.ascontiguousarray(P, float))), "scf_load")
+
+    def scf_iterate_rhf(self, nocc, damp=False):
+        e = _D(0.0); pd = _D(0.0)
+        _chk(lib.unomol_b200_scf_iterate_rhf(self.h, nocc, int(damp), ctypes.byref(e), ctypes.byref(pd)), "scf_iterate_rhf")
+        return e.value, pd.value
+
+    def scf_iterate_rhf_begin(self, damp=False):
+        _chk(lib.unomol_b200_scf_iterate_rhf_begin(self.h, int(damp)), "scf_iterate_rhf_begin")
+
+    def scf_iterate_rhf_finish(self, nocc):
+        e = _D(0.0); pd = _D(0.0)
+        _chk(lib.unomol_b200_scf_iterate_rhf_finish(self.h, nocc, ctypes.byref(e), ctypes.byref(pd)), "scf_iterate_rhf_finish")
+        return e.value, pd.value
+
+    def scf_fetch(self, want_c=False):
+        P = np.zeros(self.no2); ev = np.zeros(self.nbf)
+        C = np.zeros((self.nbf, self.nbf)) if want_c else None
+        _chk(lib.unomol_b200_scf_fetch(self.h, _dp(P), _dp(ev), _dp(C) if want_c else None), "scf_fetch")
+        return (P, ev, C) if want_c else (P, ev)
 
     def scf_diag(self, F, nocc, want_c=False):
         F = np.ascontiguousarray(F, float)

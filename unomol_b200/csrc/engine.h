@@ -107,6 +107,8 @@ struct unomol_b200 {
     double *d_X = nullptr, *d_F = nullptr, *d_W = nullptr, *d_T = nullptr, *d_evals = nullptr, *d_work = nullptr;
     int *d_info = nullptr;
     int lwork = 0;
+    // device-resident RHF iteration: packed core Hamiltonian, previous density, two reduction scalars
+    double *d_scfH = nullptr, *d_scfPold = nullptr, *d_scfRed = nullptr;
     // NCCL
     void *nccl_comm = nullptr;
     std::string last_error;

@@ -45,6 +45,67 @@ __global__ void scale_columns_kernel(double *__restrict__ U, const double *__res
     U[idx] *= rsqrt(f);
 }
 
+// ---- device-resident RHF iteration (packed matrices, idx = i(i+1)/2 + j) ---------------------------------------
+__device__ __forceinline__ int packed_row(size_t idx) {
+    int i = (int)floor((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+    while ((size_t)i * (i + 1) / 2 > idx) --i;
+    while ((size_t)(i + 1) * (i + 2) / 2 <= idx) ++i;
+    return i;
+}
+
+__device__ __forceinline__ void block_sum_to(double v, double *dst) {
+    __shared__ double red[32];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < (int)(blockDim.x >> 5) ? red[lane] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) atomicAdd(dst, v);
+    }
+}
+
+// P <- (P + Pold)/2   (scf_converger, reference RHF.hpp:564-567)
+__global__ void scf_damp_kernel(double *__restrict__ P, const double *__restrict__ Pold, size_t no2) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < no2) P[idx] = (P[idx] + Pold[idx]) * 0.5;
+}
+
+// E = 2 tr(P H) + tr(P G) with full-matrix traces (TraceSymmPackProduct, SymmPack.cpp:7-18; RHF.hpp:94-96);
+// F = H + G unpacked to the square work matrix; Pold <- P
+__global__ void scf_energy_fock_kernel(const double *__restrict__ P, const double *__restrict__ H, const double *__restrict__ G,
+                                       double *__restrict__ Pold, double *__restrict__ Ffull, int n, double *__restrict__ red) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t no2 = (size_t)n * (n + 1) / 2;
+    double e = 0.0;
+    if (idx < no2) {
+        const int i = packed_row(idx), j = (int)(idx - (size_t)i * (i + 1) / 2);
+        const double p = P[idx], hh = H[idx], g = G[idx], f = hh + g;
+        e = (i == j ? 1.0 : 2.0) * p * (2.0 * hh + g);
+        Ffull[(size_t)i * n + j] = f;
+        Ffull[(size_t)j * n + i] = f;
+        Pold[idx] = p;
+    }
+    block_sum_to(e, red);
+}
+
+// packs the new density and accumulates ||P - Pold||_F^2 with the full-matrix weights (SymmPackDiffNorm, SymmPack.cpp:20-36)
+__global__ void scf_pack_diff_kernel(const double *__restrict__ Pfull, const double *__restrict__ Pold, double *__restrict__ P, int n,
+                                     double *__restrict__ red) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t no2 = (size_t)n * (n + 1) / 2;
+    double d2 = 0.0;
+    if (idx < no2) {
+        const int i = packed_row(idx), j = (int)(idx - (size_t)i * (i + 1) / 2);
+        const double p = Pfull[(size_t)j * n + i];
+        const double d = p - Pold[idx];
+        P[idx] = p;
+        d2 = (i == j ? 1.0 : 2.0) * d * d;
+    }
+    block_sum_to(d2, red + 1);
+}
+
 int scf_ensure(unomol_b200 *h) {
     if (h->cusolver) return UNOMOL_OK;
     const int n = h->basis.nbf;
@@ -80,6 +141,8 @@ void unomol_scf_free(unomol_b200 *h) {
     h->cusolver = h->cublas = nullptr;
     cudaFree(h->d_X); cudaFree(h->d_F); cudaFree(h->d_W); cudaFree(h->d_T);
     cudaFree(h->d_evals); cudaFree(h->d_work); cudaFree(h->d_info);
+    cudaFree(h->d_scfH); cudaFree(h->d_scfPold); cudaFree(h->d_scfRed);
+    h->d_scfH = h->d_scfPold = h->d_scfRed = nullptr;
     h->d_X = h->d_F = h->d_W = h->d_T = h->d_evals = h->d_work = nullptr;
     h->d_info = nullptr;
 }
@@ -156,6 +219,104 @@ int unomol_b200_scf_diag(unomol_b200_t *h, const double *F, int nocc, double *ev
     cudaError_t e = cudaStreamSynchronize(h->stream);
     cudaFree(d_packed);
     if (e != cudaSuccess || info != 0) return UNOMOL_E_CUDA;
+    if (C)
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < n; ++k) C[(size_t)i * n + k] = ccm[(size_t)k * n + i];   // row-major, eigenvectors in columns
+    return UNOMOL_OK;
+}
+
+
+// ---- device-resident RHF iteration: the density, G, F and the core Hamiltonian stay on the GPU ---------------
+int unomol_b200_scf_load(unomol_b200_t *h, const double *H, const double *P) {
+    if (!h || !H || !P) return UNOMOL_E_ARG;
+    if (!h->cusolver || !h->d_X) return UNOMOL_E_STATE;
+    cudaSetDevice(h->device);
+    double *dP[2], *dG[2];
+    int rc = unomol_b200_device_buffers(h, nullptr, dP, dG);
+    if (rc) return rc;
+    const size_t n = h->basis.nbf, no2 = n * (n + 1) / 2;
+    if (!h->d_scfH) {
+        if (cudaMalloc(&h->d_scfH, sizeof(double) * no2) != cudaSuccess) return UNOMOL_E_NOMEM;
+        if (cudaMalloc(&h->d_scfPold, sizeof(double) * no2) != cudaSuccess) return UNOMOL_E_NOMEM;
+        if (cudaMalloc(&h->d_scfRed, sizeof(double) * 2) != cudaSuccess) return UNOMOL_E_NOMEM;
+    }
+    cudaMemcpyAsync(h->d_scfH, H, sizeof(double) * no2, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(dP[0], P, sizeof(double) * no2, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(h->d_scfPold, P, sizeof(double) * no2, cudaMemcpyHostToDevice, h->stream);
+    return cudaStreamSynchronize(h->stream) == cudaSuccess ? UNOMOL_OK : UNOMOL_E_CUDA;
+}
+
+int unomol_b200_scf_iterate_rhf_begin(unomol_b200_t *h, int damp) {
+    if (!h) return UNOMOL_E_ARG;
+    if (!h->d_scfH) return UNOMOL_E_STATE;
+    cudaSetDevice(h->device);
+    double *dP[2], *dG[2];
+    int rc = unomol_b200_device_buffers(h, nullptr, dP, dG);
+    if (rc) return rc;
+    const size_t n = h->basis.nbf, no2 = n * (n + 1) / 2;
+    if (damp) scf_damp_kernel<<<(unsigned)((no2 + 255) / 256), 256, 0, h->stream>>>(dP[0], h->d_scfPold, no2);
+    return unomol_b200_fock_rhf_device(h, dP[0], dG[0], /*async=*/1);
+}
+
+int unomol_b200_scf_iterate_rhf_finish(unomol_b200_t *h, int nocc, double *e_elec, double *pdiff) {
+    if (!h || !e_elec || !pdiff || nocc < 0 || nocc > h->basis.nbf) return UNOMOL_E_ARG;
+    if (!h->d_scfH) return UNOMOL_E_STATE;
+    cudaSetDevice(h->device);
+    double *dP[2], *dG[2];
+    int rc = unomol_b200_device_buffers(h, nullptr, dP, dG);
+    if (rc) return rc;
+    const int n = h->basis.nbf;
+    const size_t nn = (size_t)n * n, no2 = (size_t)n * (n + 1) / 2;
+    cublasHandle_t cb = (cublasHandle_t)h->cublas;
+    const unsigned blocks = (unsigned)((no2 + 255) / 256);
+    cudaMemsetAsync(h->d_scfRed, 0, sizeof(double) * 2, h->stream);
+    scf_energy_fock_kernel<<<blocks, 256, 0, h->stream>>>(dP[0], h->d_scfH, dG[0], h->d_scfPold, h->d_F, n, h->d_scfRed);
+    const double one = 1.0, zero = 0.0;
+    cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, &one, h->d_F, n, h->d_X, n, &zero, h->d_T, n);
+    cublasDgemm(cb, CUBLAS_OP_T, CUBLAS_OP_N, n, n, n, &one, h->d_X, n, h->d_T, n, &zero, h->d_W, n);
+    cudaMemsetAsync(h->d_info, 0, sizeof(int) * 2, h->stream);
+    if (cusolverDnDsyevd((cusolverDnHandle_t)h->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, h->d_W, n,
+                         h->d_evals, h->d_work, h->lwork, h->d_info) != CUSOLVER_STATUS_SUCCESS)
+        return UNOMOL_E_CUDA;
+    cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, &one, h->d_X, n, h->d_W, n, &zero, h->d_T, n);   // C = X W
+    if (nocc > 0)
+        cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_T, n, n, nocc, &one, h->d_T, n, h->d_T, n, &zero, h->d_F, n);
+    else
+        cudaMemsetAsync(h->d_F, 0, sizeof(double) * nn, h->stream);
+    scf_pack_diff_kernel<<<blocks, 256, 0, h->stream>>>(h->d_F, h->d_scfPold, dP[0], n, h->d_scfRed);
+    double red[2] = {0.0, 0.0};
+    int info = 0;
+    cudaMemcpyAsync(red, h->d_scfRed, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(&info, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess || info != 0) return UNOMOL_E_CUDA;
+    *e_elec = red[0];
+    *pdiff = sqrt(red[1]) / n;
+    return UNOMOL_OK;
+}
+
+int unomol_b200_scf_iterate_rhf(unomol_b200_t *h, int nocc, int damp, double *e_elec, double *pdiff) {
+    int rc = unomol_b200_scf_iterate_rhf_begin(h, damp);
+    if (rc) return rc;
+    return unomol_b200_scf_iterate_rhf_finish(h, nocc, e_elec, pdiff);
+}
+
+int unomol_b200_scf_fetch(unomol_b200_t *h, double *P, double *evals, double *C) {
+    if (!h) return UNOMOL_E_ARG;
+    if (!h->d_scfH) return UNOMOL_E_STATE;
+    cudaSetDevice(h->device);
+    double *dP[2], *dG[2];
+    int rc = unomol_b200_device_buffers(h, nullptr, dP, dG);
+    if (rc) return rc;
+    const int n = h->basis.nbf;
+    const size_t nn = (size_t)n * n, no2 = (size_t)n * (n + 1) / 2;
+    if (P) cudaMemcpyAsync(P, dP[0], sizeof(double) * no2, cudaMemcpyDeviceToHost, h->stream);
+    if (evals) cudaMemcpyAsync(evals, h->d_evals, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
+    std::vector<double> ccm;
+    if (C) {
+        ccm.resize(nn);
+        cudaMemcpyAsync(ccm.data(), h->d_T, sizeof(double) * nn, cudaMemcpyDeviceToHost, h->stream);
+    }
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return UNOMOL_E_CUDA;
     if (C)
         for (int i = 0; i < n; ++i)
             for (int k = 0; k < n; ++k) C[(size_t)i * n + k] = ccm[(size_t)k * n + i];   // row-major, eigenvectors in columns

@@ -90,6 +90,15 @@ class RestrictedHartreeFock {
     }
 
     void update() noexcept {
+        if (on_device) {
+            // device-resident iteration: P, G, F, H stay on the GPU; mixing (scf_converger) is done there too
+            scf_check(unomol_b200_scf_iterate_rhf(tints.handle(), nocc, mix_next ? 1 : 0, &energy, &pdiff), "scf_iterate_rhf");
+            mix_next = false;
+            ediff = energy - eold;
+            eold = energy;
+            ++iteration;
+            return;
+        }
         for (int i = 0; i < no2; ++i) Gmat[i] = 0.0;
         tints.formGmatrix(Pmat.data(), Gmat.data());
         const double e1 = SymmPack::TraceSymmPackProduct(Pmat.data(), Hmat.data(), no) * 2.0;
@@ -116,6 +125,10 @@ class RestrictedHartreeFock {
         } else {
             PmatrixGuess();
         }
+        // One GPU: keep the whole iteration on the device (UNOMOL_HOST_SCF=1 forces the host-side bookkeeping of the
+        // reference's update()); several GPUs in this process: partial G's are summed on the host, so stay on the host path.
+        on_device = tints.number_of_gpus() == 1 && !std::getenv("UNOMOL_HOST_SCF");
+        if (on_device) scf_check(unomol_b200_scf_load(tints.handle(), Hmat.data(), Pmat.data()), "scf_load");
         iteration = 0;
         eold = 0.0;
         update();
@@ -131,6 +144,7 @@ class RestrictedHartreeFock {
             if (is_converged()) break;
             report();
         }
+        if (on_device) scf_check(unomol_b200_scf_fetch(tints.handle(), Pmat.data(), Evals.data(), Cmat.data()), "scf_fetch");
         FILE *fp = fopen("PMATRIX.DAT", "w");
         if (fp) { fwrite(Pmat.data(), sizeof(double), no2, fp); fclose(fp); }
         final_output(init_energy);
@@ -149,6 +163,10 @@ class RestrictedHartreeFock {
     }
 
     void scf_converger() {
+        if (on_device) {          // the mixing itself happens on the device at the start of the next iteration
+            mix_next = !(ediff < 0.0);
+            return;
+        }
         if (ediff < 0.0) {
             Pold2 = Pold;
             Pold = Pmat;
@@ -226,6 +244,7 @@ class RestrictedHartreeFock {
     int no = 0, no2 = 0, ncen = 0, nocc = 0, maxits = 0, scf_accel = 0, cflag = 0, iteration = 0;
     double eps = 0, ediff = 10.0, pdiff = 10.0, eold = 0, nucrep = 0, energy = 0, init_energy = 0;
     std::vector<double> Pold2, Pold, Pmat, Gmat, Hmat, Fock, Tmat, Smat, Evals, Cmat;
+    bool on_device = false, mix_next = false;
 };
 
 class UnRestrictedHartreeFock {

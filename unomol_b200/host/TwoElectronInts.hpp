@@ -114,6 +114,7 @@ class TwoElectronInts {
     void directFormGMatrix(const double *Pmat, double *Gmat, const BasisT &) { formGmatrix(Pmat, Gmat); }
 
     unomol_b200_t *handle() const noexcept { return h; }
+    int number_of_gpus() const noexcept { return ngpu; }
 
   private:
     static void check(int rc, const char *what) {
