@@ -19,11 +19,24 @@ RUNS = json.load(open(os.path.join(GOLDEN, "ref_runs.json")))
 E_TOL = 1e-9
 
 
+_CACHE = {}
+
+
 def run_scf(name, tmp_path, env=None):
-    shutil.copyfile(golden_input(name), tmp_path / "patin.dat")
-    p = subprocess.run([BIN], cwd=tmp_path, capture_output=True, text=True, timeout=900,
-                       env=dict(os.environ, **env) if env else None)
-    assert p.returncode == 0, p.stderr[-2000:]
+    """one driver run per (input, environment) and test session: every run pays ~2 s of CUDA / cuSOLVER start-up, and
+    several tests look at different output files of the same run"""
+    import tempfile
+    key = (name, tuple(sorted((env or {}).items())))
+    if key not in _CACHE:
+        d = tempfile.mkdtemp(prefix="unomol_scf_")
+        shutil.copyfile(golden_input(name), os.path.join(d, "patin.dat"))
+        p = subprocess.run([BIN], cwd=d, capture_output=True, text=True, timeout=900,
+                           env=dict(os.environ, **env) if env else None)
+        assert p.returncode == 0, p.stderr[-2000:]
+        _CACHE[key] = d
+    d = _CACHE[key]
+    for f in os.listdir(d):
+        shutil.copyfile(os.path.join(d, f), tmp_path / f)
     e0, e1, de = [float(x) for x in open(tmp_path / "short.gs.out").read().split()]
     out = open(tmp_path / "scfout.gs.out").read()
     return e0, e1, de, out
