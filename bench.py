@@ -340,19 +340,36 @@ def main():
     # (identity-like overlap): the O(N^3) algebra does not depend on their values.
     scf_ms = None
     if basis.nbf <= 6000:
-        # N > 1: every rank holds the all-reduced G and runs the (replicated) device algebra on its own GPU, the
-        # counterpart of RHF_MPI::update where rank 0 does the algebra and broadcasts P (reference RHF_MPI.hpp:101-131)
+        # One full SCF iteration, device-resident (unomol_b200_scf_iterate_rhf = reference RHF.hpp:87-112 with P, G, F, H on
+        # the GPU): Fock build -> energy -> F = H + G -> X^T F X -> eigen-decomposition -> C -> P -> |dP|.  N > 1: every rank
+        # builds its partial G, the packed device G is all-reduced over NCCL on the library stream, and every rank runs the
+        # (replicated) cuSOLVER/cuBLAS algebra on its own GPU -- the counterpart of RHF_MPI::update, where rank 0 does the
+        # algebra and broadcasts P (reference RHF_MPI.hpp:101-131).  H and S are synthetic (identity overlap): the O(N^3)
+        # algebra does not depend on their values.
         n = basis.nbf
         Sd = np.zeros(no2); Sd[np.cumsum(np.arange(1, n + 1)) - 1] = 1.0
         h.scf_set_overlap(Sd)
         nocc = max(1, getattr(basis, "nelec", 2) // 2)
         Hn = -np.abs(Pn)
-        e2e_step()
-        h.scf_diag(Hn + Gn, nocc)          # warm-up: cuSOLVER handle, workspace query and allocation
+        h.scf_load(Hn, Pn)
+        _, _, dGlib = h.device_buffers()
+
+        class _DevView:                      # zero-copy torch view of the library's packed device G
+            __cuda_array_interface__ = {"shape": (no2,), "typestr": "<f8", "data": (int(dGlib[0]), False), "version": 2}
+        Gview = torch.as_tensor(_DevView(), device=torch.device("cuda", local)) if world > 1 else None
+
+        def scf_iteration():
+            if world == 1:
+                return h.scf_iterate_rhf(nocc)
+            with torch.cuda.stream(ext):
+                h.scf_iterate_rhf_begin()
+                dist.all_reduce(Gview)
+            return h.scf_iterate_rhf_finish(nocc)
+
+        scf_iteration()                      # warm-up: cuSOLVER workspace, first-use allocations
         sync_all(); t0 = time.perf_counter()
         for _ in range(2):
-            e2e_step()
-            ev, Pnew = h.scf_diag(Hn + Gn, nocc)
+            scf_iteration()
         sync_all()
         t = torch.tensor([(time.perf_counter() - t0) / 2 * 1e3], dtype=torch.float64, device="cuda")
         if world > 1:
