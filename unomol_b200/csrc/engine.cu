@@ -543,7 +543,15 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         } else if (pl.use_reg) {
             CUDA_TRY(h, launch_reg_class(pl.cb / NSUB, pl.ck / NSUB, task, std::min(nmine, 148 * 16), st, h->stage_rows != 0));
         } else {
-            CUDA_TRY(h, launch_quartet_class(pl.cb / NSUB, pl.ck / NSUB, task, MODE_DIGEST, std::min(nmine, 148 * 32), st));
+            // generic kernel: a warp takes (bra, slice) items; split the kets of a bra over several warps when the list has
+            // fewer bras than the GPU keeps warps busy (small molecules), every rank choosing the same split
+            const int warps = 148 * 16 * 2;
+            int split = pl.nbra_eff >= warps ? 1 : std::min(64, (warps + pl.nbra_eff - 1) / std::max(1, pl.nbra_eff));
+            if (!h->bra_split_enabled) split = 1;
+            task.bra_split = split;
+            const long long items = (long long)(work ? pl.nbra_eff : nmine) * split;
+            const int ctas = (int)std::min<long long>((items + 3) / 4, 148 * 32);   // 4 warps per CTA
+            CUDA_TRY(h, launch_quartet_class(pl.cb / NSUB, pl.ck / NSUB, task, MODE_DIGEST, std::max(ctas, 1), st));
         }
         ++nlaunch;
     }
@@ -679,6 +687,7 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
     if (!strcmp(name, "device_pairs")) { h->device_pairs = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "col_blocks")) { h->col_blocks = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "stage_rows")) { h->stage_rows = (int)value; return UNOMOL_OK; }
+    if (!strcmp(name, "bra_split")) { h->bra_split_enabled = value != 0.0; return UNOMOL_OK; }
     if (!strcmp(name, "value_cut")) { h->value_cut = value; return UNOMOL_OK; }
     if (!strcmp(name, "debug_flags")) { h->debug_flags = (int)value; return UNOMOL_OK; }
     if (!strcmp(name, "reg_kernels")) {

@@ -73,6 +73,7 @@ struct unomol_b200 {
     int use_reg_kernels = 1;
     int device_pairs = 1;           // option "device_pairs": build the pair tables on the GPU (0 = threaded host path)
     int col_blocks = 0;             // option "col_blocks": spatial blocks per pair list (0 = choose from N so a launch fits L2)
+    bool bra_split_enabled = true;  // option "bra_split": generic kernel deals the kets of one bra to several warps for short bra lists
     int stage_rows = 1;             // option "stage_rows": stage the bra's rows of P in shared memory (TMA) when they fit
     int debug_flags = 0;            // option "debug_flags" (profiling experiments; see ClassTask)
     int bucket_min_pairs = 20000;   // primitive-count bucketing only pays off for large pair lists   // option "reg_kernels": 0 forces the generic kernel for every class

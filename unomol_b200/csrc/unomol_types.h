@@ -70,6 +70,7 @@ struct ClassTask {
     unsigned long long *work_counter;  // dynamic self-scheduling: next unclaimed bra of this launch (device-local, or on rank 0's
                               // GPU and IPC/NVLink-mapped into every rank: work stealing across the GPUs of the box); null = static
     int chunk;                // bras claimed per atomic
+    int bra_split;            // generic kernel: warps that share the kets of one bra (work item = (bra, slice)); >= 1
     double prim_cut;          // reference's sr < 1e-12 cut
     double value_cut;         // reference's |val| > 1e-14 storage threshold (TwoElectronInts.cpp:513)
     // digestion
