@@ -634,6 +634,7 @@ int unomol_b200_create(const unomol_basis_desc *b, int start_shell, int device, 
     B.nshell = b->nshell; B.nbf = b->nbf; B.ncen = b->ncen; B.maxl = b->maxl;
     B.npr.assign(b->npr, b->npr + b->nshell);
     B.lv.assign(b->lv, b->lv + b->nshell);
+    for (int s = 0; s < b->nshell; ++s) B.maxl = std::max(B.maxl, B.lv[s]);   // sizes the runtime-L scratch: do not trust the header field
     B.cen.assign(b->cen, b->cen + b->nshell);
     B.off.assign(b->off, b->off + b->nshell);
     B.poff.assign(b->poff, b->poff + b->nshell);
