@@ -400,7 +400,7 @@ def main():
                         "d2h_bytes_per_step": int(no2 * 8), "s_per_step": e2e_s / args.steps},
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": achieved / peak if peak else None, "traffic": traffic, "l2_bytes": l2_bytes,
-                             "kernel": "eri_class_kernel<*> (fused ERI + J/K digestion, all class launches of one build)",
+                             "kernel": "eri_reg_kernel<*> / eri_class_kernel<*> (fused ERI + J/K digestion, all class launches of one build)",
                              "kernel_ms_per_build": kernel_ms, "model_gflop_per_build": model_flops / 1e9,
                              "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)"}}
         if world == 1:
