@@ -5,8 +5,9 @@ TEST-INFRASTRUCTURE / BUILD TOOL.  Runs only where /root/reference exists (this 
 
 The reference evaluates Rys roots/weights for 1..5 roots with the classic piecewise fits in
 X (Rys.cpp:314-2197).  Bit-for-tolerance parity (1e-12 per integral) needs the same fit
-*coefficients*; the evaluators themselves are rewritten table-driven (oracle/rys_roots_oracle.c,
-unomol_b200/csrc/rys_roots.cuh).  This script:
+*coefficients* in the CHECKER; oracle/rys_roots_oracle.c is emitted from here.  The product's evaluator
+(unomol_b200/csrc/rys_roots.cuh + tools/gen_rys_tables.py) is independent of this script and of the
+reference's fits.  This script:
 
   1. parses the five functions with a small C-expression parser,
   2. symbolically executes each X band (probe x between consecutive breakpoints),
@@ -15,7 +16,7 @@ unomol_b200/csrc/rys_roots.cuh).  This script:
      (Horner steps only shift/insert coefficients, no arithmetic on them; the script asserts that
      no power ever receives two contributions),
   4. emits (a) a human-readable IR listing (--ir) used to write the evaluators by hand and
-     (b) the coefficient tables as a C header (--emit-c PATH / --emit-cuda PATH).
+     (b) the oracle's C source (--emit-c PATH).
 
 Usage:  python oracle/tools/rys_extract.py --ref /root/reference --ir
 """
@@ -436,108 +437,14 @@ def emit_c(res, path):
                 "    }\n}\n")
 
 
-def emit_f0f1_body(res, indent="    "):
-    """one-root variant returning w = F0 and f1 = w*t^2 = F1 without the root division (device hot path)"""
-    L = []
-    bands = res[1]
-    first = True
-    for b in bands:
-        cond = "x <= %s" % _lit(repr(b["hi"])) if b["hi"] != float("inf") else None
-        L.append(indent + (("if (%s) {" % cond) if first else (("else if (%s) {" % cond) if cond else "else {")))
-        first = False
-        if b["y0"] is not None: L.append(indent * 2 + "const double y = x - %s;" % lit(b["y0"]))
-        names = {"roots": "r", "weights": "w"}
-        have_f1 = any(name == "f1" for name, _, _ in b["rows"])
-        tail = []
-        sq = "%.17g" % (float(b["consts"].get("pie4", "0.785398163397448")) ** 0.5)
-        for name, ae, polys in b["rows"]:
-            ex = emit_expr(ae, polys, b["consts"], True, names).replace("w[0]", "w")
-            # cheaper, rounding-equivalent forms: 1/x and sqrt(pie4/x) from one rsqrt, no division by 2x
-            ex = re.sub(r"sqrt\(\((?:RC\(\d+, )?0\.785398163397448\)? \* xinv\)\)", "(%s * rx)" % lit(sq), ex)
-            ex = ex.replace("((w - g) / (x + x))", "(((w - g) * 0.5) * xinv)")
-            if name == "roots[0]":
-                if have_f1: continue
-                if ex.startswith("(0.5 / "):          # pure asymptotic band: t^2 = 0.5/x exactly
-                    tail.append(indent * 2 + "f1 = (w * 0.5) * xinv;")
-                else:
-                    tail.append(indent * 2 + "const double r0 = %s;" % ex)
-                    tail.append(indent * 2 + "f1 = w * (r0 / (1.0 + r0));")
-            elif name == "weights[0]": L.append(indent * 2 + "w = %s;" % ex)
-            elif name == "f1": L.append(indent * 2 + "f1 = %s;" % ex)
-            elif name == "xinv":
-                L.append(indent * 2 + "const double rx = ub_rsqrt(x);")
-                L.append(indent * 2 + "const double xinv = rx * rx;")
-            else: L.append(indent * 2 + "const double %s = %s;" % (name, ex))
-        L.extend(tail)
-        L.append(indent + "}")
-    return L
-
-
-def hoist_common(lines, indent="    "):
-    """Device code: the bands of one fit repeat exp(-x), 1/x, sqrt(pie4/x) (and rsqrt(x) in the one-root variant).  On the
-    GPU the lanes of a warp fall into different bands, so every copy runs with the few lanes of its band (ncu, (ss|ss)
-    kernel: 47 % of the issued warp instructions had <= 3 active lanes).  Evaluating these once before the band dispatch
-    costs the lanes that do not need them nothing they would not have waited for anyway, and is bit-identical."""
-    body = "\n".join(lines)
-    top = []
-    if "exp((-x))" in body:
-        top.append(indent + "const double ub_g = exp((-x));")
-        body = body.replace("exp((-x))", "ub_g")
-    if "double xinv = (1.0 / x);" in body:
-        top.append(indent + "const double ub_xinv = (1.0 / x);")
-        body = body.replace("double xinv = (1.0 / x);", "double xinv = ub_xinv;")
-        m = re.search(r"sqrt\(\((RC\(\d+, 0\.785398163397448\)) \* xinv\)\)", body)
-        if m:
-            top.append(indent + "const double ub_sq = sqrt((%s * ub_xinv));" % m.group(1))
-            body = body.replace(m.group(0), "ub_sq")
-    if "const double rx = ub_rsqrt(x);" in body:
-        top.append(indent + "const double ub_rx = ub_rsqrt(x);")
-        body = body.replace("const double rx = ub_rsqrt(x);", "const double rx = ub_rx;")
-    return top + drop_unused_locals(body.split("\n"))   # e.g. xinv when its only use became ub_sq
-
-
-def emit_cuda(res, path):
-    global CONST_TABLE
-    host_bodies = emit_function_bodies(res, fma=True, names={"roots": "r", "weights": "w"})
-    CONST_TABLE = []
-    CONST_INDEX.clear()
-    bodies = emit_function_bodies(res, fma=True, names={"roots": "r", "weights": "w"})
-    f0f1 = emit_f0f1_body(res)
-    table = list(CONST_TABLE)
-    CONST_TABLE = None
-    with open(path, "w") as f:
-        f.write("// unomol_b200/csrc/rys_roots.cuh -- Rys quadrature roots and weights, 1..5 roots, FP64.\n/*\n" + HDR_NOTE +
-                " * Product code (host+device).  r[i] = t_i^2/(1-t_i^2), w[i] = weights, as in reference Rys.hpp:145-164.\n"
-                " * Horner steps are explicit fma(); in device code the coefficients come from a __constant__ table\n"
-                " * (RC(i, literal)) so they are constant-bank operands of the DFMA instead of UMOV-materialised\n"
-                " * immediates (ncu: 21 % of the issued instructions of the (ss|ss) kernel were UMOV before this).\n"
-                " * exp(-x), 1/x, sqrt(pie4/x) and rsqrt(x) are evaluated once before the band dispatch (hoist_common in the\n"
-                " * generator): the lanes of a warp land in different bands, and per-band copies ran with a few lanes each.\n */\n")
-        f.write("#pragma once\n#include <math.h>\n\n#ifdef __CUDACC__\n#define UNOMOL_HD __host__ __device__ __forceinline__\n#else\n#define UNOMOL_HD inline\n#endif\n\nnamespace ub200 {\n\n")
-        f.write("#ifdef __CUDACC__\nstatic __constant__ double rys_ctab[%d] = {\n" % len(table))
-        for i in range(0, len(table), 4):
-            f.write("    " + ", ".join(table[i:i + 4]) + ",\n")
-        f.write("};\n#endif\n#ifdef __CUDA_ARCH__\n#define RC(i, v) rys_ctab[i]\n#else\n#define RC(i, v) (v)\n#endif\n\n")
-        f.write("UNOMOL_HD double ub_rsqrt(double x) {\n#ifdef __CUDA_ARCH__\n    return rsqrt(x);\n#else\n    return 1.0 / sqrt(x);\n#endif\n}\n\n")
-        f.write("template <int N> UNOMOL_HD void rys_roots(double x, double *r, double *w);\n\n")
-        for n in sorted(bodies):
-            f.write("template <> UNOMOL_HD void rys_roots<%d>(double x, double *r, double *w) {\n" % n)
-            f.write("\n".join(hoist_common(drop_unused_locals(bodies[n]))) + "\n}\n\n")
-        f.write("// one root, division-free on the hot bands: w = F0(x), f1 = w*t^2 = F1(x) (same fit as rys_roots<1>)\n")
-        f.write("UNOMOL_HD void rys1_f0f1(double x, double &w, double &f1) {\n" + "\n".join(hoist_common(drop_unused_locals(f0f1))) + "\n}\n\n")
-        f.write("#undef RC\n}  // namespace ub200\n")
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--ir", action="store_true")
     ap.add_argument("--emit-c")
-    ap.add_argument("--emit-cuda")
     args = ap.parse_args()
     res = analyse(args.ref)
     if args.emit_c: emit_c(res, args.emit_c)
-    if args.emit_cuda: emit_cuda(res, args.emit_cuda)
     if args.ir:
         for n, bands in res.items():
             print("=" * 30, "nroots", n)

@@ -87,6 +87,7 @@ int hl_emul_quartet(int ns, int nbf, const int *npr, const int *lv, const int *c
     std::vector<double> V((size_t)NA * NB * NC * ND);
     std::vector<double> sm(HL_SMEM_DOUBLES + 4 * HL_NC);
     hl.scratch = V.data(); hl.slab = (long long)V.size();
+    hl.rys = rys_host_tables();
     hl_init_tables(hl, sm.data());
     hl_quartet_block(hl, bra, ket, P.prims.data(), prim_cut, one_centre(bra), one_centre(ket), sm.data(), V.data());
     const bool sw1 = (ish != jsh) && bra.sha != ish, sw2 = (ksh != lsh) && ket.sha != ksh;
@@ -132,6 +133,7 @@ int hl_emul_fock(int ns, int nbf, const int *npr, const int *lv, const int *cen,
             hl.la = lv[bra.sha]; hl.lb = lv[bra.shb]; hl.lc = lv[ket.sha]; hl.ld = lv[ket.shb];
             if (only_highl && std::max(std::max(hl.la, hl.lb), std::max(hl.lc, hl.ld)) <= 2) continue;
             hl.scratch = V.data(); hl.slab = 50625;
+            hl.rys = rys_host_tables();
             hl_init_tables(hl, sm.data());
             hl_quartet_block(hl, bra, ket, P.prims.data(), prim_cut, one_centre(bra), one_centre(ket), sm.data(), V.data());
             double sym = 1.0;

@@ -1,0 +1,24 @@
+// tests/host_emul/rys_host.cpp -- TEST INFRASTRUCTURE: the product's Rys evaluator (unomol_b200/csrc/rys_roots.cuh, a
+// host + device header) compiled as plain C++ so that the CPU suite can check it against the reference's roots and
+// weights (tests/golden/rys_grid.npz) and against its own defining moments.
+#include "../../unomol_b200/csrc/rys_roots.cuh"
+
+using namespace ub200;
+
+extern "C" int unomol_rys_host(int n, double x, int exact, double *r, double *w) {
+    const RysTables T = rys_host_tables(exact);
+    switch (n) {
+        case 1: rys_roots<1>(x, r, w, T); return 0;
+        case 2: rys_roots<2>(x, r, w, T); return 0;
+        case 3: rys_roots<3>(x, r, w, T); return 0;
+        case 4: rys_roots<4>(x, r, w, T); return 0;
+        case 5: rys_roots<5>(x, r, w, T); return 0;
+    }
+    return -1;
+}
+
+// F_0(x) .. F_3(x) through the grid path (x < 46)
+extern "C" void unomol_boys_host(double x, double *F) {
+    const RysTables T = rys_host_tables(0);
+    boys_grid<3>(x, T.boys, F);
+}

@@ -82,6 +82,7 @@ cudaError_t launch_any_class(unomol_b200 *h, int cb, int ck, const ClassTask &ta
     pair_class_l(ck, hl.lc, hl.ld);
     hl.scratch = h->d_hl_scratch;
     hl.slab = h->hl_slab;
+    hl.rys = h->rys;
     return launch_highl(task, hl, mode, std::min(grid, unomol_b200::HL_GRID), s);
 }
 static int any_groups_per_cta(int cb, int ck) { return is_highl(cb, ck) ? 1 : class_groups_per_cta(cb, ck); }
@@ -335,6 +336,7 @@ static int build_pairs(unomol_b200 *h) {
         CUDA_TRY(h, cudaMalloc(&d_q, sizeof(double) * L.n));
         CUDA_TRY(h, cudaMemcpyAsync(d_tl, tl.data(), sizeof(int2) * L.n, cudaMemcpyHostToDevice, h->stream));
         ClassTask task{};
+        task.rys = h->rys;
         task.bra = L.d_pairs; task.ket = L.d_pairs; task.prims = h->d_prims;
         task.nbra = L.n; task.nket = L.n;
         // no primitive cut here: the bound must hold for quartets whose partner pair is strong, where the
@@ -516,6 +518,7 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         // the runtime-L launches share one scratch area: keep them on one stream
         cudaStream_t st = pl.highl ? h->aux[0] : h->aux[io % unomol_b200::NAUX];
         ClassTask task{};
+        task.rys = h->rys;
         task.bra = h->cls[pl.cb].d_pairs; task.ket = h->cls[pl.ck].d_pairs; task.prims = h->d_prims;
         task.ket_hot = h->cls[pl.ck].d_hot;
         task.ket_count = pl.d_ket_count;
@@ -645,6 +648,7 @@ int unomol_b200_create(const unomol_basis_desc *b, int start_shell, int device, 
     B.xyz.assign(b->xyz, b->xyz + 3 * b->ncen);
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return UNOMOL_E_CUDA; }
     cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
+    if (rys_device_tables(&h->rys) != cudaSuccess) { unomol_b200_destroy(h); return UNOMOL_E_CUDA; }
     h->stats.nbf = B.nbf; h->stats.nshell = B.nshell; h->stats.rank = rank; h->stats.nranks = nranks;
     int rc = build_pairs(h);
     if (rc) { unomol_b200_destroy(h); return rc; }
@@ -691,6 +695,9 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
     if (!strcmp(name, "bra_split")) { h->bra_split_enabled = value != 0.0; return UNOMOL_OK; }
     if (!strcmp(name, "value_cut")) { h->value_cut = value; return UNOMOL_OK; }
     if (!strcmp(name, "debug_flags")) { h->debug_flags = (int)value; return UNOMOL_OK; }
+    // two-root quadrature: 0 = reproduce the reference's behaviour for 15 < X <= 40 (parity, default), 1 = exact.  The
+    // Schwarz bounds depend on it, so the pair tables are rebuilt.
+    if (!strcmp(name, "rys2_exact")) { h->rys.rys2_exact = value != 0.0; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "reg_kernels")) {
         h->use_reg_kernels = value != 0.0;
         if (h->pairs_ready) return build_plans(h);
@@ -889,6 +896,7 @@ int unomol_b200_eri_quartet(unomol_b200_t *h, int ish, int jsh, int ksh, int lsh
     CUDA_TRY(h, cudaMemcpyAsync(d_tl, &tl, sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(d_off, &off0, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
     ClassTask task{};
+        task.rys = h->rys;
     task.bra = h->cls[cb].d_pairs; task.ket = h->cls[ck].d_pairs; task.prims = h->d_prims;
     task.nbra = h->cls[cb].n; task.nket = h->cls[ck].n;
     task.prim_cut = h->prim_cut;
@@ -960,6 +968,7 @@ int unomol_b200_dump_eris(unomol_b200_t *h, double thresh, unomol_twoint *buf, s
         CUDA_TRY(h, cudaMemcpyAsync(d_tl, tl.data(), sizeof(int2) * tl.size(), cudaMemcpyHostToDevice, h->stream));
         CUDA_TRY(h, cudaMemcpyAsync(d_off, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice, h->stream));
         ClassTask task{};
+        task.rys = h->rys;
         task.bra = h->cls[cmb.cb].d_pairs; task.ket = h->cls[cmb.ck].d_pairs; task.prims = h->d_prims;
         task.nbra = nb; task.nket = nk; task.prim_cut = h->prim_cut;
         task.task_list = d_tl; task.task_out = d_off; task.ntask = (int)tl.size(); task.out = d_out;

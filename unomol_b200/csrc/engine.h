@@ -30,6 +30,8 @@ inline void pair_class_l(int cls, int &la, int &lb) {
     while ((la + 1) * (la + 2) / 2 <= cls) ++la;
     lb = cls - la * (la + 1) / 2;
 }
+// device addresses of the generated Rys / Boys tables on the current device (rys_tables.cu)
+cudaError_t rys_device_tables(RysTables *out);
 // runtime-L kernel for quartets with f/g shells (eri_highl.cu)
 struct HighLArgs;
 cudaError_t launch_highl(const ClassTask &task, const HighLArgs &hl, int mode, int grid, cudaStream_t stream);
@@ -69,6 +71,7 @@ struct unomol_b200 {
     cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr, nullptr, nullptr};
     ub200::HostBasis basis;
+    ub200::RysTables rys{};         // device table pointers + option "rys2_exact"
     double tau = 1e-12, prim_cut = 1e-12, value_cut = 1e-14;
     int use_reg_kernels = 1;
     int device_pairs = 1;           // option "device_pairs": build the pair tables on the GPU (0 = threaded host path)

@@ -64,6 +64,7 @@ struct HighLArgs {
     int la, lb, lc, ld;          // class of the bra list (la >= lb) and of the ket list (lc >= ld)
     double *scratch;             // per-CTA slabs for the Cartesian block
     long long slab;              // doubles per slab (>= ncart(la) ncart(lb) ncart(lc) ncart(ld))
+    RysTables rys;               // Boys grid / piecewise root tables (device pointers; host arrays in the emulation build)
 };
 
 HL_FN int hl_ncart(int l) { return (l + 1) * (l + 2) / 2; }
@@ -139,14 +140,14 @@ HL_FN void hl_vrr(double *G, int La, int Lb, double B00, double B1, double B1p, 
 }
 
 template <int NR>
-HL_FN void hl_roots_n(double X, double *rt, double *wt) { rys_roots<NR>(X, rt, wt); }
-HL_FN void hl_roots(int nr, double X, double *rt, double *wt) {
+HL_FN void hl_roots_n(double X, double *rt, double *wt, const RysTables &T) { rys_roots<NR>(X, rt, wt, T); }
+HL_FN void hl_roots(int nr, double X, double *rt, double *wt, const RysTables &T) {
     switch (nr) {
-        case 1: hl_roots_n<1>(X, rt, wt); break;
-        case 2: hl_roots_n<2>(X, rt, wt); break;
-        case 3: hl_roots_n<3>(X, rt, wt); break;
-        case 4: hl_roots_n<4>(X, rt, wt); break;
-        default: hl_roots_n<5>(X, rt, wt); break;
+        case 1: hl_roots_n<1>(X, rt, wt, T); break;
+        case 2: hl_roots_n<2>(X, rt, wt, T); break;
+        case 3: hl_roots_n<3>(X, rt, wt, T); break;
+        case 4: hl_roots_n<4>(X, rt, wt, T); break;
+        default: hl_roots_n<5>(X, rt, wt, T); break;
     }
 }
 
@@ -200,7 +201,7 @@ HL_FN unsigned long long hl_quartet_block(const HighLArgs &hl, const ShellPair &
                 const double pq[3] = {b.P[0] - k.P[0], b.P[1] - k.P[1], b.P[2] - k.P[2]};
                 const double X = b.p * k.p * itx * (pq[0] * pq[0] + pq[1] * pq[1] + pq[2] * pq[2]);
                 double rt[5], wt[5];
-                hl_roots(nr, X, rt, wt);
+                hl_roots(nr, X, rt, wt, hl.rys);
                 for (int tsk = tid; tsk < 3 * nr; tsk += nt) {
                     const int ir = tsk / 3, ax = tsk - 3 * ir;
                     const double dr = rt[ir] / (1.0 + rt[ir]);

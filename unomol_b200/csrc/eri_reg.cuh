@@ -275,19 +275,19 @@ __global__ void __launch_bounds__(ROWS ? REG_THREADS_ROWS : REG_THREADS) eri_reg
                         acc[0] += sr * X;   // timing experiment: no integral evaluation at all
                     } else if constexpr (NR == 1 && GI * GJ == 1) {
                         double w = 1.0, f1 = 0.0;
-                        if (!(task.debug_flags & 2)) rys1_f0f1(X, w, f1);
+                        if (!(task.debug_flags & 2)) rys1_f0f1(X, w, f1, task.rys);
                         acc[0] = fma(sr, w, acc[0]);
                     } else if constexpr (NR == 1) {
                         // (ps|ss): one root, G[1][0] = C per axis: sr*w*C = sr*(PA*w - q/(p+q)*PQ*F1)
                         double w = 1.0, f1 = 0.0;
-                        if (!(task.debug_flags & 2)) rys1_f0f1(X, w, f1);
+                        if (!(task.debug_flags & 2)) rys1_f0f1(X, w, f1, task.rys);
                         const double a = sr * w, bq = sr * f1 * k.p * itx;
                         acc[0] = fma(a, bp[ib].PA[0], fma(-bq, pq0, acc[0]));
                         acc[1] = fma(a, bp[ib].PA[1], fma(-bq, pq1, acc[1]));
                         acc[2] = fma(a, bp[ib].PA[2], fma(-bq, pq2, acc[2]));
                     } else {
                         double rt[NR], wt[NR];
-                        rys_roots<NR>(X, rt, wt);
+                        rys_roots<NR>(X, rt, wt, task.rys);
 #pragma unroll
                         for (int ir = 0; ir < NR; ++ir) {
                             const double dr = rt[ir] / (1.0 + rt[ir]);

@@ -1,19 +1,29 @@
-// unomol_b200/csrc/rys_roots.cuh -- Rys quadrature roots and weights, 1..5 roots, FP64.
-/*
- * GENERATED by oracle/tools/rys_extract.py -- do not edit by hand.
- * Piecewise fits for Rys roots/weights, 1..5 roots.  The fit COEFFICIENTS and band limits are those the
- * reference uses (reference Rys.cpp:314-2197; the classic fits for the Rys quadrature in X = rho*|PQ|^2),
- * required for 1e-12 per-integral parity; the evaluator is restated table-driven: each band is a short
- * list of Laurent polynomials in x or in y = x - x0 evaluated by Horner's rule, plus the band's closing
- * algebra.  Includes, on purpose, the reference's two-root behaviour for 15 < X <= 33 (Rys.cpp:614-624:
- * no dedicated fit, the (33,40] asymptotic form is used) -- see SURVEY.md section 7.
- * Product code (host+device).  r[i] = t_i^2/(1-t_i^2), w[i] = weights, as in reference Rys.hpp:145-164.
- * Horner steps are explicit fma(); in device code the coefficients come from a __constant__ table
- * (RC(i, literal)) so they are constant-bank operands of the DFMA instead of UMOV-materialised
- * immediates (ncu: 21 % of the issued instructions of the (ss|ss) kernel were UMOV before this).
- * exp(-x), 1/x, sqrt(pie4/x) and rsqrt(x) are evaluated once before the band dispatch (hoist_common in the
- * generator): the lanes of a warp land in different bands, and per-band copies ran with a few lanes each.
- */
+// unomol_b200/csrc/rys_roots.cuh -- Rys quadrature roots and weights for 1..5 roots, FP64, host + device.
+//
+// Replaces the reference's Rys::root1..root5 (reference Rys.cpp:314-2197, dispatch Rys.hpp:145-164): same
+// contract -- r[i] = t_i^2 / (1 - t_i^2), w[i] = weights of the n-point quadrature for the weight function
+// exp(-X t^2) on [0,1], roots ascending -- but an independent evaluator.  Nothing here is taken from the
+// reference's piecewise fits; all table data comes from tools/gen_rys_tables.py (mpmath, 60 digits):
+//
+//   * Boys function F_m(X) from ONE 16-byte table entry {F_10(X_i), exp(-X_i)} on the grid X_i = i/16: downward
+//     recursion at X_i (all terms positive: stable), an 8-term Taylor series for the highest order needed
+//     (dF_m/dX = -F_{m+1}), exp(-X) = exp(-X_i) exp(X_i - X) by the same 8 terms, downward recursion at X for the
+//     lower orders.  No exp(), sqrt() or division on this path and no X-dependent branch below the asymptotic
+//     limit, so the lanes of a warp stay together whatever their X (the reference's seven-band fits ran with 17 of
+//     32 lanes on average: profiles/r1_ncu_water154_top2_final.txt).
+//   * one root:  w = F_0, r = F_1 / (F_0 - F_1).
+//   * two roots: closed form from the moments F_0..F_3 (2x2 Hankel system -> monic orthogonal polynomial ->
+//     quadratic), differences of products evaluated with the fma correction.
+//   * 3..5 roots: degree-12 polynomials on unit intervals of X (coefficients in global memory, Horner), good to
+//     2.2e-16; beyond X = 52 / 58 / 64 the Gauss-Hermite limit.
+//
+// PARITY MODE (default, RysTables::rys2_exact == 0).  For two roots and 15 < X <= 40 the reference evaluates
+//     r_i = (a_i X + b_i) exp(-X) + R_i/(X - R_i),  w_1 = (a_w X + b_w) exp(-X) + W_1 sqrt(pi/4X),  w_0 = sqrt(pi/4X) - w_1
+// (reference Rys.cpp:614-624): the classic (33,40] form, which the reference ALSO applies to 15 < X <= 33 where its
+// dedicated fit is missing, so its two-root quadrature is off by up to 8.7e-7 there.  Per-quartet
+// parity at 1e-12 and SCF energies at 1e-9 Eh need that behaviour, so rys2_compat_band() below restates exactly
+// that formula with its six fit constants; everything else in the two-root routine is ours.  rys2_exact = 1 (engine
+// option "rys2_exact") uses the moment formula up to X = 46 instead and is the mathematically correct quadrature.
 #pragma once
 #include <math.h>
 
@@ -25,488 +35,31 @@
 
 namespace ub200 {
 
+// grid parameters (macros) and the Gauss-Hermite limits; the arrays live inside a constexpr function so that device
+// code can fold them after unrolling
 #ifdef __CUDACC__
-static __constant__ double rys_ctab[1881] = {
-    3e-07, -8.36313918003957e-8, 1.21222603512827e-6, -1.15662609053481e-5,
-    9.25197374512647e-5, -6.40994113129432e-4, 0.00378787044215009, -0.0185185172458485,
-    0.0714285713298222, -0.199999999997023, 0.333333333333318, -1.61702782425558e-10,
-    1.96215250865776e-9, -2.14234468198419e-8, 2.17216556336318e-7, -1.98850171329371e-6,
-    1.62429321438911e-5, -1.16740298039895e-4, 7.24888732052332e-4, -0.00379490003707156,
-    0.0161723488664661, -0.0529428148329736, 0.115702180856167, -2.62453564772299e-11,
-    3.24031041623823e-10, -3.614965656163e-9, 3.760256799971e-8, -3.553558319675e-7,
-    3.022556449731e-6, -2.290098979647e-5, 1.526537461148e-4, -8.81947375894379e-4,
-    0.00433207949514611, -0.0175257821619926, 0.0528406320615584, -3.1501078774085e-6,
-    0.46897511375022, -0.69955602298985, 0.53689283271887, -0.32883030418398,
-    0.24645596956002, -0.49984072848436, 0.785398163397448, -2.1916512131607e-5,
-    -0.18784686463512, 0.22991849164985, -0.49893752514047, -6.0156581186481e-5,
-    0.1962326414943, -0.4969524146449, -0.0290430236082028, 0.130693606237085,
-    -0.637623643058102, 2.86930639376291, -0.122713621927067, 0.652145154862545,
-    -0.210619711404725, 0.347854845137453, -2.35234358048491e-9, 2.49173650389842e-8,
-    -4.558315364581e-8, -2.447252174587e-6, 4.743292959463e-5, -5.33184749432408e-4,
-    0.00444654947116579, -0.0290430236084697, -2.4740490232917e-8, 2.36809910635906e-7,
-    1.83536773631e-6, -2.066168802076e-5, -1.345693393936e-4, -5.88154362858038e-5,
-    0.0532735082098139, -0.637623643056745, 2.86930639376289, -6.36859636616415e-12,
-    8.4741706477627e-11, -5.152207846962e-10, -3.846389873308e-10, 8.47225338838e-8,
-    -1.85306035634293e-6, 2.47191693238413e-5, -2.49018321709815e-4, 0.00219173220020161,
-    -0.0163329339286794, 0.0868085688285261, 1.45331350488343e-10, 2.07111465297976e-9,
-    -1.878920917404e-8, -1.725838516261e-7, 2.247389642339e-6, 9.76783813082564e-6,
-    -1.93160765581969e-4, -0.00158064140671893, 0.0485928174507904, -0.430761584997596,
-    1.8040097453795, -4.11560117487296e-12, 7.10910223886747e-11, -1.73508862390291e-9,
-    5.93066856324744e-8, -9.76085576741771e-7, 1.08484384385679e-5, -1.12608004981982e-4,
-    0.00116210907653515, -0.00989572595720351, 0.0612589701086408, -1.80555625241001e-10,
-    5.44072475994123e-10, 1.60349804524e-8, -1.497986283037e-7, -7.017002532106e-7,
-    1.85882653064034e-5, -2.04685420150802e-5, -0.00249327728643089, 0.0356550690684281,
-    -0.260417417692375, 1.12155283108289, -1.43632730148572e-16, 2.38198922570405e-16,
-    1.3583196188e-14, -7.064522786879e-14, -7.719300212748e-13, 7.802544789997e-12,
-    6.628721099436e-11, -1.775564159743e-9, 1.71382882399e-8, -1.497500187053e-7,
-    2.283485114279e-6, -3.76953869614706e-5, 4.74791204651451e-4, -0.00460448960876139,
-    0.0372458587837249, 2.487916227989e-14, -1.36113510175724e-13, -2.224334349799e-12,
-    4.190559455515e-11, -2.222722579924e-10, -2.624183464275e-9, 6.128153450169e-8,
-    -4.383376014528e-7, -2.4995220023291e-6, 1.0323664788832e-4, -0.00144614664924989,
-    0.0135094294917224, -0.0953478510453887, 0.54476524568679, -1.01041157064226e-5,
-    0.00119483054115173, -0.0673760231824074, 1.25705571069895, -23.8570496490846,
-    -8576.09422987199, 5910.05939591842, -1708.07677109425, 264.536689959503,
-    0.275255128608411, -0.275255128608411, 3.39024225137123e-4, -0.0934976436343509,
-    -4.2221648330632, 8.00839033297501, -2084.57050986847, -1049.99071905664,
-    339.891508992661, -156.184800325063, 2.72474487139158, -2.72474487139158,
-    -0.87894730749888, 10.9243702330261, -9.28903924275977, 81.0642367843811,
-    4.468573893084, -77.9250653461045, 0.0917517095361369, -0.00928875764357368,
-    0.0603769246832797, -0.119511285527878, 0.776823355931043, -1.02504611068957,
-    6.66279971938567, -0.0564876917232519, 0.467913934572691, -0.149077186455208,
-    0.360761573048137, -0.127768455150979, 0.171324492379169, -5.1018669153887e-10,
-    2.4013441570345e-8, -5.01081057744427e-7, 7.58291285499256e-6, -9.55085533670919e-5,
-    0.00102893039315878, -0.00928875764374337, 0.060376924683281, -1.29646524960555e-8,
-    7.74602292865683e-8, 1.56022811158727e-6, -1.58051990661661e-5, -3.30447806384059e-4,
-    0.00974266885190267, -0.119511285526388, 0.776823355931033, -9.28536484109606e-9,
-    -3.02786290067014e-7, -2.507344770642e-6, -7.32728109752881e-6, 2.44217481700129e-4,
-    0.0494758452357327, -1.02504611065774, 6.66279971938553, -7.6091148609885e-8,
-    1.09552870123182e-6, -1.03463270693454e-5, 8.16324851790106e-5, -5.55526624875562e-4,
-    0.00320512054753924, -0.015151513983854, 0.0555555554649585, -0.142857142854412,
-    0.199999999999986, 1.44687969563318e-12, 4.85300143926755e-12, -6.55098264095516e-10,
-    1.56592951656828e-8, -2.60122498274734e-7, 3.86118485517386e-6, -5.13430986707889e-5,
-    6.03194524398109e-4, -0.0061121934982509, 0.0452578254679079, 6.95964248788138e-10,
-    -5.35281831445517e-9, -6.745205954533e-8, 1.502366784525e-6, 9.923326947376e-7,
-    -3.89147469249594e-4, 0.00751549330892401, -0.08487781203634, 0.573928229597613,
-    -2.81496588401439e-10, 3.61058041895031e-9, 4.53631789436255e-8, -1.40971837780847e-7,
-    -6.05865557561067e-6, -5.15964042227127e-5, 3.34761560498171e-5, 0.0504871005319119,
-    -0.824708946991557, 4.81234667357205, -1.4804423107214e-10, 1.78157031325097e-9,
-    -1.92514145088973e-8, 1.92804632038796e-7, -1.73806555021045e-6, 1.39195169625425e-5,
-    -9.74574633246452e-5, 5.83701488646511e-4, -0.00289955494844975, 0.011384700111381,
-    -0.0323446977320647, 0.0529428148329709, 1.44265709189601e-11, -4.66622033006074e-10,
-    7.649155832025e-9, -1.229940017368e-7, 2.026002142457e-6, -2.87048671521677e-5,
-    3.70326938096287e-4, -0.00421006346373634, 0.0350898470729044, -2.65526039155651e-11,
-    1.97549041402552e-10, 2.15971131403034e-9, -7.95045680685193e-8, 5.15021914287057e-7,
-    1.11788717230514e-5, -3.33739312603632e-4, 0.00530601428208358, -0.0593483267268959,
-    0.431180523260239, -3.92833750584041e-10, -4.1642322978228e-9, 4.42413039572867e-8,
-    6.40574545989551e-7, -3.05512456576552e-6, -1.05296443527943e-4, -6.14120969315617e-4,
-    0.0489665802767005, -0.624498381002855, 3.36412312243724, -2.36788772599074e-11,
-    2.89147476459092e-10, -3.18111322308846e-9, 3.25336816562485e-8, -3.00873821471489e-7,
-    2.48749160874431e-6, -1.81353179793672e-5, 1.14504948737066e-4, -6.10614987696677e-4,
-    0.00264584212770942, -0.00866415899015349, 0.0175257821619922, 5.74429401360115e-16,
-    7.11884203790984e-16, -6.736701449826e-14, -6.264613873998e-13, 1.31541892704e-11,
-    -4.23879635610964e-11, 1.39032379769474e-9, -4.65449552856856e-8, 7.34609900170759e-7,
-    -1.08656008854077e-5, 1.77930381549953e-4, -0.00239864911618015, 0.0239112249488821,
-    1.1346409620912e-14, 6.99375313934242e-15, -8.595618132088e-13, -5.293620408757e-12,
-    -2.492175211635e-11, 2.73681574882729e-9, -1.06656985608482e-8, -4.40252529648056e-7,
-    9.68100917793911e-6, -1.68211091755327e-4, 0.00269443611274173, -0.0323845035189063,
-    0.275969447451882, 6.66339416996191e-15, 1.84955640200794e-13, -1.985141104444e-12,
-    -2.309293727603e-11, 3.917984522103e-10, 1.663165279876e-9, -6.205591993923e-8,
-    8.769581622041e-9, 8.97224398620038e-6, -3.14232666170796e-5, -0.00183917335649633,
-    0.0351246831672571, -0.32233505127086, 1.7358283175543, 4.4213300128309e-16,
-    -2.77189767070441e-15, -4.084026087887e-14, 5.379885121517e-13, 1.882093066702e-12,
-    -8.67286219861085e-11, 7.11372337079797e-10, -3.55578027040563e-9, 1.29454702851936e-7,
-    -4.14222202791434e-6, 8.04427643593792e-5, -0.00118587782909876, 0.0153435577063174,
-    6.85146742119357e-15, -1.08257654410279e-14, -8.579165965128e-13, 6.642452485783e-12,
-    4.798806828724e-11, -1.13413908163831e-9, 7.08558457182751e-9, -5.59678576054633e-8,
-    2.51020389884249e-6, -6.63678914608681e-5, 0.00111888323089714, -0.0145361636398178,
-    0.165077877454402, 3.20622388697743e-15, -2.73458804864628e-14, -3.157134329361e-13,
-    8.654129268056e-12, -5.625235879301e-11, -7.718080513708e-10, 2.064664199164e-8,
-    -1.567725007761e-7, -1.57938204115055e-6, 6.27436306915967e-5, -0.00101308723606946,
-    0.0113901881430697, -0.10144965289945, 0.777203937334739, -2.43270989903742e-6,
-    3.57901398988359e-4, -0.0234112415981143, 0.781425144913975, -17.3209218219175,
-    243.517435690398, -2079.70687843258, -19761.1541576986, 9824.41363463929,
-    0.190163509193487, -0.190163509193487, -2.62627010965435e-4, 0.0349187925428138,
-    -3.0933761873188, 107.037141010778, -2366.59637247087, 33520.2872835409,
-    -2916691.1368102, 1411295.05262758, -291532.335433779, 1.78449274854325,
-    -1.78449274854325, 9.31856404738601e-5, -0.0287029400759565, -0.783503697918455,
-    -18.4338896480695, 404.996712650414, -6881.45821789955, -189829.509315154,
-    51149.8390849158, 5.52534374226326, -5.52534374226326, -4.97561537069643e-4,
-    -0.0500929599665316, 1.31099142238996, -18.8336409225481, 164.931462413877,
-    -660.344754467191, -0.00448218898474906, -0.517373211334924, 11.3691058739678,
-    -165.426392885291, 1522.31757709236, -6309.09125686731, -0.0138368602394293,
-    -1.77293428863008, 17.3639054044562, -357.615122086961, 2698.31813951849,
-    -14573.4701095912, -7.39058467995275, 321.318352526305, -3994.33696473658,
-    -73.8726243906513, 3135.69966333873, -38686.2867311321, -263.750565461336,
-    10441.2168692352, -128094.577915394, 0.152258947224714, -8.30661900042651,
-    192.977367967984, -1677.87926005344, 0.00511156880411248, 61.5072615497811,
-    -2919.80647450269, 38079.4303087338, 0.177231492083829, -0.00409645850660395,
-    0.0348198973061471, -0.0448902570656719, 0.381567185080042, -0.204389090547327,
-    1.73730726945891, -1.39368301742312, 11.8463056481549, -0.0313844305713928,
-    0.362683783378362, -0.0898046242557724, 0.313706645877886, -0.129314370958973,
-    0.222381034453372, -0.0828299075414321, 0.101228536290376, -1.95309614628539e-10,
-    5.19765728707592e-9, -1.01756452250573e-7, 1.72365935872131e-6, -2.61203523522184e-5,
-    3.5292130876988e-4, -0.00409645850658433, 0.0348198973061469, -1.89554881382342e-8,
-    3.07583114342365e-7, 1.270981734393e-6, -1.417298563884e-4, 0.003226979163176,
-    -0.0448902570678178, 0.381567185080039, 1.77280535300416e-9, 3.36524958870615e-8,
-    -2.58341529013893e-7, -1.1364489566232e-5, -7.91549618884063e-5, 0.0103825827346828,
-    -0.204389090525137, 1.73730726945889, -5.61188882415248e-8, -2.4948073307246e-7,
-    3.428685057114e-6, 1.679007454539e-4, 0.04722855585715, -1.39368301737828,
-    11.8463056481543, -1.14649303201279e-8, 1.88015570196787e-7, -2.33305875372323e-6,
-    2.68880044371597e-5, -2.94268428977387e-4, 0.00306548909776613, -0.0313844305680096,
-    0.362683783378335, -4.11720483772634e-9, 6.54963481852134e-8, -7.20045285129626e-7,
-    6.93779646721723e-6, -6.05367572016373e-5, 4.74241566251899e-4, -0.00326956188125316,
-    0.0191883866626681, -0.0898046242565811, -3.41688436990215e-8, 5.07238960340773e-7,
-    -5.0167562840822e-6, 4.20363420922845e-5, -3.08040221166823e-4, 0.00194431864731239,
-    -0.0102477820460278, 0.0428670143840073, -0.129314370962569, 0.222381034453369,
-    4.99660550769508e-9, -7.9458596331012e-8, 8.359072409485e-7, -7.42236921061e-6,
-    5.76337430816e-5, -3.86645606718233e-4, 0.00218417516259781, -0.00999791027771119,
-    0.034879109737737, -0.0828299075413889, -1.48570633747284e-15, -1.33273068108777e-13,
-    4.06854369667e-12, -9.163164161821e-11, 2.046819017845e-9, -4.03076426299031e-8,
-    7.29407420660149e-7, -1.23118059980833e-5, 1.88796581246938e-4, -0.00253262912046853,
-    0.0251198234505021, 1.35830583483312e-13, -2.29772605964836e-12, -3.821500128045e-12,
-    6.844424214735e-10, -1.048063352259e-8, 1.50083186233363e-8, 3.48848942324454e-6,
-    -1.08694174399193e-4, 0.00208048885251999, -0.0291205805373793, 0.272276489515713,
-    5.02799392850289e-13, 1.07461812944084e-11, -1.482277886411e-10, -2.153585661215e-9,
-    3.654087802817e-8, 5.1592957583012e-7, -9.52388379435709e-6, -2.16552440036426e-4,
-    0.0090355146956832, -0.145505469175613, 1.21449092319186, -1.08510370291979e-12,
-    6.41492397277798e-11, 7.542387436125e-10, -2.213111836647e-9, -1.448228963549e-7,
-    -1.95670833237101e-6, -1.07481314670844e-5, 1.49335941252765e-4, 0.0487791531990593,
-    -1.10559909038653, 8.0950202861178, -4.65801912689961e-14, 7.586695071068e-13,
-    -1.186387548048e-11, 1.862334710665e-10, -2.799399389539e-9, 4.148972684255e-8,
-    -5.9335680796e-7, 8.168349266115e-6, -1.08989176177409e-4, 0.00141357961729531,
-    -0.0187588361833659, 0.289898651436026, -1.46345073267549e-14, 2.25644205432182e-13,
-    -3.116258693847e-12, 4.32190875661e-11, -5.673270062669e-10, 7.00629596296e-9,
-    -8.120186517e-8, 8.77529464577e-7, -8.77829235749024e-6, 8.04372147732379e-5,
-    -6.64149238804153e-4, 0.00481181506827225, -0.0288982669486183, 0.156247249979288,
-    9.06812118895365e-15, -1.40541322766087e-13, 1.919270015269e-12, -2.60513573901e-11,
-    3.299685839012e-10, -3.86354139348735e-9, 4.16265847927498e-8, -4.0946283547147e-7,
-    3.64018881086111e-6, -2.88665153269386e-5, 2.00515819789028e-4, -0.00118791896897934,
-    0.00575223633388589, -0.0209400418772687, 0.0485368861938873, -9.74835552342257e-16,
-    1.57857099317175e-14, -2.249993780112e-13, 3.173422008953e-12, -4.16115945968e-11,
-    5.021343560166e-10, -5.545047534808e-9, 5.554146993491e-8, -4.99048696190133e-7,
-    3.96650392371311e-6, -2.73816413291214e-5, 1.60106988333186e-4, -7.64560567879592e-4,
-    0.00281330044426892, -0.00716227030134947, 0.00966077262223353, 4.64217329776215e-15,
-    -6.27892383644164e-15, 3.462236347446e-13, -2.92722935535e-11, 5.090355371676e-10,
-    -9.97272656345253e-9, 2.37835295639281e-7, -4.60301761310921e-6, 8.42824204233222e-5,
-    -0.00137983082233081, 0.0166630865869375, 2.93981127919047e-14, 8.47635639065744e-13,
-    -1.446314544774e-11, -6.149155555753e-12, 8.484275604612e-10, -6.10898827887652e-8,
-    2.39156093611106e-6, -5.35837089462592e-5, 0.00100967602595557, -0.0157769317127372,
-    0.174853819464285, 2.93523563363e-14, -6.4004177666702e-14, -2.695740446312e-12,
-    1.027082960169e-10, -5.82203865678e-10, -3.159991002539e-8, 4.327249251331e-7,
-    4.856768455119e-6, -2.54617989427762e-4, 0.00554843378106589, -0.0795013029486684,
-    0.720206142703162, -1.62212382394553e-14, 7.68943641360593e-13, 5.764015756615e-12,
-    -1.380635298784e-10, -1.476849808675e-9, 1.84347052385605e-8, 3.34382940759405e-7,
-    -1.39428366421645e-6, -7.50249313713996e-5, -6.26495899187507e-4, 0.0469716410901162,
-    -0.666871297428209, 4.11207530217806, -1.65995045235997e-15, 6.91838935879598e-14,
-    -9.131223418888e-13, 1.403341829454e-11, -3.672235069444e-10, 6.36696254699e-9,
-    -1.039220021671e-7, 1.959098751715e-6, -3.33474893152939e-5, 5.72164211151013e-4,
-    -0.0105583210553392, 0.226696066029591, -3.57248951192047e-16, 6.25708409149331e-15,
-    -9.657033089714e-14, 1.507864898748e-12, -2.33252225611e-11, 3.428545616603e-10,
-    -4.698730937661e-9, 6.21997763513e-8, -7.83008889613661e-7, 9.08621687041567e-6,
-    -9.86368311253873e-5, 9.69632496710088e-4, -0.00814594214284187, 0.0850218447733457,
-    1.64742458534277e-16, -2.6851226592841e-15, 3.788890667676e-14, -5.508918529823e-13,
-    7.555896810069e-12, -9.69039768312637e-11, 1.16034263529672e-9, -1.28771698573873e-8,
-    1.31949431805798e-7, -1.23673915616005e-6, 1.04189803544936e-5, -7.79566003744742e-5,
-    5.03162624754434e-4, -0.00255138844587555, 0.0113250730954014, -1.55714130075679e-17,
-    2.57193722698891e-16, -3.626606654097e-15, 5.234734676175e-14, -7.067105402134e-13,
-    8.79351266489e-12, -1.006088923498e-10, 1.050565098393e-9, -9.91517881772662e-9,
-    8.35835975882941e-8, -6.19785782240693e-7, 3.95841149373135e-6, -2.11366761402403e-5,
-    9.00474771229507e-5, -2.78777909813289e-4, 5.26543779837487e-4, 4.94869622744119e-17,
-    8.0356880573916e-16, -5.599125915431e-15, -1.378685560217e-13, 7.006511663249e-13,
-    1.30391406991118e-11, 8.06987313467541e-11, -5.20644072732933e-9, 7.72794187755457e-8,
-    -1.61512612564194e-6, 4.15083811185831e-5, -7.87855975560199e-4, 0.0114189319050009,
-    4.89224285522336e-16, 1.06390248099712e-14, -5.446260182933e-14, -1.613630106295e-12,
-    3.910179118937e-12, 1.90712434258806e-10, 8.78470199094761e-10, -5.97332993206797e-8,
-    9.25750831481589e-7, -2.02362185197088e-5, 4.92341968336776e-4, -0.00868438439874703,
-    0.115825965127958, 6.12419396208408e-14, 1.12328861406073e-13, -9.051094103059e-12,
-    -4.781797525341e-11, 1.660828868694e-9, 4.499058798868e-10, -2.519549641933e-7,
-    4.97744404018e-6, -1.25858350034589e-4, 0.00270279176970044, -0.0399327850801083,
-    0.433467200855434, 4.63414725924048e-14, -4.72757262693062e-14, -1.001926833832e-11,
-    6.074107718414e-11, 1.576976911942e-9, -2.01186401974027e-8, -1.84530195217118e-7,
-    5.02333087806827e-6, 9.66961790843006e-6, -0.00158522208889528, 0.0280539673938339,
-    -0.278953904330072, 1.82835655238235, 2.90401781000996e-18, -4.63389683098251e-17,
-    6.274018198326e-16, -8.936002188168e-15, 1.194719074934e-13, -1.45501321259466e-12,
-    1.64090830181013e-11, -1.71987745310181e-10, 1.63738403295718e-9, -1.39237504892842e-8,
-    1.06527318142151e-7, -7.27634957230524e-7, 4.12159381310339e-6, -1.74648169719173e-5,
-    8.50290130067818e-5, -4.1956914545948e-17, 5.94344180261644e-16, -1.148797566469e-14,
-    1.881303962576e-13, -2.413554618391e-12, 3.372127423047e-11, -4.933988617784e-10,
-    6.116545396281e-9, -6.69965691739299e-8, 7.52380085447161e-7, -8.08708393262321e-6,
-    6.88603417296672e-5, -4.67067112993427e-4, 0.00542313365864597, -6.22272689880615e-15,
-    1.04126809657554e-13, -6.842418230913e-13, 1.576841731919e-11, -4.203948834175e-10,
-    6.287255934781e-9, -8.307159819228e-8, 1.356478091922e-6, -2.08065576105639e-5,
-    2.5239673033234e-4, -0.00294484050194539, 0.0601396183129168, 4.36701759531398e-17,
-    -1.12860600219889e-16, -6.149849164164e-15, 5.820231579541e-14, 4.396602872143e-13,
-    -1.24330365320172e-11, 6.71083474044549e-11, 2.43865205376067e-10, 1.67559587099969e-8,
-    -9.32738632357572e-7, 2.39030487004977e-5, -4.68648206591515e-4, 0.00834977776583956,
-    4.98913142288158e-16, -2.60732537093612e-16, -7.775156445127e-14, 5.766105220086e-13,
-    6.4326967296e-12, -1.39571683725792e-10, 5.95451479522191e-10, 2.42471442836205e-9,
-    2.4748571014312e-7, -1.14710398652091e-5, 2.71252453754519e-4, -0.00496812745851408,
-    0.082602060202678, 1.91498302509009e-15, 1.48840394311115e-14, -4.316925145767e-13,
-    1.186495793471e-12, 4.615806713055e-11, -5.54336148667141e-10, 3.48789978951367e-10,
-    -2.79188977451042e-9, 2.09563208958551e-6, -6.76512715080324e-5, 0.00132129867629062,
-    -0.0205062147771513, 0.288068671894324, -5.43697691672942e-15, -1.12483395714468e-13,
-    2.826607936174e-12, -1.26673449328e-11, -4.258722866437e-10, 9.45486578503261e-9,
-    -5.86635622821309e-8, -1.28835028104639e-6, 4.41413815691885e-5, -7.61738385590776e-4,
-    0.0096609090298555, -0.101410568057649, 0.954714798156712, -7.56882223582704e-19,
-    7.53541779268175e-18, -1.157318032236e-16, 2.411195002314e-15, -3.601794386996e-14,
-    4.082150659615e-13, -4.289542980767e-12, 5.086829642731e-11, -6.35435561050807e-10,
-    6.82309323251123e-9, -5.63374555753167e-8, 3.57005361100431e-7, -2.40050045173721e-6,
-    4.94171300536397e-5, -5.54451040921657e-17, 2.68748367250999e-16, 1.349020069254e-14,
-    -2.507452792892e-13, 1.944339743818e-12, -1.29816917658823e-11, 3.49977768819641e-10,
-    -8.67270669346398e-9, 1.31381116840118e-7, -1.36790720600822e-6, 1.1921069767316e-5,
-    -1.42181943986587e-4, 0.00412615396191829, -1.865060577297e-16, 1.16661114435809e-15,
-    2.563712856363e-14, -4.498350984631e-13, 1.765194089338e-12, 9.04483676345625e-12,
-    4.98930345609785e-10, -2.11964170928181e-8, 3.98295476005614e-7, -5.49390160829409e-6,
-    7.74065155353262e-5, -0.00148201933009105, 0.0497836392625268, -4.45711399441838e-5,
-    0.00127267770241379, -0.236954961381262, 15.4330657903756, -522.799159267808,
-    10595.1216669313, -129194.382386499, -2511772.35556236, 872975.373557709,
-    0.145303521503316, -0.145303521503316, -0.0785617372254488, 6.35653573484868,
-    -338.29693876399, 12512.0495802096, -316847.570511637, 5386142.11391604,
-    -1024274661.27427, 370104713.293016, -58711900.5093822, 1.33909728812636,
-    -1.33909728812636, -0.237900485051067, 18.4122184400896, -1002.00731304146,
-    37515.1841595736, -950626.66339013, 16041939.0230055, -2881390146.51985,
-    1066259150.44526, -172465289.687396, 3.92696350135829, -3.92696350135829,
-    -6.00691586407385e-4, -0.364479545338439, 15.7496131755179, -654.944248734901,
-    17083.0039597097, -290517.939780207, 2968179.40164703, 34905969.8304732,
-    -16494452.2586065, 8.58863568901199, -8.58863568901199, 2.33766206773151e-7,
-    -3.81542906607063e-5, 0.00351416601267, -0.166538571864728, 4.80006136831847,
-    -87.3165934223603, 977.683627474638, -6144.79071209961, 16600.094511764,
-    2.25229076750736e-4, 2.36392855180768e-4, -0.00916785337967013, 0.462186525041313,
-    -19.694378600654, 499.169195295559, -6214.1984584509, -2815.01182042707,
-    52144505.3212414, -13411346.4389309, 1136732.98305631, 0.0192704402415764,
-    7.29841848989391e-4, -0.0353899555749875, 2.07797425718513, -100.464709786287,
-    3152.06108877819, -62705.4715090012, 767135.400969617, 15472124.6264919,
-    -5260743.91316381, 0.234479815323517, 5.74245945342286e-6, -7.58735928102351e-5,
-    2.35072857922892e-4, -0.00378812134013125, 0.309871652785805, -7.11108633061306,
-    55.5297573149528, -0.00219135070169653, -0.119108256987623, -0.750238795695573,
-    -9.65842534508637e-4, -0.0449822013469279, 0.608784033347757, -3.62569791162153e-4,
-    -0.00909231717268466, 0.184336760556262, -4.075575259146e-5, -6.88846864931685e-4,
-    0.0174725309199384, 5.7663198200099e-6, -7.8918728380489e-5, 3.28297971853126e-4,
-    2.0829496985723e-4, -0.00377489954837361, 0.0209857151617436, 6.16374517326469e-4,
-    -0.0126711744680092, 0.0814504890732155, -0.00215865967920897, 0.0226659266316985,
-    -0.0220258754389745, 0.231271692140903, -0.0816520023025515, 0.857346024118836,
-    -0.283193369647137, 2.97353038120346, -1.75382723579439, 18.4151859759051,
-    -0.0196867576909777, 0.295524224714752, -0.0561737590184721, 0.269266719309995,
-    -0.0971152726793658, 0.219086362515981, -0.102979262193565, 0.14945134915058,
-    -0.0573782817488315, 0.0666713443086877, -4.46679165328413e-11, 1.21879111988031e-9,
-    -2.62975022612104e-8, 5.15106194905897e-7, -9.27933625824749e-6, 1.51794097682482e-4,
-    -0.00215865967920301, 1.93117331714174e-10, -4.57267589660699e-9, 2.48339908218932e-8,
-    1.50716729438474e-6, -6.07268757707381e-5, 0.00137506939145643, -0.0220258754419939,
-    0.231271692140905, 4.84989776180094e-9, 1.31538893944284e-7, -2.766753852879e-6,
-    -7.651163510626e-5, 0.004033058545972, -0.0816520022916145, 0.857346024118779,
-    -2.48581772214623e-7, -4.34482635782585e-6, -7.4601825798763e-7, 0.0101210776517279,
-    -0.283193369640005, 2.97353038120345, -8.92432153868554e-9, 1.77288899268988e-8,
-    3.040754680666e-6, 1.058229325071e-4, 0.04596379534985, -1.75382723579114,
-    18.4151859759049, -2.03822632771791e-9, 3.8911022913381e-8, -5.84914787904823e-7,
-    8.30316168666696e-6, -1.13218402310546e-4, 0.0014912888858679, -0.0196867576904816,
-    0.295524224714749, 8.6284811839757e-9, -1.38975551148989e-7, 1.602894068228e-6,
-    -1.646364300836e-5, 1.538445806778e-4, -0.00128848868034502, 0.00938866933338584,
-    -0.0561737590178812, 0.269266719309991, -9.41953204205665e-9, 1.47452251067755e-7,
-    -1.57456991199322e-6, 1.45098401798393e-5, -1.18858834181513e-4, 8.5369767598421e-4,
-    -0.00522877807397165, 0.0260854524809786, -0.0971152726809059, 0.219086362515979,
-    -3.84961617022042e-8, 5.6659539654447e-7, -5.52351805403748e-6, 4.53160377546073e-5,
-    -3.22542784865557e-4, 0.00195682017370967, -0.00977232537679229, 0.0379455945268632,
-    -0.102979262192227, 0.149451349150573, 4.0959481252143e-9, -6.47097874264417e-8,
-    6.743541482689e-7, -5.917993920224e-6, 4.531969237381e-5, -2.99102856679638e-4,
-    0.00165695765202643, -0.00740671222520653, 0.0250889946832192, -0.0573782817487958,
-    -2.58163897135138e-14, 8.14127461488273e-13, -2.11414838976129e-11, 5.09822003260014e-10,
-    -1.16002134438663e-8, 2.4681069441454e-7, -4.92556826124502e-6, 9.02580687971053e-5,
-    -0.00145190025120726, 0.0173416786387475, 1.04525287289788e-14, 5.44611782010773e-14,
-    -4.831059411392e-12, 1.136643908832e-10, -1.104373076913e-9, -2.35346740649916e-8,
-    1.43772622028764e-6, -4.23405023015273e-5, 9.12034574793379e-4, -0.0152479441718739,
-    0.176055265928744, -6.89693150857911e-14, 5.92064260918861e-13, 1.847170956043e-11,
-    -3.390752744265e-10, -2.995532064116e-9, 1.57456141058535e-7, -3.95859409711346e-7,
-    -9.58924580919747e-5, 0.00323551502557785, -0.0597587007636479, 0.646432853383057,
-    -3.61293809667763e-12, -2.70803518291085e-11, 8.83758848468769e-10, 1.59166632851267e-8,
-    -1.32581997983422e-7, -7.60223407443995e-6, -7.41019244900952e-5, 0.00981432631743423,
-    -0.223055570487771, 2.21460798080643, 7.12332088345321e-13, 3.16578501501894e-12,
-    -8.776668218053e-11, -2.342817613343e-9, -3.496962018025e-8, -3.03172870136802e-7,
-    1.50511293969805e-6, 1.37704919387696e-4, 0.0470723869619745, -1.47486623003693,
-    13.5704792175847, 1.04348658616398e-13, -1.94147461891055e-12, 3.485512360993e-11,
-    -6.277497362235e-10, 1.100758247388e-8, -1.88329804969573e-7, 3.12338120839468e-6,
-    -5.04404167403568e-5, 8.00338056610995e-4, -0.0130892406559521, 0.247383140241103,
-    3.23496149760478e-14, -5.24314473469311e-13, 7.743219385056e-12, -1.146022750992e-10,
-    1.615238462197e-9, -2.15479017572233e-8, 2.70933462557631e-7, -3.18750295288531e-6,
-    3.47425221210099e-5, -3.45558237388223e-4, 0.00305779768191621, -0.0229118251223003,
-    0.159834227924213, -3.42790561802876e-14, 5.26475736681542e-13, -7.184330797139e-12,
-    9.763932908544e-11, -1.244014559219e-9, 1.472744068942e-8, -1.611749975234e-7,
-    1.616487851917e-6, -1.46852359124154e-5, 1.18900349101069e-4, -8.37562373221756e-4,
-    0.00493752683045845, -0.0225514728915673, 0.0695211812453929, 1.04072340345039e-14,
-    -1.60808044529211e-13, 2.183534866798e-12, -2.939403008391e-11, 3.679254029085e-10,
-    -4.23775673047899e-9, 4.46559231067006e-8, -4.26488836563267e-7, 3.64721335274973e-6,
-    -2.74868382777722e-5, 1.78586118867488e-4, -9.68428981886534e-4, 0.00416002324339929,
-    -0.0128290192663141, 0.0222353727685016, -8.16770412525963e-16, 1.31376515047977e-14,
-    -1.856950818865e-13, 2.596836515749e-12, -3.372639523006e-11, 4.025371849467e-10,
-    -4.389453269417e-9, 4.332753856271e-8, -3.82673275931962e-7, 2.98006900751543e-6,
-    -2.00718990300052e-5, 1.13876001386361e-4, -5.23627942443563e-4, 0.00183524565118203,
-    -0.00437785737450783, 0.00536963805223095, -1.13825201010775e-14, 1.89737681670375e-13,
-    -4.81561201185876e-12, 1.56666512163407e-10, -3.73782213255083e-9, 9.15858355075147e-8,
-    -2.13775073585629e-6, 4.56547356365536e-5, -8.6800390932374e-4, 0.0122703754069176,
-    -3.67160504428358e-15, 1.27876280158297e-14, -1.296476623788e-12, 1.477175434354e-11,
-    5.464102147892e-10, -2.42538340602723e-8, 8.20460740637617e-7, -2.20379304598661e-5,
-    4.90295372978785e-4, -0.00914294111576119, 0.12259040340369, 1.39017367502123e-14,
-    -6.9639138542689e-13, 1.176946020731e-12, 1.725627235645e-10, -3.6863838563e-9,
-    2.87495324207095e-8, 1.71307311000282e-6, -7.94273603184629e-5, 0.00200938064965897,
-    -0.0363329491677178, 0.434393683888443, -1.27815158195209e-14, 1.99910415869821e-14,
-    3.753542914426e-12, -2.708018219579e-11, -1.190574776587e-9, 1.106696436509e-8,
-    3.954955671326e-7, -4.398596059588e-6, -2.01087998907735e-4, 0.00789092425542937,
-    -0.142056749162695, 1.39964149420683, -1.19442341030461e-13, -2.34074833275956e-12,
-    6.861649627426e-12, 6.082671496226e-10, 5.38116010542e-9, -6.2532971387e-8,
-    -2.13596683505e-6, -2.373394341886e-5, 2.88711171412814e-6, 0.0485221195290753,
-    -1.04346091985269, 7.89901551676692, 7.95526040108997e-15, -2.48593096128045e-13,
-    4.76124620872e-12, -9.535763686605e-11, 2.225273630974e-9, -4.49796778054865e-8,
-    9.17812870287386e-7, -1.86764236490502e-5, 3.76807779068053e-4, -0.00810456360143408,
-    0.201097936411496, 1.25678686624734e-15, -2.34266248891173e-14, 3.973252415832e-13,
-    -6.830539401049e-12, 1.140771033372e-10, -1.82546185762009e-9, 2.77209637550134e-8,
-    -4.01726946190383e-7, 5.48227244014763e-6, -6.95676245982121e-5, 8.05193921815776e-4,
-    -0.00815528438784469, 0.0971769901268114, -8.20929494859896e-16, 1.37356038393016e-14,
-    -2.02286306522e-13, 3.058055403795e-12, -4.387890955243e-11, 5.923946274445e-10,
-    -7.503659964159e-9, 8.851599803902e-8, -9.65561998415038e-7, 9.60884622778092e-6,
-    -8.56551787594404e-5, 6.66057194311179e-4, -0.00417753183902198, 0.0225443826852447,
-    -1.0876461248879e-17, 1.85299909689937e-16, -2.730195628655e-15, 4.127368817265e-14,
-    -5.881379088074e-13, 7.805245193391e-12, -9.632707991704e-11, 1.099047050624e-9,
-    -1.15042731790748e-8, 1.09415155268932e-7, -9.33687124875935e-7, 7.02338477986218e-6,
-    -4.53759748787756e-5, 2.41722511389146e-4, -9.75935943447037e-4, 0.00257520532789644,
-    7.28996979748849e-19, -1.26518146195173e-17, 1.886145834486e-16, -2.876728287383e-15,
-    4.114588668138e-14, -5.44436631413933e-13, 6.64976446790959e-12, -7.4456006997494e-11,
-    7.57553198166848e-10, -6.92956101109829e-9, 5.62222859033624e-8, -3.97500114084351e-7,
-    2.3903912613814e-6, -1.18023950002105e-5, 4.52254031046244e-5, -1.2111378215037e-4,
-    1.75013126731224e-4, -4.16387977337393e-17, 7.2087299737386e-16, 1.395993802064e-14,
-    3.660484641252e-14, -4.154857548139e-12, 2.301379846544e-11, -1.033307012866e-9,
-    3.997777641049e-8, -9.35118186333939e-7, 2.38589932752937e-5, -5.35185183652937e-4,
-    0.00885218988709735, -4.56279214732217e-16, 6.24941647247927e-15, 1.737896339191e-13,
-    8.964205979517e-14, -3.538906780633e-11, 9.561341254948e-11, -9.77283189131e-9,
-    4.24034019462e-7, -1.02384302866534e-5, 2.57987709704822e-4, -0.00554735977651677,
-    0.0868245143991948, -2.52879337929239e-15, 2.13925810087833e-14, 7.884307667104e-13,
-    -9.02339815951e-13, -5.814101544957e-11, -1.333480437968e-9, -2.217064940373e-8,
-    1.643290788086e-6, -4.39602147345028e-5, 0.00108648982748911, -0.0213014521653498,
-    0.294150684465425, -6.42391438038888e-15, 5.37848223438815e-15, 8.960828117859e-13,
-    5.214153461337e-11, -1.106601744067e-10, -2.007890743962e-8, 1.543764346501e-7,
-    4.520749076914e-6, -1.88893338587047e-4, 0.00473264487389288, -0.0791197893350253,
-    0.860057928514554, -2.24366166957225e-14, 4.87224967526081e-14, 5.587369053655e-12,
-    -3.045253104617e-12, -1.22398388308e-9, -2.05603889396319e-9, 2.58604071603561e-7,
-    1.34240904266268e-6, -5.72877569731162e-5, -9.56275105032191e-4, 0.0423367010370921,
-    -0.576800927133412, 3.87328263873381, 8.98007931950169e-15, 7.25673623859497e-14,
-    5.851494250405e-14, -4.234204823846e-11, 3.911507312679e-10, -9.65094802088511e-9,
-    3.42197444235714e-7, -7.51821178144509e-6, 1.94218051498662e-4, -0.00538533819142287,
-    0.168122596736809, -1.05490525395105e-15, 1.96855386549388e-14, -5.500330153548e-13,
-    1.003849567976e-11, -1.720997242621e-10, 3.533277061402e-9, -6.389171736029e-8,
-    1.046236652393e-6, -1.73148206795827e-5, 2.57820531617185e-4, -0.0034618826533835,
-    0.0703302497508176, 3.60020423754545e-16, -6.24245825017148e-15, 9.945311467434e-14,
-    -1.749051512721e-12, 2.768503957853e-11, -4.08688551136506e-10, 6.0418906330361e-9,
-    -8.23540111024147e-8, 1.01503783870262e-6, -1.20490761741576e-5, 1.26928442448148e-4,
-    -0.00105539461930597, 0.0115543698537013, 2.51163533058925e-18, -4.31723745510697e-17,
-    6.557620865832e-16, -1.016528519495e-14, 1.491302084832e-13, -2.06638666222265e-12,
-    2.67958697789258e-11, -3.23322654638336e-10, 3.63722952167779e-9, -3.75484943783021e-8,
-    3.49164261987184e-7, -2.92658670674908e-6, 2.12937256719543e-5, -1.19434130620929e-4,
-    6.45524336158384e-4, -1.29043630202811e-19, 2.16234952241296e-18, -3.107631557965e-17,
-    4.570804313173e-16, -6.301348858104e-15, 8.031304476153e-14, -9.446196472547e-13,
-    1.018245804339e-11, -9.96995451348129e-11, 8.77489010276305e-10, -6.84655877575364e-9,
-    4.64460857084983e-8, -2.66924538268397e-7, 1.24621276265907e-6, -4.30868944351523e-6,
-    9.94307982432868e-6, 1.9187576454574e-16, 7.8357401095707e-16, -3.260875931644e-14,
-    -1.186752035569e-13, 4.275180095653e-12, 3.357056136731e-11, -1.123776903884e-9,
-    1.231203269887e-8, -3.99851421361031e-7, 1.45418822817771e-5, -3.49912254976317e-4,
-    0.00667768703938812, 2.02778478673555e-15, 1.01640716785099e-14, -3.385363492036e-13,
-    -1.615655871159e-12, 4.527419140333e-11, 3.853670706486e-10, -1.184607130107e-8,
-    1.347873288827e-7, -4.47788241748377e-6, 1.54942754358273e-4, -0.00355524254280266,
-    0.0644912219301603, 7.79850771456444e-15, 6.00464406395001e-14, -1.249779730869e-12,
-    -1.020720636353e-11, 1.814709816693e-10, 1.766397336977e-9, -4.60355944901e-8,
-    5.863956443581e-7, -2.03797212506691e-5, 6.31405161185185e-4, -0.0130102750145071,
-    0.210244289044705, -2.92397030777912e-15, 1.94152129078465e-14, 4.85944766585e-13,
-    -3.217227223463e-12, -7.484522135512e-11, 7.19101516047753e-10, 6.88409355245582e-9,
-    -1.44374545515769e-7, 2.74941013315834e-6, -1.02790452049013e-4, 0.00259924221372643,
-    -0.0435712368303551, 0.562170709585029, 1.1797612684006e-14, 1.24156229350669e-13,
-    -3.89274162228e-12, -7.755793199043e-12, 9.492190032313e-10, -4.98680128123353e-9,
-    -1.81502268782664e-7, 2.69463269394888e-6, 2.5003215442164e-5, -0.00133684303917681,
-    0.0229121951862538, -0.245653725061323, 1.89999883453047, 1.74841995087592e-15,
-    -6.95671892641256e-16, -3.000659497257e-13, 2.021279817961e-13, 3.8535969354e-11,
-    1.461418533652e-10, -1.014517563435e-8, 1.132736008979e-7, -2.86605475073259e-6,
-    1.21958354908768e-4, -0.00386293751153466, 0.145298342081522, -1.11199320525573e-15,
-    1.85007587796671e-15, 1.220613939709e-13, 1.275068098526e-12, -5.341838883262e-11,
-    6.161037256669e-10, -1.00914787975e-8, 2.907862965346e-7, -6.12300038720919e-6,
-    1.00104454489518e-4, -0.00180677298502757, 0.057800991453663, -9.49816486853687e-16,
-    6.67922080354234e-15, 2.606163540537e-15, 1.98379995015e-12, -5.400548574357e-11,
-    6.638043374114e-10, -8.799518866802e-9, 1.791418482685e-7, -2.96075397351101e-6,
-    3.38028206156144e-5, -3.58426847857878e-4, 0.00839213709428516, 1.3382997106018e-17,
-    -3.4484187784414e-16, 4.745009557656e-15, -6.033814209875e-14, 1.049256040808e-12,
-    -1.70859789556117e-11, 2.15219425727959e-10, -2.52746574206884e-9, 3.2776171442296e-8,
-    -3.90387662925193e-7, 3.4634020459387e-6, -2.43236345136782e-5, 3.54846978585226e-4,
-    2.69412277020887e-20, -4.24837886165685e-19, 6.030500065438e-18, -9.069722758289e-17,
-    1.246599177672e-15, -1.56872999797549e-14, 1.87305099552692e-13, -2.09498886675861e-12,
-    2.11630022068394e-11, -1.92566242323525e-10, 1.62012436344069e-9, -1.23621614171556e-8,
-    7.72165684563049e-8, -3.59858901591047e-7, 2.43682618601e-6, -1.13927848238726e-15,
-    7.39404133595713e-15, 1.445982921243e-13, -2.676703245252e-12, 5.823521627177e-12,
-    2.17264723874381e-10, 3.56242145897468e-9, -3.03763737404491e-7, 9.46859114120901e-6,
-    -2.30896753853196e-4, 0.00524663913001114, 2.89872355524581e-16, -1.22296292045864e-14,
-    6.1840650972e-14, 1.64984659123e-12, -2.729713905266e-11, 3.70991379065e-11,
-    2.216486288382e-9, 4.616160236414e-8, -3.32380270861364e-6, 9.84635072633776e-5,
-    -0.00230092118015697, 0.0500845183695073, 1.97068646590923e-15, -4.894192706268e-14,
-    1.136466605916e-13, 7.546203883874e-12, -9.635646767455e-11, -8.295965491209e-11,
-    7.534109114453e-9, 2.699970652707e-7, -1.42982334217081e-5, 3.78290946669264e-4,
-    -0.00803133015084373, 0.158689469640791, 1.33642069941389e-14, -1.55850612605745e-13,
-    -7.522712577474e-13, 3.209520801187e-11, -2.075594313618e-10, -2.070575894402e-9,
-    7.323046997451e-9, 1.851491550417e-6, -6.37524802411383e-5, 0.00136795464918785,
-    -0.0242051126993146, 0.397847167557815, -6.07053986130526e-14, 1.04447493138843e-12,
-    -4.286617818951e-13, -2.632066100073e-10, 4.804518986559e-9, -1.835675889421e-8,
-    -1.068175391334e-6, 3.292234974141e-5, -5.94805357558251e-4, 0.00829382168612791,
-    -0.0993122509049447, 1.09857804755042, -9.10338640266542e-15, 1.00438927627833e-13,
-    7.817349237071e-13, -2.547619474232e-11, 1.479321506529e-10, 1.52314028857627e-9,
-    9.20072040917242e-9, -2.19427111221848e-6, 8.65797782880311e-5, -0.00282718629312875,
-    0.128718310443295, 5.5238092761876e-15, -6.43424400204124e-14, -2.358734508092e-13,
-    8.261326648131e-12, 9.229645304956e-11, -5.68108973828949e-9, 1.22477891136278e-7,
-    -2.11919643127927e-6, 4.23605032368922e-5, -0.00114423444576221, 0.0506607252890186,
-    3.99457454087556e-15, -5.11826702824182e-14, -4.157593182747e-14, 4.214670817758e-12,
-    6.705582751532e-11, -3.36086411698418e-9, 6.07453633298986e-8, -7.40736211041247e-7,
-    8.84176371665149e-6, -1.72559275066834e-4, 0.00716639814253567, -2.14649508112234e-18,
-    -2.45525846412281e-18, 6.126212599772e-16, -8.526651626939e-15, 4.826636065733e-14,
-    -3.3955416364974e-13, 1.67070784862985e-11, -4.42671979311163e-10, 6.773680559084e-9,
-    -7.03520999708859e-8, 6.04993294708874e-7, -7.80555094280483e-6, 2.85954806605017e-4,
-    -5.63938733073804e-21, 6.92182516324628e-20, -1.586937691507e-18, 3.357639744582e-17,
-    -4.810285046442e-16, 5.386312669975e-15, -6.117895297439e-14, 8.441808227634e-13,
-    -1.18527596836592e-11, 1.36296870441445e-10, -1.17842611094141e-9, 7.80430641995926e-9,
-    -5.9776741740054e-8, 1.65186146094969e-6, -1.73363958895356e-6, 1.19921331441483e-4,
-    -0.0159437614121125, 1.13467897349442, -44.7216460864586, 1062.51216612604,
-    -15207.3917378512, 120662.887111273, -407186.366852475, 0.117581320211778,
-    -0.117581320211778, -1.6010254262171e-5, 0.00110331262112395, -0.150043662589017,
-    10.5563640866077, -410.468817024806, 9626.04416506819, -135888.06983827,
-    1061075.7703834, -3511907.92816119, 1.0745620124369, -1.0745620124369,
-    -4.48880032128422e-5, 0.00269025112122177, -0.401048115525954, 27.8360021977405,
-    -1048.91729356965, 23698.5942687423, -319504.627257548, 2348796.93563358,
-    -7163415.68174085, 3.08593744371754, -3.08593744371754, -6.38526371092582e-5,
-    -0.00229263585792626, -0.0765735935499627, 9.12692349152792, -232.077034386717,
-    281.839578728845, 95952.9683876419, -1776389.56809518, 10248975.964541,
-    6.41472973366203, -6.41472973366203, -3.59049364231569e-5, -0.0225963977930044,
-    1.12594870794668, -45.6752462103909, 1058.04526830637, -11600.3199605875,
-    -40729.7627297272, 2222155.28319857, -16119645.5032613, 11.8071894899717,
-    -11.8071894899717, -4.6110090613397e-10, 1.43069932644286e-7, -1.6396091543108e-5,
-    0.00115791154612838, -0.0530573476742071, 1.61156533367153, -32.3248143316007,
-    412.007318109157, -3022.60070158372, 9715.75094154768, 8.62130526143657e-6,
-    -2.4079943580995e-8, 8.12621667601546e-6, -9.04491430884113e-4, 0.0637686375770059,
-    -2.96135703135647, 91.514235699633, -1869.71865249111, 24294.5528916947,
-    -181852.473229081, 596854.758661427, 0.00151614186862443, 1.83574464457207e-5,
-    -0.00154837969489927, 0.118520453711586, -6.69649981309161, 244.789386487321,
-    -5688.32664556359, 81450.7604229357, -655181.056671474, 2264108.96607237,
-    0.0382231610015404, 2.7777834587065e-5, -0.0022283501765589, 0.161077633475573,
-    -8.96743743396132, 328.062687293374, -7657.22701219557, 110255.055017664,
-    -892528.122219324, 3106386.27744347, 0.270967405960535, 0.01962,
-    -0.0243758528330205, 2.07301567989771, -64.5964225381113, 714.16008865547,
-    -0.228861955413636, 19.3190784733691, -599.774730340912, 6618.44165304871,
-    -0.695053039285586, 57.6874090316016, -1777.0414322552, 19536.6082947811,
-    -1.58072809087018, 127.050801091948, -3866.8735091428, 42302.482812142,
-    -3.33963830405396, 251.830424600204, -7577.28527654961, 82196.681659569,
-    1.35482430510942e-8, -3.27722199212781e-7, 2.41522703684296e-6, 1.23464092261605e-6,
-    -3.5522456427559e-5, 3.03274662192286e-4, 1.34547929260279e-5, -4.19389884772726e-4,
-    0.00387706687610809, 2.09539509123135e-5, -6.87646614786982e-4, 0.00668743788585688,
-    0.88622692545275783,
-};
+__host__ __device__
 #endif
-#ifdef __CUDA_ARCH__
-#define RC(i, v) rys_ctab[i]
-#else
-#define RC(i, v) (v)
-#endif
+constexpr double rys_herm(int weights, int i) {
+#define RYS_CONST(name, n) constexpr double name[n]
+#include "rys_consts.inc"
+#undef RYS_CONST
+    return weights ? rys_herm_w[i] : rys_herm_r[i];
+}
 
-UNOMOL_HD double ub_rsqrt(double x) {
+// Table pointers in the caller's address space: device global memory (rys_tables.cu) or a shared-memory copy of the
+// Boys grid inside kernels, the host arrays of rys_host_tables() in host code.
+struct RysTables {
+    const double *boys;        // [RYS_BOYS_NPTS][2] = {F_MTOP(X_i), exp(-X_i)}, X_i = i / RYS_BOYS_HINV
+    const double *piece[3];    // 3, 4, 5 roots: [interval][k = 0..12][r_0..r_{n-1}, w_0..w_{n-1}]
+    int rys2_exact;            // 0: reference-compatible two-root band (see above); 1: exact two-root quadrature
+    int pad;
+};
+
+constexpr double RYS_SQRT_PI_4 = 0.88622692545275801;   // sqrt(pi/4)
+constexpr double RYS_X_ASYM1 = 35.0;                     // F_0 = sqrt(pi/4X) to 6e-17 beyond (exp(-35)/70 = 9e-18)
+
+UNOMOL_HD double rys_rsqrt(double x) {
 #ifdef __CUDA_ARCH__
     return rsqrt(x);
 #else
@@ -514,605 +67,187 @@ UNOMOL_HD double ub_rsqrt(double x) {
 #endif
 }
 
-template <int N> UNOMOL_HD void rys_roots(double x, double *r, double *w);
+// a*b - c*d with one rounding of the dominant error (Kahan)
+UNOMOL_HD double rys_dop(double a, double b, double c, double d) {
+    const double cd = c * d;
+    const double err = fma(-c, d, cd);
+    return fma(a, b, -cd) + err;
+}
 
-template <> UNOMOL_HD void rys_roots<1>(double x, double *r, double *w) {
-    const double ub_g = exp((-x));
-    const double ub_xinv = (1.0 / x);
-    const double ub_sq = sqrt((RC(42, 0.785398163397448) * ub_xinv));
-    if (x <= RC(0, 3e-07)) {
-        r[0] = (0.5 - (x / 5.0));
-        w[0] = (1.0 - (x / 3.0));
+// F[0..MT] = F_0(x) .. F_MT(x) for 0 <= x < RYS_BOYS_XMAX
+template <int MT>
+UNOMOL_HD void boys_grid(double x, const double *tab, double *F) {
+    static_assert(MT + 7 <= RYS_BOYS_MTOP, "the Taylor series of the top order reaches F_{MT+7}");
+    const int i = (int)fma(x, (double)RYS_BOYS_HINV, 0.5);
+    const double xi = (double)i * (1.0 / RYS_BOYS_HINV);
+    const double d = xi - x;                       // |d| <= 1/32;  F_m(x) = sum_k F_{m+k}(xi) d^k / k!
+#ifdef __CUDA_ARCH__
+    const double2 te = *reinterpret_cast<const double2 *>(tab + 2 * i);
+    double f = te.x;
+    const double e = te.y;
+#else
+    double f = tab[2 * i];
+    const double e = tab[2 * i + 1];
+#endif
+    const double x2 = xi + xi;
+    double g[8];                                   // F_MT(xi) .. F_{MT+7}(xi)
+#pragma unroll
+    for (int m = RYS_BOYS_MTOP; m > MT + 7; --m) f = fma(x2, f, e) * (1.0 / (2 * m - 1));
+    g[7] = f;
+#pragma unroll
+    for (int k = 7; k > 0; --k) g[k - 1] = fma(x2, g[k], e) * (1.0 / (2 * (MT + k) - 1));
+    // Horner in d with the 1/k! folded in: t_k = d/k
+    double dk[8];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) dk[k] = d * (1.0 / k);
+    double t = g[7], ex = 1.0 + d * (1.0 / 8);
+#pragma unroll
+    for (int k = 7; k > 0; --k) {
+        t = fma(t, dk[k], g[k - 1]);
+        ex = fma(ex, dk[k], 1.0);
     }
-    else if (x <= 1.0) {
-        double f1 = (fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1, -8.36313918003957e-8), x, RC(2, 1.21222603512827e-6)), x, RC(3, -1.15662609053481e-5)), x, RC(4, 9.25197374512647e-5)), x, RC(5, -6.40994113129432e-4)), x, RC(6, 0.00378787044215009)), x, RC(7, -0.0185185172458485)), x, RC(8, 0.0714285713298222)), x, RC(9, -0.199999999997023)), x, RC(10, 0.333333333333318)));
-        w[0] = (((x + x) * f1) + ub_g);
-        r[0] = (f1 / (w[0] - f1));
-    }
-    else if (x <= 3.0) {
-        const double y = x - 2.0;
-        double f1 = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(11, -1.61702782425558e-10), y, RC(12, 1.96215250865776e-9)), y, RC(13, -2.14234468198419e-8)), y, RC(14, 2.17216556336318e-7)), y, RC(15, -1.98850171329371e-6)), y, RC(16, 1.62429321438911e-5)), y, RC(17, -1.16740298039895e-4)), y, RC(18, 7.24888732052332e-4)), y, RC(19, -0.00379490003707156)), y, RC(20, 0.0161723488664661)), y, RC(21, -0.0529428148329736)), y, RC(22, 0.115702180856167)));
-        w[0] = (((x + x) * f1) + ub_g);
-        r[0] = (f1 / (w[0] - f1));
-    }
-    else if (x <= 5.0) {
-        const double y = x - 4.0;
-        double f1 = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(23, -2.62453564772299e-11), y, RC(24, 3.24031041623823e-10)), y, RC(25, -3.614965656163e-9)), y, RC(26, 3.760256799971e-8)), y, RC(27, -3.553558319675e-7)), y, RC(28, 3.022556449731e-6)), y, RC(29, -2.290098979647e-5)), y, RC(30, 1.526537461148e-4)), y, RC(31, -8.81947375894379e-4)), y, RC(32, 0.00433207949514611)), y, RC(33, -0.0175257821619926)), y, RC(34, 0.0528406320615584)));
-        w[0] = (((x + x) * f1) + ub_g);
-        r[0] = (f1 / (w[0] - f1));
-    }
-    else if (x <= 10.0) {
-        double xinv = ub_xinv;
-        double g = ub_g;
-        w[0] = (((RC(35, -3.1501078774085e-6) + (xinv * fma(fma(fma(fma(fma(RC(36, 0.46897511375022), xinv, RC(37, -0.69955602298985)), xinv, RC(38, 0.53689283271887)), xinv, RC(39, -0.32883030418398)), xinv, RC(40, 0.24645596956002)), xinv, RC(41, -0.49984072848436)))) * g) + ub_sq);
-        double f1 = ((w[0] - g) / (x + x));
-        r[0] = (f1 / (w[0] - f1));
-    }
-    else if (x <= 15.0) {
-        double xinv = ub_xinv;
-        double g = ub_g;
-        w[0] = (((RC(43, -2.1916512131607e-5) + (xinv * fma(fma(RC(44, -0.18784686463512), xinv, RC(45, 0.22991849164985)), xinv, RC(46, -0.49893752514047)))) * g) + ub_sq);
-        double f1 = (((w[0] - g) * 0.5) * xinv);
-        r[0] = (f1 / (w[0] - f1));
-    }
-    else if (x <= 33.0) {
-        double xinv = ub_xinv;
-        double g = ub_g;
-        w[0] = (((RC(47, -6.0156581186481e-5) + (xinv * fma(RC(48, 0.1962326414943), xinv, RC(49, -0.4969524146449)))) * g) + ub_sq);
-        double f1 = (((w[0] - g) * 0.5) * xinv);
-        r[0] = (f1 / (w[0] - f1));
-    }
-    else {
-        w[0] = ub_sq;
-        r[0] = (0.5 / (fma(1.0, x, -0.5)));
+    F[MT] = t;
+    ex *= e;                                       // exp(-x)
+    const double xx = x + x;
+#pragma unroll
+    for (int m = MT; m > 0; --m) F[m - 1] = fma(xx, F[m], ex) * (1.0 / (2 * m - 1));
+}
+
+// Gauss-Hermite limit (all exp(-X) terms below double precision)
+template <int N>
+UNOMOL_HD void rys_hermite_limit(double x, double *r, double *w) {
+    const double s = RYS_SQRT_PI_4 * rys_rsqrt(x);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double R = rys_herm(0, 5 * (N - 1) + i);
+        r[i] = R / (x - R);
+        w[i] = rys_herm(1, 5 * (N - 1) + i) * s;
     }
 }
 
-template <> UNOMOL_HD void rys_roots<2>(double x, double *r, double *w) {
-    const double ub_g = exp((-x));
-    const double ub_xinv = (1.0 / x);
-    const double ub_sq = sqrt((RC(42, 0.785398163397448) * ub_xinv));
-    if (x <= RC(0, 3e-07)) {
-        r[0] = (fma(RC(50, -0.0290430236082028), x, RC(51, 0.130693606237085)));
-        r[1] = (fma(RC(52, -0.637623643058102), x, RC(53, 2.86930639376291)));
-        w[0] = (fma(RC(54, -0.122713621927067), x, RC(55, 0.652145154862545)));
-        w[1] = (fma(RC(56, -0.210619711404725), x, RC(57, 0.347854845137453)));
-    }
-    else if (x <= 1.0) {
-        double f1 = (fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1, -8.36313918003957e-8), x, RC(2, 1.21222603512827e-6)), x, RC(3, -1.15662609053481e-5)), x, RC(4, 9.25197374512647e-5)), x, RC(5, -6.40994113129432e-4)), x, RC(6, 0.00378787044215009)), x, RC(7, -0.0185185172458485)), x, RC(8, 0.0714285713298222)), x, RC(9, -0.199999999997023)), x, RC(10, 0.333333333333318)));
-        w[0] = (((x + x) * f1) + ub_g);
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(fma(RC(58, -2.35234358048491e-9), x, RC(59, 2.49173650389842e-8)), x, RC(60, -4.558315364581e-8)), x, RC(61, -2.447252174587e-6)), x, RC(62, 4.743292959463e-5)), x, RC(63, -5.33184749432408e-4)), x, RC(64, 0.00444654947116579)), x, RC(65, -0.0290430236084697)), x, RC(51, 0.130693606237085)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(fma(RC(66, -2.4740490232917e-8), x, RC(67, 2.36809910635906e-7)), x, RC(68, 1.83536773631e-6)), x, RC(69, -2.066168802076e-5)), x, RC(70, -1.345693393936e-4)), x, RC(71, -5.88154362858038e-5)), x, RC(72, 0.0532735082098139)), x, RC(73, -0.637623643056745)), x, RC(74, 2.86930639376289)));
-        w[1] = (((((f1 - w[0]) * r[0]) + f1) * (r[1] + 1.0)) / (r[1] - r[0]));
-        w[0] = (w[0] - w[1]);
-    }
-    else if (x <= 3.0) {
-        const double y = x - 2.0;
-        double f1 = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(11, -1.61702782425558e-10), y, RC(12, 1.96215250865776e-9)), y, RC(13, -2.14234468198419e-8)), y, RC(14, 2.17216556336318e-7)), y, RC(15, -1.98850171329371e-6)), y, RC(16, 1.62429321438911e-5)), y, RC(17, -1.16740298039895e-4)), y, RC(18, 7.24888732052332e-4)), y, RC(19, -0.00379490003707156)), y, RC(20, 0.0161723488664661)), y, RC(21, -0.0529428148329736)), y, RC(22, 0.115702180856167)));
-        w[0] = (((x + x) * f1) + ub_g);
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(75, -6.36859636616415e-12), y, RC(76, 8.4741706477627e-11)), y, RC(77, -5.152207846962e-10)), y, RC(78, -3.846389873308e-10)), y, RC(79, 8.47225338838e-8)), y, RC(80, -1.85306035634293e-6)), y, RC(81, 2.47191693238413e-5)), y, RC(82, -2.49018321709815e-4)), y, RC(83, 0.00219173220020161)), y, RC(84, -0.0163329339286794)), y, RC(85, 0.0868085688285261)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(86, 1.45331350488343e-10), y, RC(87, 2.07111465297976e-9)), y, RC(88, -1.878920917404e-8)), y, RC(89, -1.725838516261e-7)), y, RC(90, 2.247389642339e-6)), y, RC(91, 9.76783813082564e-6)), y, RC(92, -1.93160765581969e-4)), y, RC(93, -0.00158064140671893)), y, RC(94, 0.0485928174507904)), y, RC(95, -0.430761584997596)), y, RC(96, 1.8040097453795)));
-        w[1] = (((((f1 - w[0]) * r[0]) + f1) * (r[1] + 1.0)) / (r[1] - r[0]));
-        w[0] = (w[0] - w[1]);
-    }
-    else if (x <= 5.0) {
-        const double y = x - 4.0;
-        double f1 = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(23, -2.62453564772299e-11), y, RC(24, 3.24031041623823e-10)), y, RC(25, -3.614965656163e-9)), y, RC(26, 3.760256799971e-8)), y, RC(27, -3.553558319675e-7)), y, RC(28, 3.022556449731e-6)), y, RC(29, -2.290098979647e-5)), y, RC(30, 1.526537461148e-4)), y, RC(31, -8.81947375894379e-4)), y, RC(32, 0.00433207949514611)), y, RC(33, -0.0175257821619926)), y, RC(34, 0.0528406320615584)));
-        w[0] = (((x + x) * f1) + ub_g);
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(97, -4.11560117487296e-12), y, RC(98, 7.10910223886747e-11)), y, RC(99, -1.73508862390291e-9)), y, RC(100, 5.93066856324744e-8)), y, RC(101, -9.76085576741771e-7)), y, RC(102, 1.08484384385679e-5)), y, RC(103, -1.12608004981982e-4)), y, RC(104, 0.00116210907653515)), y, RC(105, -0.00989572595720351)), y, RC(106, 0.0612589701086408)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(107, -1.80555625241001e-10), y, RC(108, 5.44072475994123e-10)), y, RC(109, 1.60349804524e-8)), y, RC(110, -1.497986283037e-7)), y, RC(111, -7.017002532106e-7)), y, RC(112, 1.85882653064034e-5)), y, RC(113, -2.04685420150802e-5)), y, RC(114, -0.00249327728643089)), y, RC(115, 0.0356550690684281)), y, RC(116, -0.260417417692375)), y, RC(117, 1.12155283108289)));
-        w[1] = (((((f1 - w[0]) * r[0]) + f1) * (r[1] + 1.0)) / (r[1] - r[0]));
-        w[0] = (w[0] - w[1]);
-    }
-    else if (x <= 10.0) {
-        const double y = x - 7.5;
-        double xinv = ub_xinv;
-        double g = ub_g;
-        w[0] = (((RC(35, -3.1501078774085e-6) + (xinv * fma(fma(fma(fma(fma(RC(36, 0.46897511375022), xinv, RC(37, -0.69955602298985)), xinv, RC(38, 0.53689283271887)), xinv, RC(39, -0.32883030418398)), xinv, RC(40, 0.24645596956002)), xinv, RC(41, -0.49984072848436)))) * g) + ub_sq);
-        double f1 = (((w[0] - g) * 0.5) * xinv);
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(118, -1.43632730148572e-16), y, RC(119, 2.38198922570405e-16)), y, RC(120, 1.3583196188e-14)), y, RC(121, -7.064522786879e-14)), y, RC(122, -7.719300212748e-13)), y, RC(123, 7.802544789997e-12)), y, RC(124, 6.628721099436e-11)), y, RC(125, -1.775564159743e-9)), y, RC(126, 1.71382882399e-8)), y, RC(127, -1.497500187053e-7)), y, RC(128, 2.283485114279e-6)), y, RC(129, -3.76953869614706e-5)), y, RC(130, 4.74791204651451e-4)), y, RC(131, -0.00460448960876139)), y, RC(132, 0.0372458587837249)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(133, 2.487916227989e-14), y, RC(134, -1.36113510175724e-13)), y, RC(135, -2.224334349799e-12)), y, RC(136, 4.190559455515e-11)), y, RC(137, -2.222722579924e-10)), y, RC(138, -2.624183464275e-9)), y, RC(139, 6.128153450169e-8)), y, RC(140, -4.383376014528e-7)), y, RC(141, -2.4995220023291e-6)), y, RC(142, 1.0323664788832e-4)), y, RC(143, -0.00144614664924989)), y, RC(144, 0.0135094294917224)), y, RC(145, -0.0953478510453887)), y, RC(146, 0.54476524568679)));
-        w[1] = (((((f1 - w[0]) * r[0]) + f1) * (r[1] + 1.0)) / (r[1] - r[0]));
-        w[0] = (w[0] - w[1]);
-    }
-    else if (x <= 15.0) {
-        double xinv = ub_xinv;
-        double g = ub_g;
-        w[0] = (((RC(43, -2.1916512131607e-5) + (xinv * fma(fma(RC(44, -0.18784686463512), xinv, RC(45, 0.22991849164985)), xinv, RC(46, -0.49893752514047)))) * g) + ub_sq);
-        double f1 = (((w[0] - g) * 0.5) * xinv);
-        r[0] = (((fma(fma(fma(fma(RC(147, -1.01041157064226e-5), x, RC(148, 0.00119483054115173)), x, RC(149, -0.0673760231824074)), x, RC(150, 1.25705571069895)), x, RC(151, -23.8570496490846)) + (xinv * fma(fma(fma(RC(152, -8576.09422987199), xinv, RC(153, 5910.05939591842)), xinv, RC(154, -1708.07677109425)), xinv, RC(155, 264.536689959503)))) * g) + (RC(156, 0.275255128608411) / (fma(1.0, x, RC(157, -0.275255128608411)))));
-        r[1] = (((fma(fma(fma(RC(158, 3.39024225137123e-4), x, RC(159, -0.0934976436343509)), x, RC(160, -4.2221648330632)), x, RC(161, 8.00839033297501)) + (xinv * fma(fma(fma(RC(162, -2084.57050986847), xinv, RC(163, -1049.99071905664)), xinv, RC(164, 339.891508992661)), xinv, RC(165, -156.184800325063)))) * g) + (RC(166, 2.72474487139158) / (fma(1.0, x, RC(167, -2.72474487139158)))));
-        w[1] = (((((f1 - w[0]) * r[0]) + f1) * (r[1] + 1.0)) / (r[1] - r[0]));
-        w[0] = (w[0] - w[1]);
-    }
-    else if (x <= 40.0) {
-        w[0] = ub_sq;
-        double g = ub_g;
-        r[0] = (((fma(RC(168, -0.87894730749888), x, RC(169, 10.9243702330261))) * g) + (RC(156, 0.275255128608411) / (fma(1.0, x, RC(157, -0.275255128608411)))));
-        r[1] = (((fma(RC(170, -9.28903924275977), x, RC(171, 81.0642367843811))) * g) + (RC(166, 2.72474487139158) / (fma(1.0, x, RC(167, -2.72474487139158)))));
-        w[1] = (((fma(RC(172, 4.468573893084), x, RC(173, -77.9250653461045))) * g) + (RC(174, 0.0917517095361369) * w[0]));
-        w[0] = (w[0] - w[1]);
-    }
-    else {
-        w[0] = ub_sq;
-        r[0] = (RC(156, 0.275255128608411) / (fma(1.0, x, RC(157, -0.275255128608411))));
-        r[1] = (RC(166, 2.72474487139158) / (fma(1.0, x, RC(167, -2.72474487139158))));
-        w[1] = (RC(174, 0.0917517095361369) * w[0]);
-        w[0] = (w[0] - w[1]);
+// One root as moments: w = F_0(x), f1 = F_1(x) = w t^2.  The (ss|ss) and (ps|ss) kernels use these directly.
+UNOMOL_HD void rys1_f0f1(double x, double &w, double &f1, const RysTables &T) {
+    if (x < RYS_X_ASYM1) {
+        double F[2];
+        boys_grid<1>(x, T.boys, F);
+        w = F[0];
+        f1 = F[1];
+    } else {
+        const double rx = rys_rsqrt(x);
+        w = RYS_SQRT_PI_4 * rx;
+        f1 = (0.5 * w) * (rx * rx);
     }
 }
 
-template <> UNOMOL_HD void rys_roots<3>(double x, double *r, double *w) {
-    const double ub_g = exp((-x));
-    const double ub_xinv = (1.0 / x);
-    const double ub_sq = sqrt((RC(42, 0.785398163397448) * ub_xinv));
-    if (x <= RC(0, 3e-07)) {
-        r[0] = (fma(RC(175, -0.00928875764357368), x, RC(176, 0.0603769246832797)));
-        r[1] = (fma(RC(177, -0.119511285527878), x, RC(178, 0.776823355931043)));
-        r[2] = (fma(RC(179, -1.02504611068957), x, RC(180, 6.66279971938567)));
-        w[0] = (fma(RC(181, -0.0564876917232519), x, RC(182, 0.467913934572691)));
-        w[1] = (fma(RC(183, -0.149077186455208), x, RC(184, 0.360761573048137)));
-        w[2] = (fma(RC(185, -0.127768455150979), x, RC(186, 0.171324492379169)));
-    }
-    else if (x <= 1.0) {
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(RC(187, -5.1018669153887e-10), x, RC(188, 2.4013441570345e-8)), x, RC(189, -5.01081057744427e-7)), x, RC(190, 7.58291285499256e-6)), x, RC(191, -9.55085533670919e-5)), x, RC(192, 0.00102893039315878)), x, RC(193, -0.00928875764374337)), x, RC(194, 0.060376924683281)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(RC(195, -1.29646524960555e-8), x, RC(196, 7.74602292865683e-8)), x, RC(197, 1.56022811158727e-6)), x, RC(198, -1.58051990661661e-5)), x, RC(199, -3.30447806384059e-4)), x, RC(200, 0.00974266885190267)), x, RC(201, -0.119511285526388)), x, RC(202, 0.776823355931033)));
-        r[2] = (fma(fma(fma(fma(fma(fma(fma(RC(203, -9.28536484109606e-9), x, RC(204, -3.02786290067014e-7)), x, RC(205, -2.507344770642e-6)), x, RC(206, -7.32728109752881e-6)), x, RC(207, 2.44217481700129e-4)), x, RC(208, 0.0494758452357327)), x, RC(209, -1.02504611065774)), x, RC(210, 6.66279971938553)));
-        double f2 = (fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(211, -7.6091148609885e-8), x, RC(212, 1.09552870123182e-6)), x, RC(213, -1.03463270693454e-5)), x, RC(214, 8.16324851790106e-5)), x, RC(215, -5.55526624875562e-4)), x, RC(216, 0.00320512054753924)), x, RC(217, -0.015151513983854)), x, RC(218, 0.0555555554649585)), x, RC(219, -0.142857142854412)), x, RC(220, 0.199999999999986)));
-        double g = ub_g;
-        double f1 = ((((x + x) * f2) + g) / 3.0);
-        w[0] = (((x + x) * f1) + g);
-        double t1 = (r[0] / (r[0] + 1.0));
-        double t2 = (r[1] / (r[1] + 1.0));
-        double t3 = (r[2] / (r[2] + 1.0));
-        double a2 = (f2 - (t1 * f1));
-        double a1 = (f1 - (t1 * w[0]));
-        w[2] = ((a2 - (t2 * a1)) / ((t3 - t2) * (t3 - t1)));
-        w[1] = (((t3 * a1) - a2) / ((t3 - t2) * (t2 - t1)));
-        w[0] = ((w[0] - w[1]) - w[2]);
-    }
-    else if (x <= 3.0) {
-        const double y = x - 2.0;
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(221, 1.44687969563318e-12), y, RC(222, 4.85300143926755e-12)), y, RC(223, -6.55098264095516e-10)), y, RC(224, 1.56592951656828e-8)), y, RC(225, -2.60122498274734e-7)), y, RC(226, 3.86118485517386e-6)), y, RC(227, -5.13430986707889e-5)), y, RC(228, 6.03194524398109e-4)), y, RC(229, -0.0061121934982509)), y, RC(230, 0.0452578254679079)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(fma(RC(231, 6.95964248788138e-10), y, RC(232, -5.35281831445517e-9)), y, RC(233, -6.745205954533e-8)), y, RC(234, 1.502366784525e-6)), y, RC(235, 9.923326947376e-7)), y, RC(236, -3.89147469249594e-4)), y, RC(237, 0.00751549330892401)), y, RC(238, -0.08487781203634)), y, RC(239, 0.573928229597613)));
-        r[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(240, -2.81496588401439e-10), y, RC(241, 3.61058041895031e-9)), y, RC(242, 4.53631789436255e-8)), y, RC(243, -1.40971837780847e-7)), y, RC(244, -6.05865557561067e-6)), y, RC(245, -5.15964042227127e-5)), y, RC(246, 3.34761560498171e-5)), y, RC(247, 0.0504871005319119)), y, RC(248, -0.824708946991557)), y, RC(249, 4.81234667357205)));
-        double f2 = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(250, -1.4804423107214e-10), y, RC(251, 1.78157031325097e-9)), y, RC(252, -1.92514145088973e-8)), y, RC(253, 1.92804632038796e-7)), y, RC(254, -1.73806555021045e-6)), y, RC(255, 1.39195169625425e-5)), y, RC(256, -9.74574633246452e-5)), y, RC(257, 5.83701488646511e-4)), y, RC(258, -0.00289955494844975)), y, RC(259, 0.011384700111381)), y, RC(260, -0.0323446977320647)), y, RC(261, 0.0529428148329709)));
-        double g = ub_g;
-        double f1 = ((((x + x) * f2) + g) / 3.0);
-        w[0] = (((x + x) * f1) + g);
-        double t1 = (r[0] / (r[0] + 1.0));
-        double t2 = (r[1] / (r[1] + 1.0));
-        double t3 = (r[2] / (r[2] + 1.0));
-        double a2 = (f2 - (t1 * f1));
-        double a1 = (f1 - (t1 * w[0]));
-        w[2] = ((a2 - (t2 * a1)) / ((t3 - t2) * (t3 - t1)));
-        w[1] = (((t3 * a1) - a2) / ((t3 - t2) * (t2 - t1)));
-        w[0] = ((w[0] - w[1]) - w[2]);
-    }
-    else if (x <= 5.0) {
-        const double y = x - 4.0;
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(fma(RC(262, 1.44265709189601e-11), y, RC(263, -4.66622033006074e-10)), y, RC(264, 7.649155832025e-9)), y, RC(265, -1.229940017368e-7)), y, RC(266, 2.026002142457e-6)), y, RC(267, -2.87048671521677e-5)), y, RC(268, 3.70326938096287e-4)), y, RC(269, -0.00421006346373634)), y, RC(270, 0.0350898470729044)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(271, -2.65526039155651e-11), y, RC(272, 1.97549041402552e-10)), y, RC(273, 2.15971131403034e-9)), y, RC(274, -7.95045680685193e-8)), y, RC(275, 5.15021914287057e-7)), y, RC(276, 1.11788717230514e-5)), y, RC(277, -3.33739312603632e-4)), y, RC(278, 0.00530601428208358)), y, RC(279, -0.0593483267268959)), y, RC(280, 0.431180523260239)));
-        r[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(281, -3.92833750584041e-10), y, RC(282, -4.1642322978228e-9)), y, RC(283, 4.42413039572867e-8)), y, RC(284, 6.40574545989551e-7)), y, RC(285, -3.05512456576552e-6)), y, RC(286, -1.05296443527943e-4)), y, RC(287, -6.14120969315617e-4)), y, RC(288, 0.0489665802767005)), y, RC(289, -0.624498381002855)), y, RC(290, 3.36412312243724)));
-        double f2 = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(291, -2.36788772599074e-11), y, RC(292, 2.89147476459092e-10)), y, RC(293, -3.18111322308846e-9)), y, RC(294, 3.25336816562485e-8)), y, RC(295, -3.00873821471489e-7)), y, RC(296, 2.48749160874431e-6)), y, RC(297, -1.81353179793672e-5)), y, RC(298, 1.14504948737066e-4)), y, RC(299, -6.10614987696677e-4)), y, RC(300, 0.00264584212770942)), y, RC(301, -0.00866415899015349)), y, RC(302, 0.0175257821619922)));
-        double g = ub_g;
-        double f1 = ((((x + x) * f2) + g) / 3.0);
-        w[0] = (((x + x) * f1) + g);
-        double t1 = (r[0] / (r[0] + 1.0));
-        double t2 = (r[1] / (r[1] + 1.0));
-        double t3 = (r[2] / (r[2] + 1.0));
-        double a2 = (f2 - (t1 * f1));
-        double a1 = (f1 - (t1 * w[0]));
-        w[2] = ((a2 - (t2 * a1)) / ((t3 - t2) * (t3 - t1)));
-        w[1] = (((t3 * a1) - a2) / ((t3 - t2) * (t2 - t1)));
-        w[0] = ((w[0] - w[1]) - w[2]);
-    }
-    else if (x <= 10.0) {
-        const double y = x - 7.5;
-        double xinv = ub_xinv;
-        double g = ub_g;
-        w[0] = (((RC(35, -3.1501078774085e-6) + (xinv * fma(fma(fma(fma(fma(RC(36, 0.46897511375022), xinv, RC(37, -0.69955602298985)), xinv, RC(38, 0.53689283271887)), xinv, RC(39, -0.32883030418398)), xinv, RC(40, 0.24645596956002)), xinv, RC(41, -0.49984072848436)))) * g) + ub_sq);
-        double f1 = ((w[0] - g) / (x + x));
-        double f2 = ((((f1 + f1) + f1) - g) / (x + x));
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(303, 5.74429401360115e-16), y, RC(304, 7.11884203790984e-16)), y, RC(305, -6.736701449826e-14)), y, RC(306, -6.264613873998e-13)), y, RC(307, 1.31541892704e-11)), y, RC(308, -4.23879635610964e-11)), y, RC(309, 1.39032379769474e-9)), y, RC(310, -4.65449552856856e-8)), y, RC(311, 7.34609900170759e-7)), y, RC(312, -1.08656008854077e-5)), y, RC(313, 1.77930381549953e-4)), y, RC(314, -0.00239864911618015)), y, RC(315, 0.0239112249488821)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(316, 1.1346409620912e-14), y, RC(317, 6.99375313934242e-15)), y, RC(318, -8.595618132088e-13)), y, RC(319, -5.293620408757e-12)), y, RC(320, -2.492175211635e-11)), y, RC(321, 2.73681574882729e-9)), y, RC(322, -1.06656985608482e-8)), y, RC(323, -4.40252529648056e-7)), y, RC(324, 9.68100917793911e-6)), y, RC(325, -1.68211091755327e-4)), y, RC(326, 0.00269443611274173)), y, RC(327, -0.0323845035189063)), y, RC(328, 0.275969447451882)));
-        r[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(329, 6.66339416996191e-15), y, RC(330, 1.84955640200794e-13)), y, RC(331, -1.985141104444e-12)), y, RC(332, -2.309293727603e-11)), y, RC(333, 3.917984522103e-10)), y, RC(334, 1.663165279876e-9)), y, RC(335, -6.205591993923e-8)), y, RC(336, 8.769581622041e-9)), y, RC(337, 8.97224398620038e-6)), y, RC(338, -3.14232666170796e-5)), y, RC(339, -0.00183917335649633)), y, RC(340, 0.0351246831672571)), y, RC(341, -0.32233505127086)), y, RC(342, 1.7358283175543)));
-        double t1 = (r[0] / (r[0] + 1.0));
-        double t2 = (r[1] / (r[1] + 1.0));
-        double t3 = (r[2] / (r[2] + 1.0));
-        double a2 = (f2 - (t1 * f1));
-        double a1 = (f1 - (t1 * w[0]));
-        w[2] = ((a2 - (t2 * a1)) / ((t3 - t2) * (t3 - t1)));
-        w[1] = (((t3 * a1) - a2) / ((t3 - t2) * (t2 - t1)));
-        w[0] = ((w[0] - w[1]) - w[2]);
-    }
-    else if (x <= 15.0) {
-        const double y = x - 12.5;
-        double xinv = ub_xinv;
-        double g = ub_g;
-        w[0] = (((RC(43, -2.1916512131607e-5) + (xinv * fma(fma(RC(44, -0.18784686463512), xinv, RC(45, 0.22991849164985)), xinv, RC(46, -0.49893752514047)))) * g) + ub_sq);
-        double f1 = ((w[0] - g) / (x + x));
-        double f2 = ((((f1 + f1) + f1) - g) / (x + x));
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(343, 4.4213300128309e-16), y, RC(344, -2.77189767070441e-15)), y, RC(345, -4.084026087887e-14)), y, RC(346, 5.379885121517e-13)), y, RC(347, 1.882093066702e-12)), y, RC(348, -8.67286219861085e-11)), y, RC(349, 7.11372337079797e-10)), y, RC(350, -3.55578027040563e-9)), y, RC(351, 1.29454702851936e-7)), y, RC(352, -4.14222202791434e-6)), y, RC(353, 8.04427643593792e-5)), y, RC(354, -0.00118587782909876)), y, RC(355, 0.0153435577063174)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(356, 6.85146742119357e-15), y, RC(357, -1.08257654410279e-14)), y, RC(358, -8.579165965128e-13)), y, RC(359, 6.642452485783e-12)), y, RC(360, 4.798806828724e-11)), y, RC(361, -1.13413908163831e-9)), y, RC(362, 7.08558457182751e-9)), y, RC(363, -5.59678576054633e-8)), y, RC(364, 2.51020389884249e-6)), y, RC(365, -6.63678914608681e-5)), y, RC(366, 0.00111888323089714)), y, RC(367, -0.0145361636398178)), y, RC(368, 0.165077877454402)));
-        r[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(369, 3.20622388697743e-15), y, RC(370, -2.73458804864628e-14)), y, RC(371, -3.157134329361e-13)), y, RC(372, 8.654129268056e-12)), y, RC(373, -5.625235879301e-11)), y, RC(374, -7.718080513708e-10)), y, RC(375, 2.064664199164e-8)), y, RC(376, -1.567725007761e-7)), y, RC(377, -1.57938204115055e-6)), y, RC(378, 6.27436306915967e-5)), y, RC(379, -0.00101308723606946)), y, RC(380, 0.0113901881430697)), y, RC(381, -0.10144965289945)), y, RC(382, 0.777203937334739)));
-        double t1 = (r[0] / (r[0] + 1.0));
-        double t2 = (r[1] / (r[1] + 1.0));
-        double t3 = (r[2] / (r[2] + 1.0));
-        double a2 = (f2 - (t1 * f1));
-        double a1 = (f1 - (t1 * w[0]));
-        w[2] = ((a2 - (t2 * a1)) / ((t3 - t2) * (t3 - t1)));
-        w[1] = (((t3 * a1) - a2) / ((t3 - t2) * (t2 - t1)));
-        w[0] = ((w[0] - w[1]) - w[2]);
-    }
-    else if (x <= 20.0) {
-        double xinv = ub_xinv;
-        double g = ub_g;
-        w[0] = (((RC(47, -6.0156581186481e-5) + (xinv * fma(RC(48, 0.1962326414943), xinv, RC(49, -0.4969524146449)))) * g) + ub_sq);
-        double f1 = ((w[0] - g) / (x + x));
-        double f2 = ((((f1 + f1) + f1) - g) / (x + x));
-        r[0] = (((fma(fma(fma(fma(fma(fma(RC(383, -2.43270989903742e-6), x, RC(384, 3.57901398988359e-4)), x, RC(385, -0.0234112415981143)), x, RC(386, 0.781425144913975)), x, RC(387, -17.3209218219175)), x, RC(388, 243.517435690398)), x, RC(389, -2079.70687843258)) + (xinv * fma(RC(390, -19761.1541576986), xinv, RC(391, 9824.41363463929)))) * g) + (RC(392, 0.190163509193487) / (fma(1.0, x, RC(393, -0.190163509193487)))));
-        r[1] = (((fma(fma(fma(fma(fma(RC(394, -2.62627010965435e-4), x, RC(395, 0.0349187925428138)), x, RC(396, -3.0933761873188)), x, RC(397, 107.037141010778)), x, RC(398, -2366.59637247087)), x, RC(399, 33520.2872835409)) + (xinv * fma(fma(RC(400, -2916691.1368102), xinv, RC(401, 1411295.05262758)), xinv, RC(402, -291532.335433779)))) * g) + (RC(403, 1.78449274854325) / (fma(1.0, x, RC(404, -1.78449274854325)))));
-        r[2] = (((fma(fma(fma(fma(fma(RC(405, 9.31856404738601e-5), x, RC(406, -0.0287029400759565)), x, RC(407, -0.783503697918455)), x, RC(408, -18.4338896480695)), x, RC(409, 404.996712650414)), x, RC(410, -6881.45821789955)) + (xinv * fma(RC(411, -189829.509315154), xinv, RC(412, 51149.8390849158)))) * g) + (RC(413, 5.52534374226326) / (fma(1.0, x, RC(414, -5.52534374226326)))));
-        double t1 = (r[0] / (r[0] + 1.0));
-        double t2 = (r[1] / (r[1] + 1.0));
-        double t3 = (r[2] / (r[2] + 1.0));
-        double a2 = (f2 - (t1 * f1));
-        double a1 = (f1 - (t1 * w[0]));
-        w[2] = ((a2 - (t2 * a1)) / ((t3 - t2) * (t3 - t1)));
-        w[1] = (((t3 * a1) - a2) / ((t3 - t2) * (t2 - t1)));
-        w[0] = ((w[0] - w[1]) - w[2]);
-    }
-    else if (x <= 33.0) {
-        double xinv = ub_xinv;
-        double g = ub_g;
-        w[0] = (((RC(47, -6.0156581186481e-5) + (xinv * fma(RC(48, 0.1962326414943), xinv, RC(49, -0.4969524146449)))) * g) + ub_sq);
-        double f1 = ((w[0] - g) / (x + x));
-        double f2 = ((((f1 + f1) + f1) - g) / (x + x));
-        r[0] = (((fma(fma(fma(fma(RC(415, -4.97561537069643e-4), x, RC(416, -0.0500929599665316)), x, RC(417, 1.31099142238996)), x, RC(418, -18.8336409225481)), x, RC(419, 164.931462413877)) + (xinv * RC(420, -660.344754467191))) * g) + (RC(392, 0.190163509193487) / (fma(1.0, x, RC(393, -0.190163509193487)))));
-        r[1] = (((fma(fma(fma(fma(RC(421, -0.00448218898474906), x, RC(422, -0.517373211334924)), x, RC(423, 11.3691058739678)), x, RC(424, -165.426392885291)), x, RC(425, 1522.31757709236)) + (xinv * RC(426, -6309.09125686731))) * g) + (RC(403, 1.78449274854325) / (fma(1.0, x, RC(404, -1.78449274854325)))));
-        r[2] = (((fma(fma(fma(fma(RC(427, -0.0138368602394293), x, RC(428, -1.77293428863008)), x, RC(429, 17.3639054044562)), x, RC(430, -357.615122086961)), x, RC(431, 2698.31813951849)) + (xinv * RC(432, -14573.4701095912))) * g) + (RC(413, 5.52534374226326) / (fma(1.0, x, RC(414, -5.52534374226326)))));
-        double t1 = (r[0] / (r[0] + 1.0));
-        double t2 = (r[1] / (r[1] + 1.0));
-        double t3 = (r[2] / (r[2] + 1.0));
-        double a2 = (f2 - (t1 * f1));
-        double a1 = (f1 - (t1 * w[0]));
-        w[2] = ((a2 - (t2 * a1)) / ((t3 - t2) * (t3 - t1)));
-        w[1] = (((t3 * a1) - a2) / ((t3 - t2) * (t2 - t1)));
-        w[0] = ((w[0] - w[1]) - w[2]);
-    }
-    else if (x <= 47.0) {
-        w[0] = ub_sq;
-        double g = ub_g;
-        r[0] = (((fma(fma(RC(433, -7.39058467995275), x, RC(434, 321.318352526305)), x, RC(435, -3994.33696473658))) * g) + (RC(392, 0.190163509193487) / (fma(1.0, x, RC(393, -0.190163509193487)))));
-        r[1] = (((fma(fma(RC(436, -73.8726243906513), x, RC(437, 3135.69966333873)), x, RC(438, -38686.2867311321))) * g) + (RC(403, 1.78449274854325) / (fma(1.0, x, RC(404, -1.78449274854325)))));
-        r[2] = (((fma(fma(RC(439, -263.750565461336), x, RC(440, 10441.2168692352)), x, RC(441, -128094.577915394))) * g) + (RC(413, 5.52534374226326) / (fma(1.0, x, RC(414, -5.52534374226326)))));
-        w[2] = (((fma(fma(fma(RC(442, 0.152258947224714), x, RC(443, -8.30661900042651)), x, RC(444, 192.977367967984)), x, RC(445, -1677.87926005344))) * g) + (RC(446, 0.00511156880411248) * w[0]));
-        w[1] = (((fma(fma(RC(447, 61.5072615497811), x, RC(448, -2919.80647450269)), x, RC(449, 38079.4303087338))) * g) + (RC(450, 0.177231492083829) * w[0]));
-        w[0] = ((w[0] - w[1]) - w[2]);
-    }
-    else {
-        w[0] = ub_sq;
-        r[0] = (RC(392, 0.190163509193487) / (fma(1.0, x, RC(393, -0.190163509193487))));
-        r[1] = (RC(403, 1.78449274854325) / (fma(1.0, x, RC(404, -1.78449274854325))));
-        r[2] = (RC(413, 5.52534374226326) / (fma(1.0, x, RC(414, -5.52534374226326))));
-        w[1] = (RC(450, 0.177231492083829) * w[0]);
-        w[2] = (RC(446, 0.00511156880411248) * w[0]);
-        w[0] = ((w[0] - w[1]) - w[2]);
+// Reference-compatible two-root band, 15 < X <= 40: restates reference Rys.cpp:614-624 (see the header comment).
+UNOMOL_HD void rys2_compat_band(double x, double *r, double *w) {
+    const double g = exp(-x);
+    const double wsum = sqrt(0.785398163397448 / x);
+    r[0] = fma(-0.87894730749888, x, 10.9243702330261) * g + 0.275255128608411 / (x - 0.275255128608411);
+    r[1] = fma(-9.28903924275977, x, 81.0642367843811) * g + 2.72474487139158 / (x - 2.72474487139158);
+    w[1] = fma(4.468573893084, x, -77.9250653461045) * g + 0.0917517095361369 * wsum;
+    w[0] = wsum - w[1];
+}
+
+template <int N>
+UNOMOL_HD void rys_roots(double x, double *r, double *w, const RysTables &T);
+
+template <>
+UNOMOL_HD void rys_roots<1>(double x, double *r, double *w, const RysTables &T) {
+    double f1;
+    rys1_f0f1(x, w[0], f1, T);
+    r[0] = f1 / (w[0] - f1);
+}
+
+template <>
+UNOMOL_HD void rys_roots<2>(double x, double *r, double *w, const RysTables &T) {
+    const double xmom = T.rys2_exact ? (double)RYS_BOYS_XMAX : 15.0;
+    if (x <= xmom) {
+        if (x >= (double)RYS_BOYS_XMAX) { rys_hermite_limit<2>(x, r, w); return; }   // exact mode, x == 46
+        double m[4];
+        boys_grid<3>(x, T.boys, m);
+        // monic orthogonal polynomial y^2 + c1 y + c0 in y = t^2:  [m0 m1; m1 m2] (c0, c1)^T = -(m2, m3)^T
+        const double det = rys_dop(m[0], m[2], m[1], m[1]);
+        const double n0 = rys_dop(m[1], m[3], m[2], m[2]);
+        const double n1 = rys_dop(m[1], m[2], m[0], m[3]);
+        const double idet = 1.0 / det;
+        const double c0 = n0 * idet, c1 = n1 * idet;       // c0 = y0 y1 > 0, c1 = -(y0 + y1) < 0
+        const double disc = sqrt(fma(c1, c1, -4.0 * c0));
+        const double y1 = 0.5 * (disc - c1);               // larger node, no cancellation
+        const double y0 = c0 / y1;
+        const double w1 = fma(-y0, m[0], m[1]) / (y1 - y0);
+        r[0] = y0 / (1.0 - y0);
+        r[1] = y1 / (1.0 - y1);
+        w[1] = w1;
+        w[0] = m[0] - w1;
+    } else if (!T.rys2_exact && x <= 40.0) {
+        rys2_compat_band(x, r, w);
+    } else {
+        rys_hermite_limit<2>(x, r, w);
     }
 }
 
-template <> UNOMOL_HD void rys_roots<4>(double x, double *r, double *w) {
-    const double ub_g = exp((-x));
-    const double ub_xinv = (1.0 / x);
-    const double ub_sq = sqrt((RC(42, 0.785398163397448) * ub_xinv));
-    if (x <= RC(0, 3e-07)) {
-        r[0] = (fma(RC(451, -0.00409645850660395), x, RC(452, 0.0348198973061471)));
-        r[1] = (fma(RC(453, -0.0448902570656719), x, RC(454, 0.381567185080042)));
-        r[2] = (fma(RC(455, -0.204389090547327), x, RC(456, 1.73730726945891)));
-        r[3] = (fma(RC(457, -1.39368301742312), x, RC(458, 11.8463056481549)));
-        w[0] = (fma(RC(459, -0.0313844305713928), x, RC(460, 0.362683783378362)));
-        w[1] = (fma(RC(461, -0.0898046242557724), x, RC(462, 0.313706645877886)));
-        w[2] = (fma(RC(463, -0.129314370958973), x, RC(464, 0.222381034453372)));
-        w[3] = (fma(RC(465, -0.0828299075414321), x, RC(466, 0.101228536290376)));
+template <int N>
+UNOMOL_HD void rys_piecewise(double x, double *r, double *w, const double *tab, double xa) {
+    if (x >= xa) { rys_hermite_limit<N>(x, r, w); return; }
+    const int iv = (int)x;                                 // unit intervals
+    const double s = fma(2.0, x - (double)iv, -1.0);       // [-1, 1]
+    const double *c = tab + (size_t)iv * ((RYS_P3_DEG + 1) * 2 * N);
+    double acc[2 * N];
+#ifdef __CUDA_ARCH__
+    // rows of 2N doubles start 16-byte aligned (even offsets into a 16-byte aligned table): N double2 loads per degree
+    const double2 *c2 = reinterpret_cast<const double2 *>(c);
+#pragma unroll
+    for (int f = 0; f < N; ++f) {
+        const double2 v = __ldg(c2 + RYS_P3_DEG * N + f);
+        acc[2 * f] = v.x;
+        acc[2 * f + 1] = v.y;
     }
-    else if (x <= 1.0) {
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(RC(467, -1.95309614628539e-10), x, RC(468, 5.19765728707592e-9)), x, RC(469, -1.01756452250573e-7)), x, RC(470, 1.72365935872131e-6)), x, RC(471, -2.61203523522184e-5)), x, RC(472, 3.5292130876988e-4)), x, RC(473, -0.00409645850658433)), x, RC(474, 0.0348198973061469)));
-        r[1] = (fma(fma(fma(fma(fma(fma(RC(475, -1.89554881382342e-8), x, RC(476, 3.07583114342365e-7)), x, RC(477, 1.270981734393e-6)), x, RC(478, -1.417298563884e-4)), x, RC(479, 0.003226979163176)), x, RC(480, -0.0448902570678178)), x, RC(481, 0.381567185080039)));
-        r[2] = (fma(fma(fma(fma(fma(fma(fma(RC(482, 1.77280535300416e-9), x, RC(483, 3.36524958870615e-8)), x, RC(484, -2.58341529013893e-7)), x, RC(485, -1.1364489566232e-5)), x, RC(486, -7.91549618884063e-5)), x, RC(487, 0.0103825827346828)), x, RC(488, -0.204389090525137)), x, RC(489, 1.73730726945889)));
-        r[3] = (fma(fma(fma(fma(fma(fma(RC(490, -5.61188882415248e-8), x, RC(491, -2.4948073307246e-7)), x, RC(492, 3.428685057114e-6)), x, RC(493, 1.679007454539e-4)), x, RC(494, 0.04722855585715)), x, RC(495, -1.39368301737828)), x, RC(496, 11.8463056481543)));
-        w[0] = (fma(fma(fma(fma(fma(fma(fma(RC(497, -1.14649303201279e-8), x, RC(498, 1.88015570196787e-7)), x, RC(499, -2.33305875372323e-6)), x, RC(500, 2.68880044371597e-5)), x, RC(501, -2.94268428977387e-4)), x, RC(502, 0.00306548909776613)), x, RC(503, -0.0313844305680096)), x, RC(504, 0.362683783378335)));
-        w[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(505, -4.11720483772634e-9), x, RC(506, 6.54963481852134e-8)), x, RC(507, -7.20045285129626e-7)), x, RC(508, 6.93779646721723e-6)), x, RC(509, -6.05367572016373e-5)), x, RC(510, 4.74241566251899e-4)), x, RC(511, -0.00326956188125316)), x, RC(512, 0.0191883866626681)), x, RC(513, -0.0898046242565811)), x, RC(462, 0.313706645877886)));
-        w[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(514, -3.41688436990215e-8), x, RC(515, 5.07238960340773e-7)), x, RC(516, -5.0167562840822e-6)), x, RC(517, 4.20363420922845e-5)), x, RC(518, -3.08040221166823e-4)), x, RC(519, 0.00194431864731239)), x, RC(520, -0.0102477820460278)), x, RC(521, 0.0428670143840073)), x, RC(522, -0.129314370962569)), x, RC(523, 0.222381034453369)));
-        w[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(524, 4.99660550769508e-9), x, RC(525, -7.9458596331012e-8)), x, RC(526, 8.359072409485e-7)), x, RC(527, -7.42236921061e-6)), x, RC(528, 5.76337430816e-5)), x, RC(529, -3.86645606718233e-4)), x, RC(530, 0.00218417516259781)), x, RC(531, -0.00999791027771119)), x, RC(532, 0.034879109737737)), x, RC(533, -0.0828299075413889)), x, RC(466, 0.101228536290376)));
-    }
-    else if (x <= 5.0) {
-        const double y = x - 3.0;
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(534, -1.48570633747284e-15), y, RC(535, -1.33273068108777e-13)), y, RC(536, 4.06854369667e-12)), y, RC(537, -9.163164161821e-11)), y, RC(538, 2.046819017845e-9)), y, RC(539, -4.03076426299031e-8)), y, RC(540, 7.29407420660149e-7)), y, RC(541, -1.23118059980833e-5)), y, RC(542, 1.88796581246938e-4)), y, RC(543, -0.00253262912046853)), y, RC(544, 0.0251198234505021)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(545, 1.35830583483312e-13), y, RC(546, -2.29772605964836e-12)), y, RC(547, -3.821500128045e-12)), y, RC(548, 6.844424214735e-10)), y, RC(549, -1.048063352259e-8)), y, RC(550, 1.50083186233363e-8)), y, RC(551, 3.48848942324454e-6)), y, RC(552, -1.08694174399193e-4)), y, RC(553, 0.00208048885251999)), y, RC(554, -0.0291205805373793)), y, RC(555, 0.272276489515713)));
-        r[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(556, 5.02799392850289e-13), y, RC(557, 1.07461812944084e-11)), y, RC(558, -1.482277886411e-10)), y, RC(559, -2.153585661215e-9)), y, RC(560, 3.654087802817e-8)), y, RC(561, 5.1592957583012e-7)), y, RC(562, -9.52388379435709e-6)), y, RC(563, -2.16552440036426e-4)), y, RC(564, 0.0090355146956832)), y, RC(565, -0.145505469175613)), y, RC(566, 1.21449092319186)));
-        r[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(567, -1.08510370291979e-12), y, RC(568, 6.41492397277798e-11)), y, RC(569, 7.542387436125e-10)), y, RC(570, -2.213111836647e-9)), y, RC(571, -1.448228963549e-7)), y, RC(572, -1.95670833237101e-6)), y, RC(573, -1.07481314670844e-5)), y, RC(574, 1.49335941252765e-4)), y, RC(575, 0.0487791531990593)), y, RC(576, -1.10559909038653)), y, RC(577, 8.0950202861178)));
-        w[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(578, -4.65801912689961e-14), y, RC(579, 7.586695071068e-13)), y, RC(580, -1.186387548048e-11)), y, RC(581, 1.862334710665e-10)), y, RC(582, -2.799399389539e-9)), y, RC(583, 4.148972684255e-8)), y, RC(584, -5.9335680796e-7)), y, RC(585, 8.168349266115e-6)), y, RC(586, -1.08989176177409e-4)), y, RC(587, 0.00141357961729531)), y, RC(588, -0.0187588361833659)), y, RC(589, 0.289898651436026)));
-        w[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(590, -1.46345073267549e-14), y, RC(591, 2.25644205432182e-13)), y, RC(592, -3.116258693847e-12)), y, RC(593, 4.32190875661e-11)), y, RC(594, -5.673270062669e-10)), y, RC(595, 7.00629596296e-9)), y, RC(596, -8.120186517e-8)), y, RC(597, 8.77529464577e-7)), y, RC(598, -8.77829235749024e-6)), y, RC(599, 8.04372147732379e-5)), y, RC(600, -6.64149238804153e-4)), y, RC(601, 0.00481181506827225)), y, RC(602, -0.0288982669486183)), y, RC(603, 0.156247249979288)));
-        w[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(604, 9.06812118895365e-15), y, RC(605, -1.40541322766087e-13)), y, RC(606, 1.919270015269e-12)), y, RC(607, -2.60513573901e-11)), y, RC(608, 3.299685839012e-10)), y, RC(609, -3.86354139348735e-9)), y, RC(610, 4.16265847927498e-8)), y, RC(611, -4.0946283547147e-7)), y, RC(612, 3.64018881086111e-6)), y, RC(613, -2.88665153269386e-5)), y, RC(614, 2.00515819789028e-4)), y, RC(615, -0.00118791896897934)), y, RC(616, 0.00575223633388589)), y, RC(617, -0.0209400418772687)), y, RC(618, 0.0485368861938873)));
-        w[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(619, -9.74835552342257e-16), y, RC(620, 1.57857099317175e-14)), y, RC(621, -2.249993780112e-13)), y, RC(622, 3.173422008953e-12)), y, RC(623, -4.16115945968e-11)), y, RC(624, 5.021343560166e-10)), y, RC(625, -5.545047534808e-9)), y, RC(626, 5.554146993491e-8)), y, RC(627, -4.99048696190133e-7)), y, RC(628, 3.96650392371311e-6)), y, RC(629, -2.73816413291214e-5)), y, RC(630, 1.60106988333186e-4)), y, RC(631, -7.64560567879592e-4)), y, RC(632, 0.00281330044426892)), y, RC(633, -0.00716227030134947)), y, RC(634, 0.00966077262223353)));
-    }
-    else if (x <= 10.0) {
-        const double y = x - 7.5;
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(635, 4.64217329776215e-15), y, RC(636, -6.27892383644164e-15)), y, RC(637, 3.462236347446e-13)), y, RC(638, -2.92722935535e-11)), y, RC(639, 5.090355371676e-10)), y, RC(640, -9.97272656345253e-9)), y, RC(641, 2.37835295639281e-7)), y, RC(642, -4.60301761310921e-6)), y, RC(643, 8.42824204233222e-5)), y, RC(644, -0.00137983082233081)), y, RC(645, 0.0166630865869375)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(646, 2.93981127919047e-14), y, RC(647, 8.47635639065744e-13)), y, RC(648, -1.446314544774e-11)), y, RC(649, -6.149155555753e-12)), y, RC(650, 8.484275604612e-10)), y, RC(651, -6.10898827887652e-8)), y, RC(652, 2.39156093611106e-6)), y, RC(653, -5.35837089462592e-5)), y, RC(654, 0.00100967602595557)), y, RC(655, -0.0157769317127372)), y, RC(656, 0.174853819464285)));
-        r[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(657, 2.93523563363e-14), y, RC(658, -6.4004177666702e-14)), y, RC(659, -2.695740446312e-12)), y, RC(660, 1.027082960169e-10)), y, RC(661, -5.82203865678e-10)), y, RC(662, -3.159991002539e-8)), y, RC(663, 4.327249251331e-7)), y, RC(664, 4.856768455119e-6)), y, RC(665, -2.54617989427762e-4)), y, RC(666, 0.00554843378106589)), y, RC(667, -0.0795013029486684)), y, RC(668, 0.720206142703162)));
-        r[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(669, -1.62212382394553e-14), y, RC(670, 7.68943641360593e-13)), y, RC(671, 5.764015756615e-12)), y, RC(672, -1.380635298784e-10)), y, RC(673, -1.476849808675e-9)), y, RC(674, 1.84347052385605e-8)), y, RC(675, 3.34382940759405e-7)), y, RC(676, -1.39428366421645e-6)), y, RC(677, -7.50249313713996e-5)), y, RC(678, -6.26495899187507e-4)), y, RC(679, 0.0469716410901162)), y, RC(680, -0.666871297428209)), y, RC(681, 4.11207530217806)));
-        w[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(682, -1.65995045235997e-15), y, RC(683, 6.91838935879598e-14)), y, RC(684, -9.131223418888e-13)), y, RC(685, 1.403341829454e-11)), y, RC(686, -3.672235069444e-10)), y, RC(687, 6.36696254699e-9)), y, RC(688, -1.039220021671e-7)), y, RC(689, 1.959098751715e-6)), y, RC(690, -3.33474893152939e-5)), y, RC(691, 5.72164211151013e-4)), y, RC(692, -0.0105583210553392)), y, RC(693, 0.226696066029591)));
-        w[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(694, -3.57248951192047e-16), y, RC(695, 6.25708409149331e-15)), y, RC(696, -9.657033089714e-14)), y, RC(697, 1.507864898748e-12)), y, RC(698, -2.33252225611e-11)), y, RC(699, 3.428545616603e-10)), y, RC(700, -4.698730937661e-9)), y, RC(701, 6.21997763513e-8)), y, RC(702, -7.83008889613661e-7)), y, RC(703, 9.08621687041567e-6)), y, RC(704, -9.86368311253873e-5)), y, RC(705, 9.69632496710088e-4)), y, RC(706, -0.00814594214284187)), y, RC(707, 0.0850218447733457)));
-        w[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(708, 1.64742458534277e-16), y, RC(709, -2.6851226592841e-15)), y, RC(710, 3.788890667676e-14)), y, RC(711, -5.508918529823e-13)), y, RC(712, 7.555896810069e-12)), y, RC(713, -9.69039768312637e-11)), y, RC(714, 1.16034263529672e-9)), y, RC(715, -1.28771698573873e-8)), y, RC(716, 1.31949431805798e-7)), y, RC(717, -1.23673915616005e-6)), y, RC(718, 1.04189803544936e-5)), y, RC(719, -7.79566003744742e-5)), y, RC(720, 5.03162624754434e-4)), y, RC(721, -0.00255138844587555)), y, RC(722, 0.0113250730954014)));
-        w[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(723, -1.55714130075679e-17), y, RC(724, 2.57193722698891e-16)), y, RC(725, -3.626606654097e-15)), y, RC(726, 5.234734676175e-14)), y, RC(727, -7.067105402134e-13)), y, RC(728, 8.79351266489e-12)), y, RC(729, -1.006088923498e-10)), y, RC(730, 1.050565098393e-9)), y, RC(731, -9.91517881772662e-9)), y, RC(732, 8.35835975882941e-8)), y, RC(733, -6.19785782240693e-7)), y, RC(734, 3.95841149373135e-6)), y, RC(735, -2.11366761402403e-5)), y, RC(736, 9.00474771229507e-5)), y, RC(737, -2.78777909813289e-4)), y, RC(738, 5.26543779837487e-4)));
-    }
-    else if (x <= 15.0) {
-        const double y = x - 12.5;
-        double xinv = ub_xinv;
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(739, 4.94869622744119e-17), y, RC(740, 8.0356880573916e-16)), y, RC(741, -5.599125915431e-15)), y, RC(742, -1.378685560217e-13)), y, RC(743, 7.006511663249e-13)), y, RC(744, 1.30391406991118e-11)), y, RC(745, 8.06987313467541e-11)), y, RC(746, -5.20644072732933e-9)), y, RC(747, 7.72794187755457e-8)), y, RC(748, -1.61512612564194e-6)), y, RC(749, 4.15083811185831e-5)), y, RC(750, -7.87855975560199e-4)), y, RC(751, 0.0114189319050009)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(752, 4.89224285522336e-16), y, RC(753, 1.06390248099712e-14)), y, RC(754, -5.446260182933e-14)), y, RC(755, -1.613630106295e-12)), y, RC(756, 3.910179118937e-12)), y, RC(757, 1.90712434258806e-10)), y, RC(758, 8.78470199094761e-10)), y, RC(759, -5.97332993206797e-8)), y, RC(760, 9.25750831481589e-7)), y, RC(761, -2.02362185197088e-5)), y, RC(762, 4.92341968336776e-4)), y, RC(763, -0.00868438439874703)), y, RC(764, 0.115825965127958)));
-        r[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(765, 6.12419396208408e-14), y, RC(766, 1.12328861406073e-13)), y, RC(767, -9.051094103059e-12)), y, RC(768, -4.781797525341e-11)), y, RC(769, 1.660828868694e-9)), y, RC(770, 4.499058798868e-10)), y, RC(771, -2.519549641933e-7)), y, RC(772, 4.97744404018e-6)), y, RC(773, -1.25858350034589e-4)), y, RC(774, 0.00270279176970044)), y, RC(775, -0.0399327850801083)), y, RC(776, 0.433467200855434)));
-        r[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(777, 4.63414725924048e-14), y, RC(778, -4.72757262693062e-14)), y, RC(779, -1.001926833832e-11)), y, RC(780, 6.074107718414e-11)), y, RC(781, 1.576976911942e-9)), y, RC(782, -2.01186401974027e-8)), y, RC(783, -1.84530195217118e-7)), y, RC(784, 5.02333087806827e-6)), y, RC(785, 9.66961790843006e-6)), y, RC(786, -0.00158522208889528)), y, RC(787, 0.0280539673938339)), y, RC(788, -0.278953904330072)), y, RC(789, 1.82835655238235)));
-        w[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(790, 2.90401781000996e-18), y, RC(791, -4.63389683098251e-17)), y, RC(792, 6.274018198326e-16)), y, RC(793, -8.936002188168e-15)), y, RC(794, 1.194719074934e-13)), y, RC(795, -1.45501321259466e-12)), y, RC(796, 1.64090830181013e-11)), y, RC(797, -1.71987745310181e-10)), y, RC(798, 1.63738403295718e-9)), y, RC(799, -1.39237504892842e-8)), y, RC(800, 1.06527318142151e-7)), y, RC(801, -7.27634957230524e-7)), y, RC(802, 4.12159381310339e-6)), y, RC(803, -1.74648169719173e-5)), y, RC(804, 8.50290130067818e-5)));
-        w[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(805, -4.1956914545948e-17), y, RC(806, 5.94344180261644e-16)), y, RC(807, -1.148797566469e-14)), y, RC(808, 1.881303962576e-13)), y, RC(809, -2.413554618391e-12)), y, RC(810, 3.372127423047e-11)), y, RC(811, -4.933988617784e-10)), y, RC(812, 6.116545396281e-9)), y, RC(813, -6.69965691739299e-8)), y, RC(814, 7.52380085447161e-7)), y, RC(815, -8.08708393262321e-6)), y, RC(816, 6.88603417296672e-5)), y, RC(817, -4.67067112993427e-4)), y, RC(818, 0.00542313365864597)));
-        w[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(819, -6.22272689880615e-15), y, RC(820, 1.04126809657554e-13)), y, RC(821, -6.842418230913e-13)), y, RC(822, 1.576841731919e-11)), y, RC(823, -4.203948834175e-10)), y, RC(824, 6.287255934781e-9)), y, RC(825, -8.307159819228e-8)), y, RC(826, 1.356478091922e-6)), y, RC(827, -2.08065576105639e-5)), y, RC(828, 2.5239673033234e-4)), y, RC(829, -0.00294484050194539)), y, RC(830, 0.0601396183129168)));
-        w[0] = ((((((RC(43, -2.1916512131607e-5) + (xinv * fma(fma(RC(44, -0.18784686463512), xinv, RC(45, 0.22991849164985)), xinv, RC(46, -0.49893752514047)))) * ub_g) + ub_sq) - w[3]) - w[2]) - w[1]);
-    }
-    else if (x <= 20.0) {
-        const double y = x - 17.5;
-        double xinv = ub_xinv;
-        w[0] = ub_sq;
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(831, 4.36701759531398e-17), y, RC(832, -1.12860600219889e-16)), y, RC(833, -6.149849164164e-15)), y, RC(834, 5.820231579541e-14)), y, RC(835, 4.396602872143e-13)), y, RC(836, -1.24330365320172e-11)), y, RC(837, 6.71083474044549e-11)), y, RC(838, 2.43865205376067e-10)), y, RC(839, 1.67559587099969e-8)), y, RC(840, -9.32738632357572e-7)), y, RC(841, 2.39030487004977e-5)), y, RC(842, -4.68648206591515e-4)), y, RC(843, 0.00834977776583956)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(844, 4.98913142288158e-16), y, RC(845, -2.60732537093612e-16)), y, RC(846, -7.775156445127e-14)), y, RC(847, 5.766105220086e-13)), y, RC(848, 6.4326967296e-12)), y, RC(849, -1.39571683725792e-10)), y, RC(850, 5.95451479522191e-10)), y, RC(851, 2.42471442836205e-9)), y, RC(852, 2.4748571014312e-7)), y, RC(853, -1.14710398652091e-5)), y, RC(854, 2.71252453754519e-4)), y, RC(855, -0.00496812745851408)), y, RC(856, 0.082602060202678)));
-        r[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(857, 1.91498302509009e-15), y, RC(858, 1.48840394311115e-14)), y, RC(859, -4.316925145767e-13)), y, RC(860, 1.186495793471e-12)), y, RC(861, 4.615806713055e-11)), y, RC(862, -5.54336148667141e-10)), y, RC(863, 3.48789978951367e-10)), y, RC(864, -2.79188977451042e-9)), y, RC(865, 2.09563208958551e-6)), y, RC(866, -6.76512715080324e-5)), y, RC(867, 0.00132129867629062)), y, RC(868, -0.0205062147771513)), y, RC(869, 0.288068671894324)));
-        r[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(870, -5.43697691672942e-15), y, RC(871, -1.12483395714468e-13)), y, RC(872, 2.826607936174e-12)), y, RC(873, -1.26673449328e-11)), y, RC(874, -4.258722866437e-10)), y, RC(875, 9.45486578503261e-9)), y, RC(876, -5.86635622821309e-8)), y, RC(877, -1.28835028104639e-6)), y, RC(878, 4.41413815691885e-5)), y, RC(879, -7.61738385590776e-4)), y, RC(880, 0.0096609090298555)), y, RC(881, -0.101410568057649)), y, RC(882, 0.954714798156712)));
-        w[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(883, -7.56882223582704e-19), y, RC(884, 7.53541779268175e-18)), y, RC(885, -1.157318032236e-16)), y, RC(886, 2.411195002314e-15)), y, RC(887, -3.601794386996e-14)), y, RC(888, 4.082150659615e-13)), y, RC(889, -4.289542980767e-12)), y, RC(890, 5.086829642731e-11)), y, RC(891, -6.35435561050807e-10)), y, RC(892, 6.82309323251123e-9)), y, RC(893, -5.63374555753167e-8)), y, RC(894, 3.57005361100431e-7)), y, RC(895, -2.40050045173721e-6)), y, RC(896, 4.94171300536397e-5)));
-        w[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(897, -5.54451040921657e-17), y, RC(898, 2.68748367250999e-16)), y, RC(899, 1.349020069254e-14)), y, RC(900, -2.507452792892e-13)), y, RC(901, 1.944339743818e-12)), y, RC(902, -1.29816917658823e-11)), y, RC(903, 3.49977768819641e-10)), y, RC(904, -8.67270669346398e-9)), y, RC(905, 1.31381116840118e-7)), y, RC(906, -1.36790720600822e-6)), y, RC(907, 1.1921069767316e-5)), y, RC(908, -1.42181943986587e-4)), y, RC(909, 0.00412615396191829)));
-        w[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(910, -1.865060577297e-16), y, RC(911, 1.16661114435809e-15)), y, RC(912, 2.563712856363e-14)), y, RC(913, -4.498350984631e-13)), y, RC(914, 1.765194089338e-12)), y, RC(915, 9.04483676345625e-12)), y, RC(916, 4.98930345609785e-10)), y, RC(917, -2.11964170928181e-8)), y, RC(918, 3.98295476005614e-7)), y, RC(919, -5.49390160829409e-6)), y, RC(920, 7.74065155353262e-5)), y, RC(921, -0.00148201933009105)), y, RC(922, 0.0497836392625268)));
-        w[0] = ((((((RC(47, -6.0156581186481e-5) + (xinv * fma(RC(48, 0.1962326414943), xinv, RC(49, -0.4969524146449)))) * ub_g) + w[0]) - w[1]) - w[2]) - w[3]);
-    }
-    else if (x <= 25.0) {
-        double xinv = ub_xinv;
-        w[0] = ub_sq;
-        double g = ub_g;
-        r[0] = (((fma(fma(fma(fma(fma(fma(RC(923, -4.45711399441838e-5), x, RC(924, 0.00127267770241379)), x, RC(925, -0.236954961381262)), x, RC(926, 15.4330657903756)), x, RC(927, -522.799159267808)), x, RC(928, 10595.1216669313)), x, RC(929, -129194.382386499)) + (xinv * fma(RC(930, -2511772.35556236), xinv, RC(931, 872975.373557709)))) * g) + (RC(932, 0.145303521503316) / (fma(1.0, x, RC(933, -0.145303521503316)))));
-        r[1] = (((fma(fma(fma(fma(fma(RC(934, -0.0785617372254488), x, RC(935, 6.35653573484868)), x, RC(936, -338.29693876399)), x, RC(937, 12512.0495802096)), x, RC(938, -316847.570511637)), x, RC(939, 5386142.11391604)) + (xinv * fma(fma(RC(940, -1024274661.27427), xinv, RC(941, 370104713.293016)), xinv, RC(942, -58711900.5093822)))) * g) + (RC(943, 1.33909728812636) / (fma(1.0, x, RC(944, -1.33909728812636)))));
-        r[2] = (((fma(fma(fma(fma(fma(RC(945, -0.237900485051067), x, RC(946, 18.4122184400896)), x, RC(947, -1002.00731304146)), x, RC(948, 37515.1841595736)), x, RC(949, -950626.66339013)), x, RC(950, 16041939.0230055)) + (xinv * fma(fma(RC(951, -2881390146.51985), xinv, RC(952, 1066259150.44526)), xinv, RC(953, -172465289.687396)))) * g) + (RC(954, 3.92696350135829) / (fma(1.0, x, RC(955, -3.92696350135829)))));
-        r[3] = (((fma(fma(fma(fma(fma(fma(RC(956, -6.00691586407385e-4), x, RC(957, -0.364479545338439)), x, RC(958, 15.7496131755179)), x, RC(959, -654.944248734901)), x, RC(960, 17083.0039597097)), x, RC(961, -290517.939780207)), x, RC(962, 2968179.40164703)) + (xinv * fma(RC(963, 34905969.8304732), xinv, RC(964, -16494452.2586065)))) * g) + (RC(965, 8.58863568901199) / (fma(1.0, x, RC(966, -8.58863568901199)))));
-        w[3] = (((fma(fma(fma(fma(fma(fma(fma(RC(967, 2.33766206773151e-7), x, RC(968, -3.81542906607063e-5)), x, RC(969, 0.00351416601267)), x, RC(970, -0.166538571864728)), x, RC(971, 4.80006136831847)), x, RC(972, -87.3165934223603)), x, RC(973, 977.683627474638)), x, RC(974, -6144.79071209961)) + (xinv * RC(975, 16600.094511764))) * g) + (RC(976, 2.25229076750736e-4) * w[0]));
-        w[2] = (((fma(fma(fma(fma(fma(fma(RC(977, 2.36392855180768e-4), x, RC(978, -0.00916785337967013)), x, RC(979, 0.462186525041313)), x, RC(980, -19.694378600654)), x, RC(981, 499.169195295559)), x, RC(982, -6214.1984584509)), x, RC(983, -2815.01182042707)) + (xinv * fma(fma(RC(984, 52144505.3212414), xinv, RC(985, -13411346.4389309)), xinv, RC(986, 1136732.98305631)))) * g) + (RC(987, 0.0192704402415764) * w[0]));
-        w[1] = (((fma(fma(fma(fma(fma(fma(RC(988, 7.29841848989391e-4), x, RC(989, -0.0353899555749875)), x, RC(990, 2.07797425718513)), x, RC(991, -100.464709786287)), x, RC(992, 3152.06108877819)), x, RC(993, -62705.4715090012)), x, RC(994, 767135.400969617)) + (xinv * fma(RC(995, 15472124.6264919), xinv, RC(996, -5260743.91316381)))) * g) + (RC(997, 0.234479815323517) * w[0]));
-        w[0] = ((((((RC(47, -6.0156581186481e-5) + (xinv * fma(RC(48, 0.1962326414943), xinv, RC(49, -0.4969524146449)))) * g) + w[0]) - w[1]) - w[2]) - w[3]);
-    }
-    else if (x <= 35.0) {
-        double xinv = ub_xinv;
-        w[0] = ub_sq;
-        double g = ub_g;
-        r[0] = (((fma(fma(fma(fma(fma(fma(RC(923, -4.45711399441838e-5), x, RC(924, 0.00127267770241379)), x, RC(925, -0.236954961381262)), x, RC(926, 15.4330657903756)), x, RC(927, -522.799159267808)), x, RC(928, 10595.1216669313)), x, RC(929, -129194.382386499)) + (xinv * fma(RC(930, -2511772.35556236), xinv, RC(931, 872975.373557709)))) * g) + (RC(932, 0.145303521503316) / (fma(1.0, x, RC(933, -0.145303521503316)))));
-        r[1] = (((fma(fma(fma(fma(fma(RC(934, -0.0785617372254488), x, RC(935, 6.35653573484868)), x, RC(936, -338.29693876399)), x, RC(937, 12512.0495802096)), x, RC(938, -316847.570511637)), x, RC(939, 5386142.11391604)) + (xinv * fma(fma(RC(940, -1024274661.27427), xinv, RC(941, 370104713.293016)), xinv, RC(942, -58711900.5093822)))) * g) + (RC(943, 1.33909728812636) / (fma(1.0, x, RC(944, -1.33909728812636)))));
-        r[2] = (((fma(fma(fma(fma(fma(RC(945, -0.237900485051067), x, RC(946, 18.4122184400896)), x, RC(947, -1002.00731304146)), x, RC(948, 37515.1841595736)), x, RC(949, -950626.66339013)), x, RC(950, 16041939.0230055)) + (xinv * fma(fma(RC(951, -2881390146.51985), xinv, RC(952, 1066259150.44526)), xinv, RC(953, -172465289.687396)))) * g) + (RC(954, 3.92696350135829) / (fma(1.0, x, RC(955, -3.92696350135829)))));
-        r[3] = (((fma(fma(fma(fma(fma(fma(RC(956, -6.00691586407385e-4), x, RC(957, -0.364479545338439)), x, RC(958, 15.7496131755179)), x, RC(959, -654.944248734901)), x, RC(960, 17083.0039597097)), x, RC(961, -290517.939780207)), x, RC(962, 2968179.40164703)) + (xinv * fma(RC(963, 34905969.8304732), xinv, RC(964, -16494452.2586065)))) * g) + (RC(965, 8.58863568901199) / (fma(1.0, x, RC(966, -8.58863568901199)))));
-        w[3] = (((fma(fma(fma(fma(fma(fma(RC(998, 5.74245945342286e-6), x, RC(999, -7.58735928102351e-5)), x, RC(1000, 2.35072857922892e-4)), x, RC(1001, -0.00378812134013125)), x, RC(1002, 0.309871652785805)), x, RC(1003, -7.11108633061306)), x, RC(1004, 55.5297573149528))) * g) + (RC(976, 2.25229076750736e-4) * w[0]));
-        w[2] = (((fma(fma(fma(fma(fma(fma(RC(977, 2.36392855180768e-4), x, RC(978, -0.00916785337967013)), x, RC(979, 0.462186525041313)), x, RC(980, -19.694378600654)), x, RC(981, 499.169195295559)), x, RC(982, -6214.1984584509)), x, RC(983, -2815.01182042707)) + (xinv * fma(fma(RC(984, 52144505.3212414), xinv, RC(985, -13411346.4389309)), xinv, RC(986, 1136732.98305631)))) * g) + (RC(987, 0.0192704402415764) * w[0]));
-        w[1] = (((fma(fma(fma(fma(fma(fma(RC(988, 7.29841848989391e-4), x, RC(989, -0.0353899555749875)), x, RC(990, 2.07797425718513)), x, RC(991, -100.464709786287)), x, RC(992, 3152.06108877819)), x, RC(993, -62705.4715090012)), x, RC(994, 767135.400969617)) + (xinv * fma(RC(995, 15472124.6264919), xinv, RC(996, -5260743.91316381)))) * g) + (RC(997, 0.234479815323517) * w[0]));
-        w[0] = ((((((RC(47, -6.0156581186481e-5) + (xinv * fma(RC(48, 0.1962326414943), xinv, RC(49, -0.4969524146449)))) * g) + w[0]) - w[1]) - w[2]) - w[3]);
-    }
-    else if (x <= 53.0) {
-        w[0] = ub_sq;
-        double d1 = (x * x);
-        double g = (ub_g * (d1 * d1));
-        r[3] = (((fma(fma(RC(1005, -0.00219135070169653), x, RC(1006, -0.119108256987623)), x, RC(1007, -0.750238795695573))) * g) + (RC(965, 8.58863568901199) / (fma(1.0, x, RC(966, -8.58863568901199)))));
-        r[2] = (((fma(fma(RC(1008, -9.65842534508637e-4), x, RC(1009, -0.0449822013469279)), x, RC(1010, 0.608784033347757))) * g) + (RC(954, 3.92696350135829) / (fma(1.0, x, RC(955, -3.92696350135829)))));
-        r[1] = (((fma(fma(RC(1011, -3.62569791162153e-4), x, RC(1012, -0.00909231717268466)), x, RC(1013, 0.184336760556262))) * g) + (RC(943, 1.33909728812636) / (fma(1.0, x, RC(944, -1.33909728812636)))));
-        r[0] = (((fma(fma(RC(1014, -4.075575259146e-5), x, RC(1015, -6.88846864931685e-4)), x, RC(1016, 0.0174725309199384))) * g) + (RC(932, 0.145303521503316) / (fma(1.0, x, RC(933, -0.145303521503316)))));
-        w[3] = (((fma(fma(RC(1017, 5.7663198200099e-6), x, RC(1018, -7.8918728380489e-5)), x, RC(1019, 3.28297971853126e-4))) * g) + (RC(976, 2.25229076750736e-4) * w[0]));
-        w[2] = (((fma(fma(RC(1020, 2.0829496985723e-4), x, RC(1021, -0.00377489954837361)), x, RC(1022, 0.0209857151617436))) * g) + (RC(987, 0.0192704402415764) * w[0]));
-        w[1] = (((fma(fma(RC(1023, 6.16374517326469e-4), x, RC(1024, -0.0126711744680092)), x, RC(1025, 0.0814504890732155))) * g) + (RC(997, 0.234479815323517) * w[0]));
-        w[0] = (((w[0] - w[1]) - w[2]) - w[3]);
-    }
-    else {
-        w[0] = ub_sq;
-        r[0] = (RC(932, 0.145303521503316) / (fma(1.0, x, RC(933, -0.145303521503316))));
-        r[1] = (RC(943, 1.33909728812636) / (fma(1.0, x, RC(944, -1.33909728812636))));
-        r[2] = (RC(954, 3.92696350135829) / (fma(1.0, x, RC(955, -3.92696350135829))));
-        r[3] = (RC(965, 8.58863568901199) / (fma(1.0, x, RC(966, -8.58863568901199))));
-        w[3] = (RC(976, 2.25229076750736e-4) * w[0]);
-        w[2] = (RC(987, 0.0192704402415764) * w[0]);
-        w[1] = (RC(997, 0.234479815323517) * w[0]);
-        w[0] = (((w[0] - w[1]) - w[2]) - w[3]);
-    }
+#pragma unroll
+    for (int k = RYS_P3_DEG - 1; k >= 0; --k)
+#pragma unroll
+        for (int f = 0; f < N; ++f) {
+            const double2 v = __ldg(c2 + k * N + f);
+            acc[2 * f] = fma(acc[2 * f], s, v.x);
+            acc[2 * f + 1] = fma(acc[2 * f + 1], s, v.y);
+        }
+#else
+#pragma unroll
+    for (int f = 0; f < 2 * N; ++f) acc[f] = c[RYS_P3_DEG * 2 * N + f];
+#pragma unroll
+    for (int k = RYS_P3_DEG - 1; k >= 0; --k)
+#pragma unroll
+        for (int f = 0; f < 2 * N; ++f) acc[f] = fma(acc[f], s, c[k * 2 * N + f]);
+#endif
+#pragma unroll
+    for (int i = 0; i < N; ++i) { r[i] = acc[i]; w[i] = acc[N + i]; }
 }
+static_assert(RYS_P3_DEG == RYS_P4_DEG && RYS_P4_DEG == RYS_P5_DEG, "one degree for all piecewise tables");
 
-template <> UNOMOL_HD void rys_roots<5>(double x, double *r, double *w) {
-    const double ub_g = exp((-x));
-    if (x <= RC(0, 3e-07)) {
-        r[0] = (fma(RC(1026, -0.00215865967920897), x, RC(1027, 0.0226659266316985)));
-        r[1] = (fma(RC(1028, -0.0220258754389745), x, RC(1029, 0.231271692140903)));
-        r[2] = (fma(RC(1030, -0.0816520023025515), x, RC(1031, 0.857346024118836)));
-        r[3] = (fma(RC(1032, -0.283193369647137), x, RC(1033, 2.97353038120346)));
-        r[4] = (fma(RC(1034, -1.75382723579439), x, RC(1035, 18.4151859759051)));
-        w[0] = (fma(RC(1036, -0.0196867576909777), x, RC(1037, 0.295524224714752)));
-        w[1] = (fma(RC(1038, -0.0561737590184721), x, RC(1039, 0.269266719309995)));
-        w[2] = (fma(RC(1040, -0.0971152726793658), x, RC(1041, 0.219086362515981)));
-        w[3] = (fma(RC(1042, -0.102979262193565), x, RC(1043, 0.14945134915058)));
-        w[4] = (fma(RC(1044, -0.0573782817488315), x, RC(1045, 0.0666713443086877)));
-    }
-    else if (x <= 1.0) {
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(RC(1046, -4.46679165328413e-11), x, RC(1047, 1.21879111988031e-9)), x, RC(1048, -2.62975022612104e-8)), x, RC(1049, 5.15106194905897e-7)), x, RC(1050, -9.27933625824749e-6)), x, RC(1051, 1.51794097682482e-4)), x, RC(1052, -0.00215865967920301)), x, RC(1027, 0.0226659266316985)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(RC(1053, 1.93117331714174e-10), x, RC(1054, -4.57267589660699e-9)), x, RC(1055, 2.48339908218932e-8)), x, RC(1056, 1.50716729438474e-6)), x, RC(1057, -6.07268757707381e-5)), x, RC(1058, 0.00137506939145643)), x, RC(1059, -0.0220258754419939)), x, RC(1060, 0.231271692140905)));
-        r[2] = (fma(fma(fma(fma(fma(fma(RC(1061, 4.84989776180094e-9), x, RC(1062, 1.31538893944284e-7)), x, RC(1063, -2.766753852879e-6)), x, RC(1064, -7.651163510626e-5)), x, RC(1065, 0.004033058545972)), x, RC(1066, -0.0816520022916145)), x, RC(1067, 0.857346024118779)));
-        r[3] = (fma(fma(fma(fma(fma(RC(1068, -2.48581772214623e-7), x, RC(1069, -4.34482635782585e-6)), x, RC(1070, -7.4601825798763e-7)), x, RC(1071, 0.0101210776517279)), x, RC(1072, -0.283193369640005)), x, RC(1073, 2.97353038120345)));
-        r[4] = (fma(fma(fma(fma(fma(fma(RC(1074, -8.92432153868554e-9), x, RC(1075, 1.77288899268988e-8)), x, RC(1076, 3.040754680666e-6)), x, RC(1077, 1.058229325071e-4)), x, RC(1078, 0.04596379534985)), x, RC(1079, -1.75382723579114)), x, RC(1080, 18.4151859759049)));
-        w[0] = (fma(fma(fma(fma(fma(fma(fma(RC(1081, -2.03822632771791e-9), x, RC(1082, 3.8911022913381e-8)), x, RC(1083, -5.84914787904823e-7)), x, RC(1084, 8.30316168666696e-6)), x, RC(1085, -1.13218402310546e-4)), x, RC(1086, 0.0014912888858679)), x, RC(1087, -0.0196867576904816)), x, RC(1088, 0.295524224714749)));
-        w[1] = (fma(fma(fma(fma(fma(fma(fma(fma(RC(1089, 8.6284811839757e-9), x, RC(1090, -1.38975551148989e-7)), x, RC(1091, 1.602894068228e-6)), x, RC(1092, -1.646364300836e-5)), x, RC(1093, 1.538445806778e-4)), x, RC(1094, -0.00128848868034502)), x, RC(1095, 0.00938866933338584)), x, RC(1096, -0.0561737590178812)), x, RC(1097, 0.269266719309991)));
-        w[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1098, -9.41953204205665e-9), x, RC(1099, 1.47452251067755e-7)), x, RC(1100, -1.57456991199322e-6)), x, RC(1101, 1.45098401798393e-5)), x, RC(1102, -1.18858834181513e-4)), x, RC(1103, 8.5369767598421e-4)), x, RC(1104, -0.00522877807397165)), x, RC(1105, 0.0260854524809786)), x, RC(1106, -0.0971152726809059)), x, RC(1107, 0.219086362515979)));
-        w[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1108, -3.84961617022042e-8), x, RC(1109, 5.6659539654447e-7)), x, RC(1110, -5.52351805403748e-6)), x, RC(1111, 4.53160377546073e-5)), x, RC(1112, -3.22542784865557e-4)), x, RC(1113, 0.00195682017370967)), x, RC(1114, -0.00977232537679229)), x, RC(1115, 0.0379455945268632)), x, RC(1116, -0.102979262192227)), x, RC(1117, 0.149451349150573)));
-        w[4] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1118, 4.0959481252143e-9), x, RC(1119, -6.47097874264417e-8)), x, RC(1120, 6.743541482689e-7)), x, RC(1121, -5.917993920224e-6)), x, RC(1122, 4.531969237381e-5)), x, RC(1123, -2.99102856679638e-4)), x, RC(1124, 0.00165695765202643)), x, RC(1125, -0.00740671222520653)), x, RC(1126, 0.0250889946832192)), x, RC(1127, -0.0573782817487958)), x, RC(1045, 0.0666713443086877)));
-    }
-    else if (x <= 5.0) {
-        const double y = x - 3.0;
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1128, -2.58163897135138e-14), y, RC(1129, 8.14127461488273e-13)), y, RC(1130, -2.11414838976129e-11)), y, RC(1131, 5.09822003260014e-10)), y, RC(1132, -1.16002134438663e-8)), y, RC(1133, 2.4681069441454e-7)), y, RC(1134, -4.92556826124502e-6)), y, RC(1135, 9.02580687971053e-5)), y, RC(1136, -0.00145190025120726)), y, RC(1137, 0.0173416786387475)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1138, 1.04525287289788e-14), y, RC(1139, 5.44611782010773e-14)), y, RC(1140, -4.831059411392e-12)), y, RC(1141, 1.136643908832e-10)), y, RC(1142, -1.104373076913e-9)), y, RC(1143, -2.35346740649916e-8)), y, RC(1144, 1.43772622028764e-6)), y, RC(1145, -4.23405023015273e-5)), y, RC(1146, 9.12034574793379e-4)), y, RC(1147, -0.0152479441718739)), y, RC(1148, 0.176055265928744)));
-        r[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1149, -6.89693150857911e-14), y, RC(1150, 5.92064260918861e-13)), y, RC(1151, 1.847170956043e-11)), y, RC(1152, -3.390752744265e-10)), y, RC(1153, -2.995532064116e-9)), y, RC(1154, 1.57456141058535e-7)), y, RC(1155, -3.95859409711346e-7)), y, RC(1156, -9.58924580919747e-5)), y, RC(1157, 0.00323551502557785)), y, RC(1158, -0.0597587007636479)), y, RC(1159, 0.646432853383057)));
-        r[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1160, -3.61293809667763e-12), y, RC(1161, -2.70803518291085e-11)), y, RC(1162, 8.83758848468769e-10)), y, RC(1163, 1.59166632851267e-8)), y, RC(1164, -1.32581997983422e-7)), y, RC(1165, -7.60223407443995e-6)), y, RC(1166, -7.41019244900952e-5)), y, RC(1167, 0.00981432631743423)), y, RC(1168, -0.223055570487771)), y, RC(1169, 2.21460798080643)));
-        r[4] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1170, 7.12332088345321e-13), y, RC(1171, 3.16578501501894e-12)), y, RC(1172, -8.776668218053e-11)), y, RC(1173, -2.342817613343e-9)), y, RC(1174, -3.496962018025e-8)), y, RC(1175, -3.03172870136802e-7)), y, RC(1176, 1.50511293969805e-6)), y, RC(1177, 1.37704919387696e-4)), y, RC(1178, 0.0470723869619745)), y, RC(1179, -1.47486623003693)), y, RC(1180, 13.5704792175847)));
-        w[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1181, 1.04348658616398e-13), y, RC(1182, -1.94147461891055e-12)), y, RC(1183, 3.485512360993e-11)), y, RC(1184, -6.277497362235e-10)), y, RC(1185, 1.100758247388e-8)), y, RC(1186, -1.88329804969573e-7)), y, RC(1187, 3.12338120839468e-6)), y, RC(1188, -5.04404167403568e-5)), y, RC(1189, 8.00338056610995e-4)), y, RC(1190, -0.0130892406559521)), y, RC(1191, 0.247383140241103)));
-        w[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1192, 3.23496149760478e-14), y, RC(1193, -5.24314473469311e-13)), y, RC(1194, 7.743219385056e-12)), y, RC(1195, -1.146022750992e-10)), y, RC(1196, 1.615238462197e-9)), y, RC(1197, -2.15479017572233e-8)), y, RC(1198, 2.70933462557631e-7)), y, RC(1199, -3.18750295288531e-6)), y, RC(1200, 3.47425221210099e-5)), y, RC(1201, -3.45558237388223e-4)), y, RC(1202, 0.00305779768191621)), y, RC(1203, -0.0229118251223003)), y, RC(1204, 0.159834227924213)));
-        w[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1205, -3.42790561802876e-14), y, RC(1206, 5.26475736681542e-13)), y, RC(1207, -7.184330797139e-12)), y, RC(1208, 9.763932908544e-11)), y, RC(1209, -1.244014559219e-9)), y, RC(1210, 1.472744068942e-8)), y, RC(1211, -1.611749975234e-7)), y, RC(1212, 1.616487851917e-6)), y, RC(1213, -1.46852359124154e-5)), y, RC(1214, 1.18900349101069e-4)), y, RC(1215, -8.37562373221756e-4)), y, RC(1216, 0.00493752683045845)), y, RC(1217, -0.0225514728915673)), y, RC(1218, 0.0695211812453929)));
-        w[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1219, 1.04072340345039e-14), y, RC(1220, -1.60808044529211e-13)), y, RC(1221, 2.183534866798e-12)), y, RC(1222, -2.939403008391e-11)), y, RC(1223, 3.679254029085e-10)), y, RC(1224, -4.23775673047899e-9)), y, RC(1225, 4.46559231067006e-8)), y, RC(1226, -4.26488836563267e-7)), y, RC(1227, 3.64721335274973e-6)), y, RC(1228, -2.74868382777722e-5)), y, RC(1229, 1.78586118867488e-4)), y, RC(1230, -9.68428981886534e-4)), y, RC(1231, 0.00416002324339929)), y, RC(1232, -0.0128290192663141)), y, RC(1233, 0.0222353727685016)));
-        w[4] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1234, -8.16770412525963e-16), y, RC(1235, 1.31376515047977e-14)), y, RC(1236, -1.856950818865e-13)), y, RC(1237, 2.596836515749e-12)), y, RC(1238, -3.372639523006e-11)), y, RC(1239, 4.025371849467e-10)), y, RC(1240, -4.389453269417e-9)), y, RC(1241, 4.332753856271e-8)), y, RC(1242, -3.82673275931962e-7)), y, RC(1243, 2.98006900751543e-6)), y, RC(1244, -2.00718990300052e-5)), y, RC(1245, 1.13876001386361e-4)), y, RC(1246, -5.23627942443563e-4)), y, RC(1247, 0.00183524565118203)), y, RC(1248, -0.00437785737450783)), y, RC(1249, 0.00536963805223095)));
-    }
-    else if (x <= 10.0) {
-        const double y = x - 7.5;
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1250, -1.13825201010775e-14), y, RC(1251, 1.89737681670375e-13)), y, RC(1252, -4.81561201185876e-12)), y, RC(1253, 1.56666512163407e-10)), y, RC(1254, -3.73782213255083e-9)), y, RC(1255, 9.15858355075147e-8)), y, RC(1256, -2.13775073585629e-6)), y, RC(1257, 4.56547356365536e-5)), y, RC(1258, -8.6800390932374e-4)), y, RC(1259, 0.0122703754069176)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1260, -3.67160504428358e-15), y, RC(1261, 1.27876280158297e-14)), y, RC(1262, -1.296476623788e-12)), y, RC(1263, 1.477175434354e-11)), y, RC(1264, 5.464102147892e-10)), y, RC(1265, -2.42538340602723e-8)), y, RC(1266, 8.20460740637617e-7)), y, RC(1267, -2.20379304598661e-5)), y, RC(1268, 4.90295372978785e-4)), y, RC(1269, -0.00914294111576119)), y, RC(1270, 0.12259040340369)));
-        r[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1271, 1.39017367502123e-14), y, RC(1272, -6.9639138542689e-13)), y, RC(1273, 1.176946020731e-12)), y, RC(1274, 1.725627235645e-10)), y, RC(1275, -3.6863838563e-9)), y, RC(1276, 2.87495324207095e-8)), y, RC(1277, 1.71307311000282e-6)), y, RC(1278, -7.94273603184629e-5)), y, RC(1279, 0.00200938064965897)), y, RC(1280, -0.0363329491677178)), y, RC(1281, 0.434393683888443)));
-        r[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1282, -1.27815158195209e-14), y, RC(1283, 1.99910415869821e-14)), y, RC(1284, 3.753542914426e-12)), y, RC(1285, -2.708018219579e-11)), y, RC(1286, -1.190574776587e-9)), y, RC(1287, 1.106696436509e-8)), y, RC(1288, 3.954955671326e-7)), y, RC(1289, -4.398596059588e-6)), y, RC(1290, -2.01087998907735e-4)), y, RC(1291, 0.00789092425542937)), y, RC(1292, -0.142056749162695)), y, RC(1293, 1.39964149420683)));
-        r[4] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1294, -1.19442341030461e-13), y, RC(1295, -2.34074833275956e-12)), y, RC(1296, 6.861649627426e-12)), y, RC(1297, 6.082671496226e-10)), y, RC(1298, 5.38116010542e-9)), y, RC(1299, -6.2532971387e-8)), y, RC(1300, -2.13596683505e-6)), y, RC(1301, -2.373394341886e-5)), y, RC(1302, 2.88711171412814e-6)), y, RC(1303, 0.0485221195290753)), y, RC(1304, -1.04346091985269)), y, RC(1305, 7.89901551676692)));
-        w[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1306, 7.95526040108997e-15), y, RC(1307, -2.48593096128045e-13)), y, RC(1308, 4.76124620872e-12)), y, RC(1309, -9.535763686605e-11)), y, RC(1310, 2.225273630974e-9)), y, RC(1311, -4.49796778054865e-8)), y, RC(1312, 9.17812870287386e-7)), y, RC(1313, -1.86764236490502e-5)), y, RC(1314, 3.76807779068053e-4)), y, RC(1315, -0.00810456360143408)), y, RC(1316, 0.201097936411496)));
-        w[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1317, 1.25678686624734e-15), y, RC(1318, -2.34266248891173e-14)), y, RC(1319, 3.973252415832e-13)), y, RC(1320, -6.830539401049e-12)), y, RC(1321, 1.140771033372e-10)), y, RC(1322, -1.82546185762009e-9)), y, RC(1323, 2.77209637550134e-8)), y, RC(1324, -4.01726946190383e-7)), y, RC(1325, 5.48227244014763e-6)), y, RC(1326, -6.95676245982121e-5)), y, RC(1327, 8.05193921815776e-4)), y, RC(1328, -0.00815528438784469)), y, RC(1329, 0.0971769901268114)));
-        w[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1330, -8.20929494859896e-16), y, RC(1331, 1.37356038393016e-14)), y, RC(1332, -2.02286306522e-13)), y, RC(1333, 3.058055403795e-12)), y, RC(1334, -4.387890955243e-11)), y, RC(1335, 5.923946274445e-10)), y, RC(1336, -7.503659964159e-9)), y, RC(1337, 8.851599803902e-8)), y, RC(1338, -9.65561998415038e-7)), y, RC(1339, 9.60884622778092e-6)), y, RC(1340, -8.56551787594404e-5)), y, RC(1341, 6.66057194311179e-4)), y, RC(1342, -0.00417753183902198)), y, RC(1343, 0.0225443826852447)));
-        w[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1344, -1.0876461248879e-17), y, RC(1345, 1.85299909689937e-16)), y, RC(1346, -2.730195628655e-15)), y, RC(1347, 4.127368817265e-14)), y, RC(1348, -5.881379088074e-13)), y, RC(1349, 7.805245193391e-12)), y, RC(1350, -9.632707991704e-11)), y, RC(1351, 1.099047050624e-9)), y, RC(1352, -1.15042731790748e-8)), y, RC(1353, 1.09415155268932e-7)), y, RC(1354, -9.33687124875935e-7)), y, RC(1355, 7.02338477986218e-6)), y, RC(1356, -4.53759748787756e-5)), y, RC(1357, 2.41722511389146e-4)), y, RC(1358, -9.75935943447037e-4)), y, RC(1359, 0.00257520532789644)));
-        w[4] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1360, 7.28996979748849e-19), y, RC(1361, -1.26518146195173e-17)), y, RC(1362, 1.886145834486e-16)), y, RC(1363, -2.876728287383e-15)), y, RC(1364, 4.114588668138e-14)), y, RC(1365, -5.44436631413933e-13)), y, RC(1366, 6.64976446790959e-12)), y, RC(1367, -7.4456006997494e-11)), y, RC(1368, 7.57553198166848e-10)), y, RC(1369, -6.92956101109829e-9)), y, RC(1370, 5.62222859033624e-8)), y, RC(1371, -3.97500114084351e-7)), y, RC(1372, 2.3903912613814e-6)), y, RC(1373, -1.18023950002105e-5)), y, RC(1374, 4.52254031046244e-5)), y, RC(1375, -1.2111378215037e-4)), y, RC(1376, 1.75013126731224e-4)));
-    }
-    else if (x <= 15.0) {
-        const double y = x - 12.5;
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1377, -4.16387977337393e-17), y, RC(1378, 7.2087299737386e-16)), y, RC(1379, 1.395993802064e-14)), y, RC(1380, 3.660484641252e-14)), y, RC(1381, -4.154857548139e-12)), y, RC(1382, 2.301379846544e-11)), y, RC(1383, -1.033307012866e-9)), y, RC(1384, 3.997777641049e-8)), y, RC(1385, -9.35118186333939e-7)), y, RC(1386, 2.38589932752937e-5)), y, RC(1387, -5.35185183652937e-4)), y, RC(1388, 0.00885218988709735)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1389, -4.56279214732217e-16), y, RC(1390, 6.24941647247927e-15)), y, RC(1391, 1.737896339191e-13)), y, RC(1392, 8.964205979517e-14)), y, RC(1393, -3.538906780633e-11)), y, RC(1394, 9.561341254948e-11)), y, RC(1395, -9.77283189131e-9)), y, RC(1396, 4.24034019462e-7)), y, RC(1397, -1.02384302866534e-5)), y, RC(1398, 2.57987709704822e-4)), y, RC(1399, -0.00554735977651677)), y, RC(1400, 0.0868245143991948)));
-        r[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1401, -2.52879337929239e-15), y, RC(1402, 2.13925810087833e-14)), y, RC(1403, 7.884307667104e-13)), y, RC(1404, -9.02339815951e-13)), y, RC(1405, -5.814101544957e-11)), y, RC(1406, -1.333480437968e-9)), y, RC(1407, -2.217064940373e-8)), y, RC(1408, 1.643290788086e-6)), y, RC(1409, -4.39602147345028e-5)), y, RC(1410, 0.00108648982748911)), y, RC(1411, -0.0213014521653498)), y, RC(1412, 0.294150684465425)));
-        r[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1413, -6.42391438038888e-15), y, RC(1414, 5.37848223438815e-15)), y, RC(1415, 8.960828117859e-13)), y, RC(1416, 5.214153461337e-11)), y, RC(1417, -1.106601744067e-10)), y, RC(1418, -2.007890743962e-8)), y, RC(1419, 1.543764346501e-7)), y, RC(1420, 4.520749076914e-6)), y, RC(1421, -1.88893338587047e-4)), y, RC(1422, 0.00473264487389288)), y, RC(1423, -0.0791197893350253)), y, RC(1424, 0.860057928514554)));
-        r[4] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1425, -2.24366166957225e-14), y, RC(1426, 4.87224967526081e-14)), y, RC(1427, 5.587369053655e-12)), y, RC(1428, -3.045253104617e-12)), y, RC(1429, -1.22398388308e-9)), y, RC(1430, -2.05603889396319e-9)), y, RC(1431, 2.58604071603561e-7)), y, RC(1432, 1.34240904266268e-6)), y, RC(1433, -5.72877569731162e-5)), y, RC(1434, -9.56275105032191e-4)), y, RC(1435, 0.0423367010370921)), y, RC(1436, -0.576800927133412)), y, RC(1437, 3.87328263873381)));
-        w[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1438, 8.98007931950169e-15), y, RC(1439, 7.25673623859497e-14)), y, RC(1440, 5.851494250405e-14)), y, RC(1441, -4.234204823846e-11)), y, RC(1442, 3.911507312679e-10)), y, RC(1443, -9.65094802088511e-9)), y, RC(1444, 3.42197444235714e-7)), y, RC(1445, -7.51821178144509e-6)), y, RC(1446, 1.94218051498662e-4)), y, RC(1447, -0.00538533819142287)), y, RC(1448, 0.168122596736809)));
-        w[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1449, -1.05490525395105e-15), y, RC(1450, 1.96855386549388e-14)), y, RC(1451, -5.500330153548e-13)), y, RC(1452, 1.003849567976e-11)), y, RC(1453, -1.720997242621e-10)), y, RC(1454, 3.533277061402e-9)), y, RC(1455, -6.389171736029e-8)), y, RC(1456, 1.046236652393e-6)), y, RC(1457, -1.73148206795827e-5)), y, RC(1458, 2.57820531617185e-4)), y, RC(1459, -0.0034618826533835)), y, RC(1460, 0.0703302497508176)));
-        w[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1461, 3.60020423754545e-16), y, RC(1462, -6.24245825017148e-15)), y, RC(1463, 9.945311467434e-14)), y, RC(1464, -1.749051512721e-12)), y, RC(1465, 2.768503957853e-11)), y, RC(1466, -4.08688551136506e-10)), y, RC(1467, 6.0418906330361e-9)), y, RC(1468, -8.23540111024147e-8)), y, RC(1469, 1.01503783870262e-6)), y, RC(1470, -1.20490761741576e-5)), y, RC(1471, 1.26928442448148e-4)), y, RC(1472, -0.00105539461930597)), y, RC(1473, 0.0115543698537013)));
-        w[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1474, 2.51163533058925e-18), y, RC(1475, -4.31723745510697e-17)), y, RC(1476, 6.557620865832e-16)), y, RC(1477, -1.016528519495e-14)), y, RC(1478, 1.491302084832e-13)), y, RC(1479, -2.06638666222265e-12)), y, RC(1480, 2.67958697789258e-11)), y, RC(1481, -3.23322654638336e-10)), y, RC(1482, 3.63722952167779e-9)), y, RC(1483, -3.75484943783021e-8)), y, RC(1484, 3.49164261987184e-7)), y, RC(1485, -2.92658670674908e-6)), y, RC(1486, 2.12937256719543e-5)), y, RC(1487, -1.19434130620929e-4)), y, RC(1488, 6.45524336158384e-4)));
-        w[4] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1489, -1.29043630202811e-19), y, RC(1490, 2.16234952241296e-18)), y, RC(1491, -3.107631557965e-17)), y, RC(1492, 4.570804313173e-16)), y, RC(1493, -6.301348858104e-15)), y, RC(1494, 8.031304476153e-14)), y, RC(1495, -9.446196472547e-13)), y, RC(1496, 1.018245804339e-11)), y, RC(1497, -9.96995451348129e-11)), y, RC(1498, 8.77489010276305e-10)), y, RC(1499, -6.84655877575364e-9)), y, RC(1500, 4.64460857084983e-8)), y, RC(1501, -2.66924538268397e-7)), y, RC(1502, 1.24621276265907e-6)), y, RC(1503, -4.30868944351523e-6)), y, RC(1504, 9.94307982432868e-6)));
-    }
-    else if (x <= 20.0) {
-        const double y = x - 17.5;
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1505, 1.9187576454574e-16), y, RC(1506, 7.8357401095707e-16)), y, RC(1507, -3.260875931644e-14)), y, RC(1508, -1.186752035569e-13)), y, RC(1509, 4.275180095653e-12)), y, RC(1510, 3.357056136731e-11)), y, RC(1511, -1.123776903884e-9)), y, RC(1512, 1.231203269887e-8)), y, RC(1513, -3.99851421361031e-7)), y, RC(1514, 1.45418822817771e-5)), y, RC(1515, -3.49912254976317e-4)), y, RC(1516, 0.00667768703938812)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1517, 2.02778478673555e-15), y, RC(1518, 1.01640716785099e-14)), y, RC(1519, -3.385363492036e-13)), y, RC(1520, -1.615655871159e-12)), y, RC(1521, 4.527419140333e-11)), y, RC(1522, 3.853670706486e-10)), y, RC(1523, -1.184607130107e-8)), y, RC(1524, 1.347873288827e-7)), y, RC(1525, -4.47788241748377e-6)), y, RC(1526, 1.54942754358273e-4)), y, RC(1527, -0.00355524254280266)), y, RC(1528, 0.0644912219301603)));
-        r[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1529, 7.79850771456444e-15), y, RC(1530, 6.00464406395001e-14)), y, RC(1531, -1.249779730869e-12)), y, RC(1532, -1.020720636353e-11)), y, RC(1533, 1.814709816693e-10)), y, RC(1534, 1.766397336977e-9)), y, RC(1535, -4.60355944901e-8)), y, RC(1536, 5.863956443581e-7)), y, RC(1537, -2.03797212506691e-5)), y, RC(1538, 6.31405161185185e-4)), y, RC(1539, -0.0130102750145071)), y, RC(1540, 0.210244289044705)));
-        r[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1541, -2.92397030777912e-15), y, RC(1542, 1.94152129078465e-14)), y, RC(1543, 4.85944766585e-13)), y, RC(1544, -3.217227223463e-12)), y, RC(1545, -7.484522135512e-11)), y, RC(1546, 7.19101516047753e-10)), y, RC(1547, 6.88409355245582e-9)), y, RC(1548, -1.44374545515769e-7)), y, RC(1549, 2.74941013315834e-6)), y, RC(1550, -1.02790452049013e-4)), y, RC(1551, 0.00259924221372643)), y, RC(1552, -0.0435712368303551)), y, RC(1553, 0.562170709585029)));
-        r[4] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1554, 1.1797612684006e-14), y, RC(1555, 1.24156229350669e-13)), y, RC(1556, -3.89274162228e-12)), y, RC(1557, -7.755793199043e-12)), y, RC(1558, 9.492190032313e-10)), y, RC(1559, -4.98680128123353e-9)), y, RC(1560, -1.81502268782664e-7)), y, RC(1561, 2.69463269394888e-6)), y, RC(1562, 2.5003215442164e-5)), y, RC(1563, -0.00133684303917681)), y, RC(1564, 0.0229121951862538)), y, RC(1565, -0.245653725061323)), y, RC(1566, 1.89999883453047)));
-        w[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1567, 1.74841995087592e-15), y, RC(1568, -6.95671892641256e-16)), y, RC(1569, -3.000659497257e-13)), y, RC(1570, 2.021279817961e-13)), y, RC(1571, 3.8535969354e-11)), y, RC(1572, 1.461418533652e-10)), y, RC(1573, -1.014517563435e-8)), y, RC(1574, 1.132736008979e-7)), y, RC(1575, -2.86605475073259e-6)), y, RC(1576, 1.21958354908768e-4)), y, RC(1577, -0.00386293751153466)), y, RC(1578, 0.145298342081522)));
-        w[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1579, -1.11199320525573e-15), y, RC(1580, 1.85007587796671e-15)), y, RC(1581, 1.220613939709e-13)), y, RC(1582, 1.275068098526e-12)), y, RC(1583, -5.341838883262e-11)), y, RC(1584, 6.161037256669e-10)), y, RC(1585, -1.00914787975e-8)), y, RC(1586, 2.907862965346e-7)), y, RC(1587, -6.12300038720919e-6)), y, RC(1588, 1.00104454489518e-4)), y, RC(1589, -0.00180677298502757)), y, RC(1590, 0.057800991453663)));
-        w[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1591, -9.49816486853687e-16), y, RC(1592, 6.67922080354234e-15)), y, RC(1593, 2.606163540537e-15)), y, RC(1594, 1.98379995015e-12)), y, RC(1595, -5.400548574357e-11)), y, RC(1596, 6.638043374114e-10)), y, RC(1597, -8.799518866802e-9)), y, RC(1598, 1.791418482685e-7)), y, RC(1599, -2.96075397351101e-6)), y, RC(1600, 3.38028206156144e-5)), y, RC(1601, -3.58426847857878e-4)), y, RC(1602, 0.00839213709428516)));
-        w[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1603, 1.3382997106018e-17), y, RC(1604, -3.4484187784414e-16)), y, RC(1605, 4.745009557656e-15)), y, RC(1606, -6.033814209875e-14)), y, RC(1607, 1.049256040808e-12)), y, RC(1608, -1.70859789556117e-11)), y, RC(1609, 2.15219425727959e-10)), y, RC(1610, -2.52746574206884e-9)), y, RC(1611, 3.2776171442296e-8)), y, RC(1612, -3.90387662925193e-7)), y, RC(1613, 3.4634020459387e-6)), y, RC(1614, -2.43236345136782e-5)), y, RC(1615, 3.54846978585226e-4)));
-        w[4] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1616, 2.69412277020887e-20), y, RC(1617, -4.24837886165685e-19)), y, RC(1618, 6.030500065438e-18)), y, RC(1619, -9.069722758289e-17)), y, RC(1620, 1.246599177672e-15)), y, RC(1621, -1.56872999797549e-14)), y, RC(1622, 1.87305099552692e-13)), y, RC(1623, -2.09498886675861e-12)), y, RC(1624, 2.11630022068394e-11)), y, RC(1625, -1.92566242323525e-10)), y, RC(1626, 1.62012436344069e-9)), y, RC(1627, -1.23621614171556e-8)), y, RC(1628, 7.72165684563049e-8)), y, RC(1629, -3.59858901591047e-7)), y, RC(1630, 2.43682618601e-6)));
-    }
-    else if (x <= 25.0) {
-        const double y = x - 22.5;
-        r[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1631, -1.13927848238726e-15), y, RC(1632, 7.39404133595713e-15)), y, RC(1633, 1.445982921243e-13)), y, RC(1634, -2.676703245252e-12)), y, RC(1635, 5.823521627177e-12)), y, RC(1636, 2.17264723874381e-10)), y, RC(1637, 3.56242145897468e-9)), y, RC(1638, -3.03763737404491e-7)), y, RC(1639, 9.46859114120901e-6)), y, RC(1640, -2.30896753853196e-4)), y, RC(1641, 0.00524663913001114)));
-        r[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1642, 2.89872355524581e-16), y, RC(1643, -1.22296292045864e-14)), y, RC(1644, 6.1840650972e-14)), y, RC(1645, 1.64984659123e-12)), y, RC(1646, -2.729713905266e-11)), y, RC(1647, 3.70991379065e-11)), y, RC(1648, 2.216486288382e-9)), y, RC(1649, 4.616160236414e-8)), y, RC(1650, -3.32380270861364e-6)), y, RC(1651, 9.84635072633776e-5)), y, RC(1652, -0.00230092118015697)), y, RC(1653, 0.0500845183695073)));
-        r[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1654, 1.97068646590923e-15), y, RC(1655, -4.894192706268e-14)), y, RC(1656, 1.136466605916e-13)), y, RC(1657, 7.546203883874e-12)), y, RC(1658, -9.635646767455e-11)), y, RC(1659, -8.295965491209e-11)), y, RC(1660, 7.534109114453e-9)), y, RC(1661, 2.699970652707e-7)), y, RC(1662, -1.42982334217081e-5)), y, RC(1663, 3.78290946669264e-4)), y, RC(1664, -0.00803133015084373)), y, RC(1665, 0.158689469640791)));
-        r[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1666, 1.33642069941389e-14), y, RC(1667, -1.55850612605745e-13)), y, RC(1668, -7.522712577474e-13)), y, RC(1669, 3.209520801187e-11)), y, RC(1670, -2.075594313618e-10)), y, RC(1671, -2.070575894402e-9)), y, RC(1672, 7.323046997451e-9)), y, RC(1673, 1.851491550417e-6)), y, RC(1674, -6.37524802411383e-5)), y, RC(1675, 0.00136795464918785)), y, RC(1676, -0.0242051126993146)), y, RC(1677, 0.397847167557815)));
-        r[4] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1678, -6.07053986130526e-14), y, RC(1679, 1.04447493138843e-12)), y, RC(1680, -4.286617818951e-13)), y, RC(1681, -2.632066100073e-10)), y, RC(1682, 4.804518986559e-9)), y, RC(1683, -1.835675889421e-8)), y, RC(1684, -1.068175391334e-6)), y, RC(1685, 3.292234974141e-5)), y, RC(1686, -5.94805357558251e-4)), y, RC(1687, 0.00829382168612791)), y, RC(1688, -0.0993122509049447)), y, RC(1689, 1.09857804755042)));
-        w[0] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1690, -9.10338640266542e-15), y, RC(1691, 1.00438927627833e-13)), y, RC(1692, 7.817349237071e-13)), y, RC(1693, -2.547619474232e-11)), y, RC(1694, 1.479321506529e-10)), y, RC(1695, 1.52314028857627e-9)), y, RC(1696, 9.20072040917242e-9)), y, RC(1697, -2.19427111221848e-6)), y, RC(1698, 8.65797782880311e-5)), y, RC(1699, -0.00282718629312875)), y, RC(1700, 0.128718310443295)));
-        w[1] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1701, 5.5238092761876e-15), y, RC(1702, -6.43424400204124e-14)), y, RC(1703, -2.358734508092e-13)), y, RC(1704, 8.261326648131e-12)), y, RC(1705, 9.229645304956e-11)), y, RC(1706, -5.68108973828949e-9)), y, RC(1707, 1.22477891136278e-7)), y, RC(1708, -2.11919643127927e-6)), y, RC(1709, 4.23605032368922e-5)), y, RC(1710, -0.00114423444576221)), y, RC(1711, 0.0506607252890186)));
-        w[2] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1712, 3.99457454087556e-15), y, RC(1713, -5.11826702824182e-14)), y, RC(1714, -4.157593182747e-14)), y, RC(1715, 4.214670817758e-12)), y, RC(1716, 6.705582751532e-11)), y, RC(1717, -3.36086411698418e-9)), y, RC(1718, 6.07453633298986e-8)), y, RC(1719, -7.40736211041247e-7)), y, RC(1720, 8.84176371665149e-6)), y, RC(1721, -1.72559275066834e-4)), y, RC(1722, 0.00716639814253567)));
-        w[3] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1723, -2.14649508112234e-18), y, RC(1724, -2.45525846412281e-18)), y, RC(1725, 6.126212599772e-16)), y, RC(1726, -8.526651626939e-15)), y, RC(1727, 4.826636065733e-14)), y, RC(1728, -3.3955416364974e-13)), y, RC(1729, 1.67070784862985e-11)), y, RC(1730, -4.42671979311163e-10)), y, RC(1731, 6.773680559084e-9)), y, RC(1732, -7.03520999708859e-8)), y, RC(1733, 6.04993294708874e-7)), y, RC(1734, -7.80555094280483e-6)), y, RC(1735, 2.85954806605017e-4)));
-        w[4] = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1736, -5.63938733073804e-21), y, RC(1737, 6.92182516324628e-20)), y, RC(1738, -1.586937691507e-18)), y, RC(1739, 3.357639744582e-17)), y, RC(1740, -4.810285046442e-16)), y, RC(1741, 5.386312669975e-15)), y, RC(1742, -6.117895297439e-14)), y, RC(1743, 8.441808227634e-13)), y, RC(1744, -1.18527596836592e-11)), y, RC(1745, 1.36296870441445e-10)), y, RC(1746, -1.17842611094141e-9)), y, RC(1747, 7.80430641995926e-9)), y, RC(1748, -5.9776741740054e-8)), y, RC(1749, 1.65186146094969e-6)));
-    }
-    else if (x <= 40.0) {
-        w[0] = sqrt((RC(42, 0.785398163397448) / x));
-        double g = ub_g;
-        r[0] = (((fma(fma(fma(fma(fma(fma(fma(fma(RC(1750, -1.73363958895356e-6), x, RC(1751, 1.19921331441483e-4)), x, RC(1752, -0.0159437614121125)), x, RC(1753, 1.13467897349442)), x, RC(1754, -44.7216460864586)), x, RC(1755, 1062.51216612604)), x, RC(1756, -15207.3917378512)), x, RC(1757, 120662.887111273)), x, RC(1758, -407186.366852475))) * g) + (RC(1759, 0.117581320211778) / (fma(1.0, x, RC(1760, -0.117581320211778)))));
-        r[1] = (((fma(fma(fma(fma(fma(fma(fma(fma(RC(1761, -1.6010254262171e-5), x, RC(1762, 0.00110331262112395)), x, RC(1763, -0.150043662589017)), x, RC(1764, 10.5563640866077)), x, RC(1765, -410.468817024806)), x, RC(1766, 9626.04416506819)), x, RC(1767, -135888.06983827)), x, RC(1768, 1061075.7703834)), x, RC(1769, -3511907.92816119))) * g) + (RC(1770, 1.0745620124369) / (fma(1.0, x, RC(1771, -1.0745620124369)))));
-        r[2] = (((fma(fma(fma(fma(fma(fma(fma(fma(RC(1772, -4.48880032128422e-5), x, RC(1773, 0.00269025112122177)), x, RC(1774, -0.401048115525954)), x, RC(1775, 27.8360021977405)), x, RC(1776, -1048.91729356965)), x, RC(1777, 23698.5942687423)), x, RC(1778, -319504.627257548)), x, RC(1779, 2348796.93563358)), x, RC(1780, -7163415.68174085))) * g) + (RC(1781, 3.08593744371754) / (fma(1.0, x, RC(1782, -3.08593744371754)))));
-        r[3] = (((fma(fma(fma(fma(fma(fma(fma(fma(RC(1783, -6.38526371092582e-5), x, RC(1784, -0.00229263585792626)), x, RC(1785, -0.0765735935499627)), x, RC(1786, 9.12692349152792)), x, RC(1787, -232.077034386717)), x, RC(1788, 281.839578728845)), x, RC(1789, 95952.9683876419)), x, RC(1790, -1776389.56809518)), x, RC(1791, 10248975.964541))) * g) + (RC(1792, 6.41472973366203) / (fma(1.0, x, RC(1793, -6.41472973366203)))));
-        r[4] = (((fma(fma(fma(fma(fma(fma(fma(fma(RC(1794, -3.59049364231569e-5), x, RC(1795, -0.0225963977930044)), x, RC(1796, 1.12594870794668)), x, RC(1797, -45.6752462103909)), x, RC(1798, 1058.04526830637)), x, RC(1799, -11600.3199605875)), x, RC(1800, -40729.7627297272)), x, RC(1801, 2222155.28319857)), x, RC(1802, -16119645.5032613))) * g) + (RC(1803, 11.8071894899717) / (fma(1.0, x, RC(1804, -11.8071894899717)))));
-        w[4] = (((fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1805, -4.6110090613397e-10), x, RC(1806, 1.43069932644286e-7)), x, RC(1807, -1.6396091543108e-5)), x, RC(1808, 0.00115791154612838)), x, RC(1809, -0.0530573476742071)), x, RC(1810, 1.61156533367153)), x, RC(1811, -32.3248143316007)), x, RC(1812, 412.007318109157)), x, RC(1813, -3022.60070158372)), x, RC(1814, 9715.75094154768))) * g) + (RC(1815, 8.62130526143657e-6) * w[0]));
-        w[3] = (((fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1816, -2.4079943580995e-8), x, RC(1817, 8.12621667601546e-6)), x, RC(1818, -9.04491430884113e-4)), x, RC(1819, 0.0637686375770059)), x, RC(1820, -2.96135703135647)), x, RC(1821, 91.514235699633)), x, RC(1822, -1869.71865249111)), x, RC(1823, 24294.5528916947)), x, RC(1824, -181852.473229081)), x, RC(1825, 596854.758661427))) * g) + (RC(1826, 0.00151614186862443) * w[0]));
-        w[2] = (((fma(fma(fma(fma(fma(fma(fma(fma(RC(1827, 1.83574464457207e-5), x, RC(1828, -0.00154837969489927)), x, RC(1829, 0.118520453711586)), x, RC(1830, -6.69649981309161)), x, RC(1831, 244.789386487321)), x, RC(1832, -5688.32664556359)), x, RC(1833, 81450.7604229357)), x, RC(1834, -655181.056671474)), x, RC(1835, 2264108.96607237))) * g) + (RC(1836, 0.0382231610015404) * w[0]));
-        w[1] = (((fma(fma(fma(fma(fma(fma(fma(fma(RC(1837, 2.7777834587065e-5), x, RC(1838, -0.0022283501765589)), x, RC(1839, 0.161077633475573)), x, RC(1840, -8.96743743396132)), x, RC(1841, 328.062687293374)), x, RC(1842, -7657.22701219557)), x, RC(1843, 110255.055017664)), x, RC(1844, -892528.122219324)), x, RC(1845, 3106386.27744347))) * g) + (RC(1846, 0.270967405960535) * w[0]));
-        w[0] = (((((w[0] - (g * RC(1847, 0.01962))) - w[1]) - w[2]) - w[3]) - w[4]);
-    }
-    else if (x <= 59.0) {
-        w[0] = sqrt((RC(42, 0.785398163397448) / x));
-        double d1 = x;
-        double xxx = (d1 * (d1 * d1));
-        double g = (xxx * ub_g);
-        r[0] = (((fma(fma(fma(RC(1848, -0.0243758528330205), x, RC(1849, 2.07301567989771)), x, RC(1850, -64.5964225381113)), x, RC(1851, 714.16008865547))) * g) + (RC(1759, 0.117581320211778) / (fma(1.0, x, RC(1760, -0.117581320211778)))));
-        r[1] = (((fma(fma(fma(RC(1852, -0.228861955413636), x, RC(1853, 19.3190784733691)), x, RC(1854, -599.774730340912)), x, RC(1855, 6618.44165304871))) * g) + (RC(1770, 1.0745620124369) / (fma(1.0, x, RC(1771, -1.0745620124369)))));
-        r[2] = (((fma(fma(fma(RC(1856, -0.695053039285586), x, RC(1857, 57.6874090316016)), x, RC(1858, -1777.0414322552)), x, RC(1859, 19536.6082947811))) * g) + (RC(1781, 3.08593744371754) / (fma(1.0, x, RC(1782, -3.08593744371754)))));
-        r[3] = (((fma(fma(fma(RC(1860, -1.58072809087018), x, RC(1861, 127.050801091948)), x, RC(1862, -3866.8735091428)), x, RC(1863, 42302.482812142))) * g) + (RC(1792, 6.41472973366203) / (fma(1.0, x, RC(1793, -6.41472973366203)))));
-        r[4] = (((fma(fma(fma(RC(1864, -3.33963830405396), x, RC(1865, 251.830424600204)), x, RC(1866, -7577.28527654961)), x, RC(1867, 82196.681659569))) * g) + (RC(1803, 11.8071894899717) / (fma(1.0, x, RC(1804, -11.8071894899717)))));
-        g = (xxx * g);
-        w[4] = (((fma(fma(RC(1868, 1.35482430510942e-8), x, RC(1869, -3.27722199212781e-7)), x, RC(1870, 2.41522703684296e-6))) * g) + (RC(1815, 8.62130526143657e-6) * w[0]));
-        w[3] = (((fma(fma(RC(1871, 1.23464092261605e-6), x, RC(1872, -3.5522456427559e-5)), x, RC(1873, 3.03274662192286e-4))) * g) + (RC(1826, 0.00151614186862443) * w[0]));
-        w[2] = (((fma(fma(RC(1874, 1.34547929260279e-5), x, RC(1875, -4.19389884772726e-4)), x, RC(1876, 0.00387706687610809))) * g) + (RC(1836, 0.0382231610015404) * w[0]));
-        w[1] = (((fma(fma(RC(1877, 2.09539509123135e-5), x, RC(1878, -6.87646614786982e-4)), x, RC(1879, 0.00668743788585688))) * g) + (RC(1846, 0.270967405960535) * w[0]));
-        w[0] = ((((w[0] - w[1]) - w[2]) - w[3]) - w[4]);
-    }
-    else {
-        w[0] = sqrt((RC(42, 0.785398163397448) / x));
-        r[0] = (RC(1759, 0.117581320211778) / (fma(1.0, x, RC(1760, -0.117581320211778))));
-        r[1] = (RC(1770, 1.0745620124369) / (fma(1.0, x, RC(1771, -1.0745620124369))));
-        r[2] = (RC(1781, 3.08593744371754) / (fma(1.0, x, RC(1782, -3.08593744371754))));
-        r[3] = (RC(1792, 6.41472973366203) / (fma(1.0, x, RC(1793, -6.41472973366203))));
-        r[4] = (RC(1803, 11.8071894899717) / (fma(1.0, x, RC(1804, -11.8071894899717))));
-        w[1] = (RC(1846, 0.270967405960535) * w[0]);
-        w[2] = (RC(1836, 0.0382231610015404) * w[0]);
-        w[3] = (RC(1826, 0.00151614186862443) * w[0]);
-        w[4] = (RC(1815, 8.62130526143657e-6) * w[0]);
-        w[0] = ((((w[0] - w[1]) - w[2]) - w[3]) - w[4]);
-    }
+template <>
+UNOMOL_HD void rys_roots<3>(double x, double *r, double *w, const RysTables &T) { rys_piecewise<3>(x, r, w, T.piece[0], RYS_P3_XA); }
+template <>
+UNOMOL_HD void rys_roots<4>(double x, double *r, double *w, const RysTables &T) { rys_piecewise<4>(x, r, w, T.piece[1], RYS_P4_XA); }
+template <>
+UNOMOL_HD void rys_roots<5>(double x, double *r, double *w, const RysTables &T) { rys_piecewise<5>(x, r, w, T.piece[2], RYS_P5_XA); }
+
+#if !defined(__CUDACC__) || defined(UNOMOL_RYS_HOST_TABLES)
+// host copies of the tables (host emulation of the kernels, CPU tests of this evaluator)
+namespace rys_host {
+#define RYS_TABLE(name, n) static const double name[n]
+#include "rys_tables.inc"
+#undef RYS_TABLE
+}  // namespace rys_host
+inline RysTables rys_host_tables(int rys2_exact = 0) {
+    RysTables T;
+    T.boys = rys_host::rys_boys_tab;
+    T.piece[0] = rys_host::rys_piece3_tab;
+    T.piece[1] = rys_host::rys_piece4_tab;
+    T.piece[2] = rys_host::rys_piece5_tab;
+    T.rys2_exact = rys2_exact;
+    T.pad = 0;
+    return T;
 }
+#endif
 
-// one root, division-free on the hot bands: w = F0(x), f1 = w*t^2 = F1(x) (same fit as rys_roots<1>)
-UNOMOL_HD void rys1_f0f1(double x, double &w, double &f1) {
-    const double ub_g = exp((-x));
-    const double ub_rx = ub_rsqrt(x);
-    if (x <= 3e-07) {
-        w = (1.0 - (x / 3.0));
-        const double r0 = (0.5 - (x / 5.0));
-        f1 = w * (r0 / (1.0 + r0));
-    }
-    else if (x <= 1.0) {
-        f1 = (fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(1, -8.36313918003957e-8), x, RC(2, 1.21222603512827e-6)), x, RC(3, -1.15662609053481e-5)), x, RC(4, 9.25197374512647e-5)), x, RC(5, -6.40994113129432e-4)), x, RC(6, 0.00378787044215009)), x, RC(7, -0.0185185172458485)), x, RC(8, 0.0714285713298222)), x, RC(9, -0.199999999997023)), x, RC(10, 0.333333333333318)));
-        w = (((x + x) * f1) + ub_g);
-    }
-    else if (x <= 3.0) {
-        const double y = x - 2.0;
-        f1 = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(11, -1.61702782425558e-10), y, RC(12, 1.96215250865776e-9)), y, RC(13, -2.14234468198419e-8)), y, RC(14, 2.17216556336318e-7)), y, RC(15, -1.98850171329371e-6)), y, RC(16, 1.62429321438911e-5)), y, RC(17, -1.16740298039895e-4)), y, RC(18, 7.24888732052332e-4)), y, RC(19, -0.00379490003707156)), y, RC(20, 0.0161723488664661)), y, RC(21, -0.0529428148329736)), y, RC(22, 0.115702180856167)));
-        w = (((x + x) * f1) + ub_g);
-    }
-    else if (x <= 5.0) {
-        const double y = x - 4.0;
-        f1 = (fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(RC(23, -2.62453564772299e-11), y, RC(24, 3.24031041623823e-10)), y, RC(25, -3.614965656163e-9)), y, RC(26, 3.760256799971e-8)), y, RC(27, -3.553558319675e-7)), y, RC(28, 3.022556449731e-6)), y, RC(29, -2.290098979647e-5)), y, RC(30, 1.526537461148e-4)), y, RC(31, -8.81947375894379e-4)), y, RC(32, 0.00433207949514611)), y, RC(33, -0.0175257821619926)), y, RC(34, 0.0528406320615584)));
-        w = (((x + x) * f1) + ub_g);
-    }
-    else if (x <= 10.0) {
-        const double rx = ub_rx;
-        const double xinv = rx * rx;
-        const double g = ub_g;
-        w = (((RC(35, -3.1501078774085e-6) + (xinv * fma(fma(fma(fma(fma(RC(36, 0.46897511375022), xinv, RC(37, -0.69955602298985)), xinv, RC(38, 0.53689283271887)), xinv, RC(39, -0.32883030418398)), xinv, RC(40, 0.24645596956002)), xinv, RC(41, -0.49984072848436)))) * g) + (RC(1880, 0.88622692545275783) * rx));
-        f1 = (((w - g) * 0.5) * xinv);
-    }
-    else if (x <= 15.0) {
-        const double rx = ub_rx;
-        const double xinv = rx * rx;
-        const double g = ub_g;
-        w = (((RC(43, -2.1916512131607e-5) + (xinv * fma(fma(RC(44, -0.18784686463512), xinv, RC(45, 0.22991849164985)), xinv, RC(46, -0.49893752514047)))) * g) + (RC(1880, 0.88622692545275783) * rx));
-        f1 = (((w - g) * 0.5) * xinv);
-    }
-    else if (x <= 33.0) {
-        const double rx = ub_rx;
-        const double xinv = rx * rx;
-        const double g = ub_g;
-        w = (((RC(47, -6.0156581186481e-5) + (xinv * fma(RC(48, 0.1962326414943), xinv, RC(49, -0.4969524146449)))) * g) + (RC(1880, 0.88622692545275783) * rx));
-        f1 = (((w - g) * 0.5) * xinv);
-    }
-    else {
-        const double rx = ub_rx;
-        const double xinv = rx * rx;
-        w = (RC(1880, 0.88622692545275783) * rx);
-        f1 = (w * 0.5) * xinv;
-    }
-}
-
-#undef RC
 }  // namespace ub200

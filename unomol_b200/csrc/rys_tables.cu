@@ -1,0 +1,29 @@
+// unomol_b200/csrc/rys_tables.cu -- device copies of the generated Rys / Boys tables (rys_tables.inc) and the
+// per-device pointer block the kernels receive through ClassTask::rys.
+#include <cuda_runtime.h>
+#include "rys_roots.cuh"
+
+namespace ub200 {
+
+#define RYS_TABLE(name, n) __device__ __align__(16) const double name[n]
+#include "rys_tables.inc"
+#undef RYS_TABLE
+
+// Device addresses of the tables on the CURRENT device (symbols exist once per device).
+cudaError_t rys_device_tables(RysTables *out) {
+    void *p = nullptr;
+    cudaError_t e;
+    if ((e = cudaGetSymbolAddress(&p, rys_boys_tab)) != cudaSuccess) return e;
+    out->boys = (const double *)p;
+    if ((e = cudaGetSymbolAddress(&p, rys_piece3_tab)) != cudaSuccess) return e;
+    out->piece[0] = (const double *)p;
+    if ((e = cudaGetSymbolAddress(&p, rys_piece4_tab)) != cudaSuccess) return e;
+    out->piece[1] = (const double *)p;
+    if ((e = cudaGetSymbolAddress(&p, rys_piece5_tab)) != cudaSuccess) return e;
+    out->piece[2] = (const double *)p;
+    out->rys2_exact = 0;
+    out->pad = 0;
+    return cudaSuccess;
+}
+
+}  // namespace ub200

@@ -1,6 +1,7 @@
 // unomol_b200/csrc/unomol_types.h -- plain structs shared by host and device code.
 #pragma once
 #include <cstdint>
+#include "rys_roots.cuh"
 
 namespace ub200 {
 
@@ -87,6 +88,7 @@ struct ClassTask {
     double *out;              // dump: blocks; schwarz: one value per task
     unsigned long long *counters;  // [0] quartets evaluated, [1] primitive quartets surviving the cut
     unsigned long long *cand_counter;  // primitive-quartet candidates tested against the cut (all launches)
+    RysTables rys;                 // Boys grid / piecewise Rys tables on this device (rys_tables.cu) + the two-root mode
     int debug_flags;               // profiling experiments only (results invalid): 1 skip exchange digestion, 2 skip root evaluation, 4 skip all digestion
 };
 

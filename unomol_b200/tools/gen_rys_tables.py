@@ -1,0 +1,200 @@
+#!/usr/bin/env python3
+"""unomol_b200/tools/gen_rys_tables.py -- generates unomol_b200/csrc/rys_tables.inc from first principles.
+
+Nothing here reads the reference: every number is computed with mpmath from the definition of the Rys
+quadrature (weight exp(-X t^2) on [0,1]; nodes x_i = t_i^2, the kernels use r_i = x_i/(1-x_i)).
+
+  * Boys grid        {F_MTOP(X_i), exp(-X_i)} on X_i = i/16, i = 0 .. 33*16+1.  The evaluator gets F_m(X_i) for every
+                     m < MTOP by the (positive-term, hence stable) downward recursion, F_top(X) by an 8-term Taylor
+                     series in X - X_i (dF_m/dX = -F_{m+1}) and the lower orders by downward recursion at X itself.
+                     One and two roots are built from these moments in closed form (rys_roots.cuh).
+  * 3, 4, 5 roots    piecewise polynomials (monomials in s in [-1,1], converted from Chebyshev interpolants
+                     computed at 60 digits) of r_i(X) and w_i(X) on uniform intervals of [0, XA_n); above XA_n the
+                     exp(-X)-free Gauss-Hermite limit is exact to double precision.
+  * Hermite limits   R_i = squared positive roots of H_2n, W_i = Gauss-Hermite weights / sqrt(pi) (n = 1..5).
+
+Run:  python unomol_b200/tools/gen_rys_tables.py [--check]      (about a minute)
+"""
+import os
+import sys
+import mpmath as mp
+
+mp.mp.dps = 60
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "..", "csrc", "rys_tables.inc")
+OUT_CONSTS = os.path.join(HERE, "..", "csrc", "rys_consts.inc")
+
+BOYS_H_INV = 16            # grid points per unit X
+BOYS_XMAX = 46             # grid end: two-root moments are used up to here in exact mode; one root switches to
+                           # the asymptotic F_0 = sqrt(pi/4X) at X = 35 already (exp(-35)/70 = 9e-18)
+BOYS_MTOP = 10             # highest order tabulated (two roots need F_0..F_3, Taylor of F_3 reaches F_10)
+NTERMS = 8                 # Taylor terms: (1/32)^8/8! = 2e-17
+
+# n: (interval width, polynomial degree, XA_n)
+PIECE = {3: (1.0, 12, 52.0), 4: (1.0, 12, 58.0), 5: (1.0, 12, 64.0)}   # measured: degree 11 leaves 1.1e-16, XA: limit good to 4e-16
+
+
+def boys(m, x):
+    x = mp.mpf(x)
+    if x == 0:
+        return mp.mpf(1) / (2 * m + 1)
+    return mp.gammainc(m + mp.mpf(1) / 2, 0, x) / (2 * x ** (m + mp.mpf(1) / 2))
+
+
+def rys_exact(n, x):
+    """nodes x_i = t_i^2 (ascending) and weights of the n-point Rys quadrature, from the moments F_k(X), k < 2n"""
+    m = [boys(k, x) for k in range(2 * n + 1)]
+    A = mp.matrix(n, n)
+    b = mp.matrix(n, 1)
+    for i in range(n):
+        for j in range(n):
+            A[i, j] = m[i + j]
+        b[i] = -m[i + n]
+    c = mp.lu_solve(A, b)                       # monic orthogonal polynomial x^n + sum c_j x^j
+    roots = mp.polyroots([mp.mpf(1)] + [c[j] for j in reversed(range(n))], maxsteps=200, extraprec=400)
+    roots = sorted([mp.re(r) for r in roots])
+    V = mp.matrix(n, n)
+    rhs = mp.matrix(n, 1)
+    for k in range(n):
+        for i in range(n):
+            V[k, i] = roots[i] ** k
+        rhs[k] = m[k]
+    w = mp.lu_solve(V, rhs)
+    return roots, [w[i] for i in range(n)]
+
+
+def hermite_limits(n):
+    """large-X limit: x_i -> R_i / X, w_i -> W_i sqrt(pi/(4X)); R_i = squared positive roots of H_2n"""
+    # Gauss-Hermite with 2n points via Golub-Welsch at high precision
+    N = 2 * n
+    J = mp.matrix(N, N)
+    for i in range(N - 1):
+        J[i, i + 1] = J[i + 1, i] = mp.sqrt(mp.mpf(i + 1) / 2)
+    E, Q = mp.eigsy(J)
+    pts = sorted([(E[i], Q[0, i] ** 2) for i in range(N)], key=lambda t: t[0])
+    pos = [(x * x, 2 * w) for (x, w) in pts if x > 0]     # weights normalised to sum 1 over the positive half
+    pos.sort(key=lambda t: t[0])
+    return [p[0] for p in pos], [p[1] for p in pos]
+
+
+def cheb_fit(fvals, deg):
+    """Chebyshev coefficients of the degree-deg interpolant through the deg+1 Chebyshev nodes (values given there)"""
+    N = deg + 1
+    c = []
+    for k in range(N):
+        s = mp.mpf(0)
+        for j in range(N):
+            s += fvals[j] * mp.cos(mp.pi * k * (j + mp.mpf(1) / 2) / N)
+        c.append(s * (2 if k else 1) / N)
+    return c
+
+
+def cheb_to_mono(c):
+    """Chebyshev series -> monomial coefficients in s (exact rational arithmetic on mp numbers)"""
+    n = len(c)
+    T0 = [mp.mpf(1)]
+    T1 = [mp.mpf(0), mp.mpf(1)]
+    out = [mp.mpf(0)] * n
+    polys = [T0, T1]
+    for k in range(2, n):
+        Tk = [mp.mpf(0)] + [2 * a for a in polys[-1]]
+        for i, a in enumerate(polys[-2]):
+            Tk[i] -= a
+        polys.append(Tk)
+    for k in range(n):
+        for i, a in enumerate(polys[k]):
+            out[i] += c[k] * a
+    return out
+
+
+def fmt(v):
+    return "%.17e" % float(v)
+
+
+def gen_piece(n, check):
+    width, deg, xa = PIECE[n]
+    nint = int(round(xa / width))
+    N = deg + 1
+    nodes = [mp.cos(mp.pi * (j + mp.mpf(1) / 2) / N) for j in range(N)]
+    rows = []          # [interval][k][func], func = r_0..r_{n-1}, w_0..w_{n-1}
+    worst = 0.0
+    for iv in range(nint):
+        x0 = mp.mpf(iv) * width
+        xc = x0 + mp.mpf(width) / 2
+        vals = []
+        for s in nodes:
+            xs, ws = rys_exact(n, xc + s * width / 2)
+            vals.append([x / (1 - x) for x in xs] + ws)
+        mono = []
+        for f in range(2 * n):
+            mono.append(cheb_to_mono(cheb_fit([v[f] for v in vals], deg)))
+        rows.append(mono)
+        if check:
+            for s in (mp.mpf(-1), mp.mpf("-0.77"), mp.mpf("-0.31"), mp.mpf("0.123"), mp.mpf("0.5"), mp.mpf("0.93"), mp.mpf(1)):
+                xs, ws = rys_exact(n, xc + s * width / 2)
+                ex = [x / (1 - x) for x in xs] + ws
+                sd = float(s)
+                for f in range(2 * n):
+                    acc = 0.0
+                    for k in range(deg, -1, -1):
+                        acc = acc * sd + float(mono[f][k])
+                    worst = max(worst, abs(acc - float(ex[f])) / abs(float(ex[f])))
+    return width, deg, xa, nint, rows, worst
+
+
+def main():
+    check = "--check" in sys.argv
+    L = []
+    C = []
+    C.append("// unomol_b200/csrc/rys_consts.inc -- GENERATED by unomol_b200/tools/gen_rys_tables.py (mpmath, 60 digits): grid")
+    C.append("// parameters of rys_tables.inc and the Gauss-Hermite limits.  Do not edit by hand.")
+    L.append("// unomol_b200/csrc/rys_tables.inc -- GENERATED by unomol_b200/tools/gen_rys_tables.py (mpmath, 60 digits) from the")
+    L.append("// definition of the Rys quadrature; nothing is taken from the reference.  Do not edit by hand.")
+    C.append("#define RYS_BOYS_HINV %d" % BOYS_H_INV)
+    C.append("#define RYS_BOYS_XMAX %d" % BOYS_XMAX)
+    C.append("#define RYS_BOYS_MTOP %d" % BOYS_MTOP)
+    nb = BOYS_XMAX * BOYS_H_INV + 2
+    C.append("#define RYS_BOYS_NPTS %d" % nb)
+    L.append("RYS_TABLE(rys_boys_tab, 2 * RYS_BOYS_NPTS) = {")
+    for i in range(nb):
+        x = mp.mpf(i) / BOYS_H_INV
+        L.append("    %s, %s," % (fmt(boys(BOYS_MTOP, x)), fmt(mp.exp(-x))))
+    L.append("};")
+    # Hermite limits
+    C.append("// large-X limit: r_i = R_i/(X - R_i), w_i = W_i sqrt(pi/(4X)); row n-1 holds n entries")
+    hr, hw = [], []
+    for n in range(1, 6):
+        R, W = hermite_limits(n)
+        hr.append(R + [mp.mpf(0)] * (5 - n))
+        hw.append(W + [mp.mpf(0)] * (5 - n))
+    C.append("RYS_CONST(rys_herm_r, 25) = {")
+    for row in hr:
+        C.append("    " + ", ".join(fmt(v) for v in row) + ",")
+    C.append("};")
+    C.append("RYS_CONST(rys_herm_w, 25) = {")
+    for row in hw:
+        C.append("    " + ", ".join(fmt(v) for v in row) + ",")
+    C.append("};")
+    for n in (3, 4, 5):
+        width, deg, xa, nint, rows, worst = gen_piece(n, check)
+        sys.stderr.write("n=%d: %d intervals of width %g, degree %d, XA %g, worst rel err on check points %.2e\n"
+                         % (n, nint, width, deg, xa, worst))
+        C.append("#define RYS_P%d_WIDTH_INV %.17g" % (n, 1.0 / width))
+        C.append("#define RYS_P%d_DEG %d" % (n, deg))
+        C.append("#define RYS_P%d_XA %.17g" % (n, xa))
+        C.append("#define RYS_P%d_NINT %d" % (n, nint))
+        L.append("// layout [interval][k = 0..deg][r_0..r_%d, w_0..w_%d]" % (n - 1, n - 1))
+        L.append("RYS_TABLE(rys_piece%d_tab, %d) = {" % (n, nint * (deg + 1) * 2 * n))
+        for iv in range(nint):
+            for k in range(deg + 1):
+                L.append("    " + ", ".join(fmt(rows[iv][f][k]) for f in range(2 * n)) + ",")
+        L.append("};")
+    with open(OUT, "w") as f:
+        f.write("\n".join(L) + "\n")
+    with open(OUT_CONSTS, "w") as f:
+        f.write("\n".join(C) + "\n")
+    sys.stderr.write("wrote %s\n" % os.path.normpath(OUT))
+
+
+if __name__ == "__main__":
+    main()
