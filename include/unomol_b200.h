@@ -68,6 +68,12 @@ typedef struct unomol_b200_stats_t {
     int nbf, nshell, rank, nranks;
     long long n_prim_quartets;    /* primitive quartets that passed the reference's sr cut in the last build */
     long long n_prim_candidates;  /* primitive quartets tested against the cut (register kernels only) */
+    int n_tile_launches;          /* of n_launches: bra-tile / ket-stationary kernels (eri_tile.cuh) */
+    int n_reg_launches;           /* one-bra-per-CTA register kernels (eri_reg.cuh); n_rows_launches of them staged rows of P */
+    int n_rows_launches;
+    int n_generic_launches;       /* shared-memory class kernels (eri_generic.cuh) */
+    int n_highl_launches;         /* runtime-L kernel (f/g shells) */
+    int last_dump_kernel;         /* eri_quartet: 0 = generic kernel produced the block, 1 = the Fock build's own kernel */
 } unomol_b200_stats_t;
 
 /* Replaces the TwoElectronInts constructor (TwoElectronInts.hpp:83-88) + calculate() set-up

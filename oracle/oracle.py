@@ -74,6 +74,8 @@ class Oracle:
         L.oracle_form_g_uhf.argtypes = [_L, ctypes.POINTER(_D), ctypes.POINTER(_I)] + [ctypes.POINTER(_D)] * 4
         L.oracle_direct_g_rhf.restype = _L
         L.oracle_direct_g_rhf.argtypes = [_P, _D, ctypes.POINTER(_D), ctypes.POINTER(_D), _L, _L, ctypes.POINTER(_L)]
+        L.oracle_direct_g_uhf.restype = _L
+        L.oracle_direct_g_uhf.argtypes = [_P, _D] + [ctypes.POINTER(_D)] * 4 + [_L, _L, ctypes.POINTER(_L)]
         L.oracle_cart_norm.restype = _D; L.oracle_cart_norm.argtypes = [_I, _I]
         L.oracle_basis_set_center.argtypes = [_P, _I, _D, _D, _D]
 
@@ -121,6 +123,31 @@ class Oracle:
         nq = self.lib.oracle_direct_g_rhf(b.h, thresh, _dp(np.ascontiguousarray(P)), _dp(G), sample_mod, sample_rem,
                                           ctypes.byref(npq))
         return G, nq, npq.value
+
+
+    def direct_g_threads(self, b, P, PB=None, thresh=1e-14, nthreads=None):
+        """direct G on all host cores: thread t digests the shell quartets with running index % nthreads == t into its own
+        G (ctypes releases the GIL); RHF when PB is None, else (GA, GB).  Same arithmetic as direct_g_rhf, summed per thread."""
+        import threading
+        nthreads = nthreads or max(1, min(32, os.cpu_count() or 1))
+        P = np.ascontiguousarray(P, float)
+        PBc = None if PB is None else np.ascontiguousarray(PB, float)
+        parts = [[np.zeros(b.no2), np.zeros(b.no2), 0] for _ in range(nthreads)]
+
+        def run(t):
+            npq = _L(0)
+            if PBc is None:
+                parts[t][2] = self.lib.oracle_direct_g_rhf(b.h, thresh, _dp(P), _dp(parts[t][0]), nthreads, t, ctypes.byref(npq))
+            else:
+                parts[t][2] = self.lib.oracle_direct_g_uhf(b.h, thresh, _dp(P), _dp(PBc), _dp(parts[t][0]), _dp(parts[t][1]),
+                                                           nthreads, t, ctypes.byref(npq))
+        th = [threading.Thread(target=run, args=(t,)) for t in range(nthreads)]
+        for x in th: x.start()
+        for x in th: x.join()
+        GA = sum(p[0] for p in parts)
+        if PBc is None:
+            return GA
+        return GA, sum(p[1] for p in parts)
 
 
 class Reference:

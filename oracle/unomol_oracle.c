@@ -267,7 +267,8 @@ static void eri_quartet_rys(const oracle_basis *b, const quartet_view *q, double
     double ab2 = ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2];
     double cd2 = cd[0] * cd[0] + cd[1] * cd[1] + cd[2] * cd[2];
     const int lvt12 = lv1 + lv2, lvt34 = lv3 + lv4, nroots = (lvt12 + lvt34) / 2 + 1;
-    static rys_tables T; /* single-threaded like the reference (TwoElectronInts.cpp:529-534) */
+    static _Thread_local rys_tables T; /* per-thread scratch: the reference is single-threaded (TwoElectronInts.cpp:529-534), the test
+                                        * harness runs several walks side by side (oracle.py: direct_g_threads) */
     for (int k = 0; k < q->len; ++k) vals[k] = 0.0;
     const int same12 = (s1 == s2), same34 = (s3 == s4); /* the reference's pointer test al1==al2 (:444,:466) */
     for (int i = 0; i < b->npr[s1]; ++i) {
@@ -372,7 +373,7 @@ static void md_ecoef(double (*E)[MD_LDIM][MD_TDIM], double abi, double ax, doubl
 /* MD_Rfunction::eval + loop_eval, MD_Rfunction.hpp:49-70, 2208-2319: R[lx][ly][lz] for lx+ly+lz <= ltot.
  * Same recurrences (z first, then y, then x; coefficient (l-1) on the l-2 term), written with one loop per
  * axis instead of the reference's unrolled l = 1, 2 cases. */
-static double g_rz[MD_RDIM][MD_RDIM][MD_RDIM][MD_RDIM + 1];
+static _Thread_local double g_rz[MD_RDIM][MD_RDIM][MD_RDIM][MD_RDIM + 1];
 static void md_rtensor(double (*R)[MD_RDIM][MD_RDIM], double sr, double t, double w, const double *pq, int ltot) {
     double *r0 = g_rz[0][0][0];
     md_fgamma(r0, t, ltot);
@@ -491,7 +492,7 @@ int oracle_quartet_block(const oracle_basis *b, int ish, int jsh, int ksh, int l
         n[t] = oracle_ncart(lv[t]);
     }
     int sw12 = lv[0] < lv[1], sw34 = lv[2] < lv[3]; /* TwoElectronInts.cpp:563,604 */
-    static quartet_view q;
+    static _Thread_local quartet_view q;
     q.s1 = sw12 ? jsh : ish; q.s2 = sw12 ? ish : jsh;
     q.s3 = sw34 ? lsh : ksh; q.s4 = sw34 ? ksh : lsh;
     int knt = 0;
@@ -516,9 +517,9 @@ typedef void (*quartet_sink)(void *ctx, const quartet_view *q, const int (*ijkl)
 static long walk_quartets(const oracle_basis *b, int start, long sample_mod, long sample_rem, quartet_sink sink,
                           void *ctx, long *ncalc, long *nprimq) {
     init_tables();
-    static quartet_view q;
-    static int ijkl[ORACLE_MAXFUNC][4];
-    static double vals[ORACLE_MAXFUNC];
+    static _Thread_local quartet_view q;
+    static _Thread_local int ijkl[ORACLE_MAXFUNC][4];
+    static _Thread_local double vals[ORACLE_MAXFUNC];
     long nq = 0, running = 0;
     for (int ish = start; ish < b->nshell; ++ish)
         for (int jsh = 0; jsh <= ish; ++jsh)
@@ -682,4 +683,25 @@ long oracle_direct_g_rhf(const oracle_basis *b, double thresh, const double *P, 
     direct_ctx c = {thresh, P, G};
     if (nprimq) *nprimq = 0;
     return walk_quartets(b, 0, sample_mod, sample_rem, direct_sink, &c, NULL, nprimq);
+}
+
+typedef struct {
+    double thresh;
+    const double *PA, *PB;
+    double *GA, *GB;
+} direct_uhf_ctx;
+
+static void direct_uhf_sink(void *vctx, const quartet_view *q, const int (*ijkl)[4], const double *vals) {
+    direct_uhf_ctx *c = (direct_uhf_ctx *)vctx;
+    for (int k = 0; k < q->len; ++k)
+        if (fabs(vals[k]) > c->thresh)
+            digest_uhf(c->PA, c->PB, c->GA, c->GB, vals[k], ijkl[k][0], ijkl[k][1], ijkl[k][2], ijkl[k][3]);
+}
+
+/* UHF twin of oracle_direct_g_rhf: the calculate() loops (TwoElectronInts.cpp:511-697) feeding formGMatrixKernel2 (:749-820) */
+long oracle_direct_g_uhf(const oracle_basis *b, double thresh, const double *PA, const double *PB, double *GA, double *GB,
+                         long sample_mod, long sample_rem, long *nprimq) {
+    direct_uhf_ctx c = {thresh, PA, PB, GA, GB};
+    if (nprimq) *nprimq = 0;
+    return walk_quartets(b, 0, sample_mod, sample_rem, direct_uhf_sink, &c, NULL, nprimq);
 }

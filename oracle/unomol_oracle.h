@@ -69,6 +69,9 @@ void oracle_form_g_uhf(long n, const double *vals, const int *ijkl, const double
 long oracle_direct_g_rhf(const oracle_basis *b, double thresh, const double *P, double *G, long sample_mod,
                          long sample_rem, long *nprimq);
 
+long oracle_direct_g_uhf(const oracle_basis *b, double thresh, const double *PA, const double *PB, double *GA, double *GB,
+                         long sample_mod, long sample_rem, long *nprimq);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,40 @@ def test_quartet_blocks_vs_reference_fixture(capi, name):
     assert worst < ERI_TOL, worst
 
 
+@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "631.co", "b.dhdz", "dh95.co2", "dh95.c2h2", "tz2p.sf6"])
+def test_quartet_blocks_from_the_fock_kernels_vs_reference_fixture(capi, name):
+    """option dump_kernel = 1: the block comes from the kernel a Fock build runs for the quartet's class (bra-tile kernel
+    for the s/p classes, one-bra register kernel for the small d classes) in its dump mode, not from the generic kernel"""
+    g = np.load(os.path.join(GOLDEN, "quartets_%s.npz" % name.replace(".", "_")))
+    b, h = _handle(capi, name)
+    h.set_option("dump_kernel", 1)
+    worst, hot = 0.0, 0
+    for q, (i, j, k, l) in enumerate(g["quartets"]):
+        ref = g["values"][g["offsets"][q]:g["offsets"][q + 1]]
+        blk = h.eri_quartet(int(i), int(j), int(k), int(l)).ravel()
+        hot += h.stats()["last_dump_kernel"]
+        worst = max(worst, np.max(np.abs(blk - ref)))
+    assert worst < ERI_TOL, worst
+    assert hot >= len(g["quartets"]) // 2, hot       # most fixture quartets belong to the register / tile classes
+
+
+@pytest.mark.parametrize("name", ["631.nh3", "631.co"])
+def test_unique_integral_list_from_the_fock_kernels(capi, name):
+    """every stored integral of the reference, with the tile / register kernels producing the blocks of their classes"""
+    g = np.load(os.path.join(GOLDEN, "eri_%s.npz" % name.replace(".", "_")))
+    b, h = _handle(capi, name)
+    h.set_option("dump_kernel", 1)
+    vals, ijkl = h.dump_eris(0.0)
+    got = {tuple(r): v for r, v in zip(ijkl.tolist(), vals)}
+    worst = 0.0
+    for r, v in zip(g["ijkl"].tolist(), g["vals"]):
+        worst = max(worst, abs(got.get(tuple(r), 0.0) - v))
+    assert worst < ERI_TOL, worst
+    h.set_option("dump_kernel", 0)
+    vals0, ijkl0 = h.dump_eris(0.0)
+    assert np.array_equal(ijkl, ijkl0) and np.max(np.abs(vals - vals0)) < 1e-13
+
+
 def test_every_shell_quartet_h2o_sto3g_vs_oracle(capi, oracle):
     b, h = _handle(capi, "3g.h2o")
     ob = oracle.basis(golden_input("3g.h2o"))
@@ -408,3 +442,74 @@ def test_device_pair_tables_match_host_pair_tables(capi):
         assert s0["n_pairs_kept"] == s1["n_pairs_kept"] and s0["n_prim_pairs"] == s1["n_prim_pairs"]
         assert np.max(np.abs(Q1 - Q0)) < 1e-13 * np.max(Q0)
         assert np.max(np.abs(G1 - G0)) < 1e-13 * np.max(np.abs(G0))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The benchmarked workload: synthetic (H2O)_n / 6-31G clusters against the oracle's integral-direct G on the same P, at the
+# engine's DEFAULT options (Schwarz tau 1e-12, bra-tile kernels) and with every code path that only engages at scale forced
+# on: primitive-count buckets (>= 20 000 shell pairs by default), spatial blocks (N > ~2500), the one-bra register kernels
+# with TMA-staged rows of P (tile_kernels = 0), static rank split.  Tolerance: 1e-12 relative to max|G|.
+def _cluster(nw, tmp_path, oracle):
+    from unomol_b200.basis import water_cluster
+    b = water_cluster(nw)
+    path = str(tmp_path / ("patin.w%d" % nw))
+    b.write_patin(path)
+    return b, oracle.basis(path)
+
+
+_WATER_ORACLE = {}
+
+
+def _water_oracle(oracle, tmp_path, nw):
+    if nw not in _WATER_ORACLE:
+        b, ob = _cluster(nw, tmp_path, oracle)
+        rng = np.random.default_rng(100 + nw)
+        P, PB = rng.standard_normal(b.no2), rng.standard_normal(b.no2)
+        G = oracle.direct_g_threads(ob, P)
+        GA, GB = oracle.direct_g_threads(ob, P, PB)
+        _WATER_ORACLE[nw] = (b, P, PB, G, GA, GB)
+    return _WATER_ORACLE[nw]
+
+
+@pytest.mark.parametrize("nw,opts", [
+    (8, {}),
+    (8, {"bucket_min_pairs": 1}),
+    (8, {"bucket_min_pairs": 1, "col_blocks": 3}),
+    (8, {"tile_kernels": 0}),
+    (8, {"tile_kernels": 0, "bucket_min_pairs": 1, "col_blocks": 2}),
+    (8, {"device_pairs": 0}),
+    (12, {}),
+    (12, {"bucket_min_pairs": 1, "col_blocks": 3}),
+])
+def test_water_cluster_g_vs_oracle(capi, oracle, tmp_path, nw, opts):
+    b, P, PB, G, GA, GB = _water_oracle(oracle, tmp_path, nw)
+    h = capi.Handle(b)
+    for k, v in opts.items():
+        h.set_option(k, v)
+    scale = np.max(np.abs(G))
+    g = h.fock_rhf(P)
+    st = h.stats()
+    assert np.max(np.abs(g - G)) < 1e-12 * scale, (np.max(np.abs(g - G)) / scale, opts)
+    if opts.get("tile_kernels", 1):
+        assert st["n_tile_launches"] > 0, st
+    else:
+        assert st["n_tile_launches"] == 0 and st["n_reg_launches"] > 0 and st["n_rows_launches"] > 0, st
+    if "bucket_min_pairs" in opts:
+        assert st["n_launches"] > 30, st          # buckets multiply the launches (6 classes -> 21 without them)
+    ga, gb = h.fock_uhf(P, PB)
+    scale_u = max(np.max(np.abs(GA)), np.max(np.abs(GB)))
+    assert max(np.max(np.abs(ga - GA)), np.max(np.abs(gb - GB))) < 1e-12 * scale_u
+    h.close()
+
+
+def test_water_cluster_two_rank_static_split_vs_oracle(capi, oracle, tmp_path):
+    """the N > 1 static (snake) split on one GPU: two handles with rank 0/2 and 1/2, partial G's summed, against the oracle"""
+    b, P, PB, G, GA, GB = _water_oracle(oracle, tmp_path, 8)
+    parts = []
+    for r in range(2):
+        h = capi.Handle(b, rank=r, nranks=2)
+        h.set_option("bucket_min_pairs", 1)
+        parts.append(h.fock_rhf(P))
+        h.close()
+    assert np.max(np.abs(parts[0] + parts[1] - G)) < 1e-12 * np.max(np.abs(G))
+    assert np.max(np.abs(parts[0])) > 0 and np.max(np.abs(parts[1])) > 0

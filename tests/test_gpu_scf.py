@@ -75,7 +75,7 @@ def test_scf_driver_on_all_gpus_of_the_box(name, tmp_path):
     if n < 2:
         pytest.skip("single-GPU box")
     e0, e1, de, out = run_scf(name, tmp_path, env={"UNOMOL_GPUS": str(min(n, 4))})
-    assert abs(e1 - RUNS[name]["e_final"]) < 5e-9, (e1, RUNS[name]["e_final"])
+    assert abs(e1 - RUNS[name]["e_final"]) < E_TOL, (e1, RUNS[name]["e_final"])
 
 
 def test_host_side_scf_bookkeeping_gives_the_same_energy(tmp_path):
@@ -136,7 +136,19 @@ def test_uhf_energy_vs_fresh_reference_run(name, tmp_path):
     p shells: the converged energy is compared, not the density."""
     e0, e1, de, out = run_scf(name, tmp_path)
     assert RUNS[name]["converged"]
-    assert abs(e1 - RUNS[name]["e_final"]) < 5e-9, (e1, RUNS[name]["e_final"])
+    assert abs(e1 - RUNS[name]["e_final"]) < E_TOL, (e1, RUNS[name]["e_final"])
+    assert abs(e0 - RUNS[name]["e_init"]) < E_TOL
+
+
+def test_uhf_c2h2_cation_first_iteration(tmp_path):
+    """BASELINE config 3 names UHF C2H2 (nelec 14 -> 13).  The unmodified reference does NOT converge this input (299
+    iterations, ref_runs.json: converged false), so there is no final energy to compare: a non-converged trajectory depends
+    on rounding.  What is deterministic is the energy of the first UHF iteration (core guess -> G_alpha, G_beta -> E),
+    compared at 1e-9 Eh, and the driver must report non-convergence like the reference does."""
+    e0, e1, de, out = run_scf("dh95.c2h2.cation", tmp_path)
+    assert not RUNS["dh95.c2h2.cation"]["converged"]
+    assert abs(e0 - RUNS["dh95.c2h2.cation"]["e_init"]) < E_TOL, (e0, RUNS["dh95.c2h2.cation"]["e_init"])
+    assert "NOT_ REACHED" in out
 
 
 def test_orbital_energies_h2o(tmp_path):

@@ -39,7 +39,9 @@ class Stats(ctypes.Structure):
                 ("n_quartets_total", ctypes.c_longlong), ("model_flops", _D), ("last_fock_ms", _D),
                 ("last_eri_kernel_ms", _D), ("precompute_ms", _D), ("n_launches", _I), ("nbf", _I),
                 ("nshell", _I), ("rank", _I), ("nranks", _I),
-                ("n_prim_quartets", ctypes.c_longlong), ("n_prim_candidates", ctypes.c_longlong)]
+                ("n_prim_quartets", ctypes.c_longlong), ("n_prim_candidates", ctypes.c_longlong),
+                ("n_tile_launches", _I), ("n_reg_launches", _I), ("n_rows_launches", _I), ("n_generic_launches", _I),
+                ("n_highl_launches", _I), ("last_dump_kernel", _I)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

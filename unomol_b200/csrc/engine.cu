@@ -33,6 +33,17 @@ using namespace ub200;
         }                                                                                        \
     } while (0)
 
+// device allocation released on every exit path (the CUDA_TRY early returns used to leak their temporaries)
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    bool alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * std::max<size_t>(n, 1)) == cudaSuccess; }
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
 namespace ub200 {
 
 // bra-class launchers (eri_class_<n>.cu)
@@ -156,8 +167,13 @@ static void free_pairs(unomol_b200 *h) {
     for (int c = 0; c < NGROUP; ++c) {
         if (h->cls[c].d_pairs) cudaFree(h->cls[c].d_pairs);
         if (h->cls[c].d_hot) cudaFree(h->cls[c].d_hot);
+        if (h->cls[c].d_tpairs) cudaFree(h->cls[c].d_tpairs);
         h->cls[c].d_pairs = nullptr;
         h->cls[c].d_hot = nullptr;
+        h->cls[c].d_tpairs = nullptr;
+        h->cls[c].slot_pos.clear();
+        h->cls[c].pos_slot.clear();
+        h->cls[c].ntiles = 0;
         h->cls[c].pairs.clear();
         h->cls[c].n = 0;
     }
@@ -166,6 +182,8 @@ static void free_pairs(unomol_b200 *h) {
     for (auto &p : h->plans) {
         if (p.d_ket_count) cudaFree(p.d_ket_count);
         if (p.d_ket_prefix) cudaFree(p.d_ket_prefix);
+        if (p.d_kc_tile) cudaFree(p.d_kc_tile);
+        if (p.d_tile_order) cudaFree(p.d_tile_order);
     }
     h->plans.clear();
     h->pairs_ready = false;
@@ -367,6 +385,36 @@ static int build_pairs(unomol_b200 *h) {
             h->pair_cls[L.pairs[i].pairid] = c;
             h->pair_pos[L.pairs[i].pairid] = i;
         }
+        // tile order for eri_tile.cuh: by first shell, Q descending inside a shell (= list position ascending)
+        L.maxnp = 0;
+        for (int i = 0; i < L.n; ++i) L.maxnp = std::max(L.maxnp, L.pairs[i].nprim);
+        if (c / NSUB < NSPDCLASS && tile_class_available(c / NSUB, 0)) {
+            const int tb = tile_b_of_class(c / NSUB);
+            std::vector<int> ord(L.n);
+            std::iota(ord.begin(), ord.end(), 0);
+            std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return L.pairs[x].sha < L.pairs[y].sha; });
+            L.slot_pos.clear();
+            L.pos_slot.assign(L.n, -1);
+            int fill = 0, cur_sh = -1;
+            for (int o : ord) {
+                if (L.pairs[o].sha != cur_sh || fill == tb) {
+                    L.slot_pos.resize(L.slot_pos.size() + TILE_SLOTS, -1);   // open a new tile
+                    fill = 0;
+                    cur_sh = L.pairs[o].sha;
+                }
+                const int slot = (int)L.slot_pos.size() - TILE_SLOTS + fill++;
+                L.slot_pos[slot] = o;
+                L.pos_slot[o] = slot;
+            }
+            L.ntiles = (int)L.slot_pos.size() / TILE_SLOTS;
+            std::vector<ShellPair> tp(L.slot_pos.size());
+            for (size_t sl = 0; sl < tp.size(); ++sl) {
+                if (L.slot_pos[sl] >= 0) tp[sl] = L.pairs[L.slot_pos[sl]];
+                else { memset(&tp[sl], 0, sizeof(ShellPair)); tp[sl].sha = tp[sl].shb = -1; tp[sl].pairid = -1; }
+            }
+            CUDA_TRY(h, cudaMalloc(&L.d_tpairs, sizeof(ShellPair) * tp.size()));
+            CUDA_TRY(h, cudaMemcpy(L.d_tpairs, tp.data(), sizeof(ShellPair) * tp.size(), cudaMemcpyHostToDevice));
+        }
     }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     int rc = build_plans(h);
@@ -385,6 +433,8 @@ static int build_plans(unomol_b200 *h) {
     for (auto &p : h->plans) {
         if (p.d_ket_count) cudaFree(p.d_ket_count);
         if (p.d_ket_prefix) cudaFree(p.d_ket_prefix);
+        if (p.d_kc_tile) cudaFree(p.d_kc_tile);
+        if (p.d_tile_order) cudaFree(p.d_tile_order);
     }
     h->plans.clear();
     long long total = 0;
@@ -426,6 +476,39 @@ static int build_plans(unomol_b200 *h) {
             for (int i = 0; i < plan.nbra_eff; ++i) maxbp = std::max(maxbp, Lb.pairs[i].nprim);
             plan.highl = is_highl(cb / NSUB, ck / NSUB);
             plan.use_reg = !plan.highl && h->use_reg_kernels && reg_class_available(cb / NSUB, ck / NSUB) && maxbp <= reg_max_bra_prims();
+            plan.use_tile = plan.use_reg && h->use_tile_kernels && tile_class_available(cb / NSUB, ck / NSUB) && Lb.ntiles > 0 &&
+                            Lb.maxnp <= TILE_MAX_BRA_PRIMS;
+            if (plan.use_tile) {
+                plan.maxbp = Lb.maxnp;
+                // ket primitives a thread keeps in shared memory: every ket of the list when that fits the budget
+                int maxkp = 0;
+                const int kmaxvis = *std::max_element(kc.begin(), kc.end());
+                for (int i = 0; i < kmaxvis; ++i) maxkp = std::max(maxkp, Lk.pairs[i].nprim);
+                plan.kslots = std::min(maxkp, 6);
+                while (plan.kslots > 0 && tile_smem_bytes(cb / NSUB, ck / NSUB, plan.maxbp, plan.kslots, h->rys.rys2_exact) > 100 * 1024) --plan.kslots;
+                if (tile_smem_bytes(cb / NSUB, ck / NSUB, plan.maxbp, plan.kslots, h->rys.rys2_exact) > 200 * 1024) plan.use_tile = false;
+            }
+            if (plan.use_tile) {
+                std::vector<int> kct(Lb.slot_pos.size(), 0);
+                std::vector<std::pair<long long, int>> cost(Lb.ntiles);
+                for (int t = 0; t < Lb.ntiles; ++t) {
+                    long long w = 0;
+                    for (int j = 0; j < TILE_SLOTS; ++j) {
+                        const int pos = Lb.slot_pos[(size_t)t * TILE_SLOTS + j];
+                        if (pos >= 0) { kct[(size_t)t * TILE_SLOTS + j] = kc[pos]; w += kc[pos]; }
+                    }
+                    cost[t] = {w, t};
+                }
+                std::stable_sort(cost.begin(), cost.end(), [](const std::pair<long long, int> &x, const std::pair<long long, int> &y) { return x.first > y.first; });
+                std::vector<int> order;
+                for (auto &ct : cost) if (ct.first > 0) order.push_back(ct.second);
+                plan.ntiles = (int)order.size();
+                if (cudaMalloc(&plan.d_kc_tile, sizeof(int) * kct.size()) != cudaSuccess) return UNOMOL_E_NOMEM;
+                if (cudaMalloc(&plan.d_tile_order, sizeof(int) * std::max<size_t>(1, order.size())) != cudaSuccess) return UNOMOL_E_NOMEM;
+                cudaMemcpyAsync(plan.d_kc_tile, kct.data(), sizeof(int) * kct.size(), cudaMemcpyHostToDevice, h->stream);
+                cudaMemcpyAsync(plan.d_tile_order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, h->stream);
+                cudaStreamSynchronize(h->stream);
+            }
             if (cudaMalloc(&plan.d_ket_count, sizeof(int) * Lb.n) != cudaSuccess) return UNOMOL_E_NOMEM;
             cudaMemcpyAsync(plan.d_ket_count, kc.data(), sizeof(int) * Lb.n, cudaMemcpyHostToDevice, h->stream);
             std::vector<long long> pre;
@@ -483,6 +566,7 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
     CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 2 * (h->plans.size() + 1), st));
     cudaEventRecord(h->ev2, st);
     int nlaunch = 2;
+    int n_tile = 0, n_reg = 0, n_rows = 0, n_gen = 0, n_hl = 0;
     // work counters of this build (see engine.h)
     unsigned long long *work = nullptr;
     if (h->d_work_shared && h->steal_enabled) {
@@ -543,8 +627,23 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
             // work items of the runtime-L kernel are single quartets
             const long long nq = work ? pl.nquartets_eff : (pl.nquartets_eff + h->nranks - 1) / h->nranks;
             CUDA_TRY(h, launch_any_class(h, pl.cb / NSUB, pl.ck / NSUB, task, MODE_DIGEST, (int)std::min<long long>(nq, 1 << 20), st));
+            ++n_hl;
+        } else if (pl.use_tile) {
+            ++n_tile;
+            task.tbra = h->cls[pl.cb].d_tpairs;
+            task.ket_count = pl.d_kc_tile;
+            task.tile_order = pl.d_tile_order;
+            task.ntiles = pl.ntiles;
+            task.tile_b = tile_b_of_class(pl.cb / NSUB);
+            task.tile_maxbp = pl.maxbp;
+            task.kslots = pl.kslots;
+            task.chunk = 1;
+            const int tmine = work ? pl.ntiles : (pl.ntiles + h->nranks - 1) / h->nranks;
+            CUDA_TRY(h, launch_tile_class(pl.cb / NSUB, pl.ck / NSUB, task, std::min(tmine, 148 * 8), st));
         } else if (pl.use_reg) {
             CUDA_TRY(h, launch_reg_class(pl.cb / NSUB, pl.ck / NSUB, task, std::min(nmine, 148 * 16), st, h->stage_rows != 0));
+            ++n_reg;
+            if (h->stage_rows && nspin == 1 && reg_rows_fit(pl.cb / NSUB, ld)) ++n_rows;
         } else {
             // generic kernel: a warp takes (bra, slice) items; split the kets of a bra over several warps when the list has
             // fewer bras than the GPU keeps warps busy (small molecules), every rank choosing the same split
@@ -555,6 +654,7 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
             const long long items = (long long)(work ? pl.nbra_eff : nmine) * split;
             const int ctas = (int)std::min<long long>((items + 3) / 4, 148 * 32);   // 4 warps per CTA
             CUDA_TRY(h, launch_quartet_class(pl.cb / NSUB, pl.ck / NSUB, task, MODE_DIGEST, std::max(ctas, 1), st));
+            ++n_gen;
         }
         ++nlaunch;
     }
@@ -576,6 +676,8 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
     }
     cudaEventRecord(h->ev1, st);
     h->stats.n_launches = nlaunch;
+    h->stats.n_tile_launches = n_tile; h->stats.n_reg_launches = n_reg; h->stats.n_rows_launches = n_rows;
+    h->stats.n_generic_launches = n_gen; h->stats.n_highl_launches = n_hl;
     return UNOMOL_OK;
 }
 
@@ -698,6 +800,12 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
     // two-root quadrature: 0 = reproduce the reference's behaviour for 15 < X <= 40 (parity, default), 1 = exact.  The
     // Schwarz bounds depend on it, so the pair tables are rebuilt.
     if (!strcmp(name, "rys2_exact")) { h->rys.rys2_exact = value != 0.0; h->pairs_ready = false; return UNOMOL_OK; }
+    if (!strcmp(name, "tile_kernels")) {
+        h->use_tile_kernels = value != 0.0;
+        if (h->pairs_ready) return build_plans(h);
+        return UNOMOL_OK;
+    }
+    if (!strcmp(name, "dump_kernel")) { h->dump_kernel = (int)value; return UNOMOL_OK; }
     if (!strcmp(name, "reg_kernels")) {
         h->use_reg_kernels = value != 0.0;
         if (h->pairs_ready) return build_plans(h);
@@ -870,6 +978,68 @@ static bool locate_pair(unomol_b200 *h, int i, int j, int &cls, int &pos, bool &
     return true;
 }
 
+// the plan a Fock build uses for (bra group, ket group), or null
+static const ComboPlan *find_plan(unomol_b200 *h, int cb, int ck) {
+    for (auto &p : h->plans) if (p.cb == cb && p.ck == ck) return &p;
+    return nullptr;
+}
+
+// One quartet (bra position pb of group cb, ket position pk of group ck) through the kernel a Fock build uses for the
+// class: the bra-tile kernel or the register kernel in their dump mode (option "dump_kernel" = 1).  Returns 1 when
+// that kernel ran, 0 when the class belongs to the generic kernel, < 0 on error.
+static int dump_quartet_hot(unomol_b200 *h, int cb, int ck, int pb, int pk, double *d_out) {
+    const ComboPlan *pl = find_plan(h, cb, ck);
+    if (!pl || (!pl->use_tile && !pl->use_reg)) return 0;
+    const PairClassList &Lb = h->cls[cb], &Lk = h->cls[ck];
+    unsigned char hostbuf[128];
+    memset(hostbuf, 0, sizeof(hostbuf));           // [0,32) ket counts of the tile's slots, [32,36) tile id 0, [64,128) offsets
+    unsigned char *d_buf = nullptr;
+    if (cudaMalloc(&d_buf, sizeof(hostbuf)) != cudaSuccess) return -UNOMOL_E_NOMEM;
+    ClassTask task{};
+    task.rys = h->rys;
+    task.prims = h->d_prims;
+    task.ket_hot = Lk.d_hot + pk;
+    task.ket = Lk.d_pairs + pk;
+    task.nket = 1;
+    task.nranks = 1;
+    task.prim_cut = h->prim_cut;
+    task.value_cut = h->value_cut;
+    task.task_out = reinterpret_cast<const long long *>(d_buf + 64);
+    task.out = d_out;
+    cudaError_t e;
+    if (pl->use_tile) {
+        const int slot = Lb.pos_slot[pb];
+        reinterpret_cast<int *>(hostbuf)[slot % TILE_SLOTS] = 1;
+        task.tbra = Lb.d_tpairs + (size_t)(slot / TILE_SLOTS) * TILE_SLOTS;
+        task.ket_count = reinterpret_cast<const int *>(d_buf);
+        task.tile_order = reinterpret_cast<const int *>(d_buf + 32);
+        task.ntiles = 1;
+        task.tile_b = tile_b_of_class(cb / NSUB);
+        task.tile_maxbp = Lb.maxnp;
+        task.kslots = std::min(6, pl->kslots);
+        task.chunk = 1;
+        task.nspin = 1;
+        cudaMemcpyAsync(d_buf, hostbuf, sizeof(hostbuf), cudaMemcpyHostToDevice, h->stream);
+        e = launch_tile_class(cb / NSUB, ck / NSUB, task, 1, h->stream);
+    } else {
+        reinterpret_cast<int *>(hostbuf)[0] = 1;
+        task.bra = Lb.d_pairs + pb;
+        task.nbra = 1;
+        task.ket_count = reinterpret_cast<const int *>(d_buf);
+        task.chunk = 1;
+        task.nspin = 1;
+        cudaMemcpyAsync(d_buf, hostbuf, sizeof(hostbuf), cudaMemcpyHostToDevice, h->stream);
+        e = launch_reg_class(cb / NSUB, ck / NSUB, task, 1, h->stream, false);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_buf);
+    if (e != cudaSuccess) {
+        h->last_error = std::string("dump_quartet_hot: ") + cudaGetErrorString(e);
+        return -UNOMOL_E_CUDA;
+    }
+    return 1;
+}
+
 int unomol_b200_eri_quartet(unomol_b200_t *h, int ish, int jsh, int ksh, int lsh, double *out) {
     if (!h || !out) return UNOMOL_E_ARG;
     const HostBasis &B = h->basis;
@@ -889,23 +1059,31 @@ int unomol_b200_eri_quartet(unomol_b200_t *h, int ish, int jsh, int ksh, int lsh
     const int pb = braket_swapped ? p2 : p1, pk = braket_swapped ? p1 : p2;
     int2 tl = make_int2(pb, pk);
     long long off0 = 0;
-    int2 *d_tl; long long *d_off; double *d_out;
-    CUDA_TRY(h, cudaMalloc(&d_tl, sizeof(int2)));
-    CUDA_TRY(h, cudaMalloc(&d_off, sizeof(long long)));
-    CUDA_TRY(h, cudaMalloc(&d_out, sizeof(double) * ntot));
-    CUDA_TRY(h, cudaMemcpyAsync(d_tl, &tl, sizeof(int2), cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(d_off, &off0, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
-    ClassTask task{};
+    DevBuf<int2> d_tl;
+    DevBuf<long long> d_off;
+    DevBuf<double> d_out;
+    if (!d_tl.alloc(1) || !d_off.alloc(1) || !d_out.alloc(ntot)) return UNOMOL_E_NOMEM;
+    CUDA_TRY(h, cudaMemsetAsync(d_out.p, 0, sizeof(double) * ntot, h->stream));
+    int ran_hot = 0;
+    if (h->dump_kernel == 1) {
+        ran_hot = dump_quartet_hot(h, cb, ck, pb, pk, d_out.p);
+        if (ran_hot < 0) return -ran_hot;
+    }
+    h->stats.last_dump_kernel = ran_hot;   // lets the tests assert which kernel produced the block
+    if (!ran_hot) {
+        CUDA_TRY(h, cudaMemcpyAsync(d_tl.p, &tl, sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(d_off.p, &off0, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+        ClassTask task{};
         task.rys = h->rys;
-    task.bra = h->cls[cb].d_pairs; task.ket = h->cls[ck].d_pairs; task.prims = h->d_prims;
-    task.nbra = h->cls[cb].n; task.nket = h->cls[ck].n;
-    task.prim_cut = h->prim_cut;
-    task.task_list = d_tl; task.task_out = d_off; task.ntask = 1; task.out = d_out;
-    CUDA_TRY(h, launch_any_class(h, cb / NSUB, ck / NSUB, task, MODE_DUMP, 1, h->stream));
+        task.bra = h->cls[cb].d_pairs; task.ket = h->cls[ck].d_pairs; task.prims = h->d_prims;
+        task.nbra = h->cls[cb].n; task.nket = h->cls[ck].n;
+        task.prim_cut = h->prim_cut;
+        task.task_list = d_tl.p; task.task_out = d_off.p; task.ntask = 1; task.out = d_out.p;
+        CUDA_TRY(h, launch_any_class(h, cb / NSUB, ck / NSUB, task, MODE_DUMP, 1, h->stream));
+    }
     std::vector<double> blk(ntot);
-    CUDA_TRY(h, cudaMemcpyAsync(blk.data(), d_out, sizeof(double) * ntot, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(blk.data(), d_out.p, sizeof(double) * ntot, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    cudaFree(d_tl); cudaFree(d_off); cudaFree(d_out);
     // block layout [a][b][c][d] in the kernel's orientation -> caller's [i][j][k][l]
     // kernel bra pair = (A,B) shells, ket pair = (C,D)
     const ShellPair &SB = h->cls[cb].pairs[pb], &SK = h->cls[ck].pairs[pk];
@@ -950,6 +1128,7 @@ int unomol_b200_dump_eris(unomol_b200_t *h, double thresh, unomol_twoint *buf, s
     if (total > (1LL << 28)) return UNOMOL_E_NOMEM;   // 2 GiB of doubles: this hook is for small systems
     double *d_out = nullptr;
     CUDA_TRY(h, cudaMalloc(&d_out, sizeof(double) * std::max<long long>(total, 1)));
+    if (cudaMemsetAsync(d_out, 0, sizeof(double) * std::max<long long>(total, 1), h->stream) != cudaSuccess) { cudaFree(d_out); return UNOMOL_E_CUDA; }
     for (auto &cmb : combos) {
         const int nb = h->cls[cmb.cb].n, nk = h->cls[cmb.ck].n;
         std::vector<int2> tl;
@@ -962,21 +1141,63 @@ int unomol_b200_dump_eris(unomol_b200_t *h, double thresh, unomol_twoint *buf, s
                 off.push_back(cmb.base + t * cmb.nint);
             }
         }
-        int2 *d_tl; long long *d_off;
-        CUDA_TRY(h, cudaMalloc(&d_tl, sizeof(int2) * tl.size()));
-        CUDA_TRY(h, cudaMalloc(&d_off, sizeof(long long) * off.size()));
-        CUDA_TRY(h, cudaMemcpyAsync(d_tl, tl.data(), sizeof(int2) * tl.size(), cudaMemcpyHostToDevice, h->stream));
-        CUDA_TRY(h, cudaMemcpyAsync(d_off, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice, h->stream));
+        const ComboPlan *pl = h->dump_kernel == 1 ? find_plan(h, cmb.cb, cmb.ck) : nullptr;
+        if (pl && (pl->use_tile || pl->use_reg)) {
+            // the kernel a Fock build uses for this class, in its dump mode: every (bra, ket) pair of the combination
+            const PairClassList &Lb = h->cls[cmb.cb];
+            const bool same = cmb.cb == cmb.ck;
+            const size_t nslot = pl->use_tile ? Lb.slot_pos.size() : (size_t)nb;
+            std::vector<int> kcnt(nslot, 0);
+            std::vector<long long> offs(nslot, 0);
+            for (size_t sl = 0; sl < nslot; ++sl) {
+                const int pos = pl->use_tile ? Lb.slot_pos[sl] : (int)sl;
+                if (pos < 0) continue;
+                kcnt[sl] = same ? pos + 1 : nk;
+                offs[sl] = cmb.base + (same ? (long long)pos * (pos + 1) / 2 : (long long)pos * nk) * cmb.nint;
+            }
+            std::vector<int> order(pl->use_tile ? Lb.ntiles : 0);
+            std::iota(order.begin(), order.end(), 0);
+            DevBuf<int> d_kc, d_order;
+            DevBuf<long long> d_offs;
+            if (!d_kc.alloc(nslot) || !d_offs.alloc(nslot) || !d_order.alloc(order.size())) { cudaFree(d_out); return UNOMOL_E_NOMEM; }
+            cudaMemcpyAsync(d_kc.p, kcnt.data(), sizeof(int) * nslot, cudaMemcpyHostToDevice, h->stream);
+            cudaMemcpyAsync(d_offs.p, offs.data(), sizeof(long long) * nslot, cudaMemcpyHostToDevice, h->stream);
+            if (!order.empty()) cudaMemcpyAsync(d_order.p, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, h->stream);
+            ClassTask task{};
+            task.rys = h->rys;
+            task.bra = Lb.d_pairs; task.ket = h->cls[cmb.ck].d_pairs; task.ket_hot = h->cls[cmb.ck].d_hot; task.prims = h->d_prims;
+            task.nbra = nb; task.nket = nk; task.prim_cut = h->prim_cut; task.value_cut = h->value_cut;
+            task.nranks = 1; task.chunk = 1; task.nspin = 1;
+            task.ket_count = d_kc.p; task.task_out = d_offs.p; task.out = d_out;
+            cudaError_t e;
+            if (pl->use_tile) {
+                task.tbra = Lb.d_tpairs; task.tile_order = d_order.p; task.ntiles = Lb.ntiles;
+                task.tile_b = tile_b_of_class(cmb.cb / NSUB); task.tile_maxbp = Lb.maxnp; task.kslots = pl->kslots;
+                e = launch_tile_class(cmb.cb / NSUB, cmb.ck / NSUB, task, std::min(Lb.ntiles, 148 * 8), h->stream);
+            } else {
+                e = launch_reg_class(cmb.cb / NSUB, cmb.ck / NSUB, task, std::min(nb, 148 * 16), h->stream, false);
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) { cudaFree(d_out); h->last_error = cudaGetErrorString(e); return UNOMOL_E_CUDA; }
+            continue;
+        }
+        DevBuf<int2> d_tl;
+        DevBuf<long long> d_off;
+        if (!d_tl.alloc(tl.size()) || !d_off.alloc(off.size())) { cudaFree(d_out); return UNOMOL_E_NOMEM; }
+        cudaMemcpyAsync(d_tl.p, tl.data(), sizeof(int2) * tl.size(), cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(d_off.p, off.data(), sizeof(long long) * off.size(), cudaMemcpyHostToDevice, h->stream);
         ClassTask task{};
         task.rys = h->rys;
         task.bra = h->cls[cmb.cb].d_pairs; task.ket = h->cls[cmb.ck].d_pairs; task.prims = h->d_prims;
         task.nbra = nb; task.nket = nk; task.prim_cut = h->prim_cut;
-        task.task_list = d_tl; task.task_out = d_off; task.ntask = (int)tl.size(); task.out = d_out;
+        task.task_list = d_tl.p; task.task_out = d_off.p; task.ntask = (int)tl.size(); task.out = d_out;
         const int groups = any_groups_per_cta(cmb.cb / NSUB, cmb.ck / NSUB);
         const int grid = std::min(((int)tl.size() + groups - 1) / groups, 148 * 16);
-        CUDA_TRY(h, launch_any_class(h, cmb.cb / NSUB, cmb.ck / NSUB, task, MODE_DUMP, grid, h->stream));
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-        cudaFree(d_tl); cudaFree(d_off);
+        {
+            cudaError_t e = launch_any_class(h, cmb.cb / NSUB, cmb.ck / NSUB, task, MODE_DUMP, grid, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) { cudaFree(d_out); h->last_error = cudaGetErrorString(e); return UNOMOL_E_CUDA; }
+        }
     }
     std::vector<double> all((size_t)std::max<long long>(total, 1));
     CUDA_TRY(h, cudaMemcpy(all.data(), d_out, sizeof(double) * all.size(), cudaMemcpyDeviceToHost));

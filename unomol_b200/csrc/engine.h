@@ -17,10 +17,18 @@ int class_groups_per_cta(int bra_class, int ket_class);
 // register-resident kernels for the small classes (eri_reg_classes.cu)
 bool reg_class_available(int bra_class, int ket_class);
 int reg_max_bra_prims();
+bool reg_rows_fit(int bra_class, int ld);   // the bra's rows of P fit the register kernels' shared-memory stage
 // device-side shell-pair / primitive-pair tables (pair_device.cu)
 int build_pair_tables_device(unomol_b200 *h, double prune_cut, std::vector<ShellPair> &kept, std::vector<int> &cls, PrimPair **d_prims_out,
                              long long *nprim_out);
 cudaError_t launch_reg_class(int bra_class, int ket_class, const ClassTask &task, int grid, cudaStream_t stream, bool allow_rows);
+// bra-tile / ket-stationary kernels for the s/p classes (eri_tile_classes.cu)
+bool tile_class_available(int bra_class, int ket_class);
+int tile_b_of_class(int bra_class);
+size_t tile_smem_bytes(int bra_class, int ket_class, int maxbp, int kslots, int rys2_exact);
+cudaError_t launch_tile_class(int bra_class, int ket_class, const ClassTask &task, int grid, cudaStream_t stream);
+constexpr int TILE_SLOTS = 8;        // = TILE_MAXB of eri_tile.cuh: slots per tile in the padded tile-ordered lists
+constexpr int TILE_MAX_BRA_PRIMS = 36;
 // SURVEY.md 8(d) flop model per primitive quartet of class (la lb | lc ld)
 double model_flops_per_primitive_quartet(int la, int lb, int lc, int ld);
 
@@ -47,6 +55,13 @@ struct PairClassList {
     ShellPair *d_pairs = nullptr;
     KetHot *d_hot = nullptr;        // hot-field mirror of d_pairs
     int n = 0;
+    // tile order (eri_tile.cuh): pairs regrouped by first shell, Q descending inside a shell, cut into tiles of
+    // tile_b_of_class() pairs; every tile owns TILE_SLOTS slots of the padded copy d_tpairs
+    ShellPair *d_tpairs = nullptr;
+    std::vector<int> slot_pos;      // [ntiles * TILE_SLOTS]: position in `pairs` or -1 (padding)
+    std::vector<int> pos_slot;      // [n]: slot of a pair
+    int ntiles = 0;
+    int maxnp = 0;                  // largest primitive-pair count in the list
 };
 
 struct ComboPlan {                  // one (bra class, ket class) launch
@@ -58,6 +73,11 @@ struct ComboPlan {                  // one (bra class, ket class) launch
     long long *d_ket_prefix = nullptr;   // runtime-L plans: exclusive prefix sum of the ket counts [nbra_eff + 1]
     double cost = 0.0;              // quartets x model flops: launch order (largest first)
     bool use_reg = false;           // register-resident kernel (small class, bra contraction fits the stage)
+    bool use_tile = false;          // bra-tile / ket-stationary kernel (s/p classes)
+    int *d_kc_tile = nullptr;       // ket counts per slot of the bra list's tile order
+    int *d_tile_order = nullptr;    // tiles with work, heaviest first
+    int ntiles = 0;
+    int kslots = 0, maxbp = 0;
     bool highl = false;             // contains an f or g shell: runtime-L kernel
 };
 
@@ -74,6 +94,8 @@ struct unomol_b200 {
     ub200::RysTables rys{};         // device table pointers + option "rys2_exact"
     double tau = 1e-12, prim_cut = 1e-12, value_cut = 1e-14;
     int use_reg_kernels = 1;
+    int use_tile_kernels = 1;       // option "tile_kernels": 0 falls back to the one-bra-per-CTA register kernels
+    int dump_kernel = 0;            // option "dump_kernel": 1 = eri_quartet / dump_eris run the kernel a Fock build uses for the class
     int device_pairs = 1;           // option "device_pairs": build the pair tables on the GPU (0 = threaded host path)
     int col_blocks = 0;             // option "col_blocks": spatial blocks per pair list (0 = choose from N so a launch fits L2)
     bool bra_split_enabled = true;  // option "bra_split": generic kernel deals the kets of one bra to several warps for short bra lists

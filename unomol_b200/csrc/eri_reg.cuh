@@ -368,9 +368,11 @@ __global__ void __launch_bounds__(ROWS ? REG_THREADS_ROWS : REG_THREADS) eri_reg
                 h1[O] = v;
             });
             double sym = 1.0;
-            if (bra.sha == bra.shb) sym *= 0.5;
-            if (ket.sha == ket.shb) sym *= 0.5;
-            if (task.same_class && bra.pairid == ket.pairid) sym *= 0.5;
+            if (!task.out) {
+                if (bra.sha == bra.shb) sym *= 0.5;
+                if (ket.sha == ket.shb) sym *= 0.5;
+                if (task.same_class && bra.pairid == ket.pairid) sym *= 0.5;
+            }
             double V[NINT];
             static_for<NINT>([&](auto oo) {
                 constexpr int O = decltype(oo)::value;
@@ -400,6 +402,13 @@ __global__ void __launch_bounds__(ROWS ? REG_THREADS_ROWS : REG_THREADS) eri_reg
                 constexpr double nrm = c_norm(LA, a) * c_norm(LB, b) * c_norm(LC, c) * c_norm(LD, d);
                 V[O] = v * (nrm * sym);
             });
+            if (task.out) {
+                // dump mode (test hook): the contracted block as computed by THIS kernel, no symmetry factor
+                double *dst = task.out + task.task_out[bi] + (size_t)ki * NINT;
+#pragma unroll
+                for (int o = 0; o < NINT; ++o) dst[o] = V[o];
+                continue;
+            }
             // The reference never stores an integral with |val| <= 1e-14 (TwoElectronInts.cpp:513,667-671), so such
             // integrals never reach its G.  A quartet whose whole block is below that threshold is therefore skipped
             // here before any gather / red (most Schwarz survivors of a large cluster are of this kind: the bound

@@ -41,6 +41,12 @@ bool reg_class_available(int cb, int ck) {
 
 int reg_max_bra_prims() { return REG_MAX_BRA_PRIMS; }
 
+bool reg_rows_fit(int cb, int ld) {
+    int la, lb;
+    pair_class_l(cb, la, lb);
+    return sizeof(double) * (size_t)((la + 1) * (la + 2) / 2 + (lb + 1) * (lb + 2) / 2) * ld <= REG_ROWS_MAX_BYTES;
+}
+
 cudaError_t launch_reg_class(int cb, int ck, const ClassTask &task, int grid, cudaStream_t stream, bool allow_rows) {
     switch (cb * 8 + ck) {
         case 0 * 8 + 0: return launch_reg<0, 0, 0, 0>(task, grid, stream, allow_rows);

@@ -1,0 +1,541 @@
+// unomol_b200/csrc/eri_tile.cuh -- bra-tile / ket-stationary fused ERI + J/K kernel for the low-angular-momentum classes.
+//
+// Why.  The round-1 register kernel (eri_reg.cuh: CTA = one bra pair, thread = one ket) was bound by the LSU -> L2 path,
+// not by FP64: every quartet cost ~20 scattered 32-byte load sectors (the ket's hot record and primitives, six density
+// gathers) and 5..19 FP64 reds (profiles/r1_ncu_water154_top2_final.txt: L2 at 83 % of its throughput, FP64 pipe at 37 %;
+// profiles/exp_red_rate.cu: the reds alone were 40 % of their measured ceiling).  Here the work item of a CTA is a TILE
+// of up to 8 bra pairs (a, b_j) that share their first shell a, and a thread keeps ONE ket (c, d) for the whole tile:
+//
+//   * the ket's hot record and its primitive pairs are fetched once per tile (primitives into a per-thread,
+//     conflict-free shared-memory slot: element (prim, field) of thread t at [(prim * NF2 + field) * T + t]);
+//   * K[a,c], K[a,d] and J[c,d] are accumulated in REGISTERS over the bras of the tile and flushed once per ket,
+//     P[a,c], P[a,d], P_J[c,d] are gathered once per ket; what remains per quartet is K[b_j,c], K[b_j,d] (reds) and
+//     P[b_j,c], P[b_j,d] (gathers): (ss|ss) 5 -> 2 + 3/B reds, (ps|ss) 9 -> 2 + 7/B, (ps|ps) 19 -> 4 + 15/B;
+//   * J[a,b_j] is accumulated per thread in shared memory (FP64 shared atomics are CAS loops; a private slot per
+//     thread is a plain load/add/store) and reduced once per tile;
+//   * the tile's ShellPair records, Schwarz ket counts and primitive pairs arrive by TMA bulk copies into a
+//     double-buffered stage (cp.async.bulk + mbarrier), the Boys grid of rys_roots.cuh sits in shared memory.
+//
+// Same arithmetic as eri_reg.cuh / eri_generic.cuh (reference TwoElectronInts.cpp:420-509 for the integrals,
+// :699-820 for the digestion); the lanes of a warp still hold Schwarz-neighbouring kets of one bra at any time, which
+// the run-ordered walk of round 1 had given up.
+#pragma once
+#include "eri_reg.cuh"
+
+namespace ub200 {
+
+constexpr int TILE_THREADS = 128;
+constexpr int TILE_MAXB = 8;       // bras per tile (slots of the padded tile-ordered bra list)
+constexpr int TILE_KC_BYTES = 32;  // TILE_MAXB ints
+
+struct TileLayout {
+    unsigned stage_bytes, off_jab, off_kp, off_boys, total;
+};
+// dynamic shared memory: [stage 0][stage 1][J_ab partials][ket primitive slots][Boys grid]
+__host__ __device__ inline TileLayout tile_layout(int maxbp, int tile_b, int nab, int kslots, int nf2, int nboys) {
+    TileLayout L;
+    L.stage_bytes = (unsigned)(TILE_MAXB * sizeof(ShellPair) + TILE_KC_BYTES + TILE_MAXB * maxbp * sizeof(PrimPair));
+    L.off_jab = 2u * L.stage_bytes;
+    L.off_kp = L.off_jab + (unsigned)(tile_b * nab * TILE_THREADS * sizeof(double));
+    L.off_boys = L.off_kp + (unsigned)(kslots * nf2 * TILE_THREADS * 16);
+    L.total = L.off_boys + (unsigned)(nboys * 16);
+    return L;
+}
+// Boys grid entries a class needs in shared memory (rys_roots.cuh): one root up to X = 35, two roots up to X = 15
+// (parity mode) or 46 (exact mode); three and more roots read their polynomial tables from global memory
+__host__ __device__ inline int tile_boys_entries(int nroots, int rys2_exact) {
+    if (nroots == 1) return 35 * RYS_BOYS_HINV + 2;
+    if (nroots == 2) return (rys2_exact ? RYS_BOYS_XMAX : 15) * RYS_BOYS_HINV + 2;
+    return 0;
+}
+
+template <int LA, int LB, int LC, int LD, int NSPIN>
+__global__ void __launch_bounds__(TILE_THREADS) eri_tile_kernel(const ClassTask task) {
+    using C = QC<LA, LB, LC, LD>;
+    constexpr int NR = C::NR, GI = C::GI, GJ = C::GJ, NE = C::NE, NF = C::NF, NEF = C::NEF;
+    constexpr int NA = C::NA, NB = C::NB, NC = C::NC, ND = C::ND, NAB = C::NAB, NCD = C::NCD, NINT = C::NINT;
+    constexpr int NF2 = (GJ > 1) ? 5 : 3;     // double2 fields of a ket primitive this class reads
+    constexpr int T = TILE_THREADS;
+    extern __shared__ __align__(16) unsigned char tsm[];
+    __shared__ __align__(8) unsigned long long bars[2];
+    __shared__ int s_next;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int maxbp = task.tile_maxbp, kslots = task.kslots;
+    const int nboys = tile_boys_entries(NR, task.rys.rys2_exact);
+    const TileLayout lay = tile_layout(maxbp, task.tile_b, NAB, kslots, NF2, nboys);
+    double *sjab = reinterpret_cast<double *>(tsm + lay.off_jab);       // [(j * NAB + ab) * T + tid]
+    double2 *skp = reinterpret_cast<double2 *>(tsm + lay.off_kp);       // [(prim * NF2 + field) * T + tid]
+    RysTables rys = task.rys;
+    if (nboys > 0) {
+        double2 *sb = reinterpret_cast<double2 *>(tsm + lay.off_boys);
+        const double2 *gb = reinterpret_cast<const double2 *>(task.rys.boys);
+        for (int i = tid; i < nboys; i += T) sb[i] = gb[i];
+        rys.boys = reinterpret_cast<const double *>(sb);
+    }
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto stage_pairs = [&](int s) { return reinterpret_cast<const ShellPair *>(tsm + (size_t)s * lay.stage_bytes); };
+    auto stage_kc = [&](int s) { return reinterpret_cast<const int *>(tsm + (size_t)s * lay.stage_bytes + TILE_MAXB * sizeof(ShellPair)); };
+    auto stage_prims = [&](int s) {
+        return reinterpret_cast<const PrimPair *>(tsm + (size_t)s * lay.stage_bytes + TILE_MAXB * sizeof(ShellPair) + TILE_KC_BYTES);
+    };
+    // thread 0: TMA one tile (slot block t of the padded tile-ordered lists) into stage s
+    auto issue = [&](int t, int s) {
+        const ShellPair *gp = task.tbra + (size_t)t * TILE_MAXB;
+        int np[TILE_MAXB], po[TILE_MAXB];
+        unsigned bytes = (unsigned)(TILE_MAXB * sizeof(ShellPair) + TILE_KC_BYTES);
+#pragma unroll
+        for (int j = 0; j < TILE_MAXB; ++j) {
+            np[j] = gp[j].nprim;
+            po[j] = gp[j].prim_off;
+            bytes += (unsigned)(np[j] * sizeof(PrimPair));
+        }
+        unsigned char *dst = tsm + (size_t)s * lay.stage_bytes;
+        mbar_expect_tx(&bars[s], bytes);
+        tma_bulk_g2s(dst, gp, (unsigned)(TILE_MAXB * sizeof(ShellPair)), &bars[s]);
+        tma_bulk_g2s(dst + TILE_MAXB * sizeof(ShellPair), task.ket_count + (size_t)t * TILE_MAXB, TILE_KC_BYTES, &bars[s]);
+        PrimPair *pd = reinterpret_cast<PrimPair *>(dst + TILE_MAXB * sizeof(ShellPair) + TILE_KC_BYTES);
+#pragma unroll
+        for (int j = 0; j < TILE_MAXB; ++j)
+            if (np[j] > 0) tma_bulk_g2s(pd + (size_t)j * maxbp, task.prims + po[j], (unsigned)(np[j] * sizeof(PrimPair)), &bars[s]);
+    };
+    // Tile sequence of this CTA: positions in task.tile_order (heaviest first).  Dynamic: thread 0 claims the next position
+    // from a counter shared by every CTA of every rank (work stealing; see eri_reg.cuh); static fallback: snake order.
+    auto pos_of = [&](int j) { return task.nranks * j + ((j & 1) ? task.nranks - 1 - task.rank : task.rank); };
+    int jb = blockIdx.x, cpos = 0, cend = 0;
+    auto advance = [&]() -> int {   // thread 0 only; returns a tile id or -1
+        int p;
+        if (task.work_counter) {
+            if (cpos >= cend) {
+                cpos = (int)atomicAdd_system(task.work_counter, (unsigned long long)task.chunk);
+                cend = cpos + task.chunk;
+            }
+            p = cpos++;
+        } else {
+            p = pos_of(jb);
+            jb += gridDim.x;
+        }
+        return p < task.ntiles ? task.tile_order[p] : -1;
+    };
+    unsigned phase[2] = {0u, 0u};
+    int s = 0;
+    if (tid == 0) {
+        const int t0 = advance();
+        s_next = t0;
+        if (t0 >= 0) issue(t0, 0);
+    }
+    __syncthreads();
+    int ti = s_next;
+    __syncthreads();
+    unsigned long long n_quart = 0, n_primq = 0, n_cand = 0;
+    const double cut2 = task.prim_cut * task.prim_cut;
+    const int n = task.nbf;
+
+    while (ti >= 0) {
+        if (tid == 0) {
+            const int t1 = advance();
+            s_next = t1;
+            if (t1 >= 0) issue(t1, s ^ 1);     // prefetch the next tile while this one is computed
+        }
+        mbar_wait(&bars[s], phase[s]);
+        phase[s] ^= 1u;
+        const ShellPair *bras = stage_pairs(s);
+        const int *kc = stage_kc(s);
+        const PrimPair *bprims = stage_prims(s);
+        int kmax = 0, nb = 0;
+#pragma unroll
+        for (int j = 0; j < TILE_MAXB; ++j) {
+            kmax = max(kmax, kc[j]);
+            if (bras[j].nprim > 0) nb = j + 1;
+        }
+        const int oa = bras[0].offa, sha = bras[0].sha;
+        for (int e = 0; e < nb * NAB; ++e) sjab[e * T + tid] = 0.0;
+
+        for (int ki = tid; ki < kmax; ki += T) {
+            const KetHot ket = load_streaming(task.ket_hot + ki);   // 32 B per thread, coalesced
+            const int oc = ket.offa, od = ket.offb, nkp = ket.nprim;
+            // ket primitives: into this thread's shared-memory slots when they fit, else read from global memory per bra
+            const double2 *kbase;
+            int kpstride, kfstride;
+            {
+                const double2 *gsrc = reinterpret_cast<const double2 *>(task.prims + ket.prim_off);
+                if (nkp <= kslots) {
+                    for (int ik = 0; ik < nkp; ++ik)
+#pragma unroll
+                        for (int f = 0; f < NF2; ++f) skp[(ik * NF2 + f) * T + tid] = __ldcs(gsrc + ik * 5 + f);
+                    kbase = skp + tid; kpstride = NF2 * T; kfstride = T;
+                } else {
+                    kbase = gsrc; kpstride = 5; kfstride = 1;
+                }
+            }
+            double cdx = 0.0, cdy = 0.0, cdz = 0.0;
+            if constexpr (LD > 0) {
+                const ShellPair *kfull = task.ket + ki;
+                cdx = kfull->AB[0]; cdy = kfull->AB[1]; cdz = kfull->AB[2];
+            }
+            // per-ket digestion state (registers): gathered once, flushed once per tile
+            double pjcd[NCD], jcd[NCD], pac[NSPIN][NA * NC], pad[NSPIN][NA * ND], kac[NSPIN][NA * NC], kad[NSPIN][NA * ND];
+            bool loaded = false, touched = false;
+
+            for (int j = 0; j < nb; ++j) {
+                if (ki >= kc[j]) continue;
+                const ShellPair &bra = bras[j];
+                if (max(max(sha, bra.shb), max(ket.sha, ket.shb)) < task.start_shell) continue;
+                const PrimPair *bp = bprims + (size_t)j * maxbp;
+                const int nbp = bra.nprim;
+                const double bumax = bra.umax, pminb = bra.pmin;
+                double acc[NEF];
+#pragma unroll
+                for (int m = 0; m < NEF; ++m) acc[m] = 0.0;
+                // Primitive quartets: the reference's sr < 1e-12 cut (TwoElectronInts.cpp:478-479) as (SR u_b u_k)^2 < cut^2 (p+q);
+                // both lists sorted by u descending -> early exits; scan-then-evaluate as in eri_reg.cuh.
+                int ik = 0, ib = 0;
+                bool have_k = false;
+                double ku = 0.0, kp_ = 0.0, kcf = 0.0, kP0 = 0.0, kP1 = 0.0, kP2 = 0.0, kip = 0.0, kA0 = 0.0, kA1 = 0.0, kA2 = 0.0;
+                double tk = 0.0;
+                for (;;) {
+                    bool found = false;
+                    while (ik < nkp) {
+                        if (!have_k) {
+                            const double2 up = kbase[ik * kpstride];
+                            ku = up.x; kp_ = up.y;
+                            tk = SR_TERM * ku;
+                            const double tb = tk * bumax;
+                            if (tb * tb < cut2 * pminb) { ik = nkp; break; }
+                            if (tb * tb < cut2 * (pminb + kp_)) { ++ik; continue; }
+                            have_k = true;
+                            ib = 0;
+                            const double2 c1 = kbase[ik * kpstride + kfstride], c2 = kbase[ik * kpstride + 2 * kfstride];
+                            kcf = c1.x; kP0 = c1.y; kP1 = c2.x; kP2 = c2.y;
+                            if constexpr (GJ > 1) {
+                                const double2 c3 = kbase[ik * kpstride + 3 * kfstride], c4 = kbase[ik * kpstride + 4 * kfstride];
+                                kip = c3.x; kA0 = c3.y; kA1 = c4.x; kA2 = c4.y;
+                            }
+                        }
+                        while (ib < nbp) {
+                            const double t = tk * bp[ib].u;
+                            ++n_cand;
+                            if (t * t >= cut2 * (bp[ib].p + kp_)) { found = true; break; }
+                            if (t * t < cut2 * (pminb + kp_)) { ib = nbp; break; }
+                            ++ib;
+                        }
+                        if (found) break;
+                        have_k = false;
+                        ++ik;
+                    }
+                    if (!found) break;
+                    {
+                        const double bpv = bp[ib].p;
+                        const double txp = bpv + kp_;
+                        const double rtx = rsqrt(txp);
+                        const double itx = rtx * rtx;
+                        double sr = tk * bp[ib].u * rtx;
+                        sr *= bp[ib].c * kcf;
+                        ++n_primq;
+                        const double pq0 = bp[ib].P[0] - kP0, pq1 = bp[ib].P[1] - kP1, pq2 = bp[ib].P[2] - kP2;
+                        const double X = bpv * kp_ * itx * (pq0 * pq0 + pq1 * pq1 + pq2 * pq2);
+                        if constexpr (NR == 1 && GI * GJ == 1) {
+                            double w, f1;
+                            rys1_f0f1(X, w, f1, rys);
+                            acc[0] = fma(sr, w, acc[0]);
+                        } else if constexpr (NR == 1) {
+                            // (ps|ss): one root, G[1][0] = C per axis: sr*w*C = sr*(PA*w - q/(p+q)*PQ*F1)
+                            double w, f1;
+                            rys1_f0f1(X, w, f1, rys);
+                            const double a = sr * w, bq = sr * f1 * kp_ * itx;
+                            acc[0] = fma(a, bp[ib].PA[0], fma(-bq, pq0, acc[0]));
+                            acc[1] = fma(a, bp[ib].PA[1], fma(-bq, pq1, acc[1]));
+                            acc[2] = fma(a, bp[ib].PA[2], fma(-bq, pq2, acc[2]));
+                        } else {
+                            double rt[NR], wt[NR];
+                            rys_roots<NR>(X, rt, wt, rys);
+#pragma unroll
+                            for (int ir = 0; ir < NR; ++ir) {
+                                const double dr = rt[ir] / (1.0 + rt[ir]);
+                                const double fff = dr * itx;
+                                const double B00 = 0.5 * fff;
+                                const double B1 = (0.5 - B00 * kp_) * bp[ib].ip;
+                                const double B1p = (0.5 - B00 * bpv) * kip;
+                                double g[3][GI][GJ];
+#pragma unroll
+                                for (int ax = 0; ax < 3; ++ax) {
+                                    const double pq = ax == 0 ? pq0 : (ax == 1 ? pq1 : pq2);
+                                    const double kA = ax == 0 ? kA0 : (ax == 1 ? kA1 : kA2);
+                                    const double Cc = bp[ib].PA[ax] - kp_ * pq * fff;
+                                    const double Cp = kA + bpv * pq * fff;
+                                    const double scale = (ax == 2) ? wt[ir] * sr : 1.0;
+                                    g[ax][0][0] = scale;
+                                    if constexpr (GJ > 1) {
+                                        g[ax][0][1] = Cp * scale;
+#pragma unroll
+                                        for (int jj = 1; jj < GJ - 1; ++jj) g[ax][0][jj + 1] = jj * B1p * g[ax][0][jj - 1] + Cp * g[ax][0][jj];
+                                    }
+#pragma unroll
+                                    for (int i = 1; i < GI; ++i) {
+                                        g[ax][i][0] = (i > 1 ? (i - 1) * B1 * g[ax][i > 1 ? i - 2 : 0][0] : 0.0) + Cc * g[ax][i - 1][0];
+                                        if constexpr (GJ > 1) {
+                                            g[ax][i][1] = i * B00 * g[ax][i - 1][0] + Cp * g[ax][i][0];
+#pragma unroll
+                                            for (int jj = 1; jj < GJ - 1; ++jj)
+                                                g[ax][i][jj + 1] = jj * B1p * g[ax][i][jj - 1] + i * B00 * g[ax][i - 1][jj] + Cp * g[ax][i][jj];
+                                        }
+                                    }
+                                }
+                                static_for<NEF>([&](auto kk) {
+                                    constexpr int K = decltype(kk)::value;
+                                    constexpr int e = K / NF, f = K % NF;
+                                    constexpr int te = r_deg(LA, e), ce = r_cmp(LA, e), tf = r_deg(LC, f), cf = r_cmp(LC, f);
+                                    constexpr int ex = c_lx(te, ce), ey = c_ly(te, ce), ez = c_lz(te, ce);
+                                    constexpr int fx = c_lx(tf, cf), fy = c_ly(tf, cf), fz = c_lz(tf, cf);
+                                    acc[K] = fma(g[0][ex][fx] * g[1][ey][fy], g[2][ez][fz], acc[K]);
+                                });
+                            }
+                        }
+                    }
+                    ++ib;
+                }
+                ++n_quart;
+                // ---- horizontal transfer in registers: ket, then bra (reference Rys.hpp:173-192, once per contracted quartet)
+                const double abx = bra.AB[0], aby = bra.AB[1], abz = bra.AB[2];
+                double h1[NE * NCD];
+                static_for<NE * NCD>([&](auto oo) {
+                    constexpr int O = decltype(oo)::value;
+                    constexpr int e = O / NCD, cd = O % NCD, c = cd / ND, d = cd % ND;
+                    constexpr int cx = c_lx(LC, c), cy = c_ly(LC, c), cz = c_lz(LC, c);
+                    constexpr int dx = c_lx(LD, d), dy = c_ly(LD, d), dz = c_lz(LD, d);
+                    double v = 0.0;
+                    static_for<dx + 1>([&](auto jx_) {
+                        constexpr int jx = decltype(jx_)::value;
+                        static_for<dy + 1>([&](auto jy_) {
+                            constexpr int jy = decltype(jy_)::value;
+                            static_for<dz + 1>([&](auto jz_) {
+                                constexpr int jz = decltype(jz_)::value;
+                                constexpr int f = r_index(LC, cx + dx - jx, cy + dy - jy, cz + dz - jz);
+                                constexpr double bn = c_binom(dx, jx) * c_binom(dy, jy) * c_binom(dz, jz);
+                                double fac = bn;
+                                if constexpr (jx >= 1) fac *= cdx;
+                                if constexpr (jx >= 2) fac *= cdx;
+                                if constexpr (jy >= 1) fac *= cdy;
+                                if constexpr (jy >= 2) fac *= cdy;
+                                if constexpr (jz >= 1) fac *= cdz;
+                                if constexpr (jz >= 2) fac *= cdz;
+                                v = fma(fac, acc[e * NF + f], v);
+                            });
+                        });
+                    });
+                    h1[O] = v;
+                });
+                double sym = 1.0;
+                if (!task.out) {
+                    if (sha == bra.shb) sym *= 0.5;
+                    if (ket.sha == ket.shb) sym *= 0.5;
+                    if (task.same_class && bra.pairid == ket.pairid) sym *= 0.5;
+                }
+                double V[NINT];
+                static_for<NINT>([&](auto oo) {
+                    constexpr int O = decltype(oo)::value;
+                    constexpr int ab = O / NCD, cd = O % NCD, a = ab / NB, b = ab % NB, c = cd / ND, d = cd % ND;
+                    constexpr int ax = c_lx(LA, a), ay = c_ly(LA, a), az = c_lz(LA, a);
+                    constexpr int bx = c_lx(LB, b), by = c_ly(LB, b), bz = c_lz(LB, b);
+                    double v = 0.0;
+                    static_for<bx + 1>([&](auto ix_) {
+                        constexpr int ix = decltype(ix_)::value;
+                        static_for<by + 1>([&](auto iy_) {
+                            constexpr int iy = decltype(iy_)::value;
+                            static_for<bz + 1>([&](auto iz_) {
+                                constexpr int iz = decltype(iz_)::value;
+                                constexpr int e = r_index(LA, ax + bx - ix, ay + by - iy, az + bz - iz);
+                                constexpr double bn = c_binom(bx, ix) * c_binom(by, iy) * c_binom(bz, iz);
+                                double fac = bn;
+                                if constexpr (ix >= 1) fac *= abx;
+                                if constexpr (ix >= 2) fac *= abx;
+                                if constexpr (iy >= 1) fac *= aby;
+                                if constexpr (iy >= 2) fac *= aby;
+                                if constexpr (iz >= 1) fac *= abz;
+                                if constexpr (iz >= 2) fac *= abz;
+                                v = fma(fac, h1[e * NCD + cd], v);
+                            });
+                        });
+                    });
+                    constexpr double nrm = c_norm(LA, a) * c_norm(LB, b) * c_norm(LC, c) * c_norm(LD, d);
+                    V[O] = v * (nrm * sym);
+                });
+                if (task.out) {
+                    // dump mode (test hook): the contracted block as computed by THIS kernel, no symmetry factor
+                    double *dst = task.out + task.task_out[(size_t)ti * TILE_MAXB + j] + (size_t)ki * NINT;
+#pragma unroll
+                    for (int o = 0; o < NINT; ++o) dst[o] = V[o];
+                    continue;
+                }
+                // blocks entirely at or below the reference's storage threshold never reach its G (TwoElectronInts.cpp:513,667-671)
+                {
+                    double vmax = 0.0;
+#pragma unroll
+                    for (int o = 0; o < NINT; ++o) vmax = fmax(vmax, fabs(V[o]));
+                    if (vmax <= task.value_cut * sym) continue;
+                }
+                // ---- J/K digestion (reference TwoElectronInts.cpp:699-820, shell-block form)
+                if (!loaded) {
+                    loaded = true;
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+#pragma unroll
+                        for (int d = 0; d < ND; ++d) {
+                            pjcd[c * ND + d] = task.PJ[(size_t)(oc + c) * n + od + d];
+                            jcd[c * ND + d] = 0.0;
+                        }
+#pragma unroll
+                    for (int sp = 0; sp < NSPIN; ++sp) {
+                        const double *P = task.PK[sp];
+#pragma unroll
+                        for (int a = 0; a < NA; ++a) {
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) { pac[sp][a * NC + c] = P[(size_t)(oa + a) * n + oc + c]; kac[sp][a * NC + c] = 0.0; }
+#pragma unroll
+                            for (int d = 0; d < ND; ++d) { pad[sp][a * ND + d] = P[(size_t)(oa + a) * n + od + d]; kad[sp][a * ND + d] = 0.0; }
+                        }
+                    }
+                }
+                touched = true;
+                const int ob = bra.offb;
+                {
+                    // J[a,b_j] += sum_cd V PJ[c,d]   (per-thread partials in shared memory, reduced once per tile)
+#pragma unroll
+                    for (int ab = 0; ab < NAB; ++ab) {
+                        double sacc = 0.0;
+#pragma unroll
+                        for (int cd = 0; cd < NCD; ++cd) sacc = fma(V[ab * NCD + cd], pjcd[cd], sacc);
+                        sjab[(j * NAB + ab) * T + tid] += sacc;
+                    }
+                    // J[c,d] += sum_ab V PJ[a,b_j]   (registers)
+                    double pab[NAB];
+#pragma unroll
+                    for (int a = 0; a < NA; ++a)
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) pab[a * NB + b] = task.PJ[(size_t)(oa + a) * n + ob + b];
+#pragma unroll
+                    for (int cd = 0; cd < NCD; ++cd) {
+                        double sacc = jcd[cd];
+#pragma unroll
+                        for (int ab = 0; ab < NAB; ++ab) sacc = fma(V[ab * NCD + cd], pab[ab], sacc);
+                        jcd[cd] = sacc;
+                    }
+                }
+#pragma unroll
+                for (int sp = 0; sp < NSPIN; ++sp) {
+                    const double *P = task.PK[sp];
+                    double *K = task.K[sp];
+                    // K[a,c] += sum_bd V P[b,d] ; K[a,d] += sum_bc V P[b,c]   (registers)
+                    double pbd[NB * ND], pbc[NB * NC];
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+#pragma unroll
+                        for (int d = 0; d < ND; ++d) pbd[b * ND + d] = P[(size_t)(ob + b) * n + od + d];
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) pbc[b * NC + c] = P[(size_t)(ob + b) * n + oc + c];
+                    }
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) {
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            double sacc = kac[sp][a * NC + c];
+#pragma unroll
+                            for (int b = 0; b < NB; ++b)
+#pragma unroll
+                                for (int d = 0; d < ND; ++d) sacc = fma(V[((a * NB + b) * NC + c) * ND + d], pbd[b * ND + d], sacc);
+                            kac[sp][a * NC + c] = sacc;
+                        }
+#pragma unroll
+                        for (int d = 0; d < ND; ++d) {
+                            double sacc = kad[sp][a * ND + d];
+#pragma unroll
+                            for (int b = 0; b < NB; ++b)
+#pragma unroll
+                                for (int c = 0; c < NC; ++c) sacc = fma(V[((a * NB + b) * NC + c) * ND + d], pbc[b * NC + c], sacc);
+                            kad[sp][a * ND + d] = sacc;
+                        }
+                    }
+                    // K[b_j,c] += sum_ad V P[a,d] ; K[b_j,d] += sum_ac V P[a,c]   (the reds that remain per quartet)
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            double sacc = 0.0;
+#pragma unroll
+                            for (int a = 0; a < NA; ++a)
+#pragma unroll
+                                for (int d = 0; d < ND; ++d) sacc = fma(V[((a * NB + b) * NC + c) * ND + d], pad[sp][a * ND + d], sacc);
+                            atomicAdd(K + (size_t)(ob + b) * n + oc + c, sacc);
+                        }
+#pragma unroll
+                        for (int d = 0; d < ND; ++d) {
+                            double sacc = 0.0;
+#pragma unroll
+                            for (int a = 0; a < NA; ++a)
+#pragma unroll
+                                for (int c = 0; c < NC; ++c) sacc = fma(V[((a * NB + b) * NC + c) * ND + d], pac[sp][a * NC + c], sacc);
+                            atomicAdd(K + (size_t)(ob + b) * n + od + d, sacc);
+                        }
+                    }
+                }
+            }
+            if (touched) {
+                // flush this ket's register accumulators: J[c,d], K[a,c], K[a,d]
+#pragma unroll
+                for (int cd = 0; cd < NCD; ++cd) atomicAdd(task.J + (size_t)(oc + cd / ND) * n + od + cd % ND, task.jscale * jcd[cd]);
+#pragma unroll
+                for (int sp = 0; sp < NSPIN; ++sp) {
+                    double *K = task.K[sp];
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) {
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) atomicAdd(K + (size_t)(oa + a) * n + oc + c, kac[sp][a * NC + c]);
+#pragma unroll
+                        for (int d = 0; d < ND; ++d) atomicAdd(K + (size_t)(oa + a) * n + od + d, kad[sp][a * ND + d]);
+                    }
+                }
+            }
+        }
+        // ---- J[a,b_j]: reduce the per-thread partials of this tile (one red per element)
+        __syncthreads();
+        const int tnext = s_next;   // written by thread 0 at the top of this iteration
+        if (!task.out) {
+            const int nel = nb * NAB;
+            for (int e = warp; e < nel; e += T / 32) {
+                double v = 0.0;
+#pragma unroll
+                for (int q = 0; q < T / 32; ++q) v += sjab[e * T + q * 32 + lane];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0 && v != 0.0) {
+                    const int j = e / NAB, ab = e % NAB;
+                    atomicAdd(task.J + (size_t)(oa + ab / NB) * n + bras[j].offb + ab % NB, task.jscale * v);
+                }
+            }
+        }
+        __syncthreads();   // everyone is done with stage[s] and the partials before they are overwritten
+        ti = tnext;
+        s ^= 1;
+    }
+    if (task.counters) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_quart += __shfl_xor_sync(0xffffffffu, n_quart, o);
+            n_primq += __shfl_xor_sync(0xffffffffu, n_primq, o);
+            n_cand += __shfl_xor_sync(0xffffffffu, n_cand, o);
+        }
+        if (lane == 0) {
+            if (task.cand_counter) atomicAdd(task.cand_counter, n_cand);
+            atomicAdd(task.counters, n_quart);
+            atomicAdd(task.counters + 1, n_primq);
+        }
+    }
+}
+
+}  // namespace ub200

@@ -61,7 +61,15 @@ struct ClassTask {
     const ShellPair *ket;     // ket pairs
     const KetHot *ket_hot;    // the same list, hot fields only
     const PrimPair *prims;
-    const int *ket_count;     // per bra: number of leading kets to visit (Schwarz prefix, triangular cap)
+    const int *ket_count;     // per bra: number of leading kets to visit (Schwarz prefix, triangular cap); tile kernel: per
+                              // slot of the padded tile-ordered bra list (0 for padding slots)
+    // bra-tile kernel (eri_tile.cuh): bras regrouped into tiles of <= tile_b pairs that share their first shell
+    const ShellPair *tbra;    // tile-ordered copy of the bra list, TILE_MAXB slots per tile (padding slots have nprim = 0)
+    const int *tile_order;    // tile ids of this launch, heaviest first
+    int ntiles;               // entries of tile_order
+    int tile_b;               // bras per tile of this bra class (<= TILE_MAXB)
+    int tile_maxbp;           // largest primitive-pair count of a bra (stride of the staged primitive slots)
+    int kslots;               // ket primitive pairs a thread keeps in its shared-memory slots (kets with more read global memory)
     const long long *ket_prefix;  // runtime-L kernel only: exclusive prefix sum of ket_count over the bras [nbra + 1]; its work
                               // items are single shell quartets (a (gg|gg) block is 50 625 integrals), not bras
     int nbra, nket;
