@@ -76,6 +76,8 @@ class Oracle:
         L.oracle_direct_g_rhf.argtypes = [_P, _D, ctypes.POINTER(_D), ctypes.POINTER(_D), _L, _L, ctypes.POINTER(_L)]
         L.oracle_direct_g_uhf.restype = _L
         L.oracle_direct_g_uhf.argtypes = [_P, _D] + [ctypes.POINTER(_D)] * 4 + [_L, _L, ctypes.POINTER(_L)]
+        L.oracle_g_elements_rhf.restype = _L
+        L.oracle_g_elements_rhf.argtypes = [_P, _D, ctypes.POINTER(_D), _I, ctypes.POINTER(_I), ctypes.POINTER(_D), _I, _I]
         L.oracle_cart_norm.restype = _D; L.oracle_cart_norm.argtypes = [_I, _I]
         L.oracle_basis_set_center.argtypes = [_P, _I, _D, _D, _D]
 
@@ -148,6 +150,24 @@ class Oracle:
         if PBc is None:
             return GA
         return GA, sum(p[1] for p in parts)
+
+
+    def g_elements(self, b, P, pairs, thresh=1e-14, nthreads=None):
+        """G_ij = sum_kl P_kl [2(ij|kl) - (ik|jl)] for a few basis-function pairs of a system too large for a full G
+        (bench.py parity block): all host cores, unscreened, with the reference's primitive cut and storage threshold."""
+        import threading
+        nthreads = nthreads or max(1, min(64, os.cpu_count() or 1))
+        P = np.ascontiguousarray(P, float)
+        ij = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1, 2))
+        outs = [np.zeros(len(ij)) for _ in range(nthreads)]
+        nblk = [0] * nthreads
+
+        def run(t):
+            nblk[t] = self.lib.oracle_g_elements_rhf(b.h, thresh, _dp(P), len(ij), _ip(ij), _dp(outs[t]), nthreads, t)
+        th = [threading.Thread(target=run, args=(t,)) for t in range(nthreads)]
+        for x in th: x.start()
+        for x in th: x.join()
+        return sum(outs), sum(nblk)
 
 
 class Reference:

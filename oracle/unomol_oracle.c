@@ -705,3 +705,58 @@ long oracle_direct_g_uhf(const oracle_basis *b, double thresh, const double *PA,
     if (nprimq) *nprimq = 0;
     return walk_quartets(b, 0, sample_mod, sample_rem, direct_uhf_sink, &c, NULL, nprimq);
 }
+
+/* A handful of G elements of a LARGE system without storing anything (bench.py parity block, tests):
+ *   G_ij = sum_kl P_kl [ 2 (ij|kl) - (ik|jl) ]      (what formGmatrix amounts to for RHF)
+ * for nelem basis-function pairs ij[2e], ij[2e+1]; every needed shell-quartet block is evaluated by the routine above
+ * (reference primitive cut sr < 1e-12 included) and an integral enters only if |val| > thresh, the reference's storage
+ * rule (TwoElectronInts.cpp:513,667-671).  Only shells ksh with ksh % mod == rem are visited (one call per host thread,
+ * partial sums added by the caller).  Returns the number of shell-quartet blocks evaluated. */
+long oracle_g_elements_rhf(const oracle_basis *b, double thresh, const double *P, int nelem, const int *ij, double *out,
+                           int mod, int rem) {
+    init_tables();
+    static _Thread_local double blk[ORACLE_MAXFUNC];
+    long nblk = 0;
+    int *shell_of = (int *)malloc(sizeof(int) * b->nbf);
+    for (int s = 0; s < b->nshell; ++s)
+        for (int c = 0; c < oracle_ncart(b->lv[s]); ++c) shell_of[b->off[s] + c] = s;
+    for (int e = 0; e < nelem; ++e) {
+        const int i = ij[2 * e], j = ij[2 * e + 1];
+        const int I = shell_of[i], J = shell_of[j], ci = i - b->off[I], cj = j - b->off[J];
+        const int nI = oracle_ncart(b->lv[I]), nJ = oracle_ncart(b->lv[J]);
+        double acc = 0.0;
+        for (int K = rem; K < b->nshell; K += mod) {
+            const int nK = oracle_ncart(b->lv[K]);
+            for (int L = 0; L < b->nshell; ++L) {
+                const int nL = oracle_ncart(b->lv[L]);
+                /* Coulomb: (I J | K L), element (ci, cj, k, l) */
+                oracle_quartet_block(b, I, J, K, L, blk);
+                for (int k = 0; k < nK; ++k)
+                    for (int l = 0; l < nL; ++l) {
+                        const double v = blk[((ci * nJ + cj) * nK + k) * nL + l];
+                        if (fabs(v) > thresh) {
+                            const int a = b->off[K] + k, c = b->off[L] + l;
+                            const int hi = a > c ? a : c, lo = a > c ? c : a;
+                            acc += 2.0 * v * P[hi * (hi + 1) / 2 + lo];
+                        }
+                    }
+                /* exchange: (I K | J L), element (ci, k, cj, l) */
+                oracle_quartet_block(b, I, K, J, L, blk);
+                for (int k = 0; k < nK; ++k)
+                    for (int l = 0; l < nL; ++l) {
+                        const double v = blk[((ci * nK + k) * nJ + cj) * nL + l];
+                        if (fabs(v) > thresh) {
+                            const int a = b->off[K] + k, c = b->off[L] + l;
+                            const int hi = a > c ? a : c, lo = a > c ? c : a;
+                            acc -= v * P[hi * (hi + 1) / 2 + lo];
+                        }
+                    }
+                nblk += 2;
+            }
+        }
+        (void)nI;
+        out[e] += acc;
+    }
+    free(shell_of);
+    return nblk;
+}

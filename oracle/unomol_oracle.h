@@ -72,6 +72,11 @@ long oracle_direct_g_rhf(const oracle_basis *b, double thresh, const double *P, 
 long oracle_direct_g_uhf(const oracle_basis *b, double thresh, const double *PA, const double *PB, double *GA, double *GB,
                          long sample_mod, long sample_rem, long *nprimq);
 
+/* G_ij = sum_kl P_kl [2 (ij|kl) - (ik|jl)] for nelem basis-function pairs (ij[2e], ij[2e+1]); shells ksh % mod == rem only;
+ * out[] accumulates.  Returns the number of shell-quartet blocks evaluated. */
+long oracle_g_elements_rhf(const oracle_basis *b, double thresh, const double *P, int nelem, const int *ij, double *out,
+                           int mod, int rem);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,5 +20,5 @@ extern "C" int unomol_rys_host(int n, double x, int exact, double *r, double *w)
 // F_0(x) .. F_3(x) through the grid path (x < 46)
 extern "C" void unomol_boys_host(double x, double *F) {
     const RysTables T = rys_host_tables(0);
-    boys_grid<3>(x, T.boys, F);
+    boys_grid<3, RYS_BOYS_MTOP>(x, T.boys, F);
 }

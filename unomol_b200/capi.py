@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libunomol_b200.so")
+# UNOMOL_B200_LIB: an alternative build of the same library (A/B kernel experiments, profiles/); never a fallback
+LIB_PATH = os.environ.get("UNOMOL_B200_LIB") or os.path.join(_HERE, "libunomol_b200.so")
 
 _D = ctypes.c_double
 _I = ctypes.c_int

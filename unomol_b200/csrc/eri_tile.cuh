@@ -44,13 +44,28 @@ __host__ __device__ inline TileLayout tile_layout(int maxbp, int tile_b, int nab
 // Boys grid entries a class needs in shared memory (rys_roots.cuh): one root up to X = 35, two roots up to X = 15
 // (parity mode) or 46 (exact mode); three and more roots read their polynomial tables from global memory
 __host__ __device__ inline int tile_boys_entries(int nroots, int rys2_exact) {
-    if (nroots == 1) return 35 * RYS_BOYS_HINV + 2;
+    if (nroots == 1) return RYS_BOYS1_NPTS;
     if (nroots == 2) return (rys2_exact ? RYS_BOYS_XMAX : 15) * RYS_BOYS_HINV + 2;
     return 0;
 }
 
+// resident CTAs per SM the register allocation is capped for (ncu: the FP64 pipe waits on dependent results, "wait" is the top
+// stall; more warps per scheduler hide that latency).  Measured alternatives in profiles/ (TILE_MINB_SET).
+#ifndef TILE_MINB_SET
+#define TILE_MINB_SET 0
+#endif
+__host__ __device__ constexpr int tile_minb(int lab, int lcd) {
+#if TILE_MINB_SET == 1
+    return lab == 0 ? 6 : (lab == 1 && lcd == 0) ? 5 : (lab == 1) ? 3 : (lcd == 0) ? 4 : 2;
+#elif TILE_MINB_SET == 2
+    return lab == 0 ? 8 : (lab == 1 && lcd == 0) ? 6 : (lab == 1) ? 4 : (lcd == 0) ? 5 : 3;
+#else
+    return 1;
+#endif
+}
+
 template <int LA, int LB, int LC, int LD, int NSPIN>
-__global__ void __launch_bounds__(TILE_THREADS) eri_tile_kernel(const ClassTask task) {
+__global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri_tile_kernel(const ClassTask task) {
     using C = QC<LA, LB, LC, LD>;
     constexpr int NR = C::NR, GI = C::GI, GJ = C::GJ, NE = C::NE, NF = C::NF, NEF = C::NEF;
     constexpr int NA = C::NA, NB = C::NB, NC = C::NC, ND = C::ND, NAB = C::NAB, NCD = C::NCD, NINT = C::NINT;
@@ -69,9 +84,10 @@ __global__ void __launch_bounds__(TILE_THREADS) eri_tile_kernel(const ClassTask 
     RysTables rys = task.rys;
     if (nboys > 0) {
         double2 *sb = reinterpret_cast<double2 *>(tsm + lay.off_boys);
-        const double2 *gb = reinterpret_cast<const double2 *>(task.rys.boys);
+        const double2 *gb = reinterpret_cast<const double2 *>(NR == 1 ? task.rys.boys1 : task.rys.boys);
         for (int i = tid; i < nboys; i += T) sb[i] = gb[i];
-        rys.boys = reinterpret_cast<const double *>(sb);
+        if (NR == 1) rys.boys1 = reinterpret_cast<const double *>(sb);
+        else rys.boys = reinterpret_cast<const double *>(sb);
     }
     if (tid == 0) {
         mbar_init(&bars[0], 1);

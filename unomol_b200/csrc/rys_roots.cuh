@@ -50,14 +50,15 @@ constexpr double rys_herm(int weights, int i) {
 // Table pointers in the caller's address space: device global memory (rys_tables.cu) or a shared-memory copy of the
 // Boys grid inside kernels, the host arrays of rys_host_tables() in host code.
 struct RysTables {
-    const double *boys;        // [RYS_BOYS_NPTS][2] = {F_MTOP(X_i), exp(-X_i)}, X_i = i / RYS_BOYS_HINV
+    const double *boys;        // [RYS_BOYS_NPTS][2] = {F_10(X_i), exp(-X_i)}, X_i = i / RYS_BOYS_HINV, X_i <= 46: two roots
+    const double *boys1;       // [RYS_BOYS1_NPTS][2] = {F_8(X_i), exp(-X_i)}, X_i <= 35: one root (two recursion steps less)
     const double *piece[3];    // 3, 4, 5 roots: [interval][k = 0..12][r_0..r_{n-1}, w_0..w_{n-1}]
     int rys2_exact;            // 0: reference-compatible two-root band (see above); 1: exact two-root quadrature
     int pad;
 };
 
 constexpr double RYS_SQRT_PI_4 = 0.88622692545275801;   // sqrt(pi/4)
-constexpr double RYS_X_ASYM1 = 35.0;                     // F_0 = sqrt(pi/4X) to 6e-17 beyond (exp(-35)/70 = 9e-18)
+constexpr double RYS_X_ASYM1 = (double)RYS_BOYS1_XMAX;    // F_0 = sqrt(pi/4X) to 6e-17 beyond (exp(-35)/70 = 9e-18)
 
 UNOMOL_HD double rys_rsqrt(double x) {
 #ifdef __CUDA_ARCH__
@@ -74,43 +75,55 @@ UNOMOL_HD double rys_dop(double a, double b, double c, double d) {
     return fma(a, b, -cd) + err;
 }
 
-// F[0..MT] = F_0(x) .. F_MT(x) for 0 <= x < RYS_BOYS_XMAX
-template <int MT>
+// compile-time constants of the scaled downward recursion (see boys_grid)
+constexpr double rys_tscale(int m, int mtab) {          // T_m = prod_{k=m+1..mtab} (2k-1);  f_m = h_m / T_m
+    double t = 1.0;
+    for (int k = m + 1; k <= mtab; ++k) t *= (double)(2 * k - 1);
+    return t;
+}
+constexpr double rys_ifact(int k) {
+    double f = 1.0;
+    for (int i = 2; i <= k; ++i) f *= (double)i;
+    return 1.0 / f;
+}
+
+// F[0..MT] = F_0(x) .. F_MT(x) for 0 <= x < (grid end); tab = {F_MTAB(X_i), exp(-X_i)} on X_i = i/16.
+// The downward recursion f_{m-1} = (2 X_i f_m + e) / (2m-1) is run on h_m = T_m f_m (T_m = (2m+1)(2m+3)..(2 MTAB - 1)),
+// which turns a step into ONE fma on the dependent chain, h_{m-1} = 2 X_i h_m + e T_m; the Taylor sum
+// F_MT(x) = sum_k f_{MT+k} d^k / k!, d = X_i - x, runs as a Horner chain in lockstep with it (it consumes h_{MT+k} in
+// the order the recursion produces them), so the critical path is MTAB - MT + 2 fma long instead of 2 (MTAB - MT) + 8:
+// the FP64 pipe of these kernels was waiting on dependent results (ncu: "wait" was the top stall reason).
+template <int MT, int MTAB>
 UNOMOL_HD void boys_grid(double x, const double *tab, double *F) {
-    static_assert(MT + 7 <= RYS_BOYS_MTOP, "the Taylor series of the top order reaches F_{MT+7}");
+    static_assert(MT + 7 <= MTAB, "the Taylor series of the top order reaches F_{MT+7}");
     const int i = (int)fma(x, (double)RYS_BOYS_HINV, 0.5);
     const double xi = (double)i * (1.0 / RYS_BOYS_HINV);
-    const double d = xi - x;                       // |d| <= 1/32;  F_m(x) = sum_k F_{m+k}(xi) d^k / k!
+    const double d = xi - x;                       // |d| <= 1/32
 #ifdef __CUDA_ARCH__
     const double2 te = *reinterpret_cast<const double2 *>(tab + 2 * i);
-    double f = te.x;
+    double h = te.x;
     const double e = te.y;
 #else
-    double f = tab[2 * i];
+    double h = tab[2 * i];
     const double e = tab[2 * i + 1];
 #endif
     const double x2 = xi + xi;
-    double g[8];                                   // F_MT(xi) .. F_{MT+7}(xi)
 #pragma unroll
-    for (int m = RYS_BOYS_MTOP; m > MT + 7; --m) f = fma(x2, f, e) * (1.0 / (2 * m - 1));
-    g[7] = f;
-#pragma unroll
-    for (int k = 7; k > 0; --k) g[k - 1] = fma(x2, g[k], e) * (1.0 / (2 * (MT + k) - 1));
-    // Horner in d with the 1/k! folded in: t_k = d/k
-    double dk[8];
-#pragma unroll
-    for (int k = 1; k < 8; ++k) dk[k] = d * (1.0 / k);
-    double t = g[7], ex = 1.0 + d * (1.0 / 8);
+    for (int m = MTAB; m > MT + 7; --m) h = fma(x2, h, e * rys_tscale(m, MTAB));
+    // h = h_{MT+7}; Horner: t <- t d + h_{MT+k} q_k with q_k = 1 / (T_{MT+k} k!)
+    double t = h * (rys_ifact(7) / rys_tscale(MT + 7, MTAB));
+    double ex = fma(d, rys_ifact(8), rys_ifact(7));          // exp(d) = sum_k d^k / k!, same Horner direction
 #pragma unroll
     for (int k = 7; k > 0; --k) {
-        t = fma(t, dk[k], g[k - 1]);
-        ex = fma(ex, dk[k], 1.0);
+        h = fma(x2, h, e * rys_tscale(MT + k, MTAB));         // h_{MT+k-1}
+        t = fma(t, d, h * (rys_ifact(k - 1) / rys_tscale(MT + k - 1, MTAB)));
+        ex = fma(ex, d, rys_ifact(k - 1));
     }
     F[MT] = t;
     ex *= e;                                       // exp(-x)
     const double xx = x + x;
 #pragma unroll
-    for (int m = MT; m > 0; --m) F[m - 1] = fma(xx, F[m], ex) * (1.0 / (2 * m - 1));
+    for (int m = MT; m > 0; --m) F[m - 1] = (m == 1) ? fma(xx, F[m], ex) : fma(xx, F[m], ex) * (1.0 / (2 * m - 1));
 }
 
 // Gauss-Hermite limit (all exp(-X) terms below double precision)
@@ -129,7 +142,7 @@ UNOMOL_HD void rys_hermite_limit(double x, double *r, double *w) {
 UNOMOL_HD void rys1_f0f1(double x, double &w, double &f1, const RysTables &T) {
     if (x < RYS_X_ASYM1) {
         double F[2];
-        boys_grid<1>(x, T.boys, F);
+        boys_grid<1, RYS_BOYS1_MTOP>(x, T.boys1, F);
         w = F[0];
         f1 = F[1];
     } else {
@@ -165,7 +178,7 @@ UNOMOL_HD void rys_roots<2>(double x, double *r, double *w, const RysTables &T) 
     if (x <= xmom) {
         if (x >= (double)RYS_BOYS_XMAX) { rys_hermite_limit<2>(x, r, w); return; }   // exact mode, x == 46
         double m[4];
-        boys_grid<3>(x, T.boys, m);
+        boys_grid<3, RYS_BOYS_MTOP>(x, T.boys, m);
         // monic orthogonal polynomial y^2 + c1 y + c0 in y = t^2:  [m0 m1; m1 m2] (c0, c1)^T = -(m2, m3)^T
         const double det = rys_dop(m[0], m[2], m[1], m[1]);
         const double n0 = rys_dop(m[1], m[3], m[2], m[2]);
@@ -241,6 +254,7 @@ namespace rys_host {
 inline RysTables rys_host_tables(int rys2_exact = 0) {
     RysTables T;
     T.boys = rys_host::rys_boys_tab;
+    T.boys1 = rys_host::rys_boys1_tab;
     T.piece[0] = rys_host::rys_piece3_tab;
     T.piece[1] = rys_host::rys_piece4_tab;
     T.piece[2] = rys_host::rys_piece5_tab;

@@ -28,6 +28,8 @@ BOYS_H_INV = 16            # grid points per unit X
 BOYS_XMAX = 46             # grid end: two-root moments are used up to here in exact mode; one root switches to
                            # the asymptotic F_0 = sqrt(pi/4X) at X = 35 already (exp(-35)/70 = 9e-18)
 BOYS_MTOP = 10             # highest order tabulated (two roots need F_0..F_3, Taylor of F_3 reaches F_10)
+BOYS1_XMAX = 35            # second grid for the one-root classes: F_8 only (Taylor of F_1 reaches F_8), up to the asymptotic switch
+BOYS1_MTOP = 8
 NTERMS = 8                 # Taylor terms: (1/32)^8/8! = 2e-17
 
 # n: (interval width, polynomial degree, XA_n)
@@ -155,10 +157,19 @@ def main():
     C.append("#define RYS_BOYS_MTOP %d" % BOYS_MTOP)
     nb = BOYS_XMAX * BOYS_H_INV + 2
     C.append("#define RYS_BOYS_NPTS %d" % nb)
+    nb1 = BOYS1_XMAX * BOYS_H_INV + 2
+    C.append("#define RYS_BOYS1_XMAX %d" % BOYS1_XMAX)
+    C.append("#define RYS_BOYS1_MTOP %d" % BOYS1_MTOP)
+    C.append("#define RYS_BOYS1_NPTS %d" % nb1)
     L.append("RYS_TABLE(rys_boys_tab, 2 * RYS_BOYS_NPTS) = {")
     for i in range(nb):
         x = mp.mpf(i) / BOYS_H_INV
         L.append("    %s, %s," % (fmt(boys(BOYS_MTOP, x)), fmt(mp.exp(-x))))
+    L.append("};")
+    L.append("RYS_TABLE(rys_boys1_tab, 2 * RYS_BOYS1_NPTS) = {")
+    for i in range(nb1):
+        x = mp.mpf(i) / BOYS_H_INV
+        L.append("    %s, %s," % (fmt(boys(BOYS1_MTOP, x)), fmt(mp.exp(-x))))
     L.append("};")
     # Hermite limits
     C.append("// large-X limit: r_i = R_i/(X - R_i), w_i = W_i sqrt(pi/(4X)); row n-1 holds n entries")
