@@ -78,6 +78,8 @@ class Oracle:
         L.oracle_direct_g_uhf.argtypes = [_P, _D] + [ctypes.POINTER(_D)] * 4 + [_L, _L, ctypes.POINTER(_L)]
         L.oracle_g_elements_rhf.restype = _L
         L.oracle_g_elements_rhf.argtypes = [_P, _D, ctypes.POINTER(_D), _I, ctypes.POINTER(_I), ctypes.POINTER(_D), _I, _I]
+        L.oracle_quartet_batch.restype = _L
+        L.oracle_quartet_batch.argtypes = [_P, _L, ctypes.POINTER(_I), ctypes.POINTER(_D), ctypes.POINTER(_D), _I]
         L.oracle_cart_norm.restype = _D; L.oracle_cart_norm.argtypes = [_I, _I]
         L.oracle_basis_set_center.argtypes = [_P, _I, _D, _D, _D]
 
@@ -170,6 +172,26 @@ class Oracle:
         return sum(outs), sum(nblk)
 
 
+def timed_quartet_batches(fn, handle, shells, P, no2, digest, nthreads):
+    """bench helper: split `shells` ([n,4] int32) over host threads, each calling the C batch routine `fn` on its share with
+    its own G; returns (seconds of the slowest thread's wall clock for the whole batch, stored integrals, summed G)"""
+    import threading
+    import time
+    shells = np.ascontiguousarray(shells, np.int32)
+    P = np.ascontiguousarray(P, float)
+    parts = [np.ascontiguousarray(shells[t::nthreads]) for t in range(nthreads)]
+    Gs = [np.zeros(no2) for _ in range(nthreads)]
+    stored = [0] * nthreads
+
+    def run(t):
+        stored[t] = fn(handle, len(parts[t]), _ip(parts[t]), _dp(P), _dp(Gs[t]), int(digest))
+    th = [threading.Thread(target=run, args=(t,)) for t in range(nthreads)]
+    t0 = time.perf_counter()
+    for x in th: x.start()
+    for x in th: x.join()
+    return time.perf_counter() - t0, sum(stored), sum(Gs)
+
+
 class Reference:
     """The unmodified reference behind oracle/ref_harness.cc."""
     PATH = os.path.join(HERE, "_ref", "libunomol_ref.so")
@@ -198,6 +220,8 @@ class Reference:
         L.ref_tints_form_g_rhf.restype = _D; L.ref_tints_form_g_rhf.argtypes = [_P] + [ctypes.POINTER(_D)] * 2
         L.ref_tints_form_g_uhf.restype = _D; L.ref_tints_form_g_uhf.argtypes = [_P] + [ctypes.POINTER(_D)] * 4
         L.ref_one_electron.argtypes = [_P] + [ctypes.POINTER(_D)] * 3
+        L.ref_quartet_batch.restype = _L
+        L.ref_quartet_batch.argtypes = [_P, _L, ctypes.POINTER(_I), ctypes.POINTER(_D), ctypes.POINTER(_D), _I]
 
     def rys_roots(self, n, x):
         r = np.zeros(5); w = np.zeros(5)

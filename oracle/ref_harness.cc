@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <cmath>
 #include <vector>
 #include <ctime>
 #include "Basis.hpp"
@@ -141,6 +142,130 @@ int ref_quartet_block(void* bp, int ish, int jsh, int ksh, int lsh, double* out)
     }
     for (int i = 0; i < n; ++i) out[i] = sints[i].val;
     return n;
+}
+
+// ---- a batch of shell quartets, timed from C (bench.py cpu_baseline / --impl reference) -----------
+// The reference's formGMatrixKernel is `inline` in TwoElectronInts.cpp (:699-747) and not exported, so the RHF digestion
+// of one stored integral is restated here (test infrastructure): same index algebra, same coincidence guards.
+static inline void harness_digest_rhf(const double* P, double* G, double val, int i, int j, int k, int l) {
+    int ii = i * (i + 1) / 2, ij = ii + j, ik = ii + k, il = ii + l, jk, jl;
+    int kk = k * (k + 1) / 2, kl = kk + l;
+    if (j >= k) {
+        int jj = j * (j + 1) / 2;
+        jk = jj + k;
+        jl = jj + l;
+    } else {
+        jk = kk + j;
+        jl = (j > l) ? j * (j + 1) / 2 + l : l * (l + 1) / 2 + j;
+    }
+    double da = val * 2.0 * P[ij], db = val * 2.0 * P[kl];
+    double sjl = val * P[ik], sjk = val * P[il], sik = val * P[jl], sil = val * P[jk];
+    if (k != l) {
+        db = db + db;
+        G[ik] -= sik;
+        if (i != j && j >= k) G[jk] -= sjk;
+    }
+    G[il] -= sil;
+    G[ij] += db;
+    if (i != j && j >= l) G[jl] -= sjl;
+    if (ij != kl) {
+        if (i != j) da = da + da;
+        if (j <= k) {
+            G[jk] -= sjk;
+            if (i == k && i != j) G[ik] -= sik;
+            if (k != l && j <= l) G[jl] -= sjl;
+        }
+        G[kl] += da;
+    }
+}
+
+// n shell quartets (shells[4q..4q+3] = two shell pairs in any order): the reference's calc_two_electron_ints_rys / _md on
+// each, called exactly as calculate() calls it (ordering, swaps, 1e-14 storage threshold), and -- when digest != 0 -- the
+// canonical-function filter of calculate() (:627-633) plus the digestion above into G (packed).  Thread-safe: scratch
+// objects are per thread, G must be per thread.  Returns the number of integrals that passed the storage threshold.
+long ref_quartet_batch(void* bp, long n, const int* shells, const double* P, double* G, int digest) {
+    const Basis& basis = *static_cast<Basis*>(bp);
+    const Shell* shell = basis.shell_ptr();
+    const Center* center = basis.center_ptr();
+    const AuxFunctions& aux(*basis.auxfun_ptr());
+    thread_local Rys* rys = nullptr;
+    thread_local MDInts* mds = nullptr;
+    thread_local ShellQuartet* sqp = nullptr;
+    thread_local TwoInts* sints = nullptr;
+    if (!rys) {
+        rys = new Rys(4);
+        mds = new MDInts(4);
+        sqp = new ShellQuartet(basis.maxLvalue() > 2 ? basis.maxLvalue() : 2);
+        sints = new TwoInts[50625];
+    }
+    ShellQuartet& sq = *sqp;
+    long stored = 0;
+    for (long q = 0; q < n; ++q) {
+        // canonical shell order of calculate(): ish >= jsh, (ish,jsh) >= (ksh,lsh), ksh >= lsh
+        int a = shells[4 * q], b = shells[4 * q + 1], c = shells[4 * q + 2], d = shells[4 * q + 3];
+        if (a < b) std::swap(a, b);
+        if (c < d) std::swap(c, d);
+        if (a < c || (a == c && b < d)) { std::swap(a, c); std::swap(b, d); }
+        // calculate() visits (ish jsh | ish lsh) for BOTH orders of jsh != lsh; the function filter splits the block between them
+        const int nrep = (digest && a == c && b != d) ? 2 : 1;
+        for (int rep = 0; rep < nrep; ++rep) {
+        const int ish = a, jsh = rep ? d : b, ksh = c, lsh = rep ? b : d;
+        int sh[4] = {ish, jsh, ksh, lsh}, lv[4], nls[4], off[4];
+        for (int t = 0; t < 4; ++t) {
+            lv[t] = (shell + sh[t])->Lvalue();
+            nls[t] = aux.number_of_lstates(lv[t]);
+            off[t] = basis.offset(sh[t]);
+        }
+        const bool use_md = lv[0] + lv[1] + lv[2] + lv[3] > 8;
+        const bool sw12 = lv[0] < lv[1], sw34 = lv[2] < lv[3];
+        const int s1 = sw12 ? jsh : ish, s2 = sw12 ? ish : jsh, s3 = sw34 ? lsh : ksh, s4 = sw34 ? ksh : lsh;
+        const Shell *p1 = shell + s1, *p2 = shell + s2, *p3 = shell + s3, *p4 = shell + s4;
+        sq.npr1 = p1->number_of_prims(); sq.lv1 = p1->Lvalue(); sq.al1 = p1->alf_ptr(); sq.co1 = p1->cof_ptr();
+        sq.npr2 = p2->number_of_prims(); sq.lv2 = p2->Lvalue(); sq.al2 = p2->alf_ptr(); sq.co2 = p2->cof_ptr();
+        sq.npr3 = p3->number_of_prims(); sq.lv3 = p3->Lvalue(); sq.al3 = p3->alf_ptr(); sq.co3 = p3->cof_ptr();
+        sq.npr4 = p4->number_of_prims(); sq.lv4 = p4->Lvalue(); sq.al4 = p4->alf_ptr(); sq.co4 = p4->cof_ptr();
+        sq.a = (center + p1->center())->r_vec();
+        sq.b = (center + p2->center())->r_vec();
+        sq.c = (center + p3->center())->r_vec();
+        sq.d = (center + p4->center())->r_vec();
+        sq.ab2 = dist_sqr(sq.a, sq.b);
+        sq.cd2 = dist_sqr(sq.c, sq.d);
+        int knt = 0;
+        for (int ia = 0; ia < nls[0]; ++ia) {
+            const int ir = off[0] + ia;
+            for (int ib = 0; ib < nls[1]; ++ib) {
+                const int jr = off[1] + ib;
+                if (digest && jr > ir) break;
+                for (int ic = 0; ic < nls[2]; ++ic) {
+                    const int kr = off[2] + ic;
+                    if (digest && kr > ir) break;
+                    for (int id = 0; id < nls[3]; ++id) {
+                        const int lr = off[3] + id;
+                        if (digest && (lr > kr || (ir == kr && lr > jr))) break;
+                        sints[knt].val = 0.0;
+                        sints[knt].i = ir; sints[knt].j = jr; sints[knt].k = kr; sints[knt].l = lr;
+                        unsigned int l12 = sw12 ? ((ib << 4) + ia) : ((ia << 4) + ib);
+                        unsigned int l34 = sw34 ? ((id << 4) + ic) : ((ic << 4) + id);
+                        sq.lstates[knt] = (l12 << 8) + l34;
+                        sq.norms[knt] = aux.normalization_factor(lv[0], ia) * aux.normalization_factor(lv[1], ib) *
+                                        aux.normalization_factor(lv[2], ic) * aux.normalization_factor(lv[3], id);
+                        ++knt;
+                    }
+                }
+            }
+        }
+        sq.len = knt;
+        if (!knt) continue;
+        if (use_md) calc_two_electron_ints_md(sq, aux, *mds, sints);
+        else calc_two_electron_ints_rys(sq, aux, *rys, sints);
+        for (int t = 0; t < knt; ++t)
+            if (std::fabs(sints[t].val) > 1.e-14) {      // storage threshold, TwoElectronInts.cpp:513,667-671
+                ++stored;
+                if (digest) harness_digest_rhf(P, G, sints[t].val, sints[t].i, sints[t].j, sints[t].k, sints[t].l);
+            }
+        }   // rep
+    }
+    return stored;
 }
 
 // ---- TwoElectronInts: the reference's stored-integral path --------------------------------------

@@ -760,3 +760,46 @@ long oracle_g_elements_rhf(const oracle_basis *b, double thresh, const double *P
     free(shell_of);
     return nblk;
 }
+
+/* Port twin of ref_harness.cc:ref_quartet_batch (bench.py cpu_baseline when oracle/_ref is absent): n shell quartets given as
+ * two shell pairs each, evaluated in calculate()'s canonical order, storage threshold 1e-14, optional RHF digestion of the
+ * canonical function quartets into G.  Returns the number of integrals above the threshold. */
+long oracle_quartet_batch(const oracle_basis *b, long n, const int *shells, const double *P, double *G, int digest) {
+    init_tables();
+    static _Thread_local double blk[ORACLE_MAXFUNC];
+    long stored = 0;
+    for (long q = 0; q < n; ++q) {
+        int a = shells[4 * q], bb = shells[4 * q + 1], c = shells[4 * q + 2], d = shells[4 * q + 3], t;
+        if (a < bb) { t = a; a = bb; bb = t; }
+        if (c < d) { t = c; c = d; d = t; }
+        if (a < c || (a == c && bb < d)) { t = a; a = c; c = t; t = bb; bb = d; d = t; }
+        /* calculate() visits (ish jsh | ish lsh) for BOTH orders of jsh != lsh; the function filter splits the block between them */
+        const int nrep = (digest && a == c && bb != d) ? 2 : 1;
+        for (int rep = 0; rep < nrep; ++rep) {
+        if (rep) { t = bb; bb = d; d = t; }
+        const int n1 = oracle_ncart(b->lv[a]), n2 = oracle_ncart(b->lv[bb]), n3 = oracle_ncart(b->lv[c]), n4 = oracle_ncart(b->lv[d]);
+        oracle_quartet_block(b, a, bb, c, d, blk);
+        for (int ia = 0; ia < n1; ++ia) {
+            const int ir = b->off[a] + ia;
+            for (int ib = 0; ib < n2; ++ib) {
+                const int jr = b->off[bb] + ib;
+                if (digest && jr > ir) break;
+                for (int ic = 0; ic < n3; ++ic) {
+                    const int kr = b->off[c] + ic;
+                    if (digest && kr > ir) break;
+                    for (int id = 0; id < n4; ++id) {
+                        const int lr = b->off[d] + id;
+                        if (digest && (lr > kr || (ir == kr && lr > jr))) break;
+                        const double v = blk[((ia * n2 + ib) * n3 + ic) * n4 + id];
+                        if (fabs(v) > 1e-14) {
+                            ++stored;
+                            if (digest) digest_rhf(P, G, v, ir, jr, kr, lr);
+                        }
+                    }
+                }
+            }
+        }
+        }   /* rep */
+    }
+    return stored;
+}

@@ -569,12 +569,18 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
     int n_tile = 0, n_reg = 0, n_rows = 0, n_gen = 0, n_hl = 0;
     // work counters of this build (see engine.h)
     unsigned long long *work = nullptr;
+    if (h->d_work_shared && h->work_owner) {
+        // The owner clears the set this build does NOT use, in EVERY build (stealing enabled or not): build k uses set k & 1, so a
+        // set is always clean again before its next use, also across work_stealing being switched off and on (build_count is
+        // never reset by that option: all ranks keep counting the same builds).  The collective that ends a build orders the
+        // reset before the next build of the other ranks.
+        const int par = (int)(h->build_count & 1);
+        CUDA_TRY(h, cudaMemsetAsync(h->d_work_shared + (size_t)(par ^ 1) * unomol_b200::MAXPLAN, 0,
+                                    sizeof(unsigned long long) * unomol_b200::MAXPLAN, st));
+    }
     if (h->d_work_shared && h->steal_enabled) {
         const int par = (int)(h->build_count & 1);
         work = h->d_work_shared + (size_t)par * unomol_b200::MAXPLAN;
-        if (h->work_owner)   // reset the other set; it is next used after the collective that ends this build
-            CUDA_TRY(h, cudaMemsetAsync(h->d_work_shared + (size_t)(par ^ 1) * unomol_b200::MAXPLAN, 0,
-                                        sizeof(unsigned long long) * unomol_b200::MAXPLAN, st));
     } else if (h->nranks == 1) {
         if (!h->d_work_local) CUDA_TRY(h, cudaMalloc(&h->d_work_local, sizeof(unsigned long long) * unomol_b200::MAXPLAN));
         CUDA_TRY(h, cudaMemsetAsync(h->d_work_local, 0, sizeof(unsigned long long) * std::max<size_t>(1, h->plans.size()), st));
@@ -790,7 +796,7 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
     }
     if (!strcmp(name, "prim_cut")) { h->prim_cut = value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "bucket_min_pairs")) { h->bucket_min_pairs = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
-    if (!strcmp(name, "work_stealing")) { h->steal_enabled = value != 0.0; h->build_count = 0; return UNOMOL_OK; }
+    if (!strcmp(name, "work_stealing")) { h->steal_enabled = value != 0.0; return UNOMOL_OK; }
     if (!strcmp(name, "device_pairs")) { h->device_pairs = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "col_blocks")) { h->col_blocks = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "stage_rows")) { h->stage_rows = (int)value; return UNOMOL_OK; }
@@ -887,6 +893,11 @@ int unomol_b200_steal_export(unomol_b200_t *h, void *handle64) {
         CUDA_TRY(h, cudaMalloc(&h->d_work_shared, sizeof(unsigned long long) * 2 * unomol_b200::MAXPLAN));
         CUDA_TRY(h, cudaMemset(h->d_work_shared, 0, sizeof(unsigned long long) * 2 * unomol_b200::MAXPLAN));
         h->work_owner = true;
+    }
+    else if (h->work_owner) {
+        // re-export: start from clean counters (no build may be in flight when handles are exchanged)
+        CUDA_TRY(h, cudaDeviceSynchronize());
+        CUDA_TRY(h, cudaMemset(h->d_work_shared, 0, sizeof(unsigned long long) * 2 * unomol_b200::MAXPLAN));
     }
     cudaIpcMemHandle_t ipc;
     CUDA_TRY(h, cudaIpcGetMemHandle(&ipc, h->d_work_shared));

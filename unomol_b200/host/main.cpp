@@ -3,6 +3,7 @@
 // runs the ground-state SCF and writes short.gs.out / scfout.gs.out / PMATRIX.DAT in the working directory.
 // The finite-field and polarisation-potential follow-ups (Unomol.cc:16-17) are outside the hot-path scope.
 #include <chrono>
+#include <cstdlib>
 #include <string>
 #include "SCF.hpp"
 
@@ -36,5 +37,14 @@ int main(int argc, char **argv) {
     }
     auto t2 = std::chrono::steady_clock::now();
     std::fprintf(stderr, "SCF time = %g s\n", std::chrono::duration<double>(t2 - t1).count());
+    if (bas.int_flags(1)) {
+        // reference Unomol.cc:16-17 runs FiniteFieldAnalysis() / the polarisation-potential grid when int_flag[1] is set.  Neither is
+        // part of this driver: say so loudly instead of letting a caller take a partial run for a full one.
+        const char *skip = std::getenv("UNOMOL_SKIP_FINITE_FIELD");
+        std::fprintf(stderr, "unomol_b200_scf: patin.dat requests the finite-field analysis (int_flag[1] = %d), which this driver does NOT "
+                             "implement; only the ground-state SCF outputs were written.%s\n", bas.int_flags(1),
+                     (skip && skip[0] == '1') ? "" : "  Set UNOMOL_SKIP_FINITE_FIELD=1 to accept that; exiting with status 3.");
+        if (!(skip && skip[0] == '1')) return 3;
+    }
     return EXIT_SUCCESS;
 }

@@ -62,10 +62,66 @@ def enable_work_stealing(handle):
     return all(gathered)
 
 
+class NcclComm:
+    """An NCCL communicator of our own over all ranks (ctypes on the libnccl that torch ships), for
+    unomol_b200_attach_nccl: the library then all-reduces the packed G itself, on its own stream, at the end of every
+    Fock build (the replacement of MPI_Reduce in RHF_MPI::update, reference RHF_MPI.hpp:108).  torch.distributed only
+    carries the 128-byte unique id to the other ranks."""
+
+    def __init__(self):
+        import ctypes
+        import glob
+        import torch.distributed as dist
+        cands = []
+        try:
+            import nvidia.nccl
+            for base in list(getattr(nvidia.nccl, "__path__", [])):
+                cands += glob.glob(os.path.join(base, "lib", "libnccl.so*"))
+        except Exception:
+            pass
+        cands += ["libnccl.so.2", "libnccl.so"]
+        self.lib = None
+        for c in cands:
+            try:
+                self.lib = ctypes.CDLL(c, mode=ctypes.RTLD_GLOBAL)   # global: the engine finds ncclAllReduce with dlsym
+                break
+            except OSError:
+                continue
+        if self.lib is None:
+            raise RuntimeError("libnccl not found")
+
+        class UniqueId(ctypes.Structure):
+            _fields_ = [("internal", ctypes.c_char * 128)]
+        self.lib.ncclGetUniqueId.argtypes = [ctypes.POINTER(UniqueId)]
+        self.lib.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, UniqueId, ctypes.c_int]
+        self.lib.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+        uid = UniqueId()
+        box = [None]
+        if dist.get_rank() == 0:
+            if self.lib.ncclGetUniqueId(ctypes.byref(uid)) != 0:
+                raise RuntimeError("ncclGetUniqueId failed")
+            box[0] = bytes(uid.internal)
+        dist.broadcast_object_list(box, src=0)
+        ctypes.memmove(ctypes.byref(uid), box[0], 128)
+        self.comm = ctypes.c_void_p()
+        rc = self.lib.ncclCommInitRank(ctypes.byref(self.comm), dist.get_world_size(), uid, dist.get_rank())
+        if rc != 0:
+            raise RuntimeError("ncclCommInitRank failed (%d)" % rc)
+
+    @property
+    def ptr(self):
+        return self.comm.value
+
+    def close(self):
+        if getattr(self, "comm", None) is not None and self.comm.value:
+            self.lib.ncclCommDestroy(self.comm)
+            self.comm = None
+
+
 class DistributedFock:
     """RHF/UHF Fock build over all ranks: the Python-side equivalent of RHF_MPI::update's Bcast/Reduce bracket."""
 
-    def __init__(self, basis, start_shell=0, tau=None):
+    def __init__(self, basis, start_shell=0, tau=None, in_library_allreduce=False):
         import torch
         from . import capi
         self.rank, self.world, self.local = env_rank()
@@ -76,6 +132,12 @@ class DistributedFock:
         self.stealing = enable_work_stealing(self.h) if self.world > 1 else False
         if self.world > 1 and not self.stealing:
             self.h.set_option("work_stealing", 0)
+        # in_library_allreduce: hand the library its own NCCL communicator (unomol_b200_attach_nccl); fock_*_device then
+        # returns the summed G and no torch collective is issued
+        self.nccl = None
+        if in_library_allreduce and self.world > 1:
+            self.nccl = NcclComm()
+            self.h.attach_nccl(self.nccl.ptr)
         self.no2 = basis.no2
         self.dP = torch.zeros(self.no2, dtype=torch.float64, device="cuda")
         self.dG = torch.zeros(self.no2, dtype=torch.float64, device="cuda")
@@ -86,5 +148,12 @@ class DistributedFock:
         self.dP.copy_(torch.from_numpy(np.ascontiguousarray(P)))
         torch.cuda.synchronize()
         self.h.fock_rhf_device(self.dP.data_ptr(), self.dG.data_ptr())
-        allreduce_packed(self.dG)
+        if self.nccl is None:
+            allreduce_packed(self.dG)
         return self.dG.cpu().numpy()
+
+    def close(self):
+        self.h.attach_nccl(0)
+        self.h.close()
+        if self.nccl is not None:
+            self.nccl.close()
