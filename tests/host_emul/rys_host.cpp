@@ -22,3 +22,9 @@ extern "C" void unomol_boys_host(double x, double *F) {
     const RysTables T = rys_host_tables(0);
     boys_grid<3, RYS_BOYS_MTOP>(x, T.boys, F);
 }
+
+// F_0(x) alone through its own grid (the (ss|ss) kernels)
+extern "C" double unomol_f0_host(double x) {
+    const RysTables T = rys_host_tables(0);
+    return rys1_f0(x, T);
+}

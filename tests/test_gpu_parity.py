@@ -44,6 +44,7 @@ def test_quartet_blocks_from_the_fock_kernels_vs_reference_fixture(capi, name):
     for the s/p classes, one-bra register kernel for the small d classes) in its dump mode, not from the generic kernel"""
     g = np.load(os.path.join(GOLDEN, "quartets_%s.npz" % name.replace(".", "_")))
     b, h = _handle(capi, name)
+    h.set_option("reg_kernels", 2); h.set_option("tile_kernels", 2)     # small molecule: force the kernels of the long lists
     h.set_option("dump_kernel", 1)
     worst, hot = 0.0, 0
     for q, (i, j, k, l) in enumerate(g["quartets"]):
@@ -60,6 +61,7 @@ def test_unique_integral_list_from_the_fock_kernels(capi, name):
     """every stored integral of the reference, with the tile / register kernels producing the blocks of their classes"""
     g = np.load(os.path.join(GOLDEN, "eri_%s.npz" % name.replace(".", "_")))
     b, h = _handle(capi, name)
+    h.set_option("reg_kernels", 2); h.set_option("tile_kernels", 2)
     h.set_option("dump_kernel", 1)
     vals, ijkl = h.dump_eris(0.0)
     got = {tuple(r): v for r, v in zip(ijkl.tolist(), vals)}
@@ -486,15 +488,19 @@ def _water_oracle(oracle, tmp_path, nw):
     return _WATER_ORACLE[nw]
 
 
+# tile_kernels / reg_kernels = 2 force those kernels on lists that the engine would give to the generic kernel because they are
+# too short to fill the GPU (what (H2O)_154 runs by default is forced here on (H2O)_8 and (H2O)_12)
 @pytest.mark.parametrize("nw,opts", [
     (8, {}),
-    (8, {"bucket_min_pairs": 1}),
-    (8, {"bucket_min_pairs": 1, "col_blocks": 3}),
-    (8, {"tile_kernels": 0}),
-    (8, {"tile_kernels": 0, "bucket_min_pairs": 1, "col_blocks": 2}),
-    (8, {"device_pairs": 0}),
+    (8, {"tile_kernels": 2, "reg_kernels": 2}),
+    (8, {"tile_kernels": 2, "reg_kernels": 2, "bucket_min_pairs": 1}),
+    (8, {"tile_kernels": 2, "reg_kernels": 2, "bucket_min_pairs": 1, "col_blocks": 3}),
+    (8, {"tile_kernels": 0, "reg_kernels": 2}),
+    (8, {"tile_kernels": 0, "reg_kernels": 2, "bucket_min_pairs": 1, "col_blocks": 2}),
+    (8, {"tile_kernels": 2, "reg_kernels": 2, "device_pairs": 0}),
     (12, {}),
-    (12, {"bucket_min_pairs": 1, "col_blocks": 3}),
+    (12, {"tile_kernels": 2, "reg_kernels": 2}),
+    (12, {"tile_kernels": 2, "reg_kernels": 2, "bucket_min_pairs": 1, "col_blocks": 3}),
 ])
 def test_water_cluster_g_vs_oracle(capi, oracle, tmp_path, nw, opts):
     b, ref = _water_oracle(oracle, tmp_path, nw)
@@ -508,9 +514,9 @@ def test_water_cluster_g_vs_oracle(capi, oracle, tmp_path, nw, opts):
         g = h.fock_rhf(P)
         st = h.stats()
         assert np.max(np.abs(g - G)) < 1e-12 * scale, (name, np.max(np.abs(g - G)) / scale, opts)
-        if opts.get("tile_kernels", 1):
+        if opts.get("tile_kernels") == 2:
             assert st["n_tile_launches"] > 0, st
-        else:
+        elif opts.get("tile_kernels") == 0:
             assert st["n_tile_launches"] == 0 and st["n_reg_launches"] > 0 and st["n_rows_launches"] > 0, st
         if "bucket_min_pairs" in opts:
             assert st["n_launches"] > 30, st          # buckets multiply the launches (6 classes -> 21 without them)
@@ -528,6 +534,7 @@ def test_water_cluster_two_rank_static_split_vs_oracle(capi, oracle, tmp_path):
     parts = []
     for r in range(2):
         h = capi.Handle(b, rank=r, nranks=2)
+        h.set_option("tile_kernels", 2); h.set_option("reg_kernels", 2)
         h.set_option("bucket_min_pairs", 1)
         parts.append(h.fock_rhf(P))
         h.close()

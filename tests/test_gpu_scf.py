@@ -30,8 +30,9 @@ def run_scf(name, tmp_path, env=None):
     if key not in _CACHE:
         d = tempfile.mkdtemp(prefix="unomol_scf_")
         shutil.copyfile(golden_input(name), os.path.join(d, "patin.dat"))
+        # the reference's inputs request the finite-field analysis (int_flag[1] = 1), which the driver refuses without this opt-out
         p = subprocess.run([BIN], cwd=d, capture_output=True, text=True, timeout=900,
-                           env=dict(os.environ, **env) if env else None)
+                           env=dict(os.environ, UNOMOL_SKIP_FINITE_FIELD="1", **(env or {})))
         assert p.returncode == 0, p.stderr[-2000:]
         _CACHE[key] = d
     d = _CACHE[key]
@@ -255,3 +256,13 @@ def test_mo_transition_dipoles_written(tmp_path):
     assert len(lines) == 7 * 8 // 2
     diag = {int(a): float(x) for a, b, x, y, z in lines if a == b}
     assert abs(diag[0] - 0.0) < 1e-2        # oxygen 1s sits at the origin
+
+
+def test_driver_refuses_a_silent_partial_run(tmp_path):
+    """reference Unomol.cc runs FiniteFieldAnalysis() when int_flag[1] is set; this driver does not implement it and must say so
+    (exit status 3) unless the caller opts out with UNOMOL_SKIP_FINITE_FIELD=1"""
+    shutil.copyfile(golden_input("3g.h2o"), tmp_path / "patin.dat")
+    env = {k: v for k, v in os.environ.items() if k != "UNOMOL_SKIP_FINITE_FIELD"}
+    p = subprocess.run([BIN], cwd=tmp_path, capture_output=True, text=True, timeout=300, env=env)
+    assert p.returncode == 3 and "finite-field" in p.stderr
+    assert os.path.exists(tmp_path / "short.gs.out")          # the ground-state outputs are still written

@@ -30,6 +30,7 @@ def rys():
     L = ctypes.CDLL(so)
     L.unomol_rys_host.argtypes = [ctypes.c_int, _D, ctypes.c_int, ctypes.POINTER(_D), ctypes.POINTER(_D)]
     L.unomol_boys_host.argtypes = [_D, ctypes.POINTER(_D)]
+    L.unomol_f0_host.argtypes = [_D]; L.unomol_f0_host.restype = _D
 
     def f(n, x, exact=0):
         r = np.zeros(5); w = np.zeros(5)
@@ -98,3 +99,12 @@ def test_boys_grid_path(rys):
             ex = boys_exact(m, x)
             worst = max(worst, abs(F[m] - ex) / ex)
     assert worst < 2e-14, worst       # scipy's gammainc is the limit here; against mpmath the grid path is good to 7e-16
+
+
+def test_f0_only_path_matches_the_one_root_weight(rys):
+    """(ss|ss) uses F_0 from its own {F_7, exp(-X_i)} grid; it must agree with the one-root weight to rounding"""
+    worst = 0.0
+    for x in np.concatenate([np.linspace(0.0, 60.0, 4801), [34.999999, 35.0, 35.000001]]):
+        r, w = rys(1, x)
+        worst = max(worst, abs(rys.lib.unomol_f0_host(float(x)) / w[0] - 1.0))
+    assert worst < 1e-15, worst

@@ -475,7 +475,20 @@ static int build_plans(unomol_b200 *h) {
             int maxbp = 0;
             for (int i = 0; i < plan.nbra_eff; ++i) maxbp = std::max(maxbp, Lb.pairs[i].nprim);
             plan.highl = is_highl(cb / NSUB, ck / NSUB);
-            plan.use_reg = !plan.highl && h->use_reg_kernels && reg_class_available(cb / NSUB, ck / NSUB) && maxbp <= reg_max_bra_prims();
+            // Thread-per-quartet kernels evaluate the Rys roots per lane: fine for the closed-form 1- and 2-root routines, but
+            // 3..5 roots read 13 x 2n table coefficients per lane from global memory (rys_roots.cuh), which the generic kernel
+            // amortises over the lanes of a quartet group.  Measured on SF6/TZ2P: (dp|pp) 5.3 ms in the register kernel, the
+            // whole build 6.1 ms with the generic kernel for every class (profiles/exp_sf6.py).  So: register kernels for <= 2
+            // roots, and for 3 roots only on long lists ((pp|pp) of the water clusters).
+            int nroots;
+            {
+                int la, lb, lc, ld;
+                pair_class_l(cb / NSUB, la, lb);
+                pair_class_l(ck / NSUB, lc, ld);
+                nroots = (la + lb + lc + ld) / 2 + 1;
+            }
+            const bool roots_ok = nroots <= 2 || (nroots == 3 && plan.nbra_eff >= 4096) || h->use_reg_kernels == 2;
+            plan.use_reg = !plan.highl && h->use_reg_kernels && roots_ok && reg_class_available(cb / NSUB, ck / NSUB) && maxbp <= reg_max_bra_prims();
             plan.use_tile = plan.use_reg && h->use_tile_kernels && tile_class_available(cb / NSUB, ck / NSUB) && Lb.ntiles > 0 &&
                             Lb.maxnp <= TILE_MAX_BRA_PRIMS;
             if (plan.use_tile) {
@@ -488,8 +501,9 @@ static int build_plans(unomol_b200 *h) {
                 while (plan.kslots > 0 && tile_smem_bytes(cb / NSUB, ck / NSUB, plan.maxbp, plan.kslots, h->rys.rys2_exact) > 100 * 1024) --plan.kslots;
                 if (tile_smem_bytes(cb / NSUB, ck / NSUB, plan.maxbp, plan.kslots, h->rys.rys2_exact) > 200 * 1024) plan.use_tile = false;
             }
+            std::vector<int> kct, order;
             if (plan.use_tile) {
-                std::vector<int> kct(Lb.slot_pos.size(), 0);
+                kct.assign(Lb.slot_pos.size(), 0);
                 std::vector<std::pair<long long, int>> cost(Lb.ntiles);
                 for (int t = 0; t < Lb.ntiles; ++t) {
                     long long w = 0;
@@ -500,9 +514,13 @@ static int build_plans(unomol_b200 *h) {
                     cost[t] = {w, t};
                 }
                 std::stable_sort(cost.begin(), cost.end(), [](const std::pair<long long, int> &x, const std::pair<long long, int> &y) { return x.first > y.first; });
-                std::vector<int> order;
                 for (auto &ct : cost) if (ct.first > 0) order.push_back(ct.second);
                 plan.ntiles = (int)order.size();
+                // a tile is the work item of a CTA: short lists (small molecules) do not fill the GPU with tiles and stay with the
+                // one-bra-per-CTA kernel (SF6/TZ2P: 17 ms with tiles, 11 ms without)
+                if (plan.ntiles < 4 * 148 && h->use_tile_kernels != 2) plan.use_tile = false;
+            }
+            if (plan.use_tile) {
                 if (cudaMalloc(&plan.d_kc_tile, sizeof(int) * kct.size()) != cudaSuccess) return UNOMOL_E_NOMEM;
                 if (cudaMalloc(&plan.d_tile_order, sizeof(int) * std::max<size_t>(1, order.size())) != cudaSuccess) return UNOMOL_E_NOMEM;
                 cudaMemcpyAsync(plan.d_kc_tile, kct.data(), sizeof(int) * kct.size(), cudaMemcpyHostToDevice, h->stream);
@@ -807,13 +825,13 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
     // Schwarz bounds depend on it, so the pair tables are rebuilt.
     if (!strcmp(name, "rys2_exact")) { h->rys.rys2_exact = value != 0.0; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "tile_kernels")) {
-        h->use_tile_kernels = value != 0.0;
+        h->use_tile_kernels = (int)value;    // 0 = off, 1 = lists with enough tiles to fill the GPU, 2 = always (tests)
         if (h->pairs_ready) return build_plans(h);
         return UNOMOL_OK;
     }
     if (!strcmp(name, "dump_kernel")) { h->dump_kernel = (int)value; return UNOMOL_OK; }
     if (!strcmp(name, "reg_kernels")) {
-        h->use_reg_kernels = value != 0.0;
+        h->use_reg_kernels = (int)value;     // 0 = generic kernel only, 1 = by class and list length, 2 = every available class
         if (h->pairs_ready) return build_plans(h);
         return UNOMOL_OK;
     }

@@ -84,9 +84,11 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
     RysTables rys = task.rys;
     if (nboys > 0) {
         double2 *sb = reinterpret_cast<double2 *>(tsm + lay.off_boys);
-        const double2 *gb = reinterpret_cast<const double2 *>(NR == 1 ? task.rys.boys1 : task.rys.boys);
+        constexpr bool F0_ONLY = (NR == 1 && GI * GJ == 1);
+        const double2 *gb = reinterpret_cast<const double2 *>(F0_ONLY ? task.rys.boys0 : (NR == 1 ? task.rys.boys1 : task.rys.boys));
         for (int i = tid; i < nboys; i += T) sb[i] = gb[i];
-        if (NR == 1) rys.boys1 = reinterpret_cast<const double *>(sb);
+        if (F0_ONLY) rys.boys0 = reinterpret_cast<const double *>(sb);
+        else if (NR == 1) rys.boys1 = reinterpret_cast<const double *>(sb);
         else rys.boys = reinterpret_cast<const double *>(sb);
     }
     if (tid == 0) {
@@ -257,9 +259,7 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                         const double pq0 = bp[ib].P[0] - kP0, pq1 = bp[ib].P[1] - kP1, pq2 = bp[ib].P[2] - kP2;
                         const double X = bpv * kp_ * itx * (pq0 * pq0 + pq1 * pq1 + pq2 * pq2);
                         if constexpr (NR == 1 && GI * GJ == 1) {
-                            double w, f1;
-                            rys1_f0f1(X, w, f1, rys);
-                            acc[0] = fma(sr, w, acc[0]);
+                            acc[0] = fma(sr, rys1_f0(X, rys), acc[0]);
                         } else if constexpr (NR == 1) {
                             // (ps|ss): one root, G[1][0] = C per axis: sr*w*C = sr*(PA*w - q/(p+q)*PQ*F1)
                             double w, f1;

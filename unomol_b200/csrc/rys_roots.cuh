@@ -52,6 +52,7 @@ constexpr double rys_herm(int weights, int i) {
 struct RysTables {
     const double *boys;        // [RYS_BOYS_NPTS][2] = {F_10(X_i), exp(-X_i)}, X_i = i / RYS_BOYS_HINV, X_i <= 46: two roots
     const double *boys1;       // [RYS_BOYS1_NPTS][2] = {F_8(X_i), exp(-X_i)}, X_i <= 35: one root (two recursion steps less)
+    const double *boys0;       // [RYS_BOYS1_NPTS][2] = {F_7(X_i), exp(-X_i)}: F_0 alone ((ss|ss))
     const double *piece[3];    // 3, 4, 5 roots: [interval][k = 0..12][r_0..r_{n-1}, w_0..w_{n-1}]
     int rys2_exact;            // 0: reference-compatible two-root band (see above); 1: exact two-root quadrature
     int pad;
@@ -87,15 +88,42 @@ constexpr double rys_ifact(int k) {
     return 1.0 / f;
 }
 
+// Constants of boys_grid<MT, MTAB> as one 32-entry block: [0, MTAB - MT) = T_{MT+1+i}, [12, 20) = q_k = 1 / (T_{MT+k} k!),
+// [20, 29) = 1 / k!.  Device code reads them from a __constant__ table so that they are constant-bank operands of the
+// DFMA / DMUL; as 64-bit immediates every use costs two UMOV (ncu, (ps|ss) tile kernel: 6.8 % of the issued instructions).
+constexpr double boys_cval(int mt, int mtab, int i) {
+    if (i < 12) return (mt + 1 + i <= mtab) ? rys_tscale(mt + 1 + i, mtab) : 0.0;
+    if (i < 20) return rys_ifact(i - 12) / rys_tscale(mt + i - 12, mtab);
+    if (i < 29) return rys_ifact(i - 20);
+    return 0.0;
+}
+constexpr int boys_cblock(int mt) { return mt == 0 ? 0 : (mt == 1 ? 1 : 2); }   // the three instances in use
+#ifdef __CUDACC__
+#define RYS_B8(mt, mtab, o) boys_cval(mt, mtab, o), boys_cval(mt, mtab, o + 1), boys_cval(mt, mtab, o + 2), boys_cval(mt, mtab, o + 3), \
+                            boys_cval(mt, mtab, o + 4), boys_cval(mt, mtab, o + 5), boys_cval(mt, mtab, o + 6), boys_cval(mt, mtab, o + 7)
+#define RYS_B32(mt, mtab) RYS_B8(mt, mtab, 0), RYS_B8(mt, mtab, 8), RYS_B8(mt, mtab, 16), RYS_B8(mt, mtab, 24)
+static __constant__ double rys_boys_ctab[96] = {RYS_B32(0, RYS_BOYS0_MTOP), RYS_B32(1, RYS_BOYS1_MTOP), RYS_B32(3, RYS_BOYS_MTOP)};
+#undef RYS_B32
+#undef RYS_B8
+#endif
+#ifdef __CUDA_ARCH__
+#define RYS_BC(mt, mtab, i) rys_boys_ctab[32 * boys_cblock(mt) + (i)]
+#else
+#define RYS_BC(mt, mtab, i) boys_cval(mt, mtab, i)
+#endif
+
 // F[0..MT] = F_0(x) .. F_MT(x) for 0 <= x < (grid end); tab = {F_MTAB(X_i), exp(-X_i)} on X_i = i/16.
 // The downward recursion f_{m-1} = (2 X_i f_m + e) / (2m-1) is run on h_m = T_m f_m (T_m = (2m+1)(2m+3)..(2 MTAB - 1)),
 // which turns a step into ONE fma on the dependent chain, h_{m-1} = 2 X_i h_m + e T_m; the Taylor sum
 // F_MT(x) = sum_k f_{MT+k} d^k / k!, d = X_i - x, runs as a Horner chain in lockstep with it (it consumes h_{MT+k} in
 // the order the recursion produces them), so the critical path is MTAB - MT + 2 fma long instead of 2 (MTAB - MT) + 8:
-// the FP64 pipe of these kernels was waiting on dependent results (ncu: "wait" was the top stall reason).
+// the FP64 pipe of these kernels was waiting on dependent results (ncu: "wait" was the top stall reason; a dependent DFMA
+// issues every 8.5 cycles, profiles/exp_fp64_latency.cu).  MT = 0 needs neither exp(-x) nor the recursion at x.
 template <int MT, int MTAB>
 UNOMOL_HD void boys_grid(double x, const double *tab, double *F) {
-    static_assert(MT + 7 <= MTAB, "the Taylor series of the top order reaches F_{MT+7}");
+    static_assert(MT + 7 <= MTAB && MTAB - MT <= 12, "the Taylor series of the top order reaches F_{MT+7}");
+    static_assert((MT == 0 && MTAB == RYS_BOYS0_MTOP) || (MT == 1 && MTAB == RYS_BOYS1_MTOP) || (MT == 3 && MTAB == RYS_BOYS_MTOP),
+                  "constant blocks exist for these instances");
     const int i = (int)fma(x, (double)RYS_BOYS_HINV, 0.5);
     const double xi = (double)i * (1.0 / RYS_BOYS_HINV);
     const double d = xi - x;                       // |d| <= 1/32
@@ -109,22 +137,27 @@ UNOMOL_HD void boys_grid(double x, const double *tab, double *F) {
 #endif
     const double x2 = xi + xi;
 #pragma unroll
-    for (int m = MTAB; m > MT + 7; --m) h = fma(x2, h, e * rys_tscale(m, MTAB));
+    for (int m = MTAB; m > MT + 7; --m) h = fma(x2, h, e * RYS_BC(MT, MTAB, m - MT - 1));
     // h = h_{MT+7}; Horner: t <- t d + h_{MT+k} q_k with q_k = 1 / (T_{MT+k} k!)
-    double t = h * (rys_ifact(7) / rys_tscale(MT + 7, MTAB));
-    double ex = fma(d, rys_ifact(8), rys_ifact(7));          // exp(d) = sum_k d^k / k!, same Horner direction
+    double t = h * RYS_BC(MT, MTAB, 12 + 7);
+    double ex = fma(d, RYS_BC(MT, MTAB, 20 + 8), RYS_BC(MT, MTAB, 20 + 7));   // exp(d) = sum_k d^k / k!, same Horner direction
 #pragma unroll
     for (int k = 7; k > 0; --k) {
-        h = fma(x2, h, e * rys_tscale(MT + k, MTAB));         // h_{MT+k-1}
-        t = fma(t, d, h * (rys_ifact(k - 1) / rys_tscale(MT + k - 1, MTAB)));
-        ex = fma(ex, d, rys_ifact(k - 1));
+        h = fma(x2, h, e * RYS_BC(MT, MTAB, k - 1));                          // h_{MT+k-1} = 2 X_i h_{MT+k} + e T_{MT+k}
+        t = fma(t, d, h * RYS_BC(MT, MTAB, 12 + k - 1));
+        if (MT > 0) ex = fma(ex, d, RYS_BC(MT, MTAB, 20 + k - 1));
     }
     F[MT] = t;
-    ex *= e;                                       // exp(-x)
-    const double xx = x + x;
+    if (MT > 0) {
+        ex *= e;                                   // exp(-x)
+        const double xx = x + x;
 #pragma unroll
-    for (int m = MT; m > 0; --m) F[m - 1] = (m == 1) ? fma(xx, F[m], ex) : fma(xx, F[m], ex) * (1.0 / (2 * m - 1));
+        for (int m = MT; m > 0; --m) F[m - 1] = (m == 1) ? fma(xx, F[m], ex) : fma(xx, F[m], ex) * (1.0 / (2 * m - 1));
+    }
 }
+
+// F_0 alone (the (ss|ss) class): Taylor series of F_0 itself from the {F_7, exp(-X_i)} grid
+UNOMOL_HD double rys1_f0(double x, const RysTables &T);
 
 // Gauss-Hermite limit (all exp(-X) terms below double precision)
 template <int N>
@@ -150,6 +183,15 @@ UNOMOL_HD void rys1_f0f1(double x, double &w, double &f1, const RysTables &T) {
         w = RYS_SQRT_PI_4 * rx;
         f1 = (0.5 * w) * (rx * rx);
     }
+}
+
+UNOMOL_HD double rys1_f0(double x, const RysTables &T) {
+    if (x < RYS_X_ASYM1) {
+        double F[1];
+        boys_grid<0, RYS_BOYS0_MTOP>(x, T.boys0, F);
+        return F[0];
+    }
+    return RYS_SQRT_PI_4 * rys_rsqrt(x);
 }
 
 // Reference-compatible two-root band, 15 < X <= 40: restates reference Rys.cpp:614-624 (see the header comment).
@@ -255,6 +297,7 @@ inline RysTables rys_host_tables(int rys2_exact = 0) {
     RysTables T;
     T.boys = rys_host::rys_boys_tab;
     T.boys1 = rys_host::rys_boys1_tab;
+    T.boys0 = rys_host::rys_boys0_tab;
     T.piece[0] = rys_host::rys_piece3_tab;
     T.piece[1] = rys_host::rys_piece4_tab;
     T.piece[2] = rys_host::rys_piece5_tab;

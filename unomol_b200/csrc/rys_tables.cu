@@ -17,6 +17,8 @@ cudaError_t rys_device_tables(RysTables *out) {
     out->boys = (const double *)p;
     if ((e = cudaGetSymbolAddress(&p, rys_boys1_tab)) != cudaSuccess) return e;
     out->boys1 = (const double *)p;
+    if ((e = cudaGetSymbolAddress(&p, rys_boys0_tab)) != cudaSuccess) return e;
+    out->boys0 = (const double *)p;
     if ((e = cudaGetSymbolAddress(&p, rys_piece3_tab)) != cudaSuccess) return e;
     out->piece[0] = (const double *)p;
     if ((e = cudaGetSymbolAddress(&p, rys_piece4_tab)) != cudaSuccess) return e;

@@ -29,7 +29,7 @@ def run_scf(basis, pmatrix=None, maxits=None, env=None, timeout=3600):
     finally:
         basis.scf_flag, basis.maxits = saved
     p = subprocess.run([BIN], cwd=d, capture_output=True, text=True, timeout=timeout,
-                       env=dict(os.environ, **env) if env else None)
+                       env=dict(os.environ, UNOMOL_SKIP_FINITE_FIELD="1", **(env or {})))
     if p.returncode != 0:
         raise RuntimeError("unomol_b200_scf failed: " + p.stderr[-2000:])
     e0, e1, de = [float(x) for x in open(os.path.join(d, "short.gs.out")).read().split()]

@@ -161,6 +161,7 @@ def main():
     C.append("#define RYS_BOYS1_XMAX %d" % BOYS1_XMAX)
     C.append("#define RYS_BOYS1_MTOP %d" % BOYS1_MTOP)
     C.append("#define RYS_BOYS1_NPTS %d" % nb1)
+    C.append("#define RYS_BOYS0_MTOP %d" % (BOYS1_MTOP - 1))
     L.append("RYS_TABLE(rys_boys_tab, 2 * RYS_BOYS_NPTS) = {")
     for i in range(nb):
         x = mp.mpf(i) / BOYS_H_INV
@@ -170,6 +171,11 @@ def main():
     for i in range(nb1):
         x = mp.mpf(i) / BOYS_H_INV
         L.append("    %s, %s," % (fmt(boys(BOYS1_MTOP, x)), fmt(mp.exp(-x))))
+    L.append("};")
+    L.append("RYS_TABLE(rys_boys0_tab, 2 * RYS_BOYS1_NPTS) = {")
+    for i in range(nb1):
+        x = mp.mpf(i) / BOYS_H_INV
+        L.append("    %s, %s," % (fmt(boys(BOYS1_MTOP - 1, x)), fmt(mp.exp(-x))))
     L.append("};")
     # Hermite limits
     C.append("// large-X limit: r_i = R_i/(X - R_i), w_i = W_i sqrt(pi/(4X)); row n-1 holds n entries")
