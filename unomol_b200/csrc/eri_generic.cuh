@@ -235,12 +235,12 @@ eri_class_kernel(const ClassTask task) {
                     const double pq0 = b.P[0] - k.P[0], pq1 = b.P[1] - k.P[1], pq2 = b.P[2] - k.P[2];
                     const double X = b.p * k.p * itx * (pq0 * pq0 + pq1 * pq1 + pq2 * pq2);
                     double rt[NR], wt[NR];
-                    rys_roots<NR>(X, rt, wt, task.rys);
+                    rys_t2<NR>(X, rt, wt, task.rys);      // rt[] = t^2
                     // 2-D recurrences: (root, axis) tables split over the lanes of the group
                     if (T > 1) __syncwarp(gmask);   // previous iteration's readers are done
                     for (int tsk = lig; tsk < 3 * NR; tsk += T) {
                         const int ir = tsk / 3, ax = tsk - 3 * ir;
-                        const double dr = rt[ir] / (1.0 + rt[ir]);
+                        const double dr = rt[ir];
                         const double fff = dr * itx;
                         const double B00 = 0.5 * fff;
                         const double B1 = (0.5 - B00 * k.p) * b.ip;

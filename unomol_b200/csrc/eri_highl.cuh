@@ -140,7 +140,7 @@ HL_FN void hl_vrr(double *G, int La, int Lb, double B00, double B1, double B1p, 
 }
 
 template <int NR>
-HL_FN void hl_roots_n(double X, double *rt, double *wt, const RysTables &T) { rys_roots<NR>(X, rt, wt, T); }
+HL_FN void hl_roots_n(double X, double *rt, double *wt, const RysTables &T) { rys_t2<NR>(X, rt, wt, T); }   // rt[] = t^2
 HL_FN void hl_roots(int nr, double X, double *rt, double *wt, const RysTables &T) {
     switch (nr) {
         case 1: hl_roots_n<1>(X, rt, wt, T); break;
@@ -204,7 +204,7 @@ HL_FN unsigned long long hl_quartet_block(const HighLArgs &hl, const ShellPair &
                 hl_roots(nr, X, rt, wt, hl.rys);
                 for (int tsk = tid; tsk < 3 * nr; tsk += nt) {
                     const int ir = tsk / 3, ax = tsk - 3 * ir;
-                    const double dr = rt[ir] / (1.0 + rt[ir]);
+                    const double dr = rt[ir];
                     const double fff = dr * itx;
                     const double B00 = 0.5 * fff;
                     const double B1 = (0.5 - B00 * k.p) * b.ip;

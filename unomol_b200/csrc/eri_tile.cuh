@@ -270,10 +270,10 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                             acc[2] = fma(a, bp[ib].PA[2], fma(-bq, pq2, acc[2]));
                         } else {
                             double rt[NR], wt[NR];
-                            rys_roots<NR>(X, rt, wt, rys);
+                            rys_t2<NR>(X, rt, wt, rys);      // rt[] = t^2
 #pragma unroll
                             for (int ir = 0; ir < NR; ++ir) {
-                                const double dr = rt[ir] / (1.0 + rt[ir]);
+                                const double dr = rt[ir];
                                 const double fff = dr * itx;
                                 const double B00 = 0.5 * fff;
                                 const double B1 = (0.5 - B00 * kp_) * bp[ib].ip;

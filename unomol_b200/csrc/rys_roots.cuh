@@ -21,7 +21,7 @@
 //     r_i = (a_i X + b_i) exp(-X) + R_i/(X - R_i),  w_1 = (a_w X + b_w) exp(-X) + W_1 sqrt(pi/4X),  w_0 = sqrt(pi/4X) - w_1
 // (reference Rys.cpp:614-624): the classic (33,40] form, which the reference ALSO applies to 15 < X <= 33 where its
 // dedicated fit is missing, so its two-root quadrature is off by up to 8.7e-7 there.  Per-quartet
-// parity at 1e-12 and SCF energies at 1e-9 Eh need that behaviour, so rys2_compat_band() below restates exactly
+// parity at 1e-12 and SCF energies at 1e-9 Eh need that behaviour, so rys2_compat_band_t2() below restates exactly
 // that formula with its six fit constants; everything else in the two-root routine is ours.  rys2_exact = 1 (engine
 // option "rys2_exact") uses the moment formula up to X = 46 instead and is the mathematically correct quadrature.
 #pragma once
@@ -53,7 +53,7 @@ struct RysTables {
     const double *boys;        // [RYS_BOYS_NPTS][2] = {F_10(X_i), exp(-X_i)}, X_i = i / RYS_BOYS_HINV, X_i <= 46: two roots
     const double *boys1;       // [RYS_BOYS1_NPTS][2] = {F_8(X_i), exp(-X_i)}, X_i <= 35: one root (two recursion steps less)
     const double *boys0;       // [RYS_BOYS1_NPTS][2] = {F_7(X_i), exp(-X_i)}: F_0 alone ((ss|ss))
-    const double *piece[3];    // 3, 4, 5 roots: [interval][k = 0..12][r_0..r_{n-1}, w_0..w_{n-1}]
+    const double *piece[3];    // 3, 4, 5 roots: [interval][k = 0..12][y_0..y_{n-1}, w_0..w_{n-1}], y = t^2
     int rys2_exact;            // 0: reference-compatible two-root band (see above); 1: exact two-root quadrature
     int pad;
 };
@@ -156,22 +156,26 @@ UNOMOL_HD void boys_grid(double x, const double *tab, double *F) {
     }
 }
 
-// F_0 alone (the (ss|ss) class): Taylor series of F_0 itself from the {F_7, exp(-X_i)} grid
-UNOMOL_HD double rys1_f0(double x, const RysTables &T);
+// ---- nodes as t^2 --------------------------------------------------------------------------------------------------
+// The two-dimensional recurrences need t_i^2 (reference Rys.hpp:127: t2 = r/(1+r)); the reference's root routines return
+// r = t^2/(1-t^2) only to divide it back.  rys_t2<N> returns t2[i] = t_i^2 (ascending) and w[i] directly -- the kernels
+// call it -- and rys_roots<N> converts to the reference's r for the parity tests of the evaluator itself.
 
-// Gauss-Hermite limit (all exp(-X) terms below double precision)
+UNOMOL_HD double rys_rcp(double x) { return 1.0 / x; }
+
+// Gauss-Hermite limit (all exp(-X) terms below double precision): t_i^2 = R_i / X, w_i = W_i sqrt(pi/4X)
 template <int N>
-UNOMOL_HD void rys_hermite_limit(double x, double *r, double *w) {
-    const double s = RYS_SQRT_PI_4 * rys_rsqrt(x);
+UNOMOL_HD void rys_hermite_limit_t2(double x, double *t2, double *w) {
+    const double rx = rys_rsqrt(x);
+    const double s = RYS_SQRT_PI_4 * rx, ix = rx * rx;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        const double R = rys_herm(0, 5 * (N - 1) + i);
-        r[i] = R / (x - R);
+        t2[i] = rys_herm(0, 5 * (N - 1) + i) * ix;
         w[i] = rys_herm(1, 5 * (N - 1) + i) * s;
     }
 }
 
-// One root as moments: w = F_0(x), f1 = F_1(x) = w t^2.  The (ss|ss) and (ps|ss) kernels use these directly.
+// One root as moments: w = F_0(x), f1 = F_1(x) = w t^2.  The (ps|ss) kernels use these directly.
 UNOMOL_HD void rys1_f0f1(double x, double &w, double &f1, const RysTables &T) {
     if (x < RYS_X_ASYM1) {
         double F[2];
@@ -194,57 +198,67 @@ UNOMOL_HD double rys1_f0(double x, const RysTables &T) {
     return RYS_SQRT_PI_4 * rys_rsqrt(x);
 }
 
-// Reference-compatible two-root band, 15 < X <= 40: restates reference Rys.cpp:614-624 (see the header comment).
-UNOMOL_HD void rys2_compat_band(double x, double *r, double *w) {
+// Reference-compatible two-root band, 15 < X <= 40: restates reference Rys.cpp:614-624 (see the header comment),
+//     r_i = (a_i X + b_i) exp(-X) + R_i / (X - R_i),   w_1 = (a_w X + b_w) exp(-X) + W_1 sqrt(pi/4X),   w_0 = sqrt(pi/4X) - w_1,
+// evaluated for t_i^2 = r_i / (1 + r_i) = N_i / (N_i + u_i) with u_i = X - R_i, N_i = (a_i X + b_i) exp(-X) u_i + R_i: one
+// reciprocal for both nodes instead of four divisions (same numbers to rounding).
+UNOMOL_HD void rys2_compat_band_t2(double x, double *t2, double *w) {
     const double g = exp(-x);
-    const double wsum = sqrt(0.785398163397448 / x);
-    r[0] = fma(-0.87894730749888, x, 10.9243702330261) * g + 0.275255128608411 / (x - 0.275255128608411);
-    r[1] = fma(-9.28903924275977, x, 81.0642367843811) * g + 2.72474487139158 / (x - 2.72474487139158);
-    w[1] = fma(4.468573893084, x, -77.9250653461045) * g + 0.0917517095361369 * wsum;
+    const double wsum = 0.886226925452758 * rys_rsqrt(x);           // sqrt(.785398163397448 / x)
+    const double u0 = x - 0.275255128608411, u1 = x - 2.72474487139158;
+    const double n0 = fma(fma(-0.87894730749888, x, 10.9243702330261) * g, u0, 0.275255128608411);
+    const double n1 = fma(fma(-9.28903924275977, x, 81.0642367843811) * g, u1, 2.72474487139158);
+    const double d0 = n0 + u0, d1 = n1 + u1;
+    const double inv = rys_rcp(d0 * d1);
+    t2[0] = n0 * (d1 * inv);
+    t2[1] = n1 * (d0 * inv);
+    w[1] = fma(fma(4.468573893084, x, -77.9250653461045), g, 0.0917517095361369 * wsum);
     w[0] = wsum - w[1];
 }
 
 template <int N>
-UNOMOL_HD void rys_roots(double x, double *r, double *w, const RysTables &T);
+UNOMOL_HD void rys_t2(double x, double *t2, double *w, const RysTables &T);
 
 template <>
-UNOMOL_HD void rys_roots<1>(double x, double *r, double *w, const RysTables &T) {
+UNOMOL_HD void rys_t2<1>(double x, double *t2, double *w, const RysTables &T) {
     double f1;
     rys1_f0f1(x, w[0], f1, T);
-    r[0] = f1 / (w[0] - f1);
+    t2[0] = f1 / w[0];
 }
 
 template <>
-UNOMOL_HD void rys_roots<2>(double x, double *r, double *w, const RysTables &T) {
+UNOMOL_HD void rys_t2<2>(double x, double *t2, double *w, const RysTables &T) {
     const double xmom = T.rys2_exact ? (double)RYS_BOYS_XMAX : 15.0;
-    if (x <= xmom) {
-        if (x >= (double)RYS_BOYS_XMAX) { rys_hermite_limit<2>(x, r, w); return; }   // exact mode, x == 46
+    if (x <= xmom && x < (double)RYS_BOYS_XMAX) {
         double m[4];
         boys_grid<3, RYS_BOYS_MTOP>(x, T.boys, m);
-        // monic orthogonal polynomial y^2 + c1 y + c0 in y = t^2:  [m0 m1; m1 m2] (c0, c1)^T = -(m2, m3)^T
-        const double det = rys_dop(m[0], m[2], m[1], m[1]);
+        // orthogonal polynomial D y^2 + n1 y + n0 in y = t^2 from the Hankel system [m0 m1; m1 m2] (c0, c1)^T = -(m2, m3)^T:
+        // D = m0 m2 - m1^2 > 0, n0 = m1 m3 - m2^2 > 0, n1 = m1 m2 - m0 m3 < 0.  With S = sqrt(n1^2 - 4 D n0):
+        // y1 = (S - n1) / (2 D), y0 = 2 n0 / (S - n1), y1 - y0 = S / D, w1 = (m1 - y0 m0) D / S.  One rsqrt (S and 1/S)
+        // and one reciprocal (of D (S - n1)) instead of a square root and three divisions.
+        const double D = rys_dop(m[0], m[2], m[1], m[1]);
         const double n0 = rys_dop(m[1], m[3], m[2], m[2]);
         const double n1 = rys_dop(m[1], m[2], m[0], m[3]);
-        const double idet = 1.0 / det;
-        const double c0 = n0 * idet, c1 = n1 * idet;       // c0 = y0 y1 > 0, c1 = -(y0 + y1) < 0
-        const double disc = sqrt(fma(c1, c1, -4.0 * c0));
-        const double y1 = 0.5 * (disc - c1);               // larger node, no cancellation
-        const double y0 = c0 / y1;
-        const double w1 = fma(-y0, m[0], m[1]) / (y1 - y0);
-        r[0] = y0 / (1.0 - y0);
-        r[1] = y1 / (1.0 - y1);
-        w[1] = w1;
-        w[0] = m[0] - w1;
+        const double disc = fma(n1, n1, -4.0 * D * n0);
+        const double iS = rys_rsqrt(disc), S = disc * iS;
+        const double q = S - n1;                        // both terms positive
+        const double inv = rys_rcp(D * q);              // 1/D = inv q, 1/q = inv D
+        const double y1 = 0.5 * q * (inv * q);
+        const double y0 = 2.0 * n0 * (inv * D);
+        t2[0] = y0;
+        t2[1] = y1;
+        w[1] = fma(-y0, m[0], m[1]) * D * iS;
+        w[0] = m[0] - w[1];
     } else if (!T.rys2_exact && x <= 40.0) {
-        rys2_compat_band(x, r, w);
+        rys2_compat_band_t2(x, t2, w);
     } else {
-        rys_hermite_limit<2>(x, r, w);
+        rys_hermite_limit_t2<2>(x, t2, w);
     }
 }
 
 template <int N>
-UNOMOL_HD void rys_piecewise(double x, double *r, double *w, const double *tab, double xa) {
-    if (x >= xa) { rys_hermite_limit<N>(x, r, w); return; }
+UNOMOL_HD void rys_piecewise_t2(double x, double *t2, double *w, const double *tab, double xa) {
+    if (x >= xa) { rys_hermite_limit_t2<N>(x, t2, w); return; }
     const int iv = (int)x;                                 // unit intervals
     const double s = fma(2.0, x - (double)iv, -1.0);       // [-1, 1]
     const double *c = tab + (size_t)iv * ((RYS_P3_DEG + 1) * 2 * N);
@@ -275,16 +289,24 @@ UNOMOL_HD void rys_piecewise(double x, double *r, double *w, const double *tab, 
         for (int f = 0; f < 2 * N; ++f) acc[f] = fma(acc[f], s, c[k * 2 * N + f]);
 #endif
 #pragma unroll
-    for (int i = 0; i < N; ++i) { r[i] = acc[i]; w[i] = acc[N + i]; }
+    for (int i = 0; i < N; ++i) { t2[i] = acc[i]; w[i] = acc[N + i]; }
 }
 static_assert(RYS_P3_DEG == RYS_P4_DEG && RYS_P4_DEG == RYS_P5_DEG, "one degree for all piecewise tables");
 
 template <>
-UNOMOL_HD void rys_roots<3>(double x, double *r, double *w, const RysTables &T) { rys_piecewise<3>(x, r, w, T.piece[0], RYS_P3_XA); }
+UNOMOL_HD void rys_t2<3>(double x, double *t2, double *w, const RysTables &T) { rys_piecewise_t2<3>(x, t2, w, T.piece[0], RYS_P3_XA); }
 template <>
-UNOMOL_HD void rys_roots<4>(double x, double *r, double *w, const RysTables &T) { rys_piecewise<4>(x, r, w, T.piece[1], RYS_P4_XA); }
+UNOMOL_HD void rys_t2<4>(double x, double *t2, double *w, const RysTables &T) { rys_piecewise_t2<4>(x, t2, w, T.piece[1], RYS_P4_XA); }
 template <>
-UNOMOL_HD void rys_roots<5>(double x, double *r, double *w, const RysTables &T) { rys_piecewise<5>(x, r, w, T.piece[2], RYS_P5_XA); }
+UNOMOL_HD void rys_t2<5>(double x, double *t2, double *w, const RysTables &T) { rys_piecewise_t2<5>(x, t2, w, T.piece[2], RYS_P5_XA); }
+
+// the reference's form: r[i] = t_i^2 / (1 - t_i^2)  (Rys.hpp:145-164); used by the evaluator's own tests
+template <int N>
+UNOMOL_HD void rys_roots(double x, double *r, double *w, const RysTables &T) {
+    rys_t2<N>(x, r, w, T);
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = r[i] / (1.0 - r[i]);
+}
 
 #if !defined(__CUDACC__) || defined(UNOMOL_RYS_HOST_TABLES)
 // host copies of the tables (host emulation of the kernels, CPU tests of this evaluator)

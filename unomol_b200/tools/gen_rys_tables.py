@@ -9,7 +9,7 @@ quadrature (weight exp(-X t^2) on [0,1]; nodes x_i = t_i^2, the kernels use r_i 
                      series in X - X_i (dF_m/dX = -F_{m+1}) and the lower orders by downward recursion at X itself.
                      One and two roots are built from these moments in closed form (rys_roots.cuh).
   * 3, 4, 5 roots    piecewise polynomials (monomials in s in [-1,1], converted from Chebyshev interpolants
-                     computed at 60 digits) of r_i(X) and w_i(X) on uniform intervals of [0, XA_n); above XA_n the
+                     computed at 60 digits) of y_i(X) = t_i^2 and w_i(X) on uniform intervals of [0, XA_n); above XA_n the
                      exp(-X)-free Gauss-Hermite limit is exact to double precision.
   * Hermite limits   R_i = squared positive roots of H_2n, W_i = Gauss-Hermite weights / sqrt(pi) (n = 1..5).
 
@@ -118,7 +118,7 @@ def gen_piece(n, check):
     nint = int(round(xa / width))
     N = deg + 1
     nodes = [mp.cos(mp.pi * (j + mp.mpf(1) / 2) / N) for j in range(N)]
-    rows = []          # [interval][k][func], func = r_0..r_{n-1}, w_0..w_{n-1}
+    rows = []          # [interval][k][func], func = y_0..y_{n-1} (y = t^2), w_0..w_{n-1}
     worst = 0.0
     for iv in range(nint):
         x0 = mp.mpf(iv) * width
@@ -126,7 +126,7 @@ def gen_piece(n, check):
         vals = []
         for s in nodes:
             xs, ws = rys_exact(n, xc + s * width / 2)
-            vals.append([x / (1 - x) for x in xs] + ws)
+            vals.append(list(xs) + ws)          # nodes as y = t^2 in (0,1): what the recurrences use
         mono = []
         for f in range(2 * n):
             mono.append(cheb_to_mono(cheb_fit([v[f] for v in vals], deg)))
@@ -134,7 +134,7 @@ def gen_piece(n, check):
         if check:
             for s in (mp.mpf(-1), mp.mpf("-0.77"), mp.mpf("-0.31"), mp.mpf("0.123"), mp.mpf("0.5"), mp.mpf("0.93"), mp.mpf(1)):
                 xs, ws = rys_exact(n, xc + s * width / 2)
-                ex = [x / (1 - x) for x in xs] + ws
+                ex = list(xs) + ws
                 sd = float(s)
                 for f in range(2 * n):
                     acc = 0.0
@@ -200,7 +200,7 @@ def main():
         C.append("#define RYS_P%d_DEG %d" % (n, deg))
         C.append("#define RYS_P%d_XA %.17g" % (n, xa))
         C.append("#define RYS_P%d_NINT %d" % (n, nint))
-        L.append("// layout [interval][k = 0..deg][r_0..r_%d, w_0..w_%d]" % (n - 1, n - 1))
+        L.append("// layout [interval][k = 0..deg][y_0..y_%d, w_0..w_%d], y = t^2" % (n - 1, n - 1))
         L.append("RYS_TABLE(rys_piece%d_tab, %d) = {" % (n, nint * (deg + 1) * 2 * n))
         for iv in range(nint):
             for k in range(deg + 1):
