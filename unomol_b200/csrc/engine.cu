@@ -487,7 +487,7 @@ static int build_plans(unomol_b200 *h) {
                 pair_class_l(ck / NSUB, lc, ld);
                 nroots = (la + lb + lc + ld) / 2 + 1;
             }
-            const bool roots_ok = nroots <= 2 || (nroots == 3 && plan.nbra_eff >= 4096) || h->use_reg_kernels == 2;
+            const bool roots_ok = nroots <= 2 || (nroots == 3 && plan.nquartets >= 1000000) || h->use_reg_kernels == 2;
             plan.use_reg = !plan.highl && h->use_reg_kernels && roots_ok && reg_class_available(cb / NSUB, ck / NSUB) && maxbp <= reg_max_bra_prims();
             plan.use_tile = plan.use_reg && h->use_tile_kernels && tile_class_available(cb / NSUB, ck / NSUB) && Lb.ntiles > 0 &&
                             Lb.maxnp <= TILE_MAX_BRA_PRIMS;
@@ -516,9 +516,14 @@ static int build_plans(unomol_b200 *h) {
                 std::stable_sort(cost.begin(), cost.end(), [](const std::pair<long long, int> &x, const std::pair<long long, int> &y) { return x.first > y.first; });
                 for (auto &ct : cost) if (ct.first > 0) order.push_back(ct.second);
                 plan.ntiles = (int)order.size();
-                // a tile is the work item of a CTA: short lists (small molecules) do not fill the GPU with tiles and stay with the
-                // one-bra-per-CTA kernel (SF6/TZ2P: 17 ms with tiles, 11 ms without)
-                if (plan.ntiles < 4 * 148 && h->use_tile_kernels != 2) plan.use_tile = false;
+                // A work item of a CTA is (tile, ket slice).  Lists with few tiles deal the kets of a tile to several CTAs so that
+                // the launch still offers ~8 CTAs per SM; a slice should keep at least two rounds of TILE_THREADS kets.
+                const int kmax = *std::max_element(kc.begin(), kc.end());
+                const int want = plan.ntiles > 0 ? (8 * 148 + plan.ntiles - 1) / plan.ntiles : 1;
+                plan.tile_slices = std::max(1, std::min(want, kmax / 256));
+                // small molecules (SF6/TZ2P: 17 ms with tiles, 11 ms without, 6 ms with the generic kernel): too little work per
+                // launch for tiles of 8 bras to pay off
+                if (plan.nquartets < 1000000 && h->use_tile_kernels != 2) plan.use_tile = false;
             }
             if (plan.use_tile) {
                 if (cudaMalloc(&plan.d_kc_tile, sizeof(int) * kct.size()) != cudaSuccess) return UNOMOL_E_NOMEM;
@@ -662,7 +667,9 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
             task.tile_maxbp = pl.maxbp;
             task.kslots = pl.kslots;
             task.chunk = 1;
-            const int tmine = work ? pl.ntiles : (pl.ntiles + h->nranks - 1) / h->nranks;
+            task.tile_slices = pl.tile_slices;
+            const int items = pl.ntiles * pl.tile_slices;
+            const int tmine = work ? items : (items + h->nranks - 1) / h->nranks;
             CUDA_TRY(h, launch_tile_class(pl.cb / NSUB, pl.ck / NSUB, task, std::min(tmine, 148 * 8), st));
         } else if (pl.use_reg) {
             CUDA_TRY(h, launch_reg_class(pl.cb / NSUB, pl.ck / NSUB, task, std::min(nmine, 148 * 16), st, h->stage_rows != 0));
@@ -1046,6 +1053,7 @@ static int dump_quartet_hot(unomol_b200 *h, int cb, int ck, int pb, int pk, doub
         task.tile_b = tile_b_of_class(cb / NSUB);
         task.tile_maxbp = Lb.maxnp;
         task.kslots = std::min(6, pl->kslots);
+        task.tile_slices = 1;
         task.chunk = 1;
         task.nspin = 1;
         cudaMemcpyAsync(d_buf, hostbuf, sizeof(hostbuf), cudaMemcpyHostToDevice, h->stream);
@@ -1202,6 +1210,7 @@ int unomol_b200_dump_eris(unomol_b200_t *h, double thresh, unomol_twoint *buf, s
             if (pl->use_tile) {
                 task.tbra = Lb.d_tpairs; task.tile_order = d_order.p; task.ntiles = Lb.ntiles;
                 task.tile_b = tile_b_of_class(cmb.cb / NSUB); task.tile_maxbp = Lb.maxnp; task.kslots = pl->kslots;
+                task.tile_slices = 1;
                 e = launch_tile_class(cmb.cb / NSUB, cmb.ck / NSUB, task, std::min(Lb.ntiles, 148 * 8), h->stream);
             } else {
                 e = launch_reg_class(cmb.cb / NSUB, cmb.ck / NSUB, task, std::min(nb, 148 * 16), h->stream, false);

@@ -76,7 +76,7 @@ struct ComboPlan {                  // one (bra class, ket class) launch
     bool use_tile = false;          // bra-tile / ket-stationary kernel (s/p classes)
     int *d_kc_tile = nullptr;       // ket counts per slot of the bra list's tile order
     int *d_tile_order = nullptr;    // tiles with work, heaviest first
-    int ntiles = 0;
+    int ntiles = 0, tile_slices = 1;
     int kslots = 0, maxbp = 0;
     bool highl = false;             // contains an f or g shell: runtime-L kernel
 };

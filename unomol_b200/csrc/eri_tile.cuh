@@ -139,28 +139,31 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
             p = pos_of(jb);
             jb += gridDim.x;
         }
-        return p < task.ntiles ? task.tile_order[p] : -1;
+        return p < task.ntiles * task.tile_slices ? p : -1;
     };
+    // a work item is (tile, ket slice): item w -> tile_order[w / tile_slices], kets slice, slice + tile_slices, ... in units of T
+    const int nslice = task.tile_slices;
     unsigned phase[2] = {0u, 0u};
     int s = 0;
     if (tid == 0) {
-        const int t0 = advance();
-        s_next = t0;
-        if (t0 >= 0) issue(t0, 0);
+        const int w0 = advance();
+        s_next = w0;
+        if (w0 >= 0) issue(task.tile_order[w0 / nslice], 0);
     }
     __syncthreads();
-    int ti = s_next;
+    int wi = s_next;
     __syncthreads();
     unsigned long long n_quart = 0, n_primq = 0, n_cand = 0;
     const double cut2 = task.prim_cut * task.prim_cut;
     const int n = task.nbf;
 
-    while (ti >= 0) {
+    while (wi >= 0) {
         if (tid == 0) {
-            const int t1 = advance();
-            s_next = t1;
-            if (t1 >= 0) issue(t1, s ^ 1);     // prefetch the next tile while this one is computed
+            const int w1 = advance();
+            s_next = w1;
+            if (w1 >= 0) issue(task.tile_order[w1 / nslice], s ^ 1);     // prefetch the next tile while this one is computed
         }
+        const int ti = task.tile_order[wi / nslice], slice = wi % nslice;
         mbar_wait(&bars[s], phase[s]);
         phase[s] ^= 1u;
         const ShellPair *bras = stage_pairs(s);
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
         const int oa = bras[0].offa, sha = bras[0].sha;
         for (int e = 0; e < nb * NAB; ++e) sjab[e * T + tid] = 0.0;
 
-        for (int ki = tid; ki < kmax; ki += T) {
+        for (int ki = slice * T + tid; ki < kmax; ki += T * nslice) {
             const KetHot ket = load_streaming(task.ket_hot + ki);   // 32 B per thread, coalesced
             const int oc = ket.offa, od = ket.offb, nkp = ket.nprim;
             // ket primitives: into this thread's shared-memory slots when they fit, else read from global memory per bra
@@ -520,7 +523,7 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
         }
         // ---- J[a,b_j]: reduce the per-thread partials of this tile (one red per element)
         __syncthreads();
-        const int tnext = s_next;   // written by thread 0 at the top of this iteration
+        const int wnext = s_next;   // written by thread 0 at the top of this iteration
         if (!task.out) {
             const int nel = nb * NAB;
             for (int e = warp; e < nel; e += T / 32) {
@@ -536,7 +539,7 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
             }
         }
         __syncthreads();   // everyone is done with stage[s] and the partials before they are overwritten
-        ti = tnext;
+        wi = wnext;
         s ^= 1;
     }
     if (task.counters) {

@@ -67,6 +67,8 @@ struct ClassTask {
     const ShellPair *tbra;    // tile-ordered copy of the bra list, TILE_MAXB slots per tile (padding slots have nprim = 0)
     const int *tile_order;    // tile ids of this launch, heaviest first
     int ntiles;               // entries of tile_order
+    int tile_slices;          // work items per tile: the kets of a tile are dealt to this many CTAs in interleaved chunks of
+                              // TILE_THREADS (lists with few tiles would not fill the GPU otherwise); >= 1
     int tile_b;               // bras per tile of this bra class (<= TILE_MAXB)
     int tile_maxbp;           // largest primitive-pair count of a bra (stride of the staged primitive slots)
     int kslots;               // ket primitive pairs a thread keeps in its shared-memory slots (kets with more read global memory)
