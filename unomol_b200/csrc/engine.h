@@ -85,6 +85,7 @@ struct ComboPlan {                  // one (bra class, ket class) launch
 
 struct unomol_b200 {
     int device = 0, rank = 0, nranks = 1, start_shell = 0;
+    int nsm = 148;                  // multiprocessors of the device (grid sizing)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     static constexpr int NAUX = 4;            // class launches of one build are spread over these streams
@@ -108,6 +109,15 @@ struct unomol_b200 {
     std::vector<ub200::PrimPair> h_prims;
     ub200::PrimPair *d_prims = nullptr;
     std::vector<int> pair_cls, pair_pos;      // per canonical shell pair id: class and position (-1 = pruned)
+    // incremental geometry updates (set_geometry with few moved centres: the polarisation-potential scan of the reference,
+    // RHF.hpp:292-388, moves ONE centre per grid point): pairs without a moved shell keep their records, primitive pairs
+    // and Schwarz bounds; the moved shells' pairs are rebuilt on the host into a reserved tail of d_prims
+    bool bucketed = false;
+    int nblock = 1;
+    int incremental = 1;                      // option "incremental_geometry"
+    long long n_prims_full = 0, d_prims_cap = 0;   // primitive pairs written by the last full build / capacity of d_prims
+    std::vector<int> inc_shells;              // moved shells the reserved tail was sized for
+    std::vector<double> xyz_built;            // geometry of the current tables
     std::vector<ub200::ComboPlan> plans;
     // density / Fock work buffers (device)
     double *d_Ppacked[2] = {nullptr, nullptr}, *d_Gpacked[2] = {nullptr, nullptr};

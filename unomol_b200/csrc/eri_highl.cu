@@ -1,6 +1,7 @@
 // unomol_b200/csrc/eri_highl.cu -- launcher of the runtime-L kernel for quartets with f/g shells (see eri_highl.cuh).
 #include <cuda_runtime.h>
 #include "eri_highl.cuh"
+#include <atomic>
 #include "engine.h"
 
 namespace ub200 {
@@ -88,10 +89,10 @@ __global__ void __launch_bounds__(HL_THREADS) eri_highl_kernel(const ClassTask t
 }
 
 cudaError_t launch_highl(const ClassTask &task, const HighLArgs &hl, int mode, int grid, cudaStream_t stream) {
-    static bool attr_done_dev[64] = {};   // per device: one process may drive several GPUs
+    static std::atomic<bool> attr_done_dev[64];   // per device: one process may drive several GPUs
     int attr_dev = 0;
     cudaGetDevice(&attr_dev);
-    bool &attr_done = attr_done_dev[attr_dev & 63];
+    std::atomic<bool> &attr_done = attr_done_dev[attr_dev & 63];
     if (!attr_done) {
         cudaFuncSetAttribute(eri_highl_kernel<MODE_DIGEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HL_SMEM_BYTES);
         cudaFuncSetAttribute(eri_highl_kernel<MODE_DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HL_SMEM_BYTES);

@@ -1,6 +1,7 @@
 // unomol_b200/csrc/eri_reg_classes.cu -- instantiations + dispatcher of the register-resident class kernels
 // (eri_reg.cuh) for the quartet classes with at most 32 contracted [e0|f0] intermediates.
 #include "eri_reg.cuh"
+#include <atomic>
 #include "engine.h"
 
 namespace ub200 {
@@ -13,10 +14,10 @@ static cudaError_t launch_reg(const ClassTask &task, int grid, cudaStream_t stre
     // stage the bra's rows of P in shared memory when they fit (RHF only): see eri_reg.cuh
     const size_t row_bytes = sizeof(double) * (size_t)(C::NA + C::NB) * task.nbf;
     if (allow_rows && task.nspin == 1 && row_bytes <= REG_ROWS_MAX_BYTES) {
-        static bool attr_done_dev[64] = {};   // per device: one process may drive several GPUs
+        static std::atomic<bool> attr_done_dev[64];   // per device: one process may drive several GPUs
         int attr_dev = 0;
         cudaGetDevice(&attr_dev);
-        bool &attr_done = attr_done_dev[attr_dev & 63];
+        std::atomic<bool> &attr_done = attr_done_dev[attr_dev & 63];
         if (!attr_done) {
             cudaFuncSetAttribute(eri_reg_kernel<LA, LB, LC, LD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REG_ROWS_MAX_BYTES);
             attr_done = true;

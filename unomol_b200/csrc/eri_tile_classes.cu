@@ -1,15 +1,16 @@
 // unomol_b200/csrc/eri_tile_classes.cu -- instantiations + dispatcher of the bra-tile / ket-stationary kernels (eri_tile.cuh).
 #include "eri_tile.cuh"
+#include <atomic>
 #include "engine.h"
 
 namespace ub200 {
 
 template <int LA, int LB, int LC, int LD, int NSPIN>
 static cudaError_t launch_tile_inst(const ClassTask &task, int grid, size_t smem, cudaStream_t stream) {
-    static size_t attr_smem_dev[64] = {};   // per device: largest dynamic shared memory size enabled so far
+    static std::atomic<size_t> attr_smem_dev[64];   // per device: largest dynamic shared memory size enabled so far
     int dev = 0;
     cudaGetDevice(&dev);
-    size_t &have = attr_smem_dev[dev & 63];
+    std::atomic<size_t> &have = attr_smem_dev[dev & 63];
     if (smem > have) {
         cudaError_t e = cudaFuncSetAttribute(eri_tile_kernel<LA, LB, LC, LD, NSPIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

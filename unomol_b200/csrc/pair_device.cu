@@ -38,6 +38,10 @@ __global__ void pair_kernel(DevBasis B, long long npairs, int *__restrict__ coun
     const long long pid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (pid >= npairs) return;
     if (MODE == 1 && count[pid] == 0) return;
+    // the fill pass must write exactly the count of the counting pass (the prune test is re-evaluated in a different template
+    // instantiation; should code generation ever flip a borderline primitive, extra survivors are dropped here and a
+    // shortfall shows up as sp.nprim < count, which the host checks)
+    const int nmax = (MODE == 1) ? count[pid] : 0x7fffffff;
     int i, j;
     pair_decode(pid, i, j);
     int a = i, b = j;   // first shell = higher l (reference swap, TwoElectronInts.cpp:563-580)
@@ -64,6 +68,7 @@ __global__ void pair_kernel(DevBasis B, long long npairs, int *__restrict__ coun
             const double p = axp + bxp, ip = 1.0 / p;
             const double u = exp(-axp * bxp * ab2 * ip) * ip;
             if (SR_TERM * u * B.umax / sqrt(p) * 1.0000001 < B.prim_cut) continue;
+            if (n >= nmax) continue;
             if (MODE == 1) {
                 PrimPair pp;
                 pp.u = u; pp.p = p; pp.ip = ip;
@@ -113,6 +118,8 @@ int build_pair_tables_device(unomol_b200 *h, double prune_cut, std::vector<Shell
     const long long np = (long long)ns * (ns + 1) / 2;
     cudaStream_t st = h->stream;
     int rc = UNOMOL_OK;
+    // offsets, slots and the scan length are 32-bit: refuse instead of overflowing (2^31 shell pairs = 65 000 shells)
+    if (np > 0x7fffffffLL) return UNOMOL_E_UNSUPPORTED;
     std::vector<double> amin(ns);
     double umax = 0.0;
     for (int s = 0; s < ns; ++s) {
@@ -164,6 +171,7 @@ int build_pair_tables_device(unomol_b200 *h, double prune_cut, std::vector<Shell
     PD_TRY(cudaMemcpyAsync(&last_slot, d_slot + np - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     PD_TRY(cudaStreamSynchronize(st));
     nprim = (long long)last_off + last_count;
+    if (last_off < 0 || nprim > 0x7fffffffLL) { rc = UNOMOL_E_UNSUPPORTED; goto done; }   // exclusive scan wrapped
     nkept = (long long)last_slot + last_flag;
     if (nprim > 0) {
         PD_TRY(cudaMalloc(&d_prims, sizeof(PrimPair) * nprim));

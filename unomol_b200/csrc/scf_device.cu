@@ -115,21 +115,35 @@ int scf_ensure(unomol_b200 *h) {
     if (cublasCreate(&cb) != CUBLAS_STATUS_SUCCESS) return UNOMOL_E_CUDA;
     cusolverDnSetStream(cs, h->stream);
     cublasSetStream(cb, h->stream);
+    // the handles are published only after EVERY allocation succeeded: a later call must not find h->cusolver set next to
+    // null work buffers.  On failure everything allocated so far is released.
+    const size_t nn = (size_t)n * n;
+    int lwork = 0;
+    bool ok = cudaMalloc(&h->d_X, sizeof(double) * nn) == cudaSuccess && cudaMalloc(&h->d_F, sizeof(double) * nn) == cudaSuccess &&
+              cudaMalloc(&h->d_W, sizeof(double) * nn) == cudaSuccess && cudaMalloc(&h->d_T, sizeof(double) * nn) == cudaSuccess &&
+              cudaMalloc(&h->d_evals, sizeof(double) * n) == cudaSuccess && cudaMalloc(&h->d_info, sizeof(int) * 2) == cudaSuccess;
+    int rc = ok ? UNOMOL_OK : UNOMOL_E_NOMEM;
+    if (ok && cusolverDnDsyevd_bufferSize(cs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, h->d_W, n, h->d_evals, &lwork) !=
+                  CUSOLVER_STATUS_SUCCESS) {
+        ok = false;
+        rc = UNOMOL_E_CUDA;
+    }
+    if (ok && cudaMalloc(&h->d_work, sizeof(double) * (lwork > 0 ? lwork : 1)) != cudaSuccess) {
+        ok = false;
+        rc = UNOMOL_E_NOMEM;
+    }
+    if (!ok) {
+        cudaGetLastError();
+        cudaFree(h->d_X); cudaFree(h->d_F); cudaFree(h->d_W); cudaFree(h->d_T); cudaFree(h->d_evals); cudaFree(h->d_info); cudaFree(h->d_work);
+        h->d_X = h->d_F = h->d_W = h->d_T = h->d_evals = h->d_work = nullptr;
+        h->d_info = nullptr;
+        cusolverDnDestroy(cs);
+        cublasDestroy(cb);
+        return rc;
+    }
+    h->lwork = lwork;
     h->cusolver = cs;
     h->cublas = cb;
-    const size_t nn = (size_t)n * n;
-    if (cudaMalloc(&h->d_X, sizeof(double) * nn) != cudaSuccess) return UNOMOL_E_NOMEM;
-    if (cudaMalloc(&h->d_F, sizeof(double) * nn) != cudaSuccess) return UNOMOL_E_NOMEM;
-    if (cudaMalloc(&h->d_W, sizeof(double) * nn) != cudaSuccess) return UNOMOL_E_NOMEM;
-    if (cudaMalloc(&h->d_T, sizeof(double) * nn) != cudaSuccess) return UNOMOL_E_NOMEM;
-    if (cudaMalloc(&h->d_evals, sizeof(double) * n) != cudaSuccess) return UNOMOL_E_NOMEM;
-    if (cudaMalloc(&h->d_info, sizeof(int) * 2) != cudaSuccess) return UNOMOL_E_NOMEM;
-    int lwork = 0;
-    if (cusolverDnDsyevd_bufferSize(cs, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, h->d_W, n, h->d_evals,
-                                    &lwork) != CUSOLVER_STATUS_SUCCESS)
-        return UNOMOL_E_CUDA;
-    h->lwork = lwork;
-    if (cudaMalloc(&h->d_work, sizeof(double) * (lwork > 0 ? lwork : 1)) != cudaSuccess) return UNOMOL_E_NOMEM;
     return UNOMOL_OK;
 }
 

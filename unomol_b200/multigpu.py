@@ -100,7 +100,7 @@ class NcclComm:
         if dist.get_rank() == 0:
             if self.lib.ncclGetUniqueId(ctypes.byref(uid)) != 0:
                 raise RuntimeError("ncclGetUniqueId failed")
-            box[0] = bytes(uid.internal)
+            box[0] = ctypes.string_at(ctypes.byref(uid), 128)      # all 128 bytes (the id contains NULs)
         dist.broadcast_object_list(box, src=0)
         ctypes.memmove(ctypes.byref(uid), box[0], 128)
         self.comm = ctypes.c_void_p()
