@@ -286,6 +286,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: unomol_b200 has no CPU fallback")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # ONE density for all ranks: the superposition density comes out of a monomer SCF converged to 1e-10, which every rank
+        # would otherwise run for itself (rank-to-rank differences of that size showed up as 8e-11 in the N-rank G)
+        tP = torch.from_numpy(Pn).cuda()
+        dist.broadcast(tP, src=0)
+        Pn = np.ascontiguousarray(tP.cpu().numpy())
 
     def sync_all():
         if world > 1:
@@ -469,7 +474,7 @@ def main():
     # ------------------------------------------------------------------ side measurements (configs 3-5 of BASELINE.json)
     def side_build(name, nspin=1, nsteps=3, opts=()):
         """ms per Fock build (all-reduce included at N > 1) and model-flop rate of another workload, same rank layout"""
-        b2, P2, _, _, d2 = load_workload(name, want_gpu_density=False)
+        b2, P2, _, _, d2 = load_workload(name, want_gpu_density=False)     # seeded synthetic P: identical on every rank
         h2, _ = make_handle(b2, opts)
         sp, _, _ = h2.device_buffers()
         s2 = torch.cuda.ExternalStream(sp, device=torch.device("cuda", local))
