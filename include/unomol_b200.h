@@ -180,6 +180,14 @@ int unomol_b200_scf_iterate_rhf_begin(unomol_b200_t *h, int damp);
 int unomol_b200_scf_iterate_rhf_finish(unomol_b200_t *h, int nocc, double *e_elec, double *pdiff);
 int unomol_b200_scf_fetch(unomol_b200_t *h, double *P, double *evals, double *C);
 
+/* Device-resident UHF iteration = UnRestrictedHartreeFock::scf_converger + update (reference UHF.hpp:690-740, 101-134):
+ * both spin densities, both G, F and H stay on the GPU.  damp != 0 first mixes BOTH densities with their predecessors;
+ * then G_alpha, G_beta = J[PA+PB] - K[P_sigma], *e_elec = tr(PA H) + tr(PB H) + (tr(PA GA) + tr(PB GB))/2, and per spin
+ * F = H + G_sigma -> X^T F X -> eigen-decomposition -> P_sigma; *pdiff = |dPA|/nbf + |dPB|/nbf (SymmPackDiffNorm, summed). */
+int unomol_b200_scf_load_uhf(unomol_b200_t *h, const double *H, const double *PA, const double *PB);
+int unomol_b200_scf_iterate_uhf(unomol_b200_t *h, int nocc_a, int nocc_b, int damp, double *e_elec, double *pdiff);
+int unomol_b200_scf_fetch_uhf(unomol_b200_t *h, double *PA, double *PB, double *evals_a, double *evals_b);
+
 /* Bench support (no reference counterpart).
  * sample_quartets: draws nsample shell quartets uniformly from the screened canonical quartet list the Fock
  * build evaluates (all ranks), deterministic in seed; shells[4*q..] = (ish,jsh,ksh,lsh).  *ntotal receives the

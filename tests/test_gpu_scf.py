@@ -86,6 +86,49 @@ def test_host_side_scf_bookkeeping_gives_the_same_energy(tmp_path):
     assert abs(e1 - SHORT["631.nh3"][1]) < E_TOL and abs(e0 - SHORT["631.nh3"][0]) < E_TOL
 
 
+def test_uhf_host_side_bookkeeping_gives_the_same_energy(tmp_path):
+    """UHF: UNOMOL_HOST_SCF=1 (P/G of both spins cross the bus, traces and mixing on the host like the reference's update())
+    against the default device-resident iteration (unomol_b200_scf_iterate_uhf), both against the reference run"""
+    e0h, e1h, _, _ = run_scf("dh95.co2.cation", tmp_path, env={"UNOMOL_HOST_SCF": "1"})
+    e0d, e1d, _, _ = run_scf("dh95.co2.cation", tmp_path)
+    ref = RUNS["dh95.co2.cation"]
+    assert abs(e1h - ref["e_final"]) < E_TOL and abs(e1d - ref["e_final"]) < E_TOL, (e1h, e1d, ref["e_final"])
+    assert abs(e0h - ref["e_init"]) < E_TOL and abs(e0d - ref["e_init"]) < E_TOL
+
+
+def test_device_resident_uhf_iteration_matches_host_algebra():
+    """unomol_b200_scf_iterate_uhf against the same iteration assembled on the host from fock_uhf + scf_diag, with and without mixing"""
+    import numpy as np
+    from unomol_b200 import capi
+    from unomol_b200.basis import Basis
+    g = np.load(os.path.join(GOLDEN, "g_fg_h2o.npz"))     # water (C2v): no degenerate orbitals, so every occupation gives a unique
+    b = Basis.from_patin(golden_input("fg.h2o"))         # density (with CO2 a cut through a pi pair leaves it to the eigensolver)
+    S, H = g["S"], g["H"]
+    n = b.nbf
+    na, nb = b.nelec // 2 + 1, b.nelec // 2 - 1
+    tri = np.tril_indices(n)
+    w = np.where(tri[0] == tri[1], 1.0, 2.0)
+    hd = capi.Handle(b); hd.set_option("schwarz_tau", 0.0); hd.scf_set_overlap(S)
+    hh = capi.Handle(b); hh.set_option("schwarz_tau", 0.0); hh.scf_set_overlap(S)
+    _, PA = hh.scf_diag(H, na); _, PB = hh.scf_diag(H, nb)
+    hd.scf_load_uhf(H, PA, PB)
+    PAo, PBo = PA.copy(), PB.copy()
+    for it, damp in enumerate([False, True, False, True]):
+        if damp:
+            PA = 0.5 * (PA + PAo); PB = 0.5 * (PB + PBo)
+        GA, GB = hh.fock_uhf(PA, PB)
+        e_ref = float(np.sum(w * ((PA + PB) * H + 0.5 * (PA * GA + PB * GB))))
+        PAo, PBo = PA.copy(), PB.copy()
+        eva, PA = hh.scf_diag(H + GA, na); evb, PB = hh.scf_diag(H + GB, nb)
+        pd_ref = float(np.sqrt(np.sum(w * (PA - PAo) ** 2)) / n + np.sqrt(np.sum(w * (PB - PBo) ** 2)) / n)
+        e, pd = hd.scf_iterate_uhf(na, nb, damp)
+        assert abs(e - e_ref) < 1e-9 * abs(e_ref), (it, e, e_ref)
+        assert abs(pd - pd_ref) < 1e-9, (it, pd, pd_ref)
+    PAd, PBd, ead, ebd = hd.scf_fetch_uhf()
+    assert np.max(np.abs(PAd - PA)) < 1e-9 and np.max(np.abs(PBd - PB)) < 1e-9
+    assert np.max(np.abs(ead - eva)) < 1e-9 and np.max(np.abs(ebd - evb)) < 1e-9
+
+
 def test_device_resident_iteration_matches_host_algebra():
     """unomol_b200_scf_iterate_rhf against the same iteration assembled on the host from fock_rhf + scf_diag, with and
     without the mixing step, and in its begin/finish form"""

@@ -54,6 +54,7 @@ EXPORTS = [
     "unomol_b200_eri_quartet", "unomol_b200_dump_eris", "unomol_b200_schwarz", "unomol_b200_stats",
     "unomol_b200_attach_nccl", "unomol_b200_steal_export", "unomol_b200_steal_import", "unomol_b200_steal_share", "unomol_b200_device_buffers", "unomol_b200_scf_set_overlap", "unomol_b200_scf_diag",
     "unomol_b200_scf_load", "unomol_b200_scf_iterate_rhf", "unomol_b200_scf_iterate_rhf_begin", "unomol_b200_scf_iterate_rhf_finish", "unomol_b200_scf_fetch",
+    "unomol_b200_scf_load_uhf", "unomol_b200_scf_iterate_uhf", "unomol_b200_scf_fetch_uhf",
     "unomol_b200_sample_quartets", "unomol_b200_fp64_peak", "unomol_b200_model_flops", "unomol_b200_strerror", "unomol_b200_version",
 ]
 
@@ -87,6 +88,9 @@ def _load():
     L.unomol_b200_scf_iterate_rhf_begin.argtypes = [_P, _I]
     L.unomol_b200_scf_iterate_rhf_finish.argtypes = [_P, _I, _pd, _pd]
     L.unomol_b200_scf_fetch.argtypes = [_P, _pd, _pd, _pd]
+    L.unomol_b200_scf_load_uhf.argtypes = [_P, _pd, _pd, _pd]
+    L.unomol_b200_scf_iterate_uhf.argtypes = [_P, _I, _I, _I, _pd, _pd]
+    L.unomol_b200_scf_fetch_uhf.argtypes = [_P, _pd, _pd, _pd, _pd]
     L.unomol_b200_sample_quartets.argtypes = [_P, ctypes.c_longlong, ctypes.c_ulonglong, _pi, ctypes.POINTER(ctypes.c_longlong)]
     L.unomol_b200_fp64_peak.argtypes = [_I, _pd]
     L.unomol_b200_model_flops.restype = _D; L.unomol_b200_model_flops.argtypes = [_I, _I, _I, _I]
@@ -244,6 +248,20 @@ class Handle:
         C = np.zeros((self.nbf, self.nbf)) if want_c else None
         _chk(lib.unomol_b200_scf_fetch(self.h, _dp(P), _dp(ev), _dp(C) if want_c else None), "scf_fetch")
         return (P, ev, C) if want_c else (P, ev)
+
+    def scf_load_uhf(self, H, PA, PB):
+        _chk(lib.unomol_b200_scf_load_uhf(self.h, _dp(np.ascontiguousarray(H, float)), _dp(np.ascontiguousarray(PA, float)),
+                                          _dp(np.ascontiguousarray(PB, float))), "scf_load_uhf")
+
+    def scf_iterate_uhf(self, nocc_a, nocc_b, damp=False):
+        e = _D(0.0); pd = _D(0.0)
+        _chk(lib.unomol_b200_scf_iterate_uhf(self.h, nocc_a, nocc_b, int(damp), ctypes.byref(e), ctypes.byref(pd)), "scf_iterate_uhf")
+        return e.value, pd.value
+
+    def scf_fetch_uhf(self):
+        PA = np.zeros(self.no2); PB = np.zeros(self.no2); ea = np.zeros(self.nbf); eb = np.zeros(self.nbf)
+        _chk(lib.unomol_b200_scf_fetch_uhf(self.h, _dp(PA), _dp(PB), _dp(ea), _dp(eb)), "scf_fetch_uhf")
+        return PA, PB, ea, eb
 
     def scf_diag(self, F, nocc, want_c=False):
         F = np.ascontiguousarray(F, float)

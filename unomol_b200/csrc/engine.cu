@@ -13,7 +13,9 @@
 #include <array>
 #include <atomic>
 #include <thread>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
@@ -171,6 +173,7 @@ static void free_pairs(unomol_b200 *h) {
         h->cls[c].d_pairs = nullptr;
         h->cls[c].d_hot = nullptr;
         h->cls[c].d_tpairs = nullptr;
+        h->cls[c].cap_pairs = h->cls[c].cap_tp = 0;
         h->cls[c].slot_pos.clear();
         h->cls[c].pos_slot.clear();
         h->cls[c].ntiles = 0;
@@ -179,13 +182,7 @@ static void free_pairs(unomol_b200 *h) {
     }
     if (h->d_prims) cudaFree(h->d_prims);
     h->d_prims = nullptr;
-    for (auto &p : h->plans) {
-        if (p.d_ket_count) cudaFree(p.d_ket_count);
-        if (p.d_ket_prefix) cudaFree(p.d_ket_prefix);
-        if (p.d_kc_tile) cudaFree(p.d_kc_tile);
-        if (p.d_tile_order) cudaFree(p.d_tile_order);
-    }
-    h->plans.clear();
+    h->plans.clear();          // their arrays live in d_plan_pool
     h->pairs_ready = false;
 }
 
@@ -255,40 +252,42 @@ static bool make_pair_host(const HostBasis &B, int i, int j, const std::vector<d
     return true;
 }
 
-// Upload one pair list (already sorted by Q descending): full records, hot mirror, tile order, position maps.
+// Upload one pair list (already sorted by Q descending): full records, hot mirror, tile order, position maps.  Device buffers
+// only grow; the host mirrors (hot_host, tp_host) persist so that the copies need no synchronisation here.
 static int finalize_list(unomol_b200 *h, int c) {
     PairClassList &L = h->cls[c];
     L.n = (int)L.pairs.size();
-    if (L.d_pairs) cudaFree(L.d_pairs);
-    if (L.d_hot) cudaFree(L.d_hot);
-    if (L.d_tpairs) cudaFree(L.d_tpairs);
-    L.d_pairs = nullptr; L.d_hot = nullptr; L.d_tpairs = nullptr;
     L.slot_pos.clear(); L.pos_slot.clear(); L.ntiles = 0; L.maxnp = 0;
     if (!L.n) return UNOMOL_OK;
-    CUDA_TRY(h, cudaMalloc(&L.d_pairs, sizeof(ShellPair) * L.n));
+    if ((size_t)L.n > L.cap_pairs) {
+        if (L.d_pairs) cudaFree(L.d_pairs);
+        if (L.d_hot) cudaFree(L.d_hot);
+        L.d_pairs = nullptr; L.d_hot = nullptr;
+        L.cap_pairs = (size_t)L.n + (size_t)L.n / 8 + 64;
+        CUDA_TRY(h, cudaMalloc(&L.d_pairs, sizeof(ShellPair) * L.cap_pairs));
+        CUDA_TRY(h, cudaMalloc(&L.d_hot, sizeof(KetHot) * L.cap_pairs));
+    }
     CUDA_TRY(h, cudaMemcpyAsync(L.d_pairs, L.pairs.data(), sizeof(ShellPair) * L.n, cudaMemcpyHostToDevice, h->stream));
-    {
-        std::vector<KetHot> hot(L.n);
-        for (int i = 0; i < L.n; ++i) {
-            const ShellPair &sp = L.pairs[i];
-            hot[i] = KetHot{sp.offa, sp.offb, sp.prim_off, sp.nprim, sp.sha, sp.shb, sp.pairid, 0};
-        }
-        CUDA_TRY(h, cudaMalloc(&L.d_hot, sizeof(KetHot) * L.n));
-        CUDA_TRY(h, cudaMemcpyAsync(L.d_hot, hot.data(), sizeof(KetHot) * L.n, cudaMemcpyHostToDevice, h->stream));
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // `hot` leaves scope
-    }
+    L.hot_host.resize(L.n);
     for (int i = 0; i < L.n; ++i) {
-        h->pair_cls[L.pairs[i].pairid] = c;
-        h->pair_pos[L.pairs[i].pairid] = i;
-        L.maxnp = std::max(L.maxnp, L.pairs[i].nprim);
+        const ShellPair &sp = L.pairs[i];
+        L.hot_host[i] = KetHot{sp.offa, sp.offb, sp.prim_off, sp.nprim, sp.sha, sp.shb, sp.pairid, 0};
+        h->pair_cls[sp.pairid] = c;
+        h->pair_pos[sp.pairid] = i;
+        L.maxnp = std::max(L.maxnp, sp.nprim);
     }
+    CUDA_TRY(h, cudaMemcpyAsync(L.d_hot, L.hot_host.data(), sizeof(KetHot) * L.n, cudaMemcpyHostToDevice, h->stream));
     // tile order for eri_tile.cuh: by first shell, Q descending inside a shell (= list position ascending)
     if (c / NSUB < NSPDCLASS && tile_class_available(c / NSUB, 0)) {
         const int tb = tile_b_of_class(c / NSUB);
-        std::vector<int> ord(L.n);
-        std::iota(ord.begin(), ord.end(), 0);
-        std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return L.pairs[x].sha < L.pairs[y].sha; });
+        // positions ordered by first shell, list order (= Q descending) inside a shell: counting sort, linear
+        const int nsh = h->basis.nshell;
+        std::vector<int> start(nsh + 1, 0), ord(L.n);
+        for (int i = 0; i < L.n; ++i) ++start[L.pairs[i].sha + 1];
+        for (int sh = 0; sh < nsh; ++sh) start[sh + 1] += start[sh];
+        for (int i = 0; i < L.n; ++i) ord[start[L.pairs[i].sha]++] = i;
         L.pos_slot.assign(L.n, -1);
+        L.slot_pos.reserve(((size_t)L.n / tb + nsh) * TILE_SLOTS);
         int fill = 0, cur_sh = -1;
         for (int o : ord) {
             if (L.pairs[o].sha != cur_sh || fill == tb) {
@@ -301,13 +300,18 @@ static int finalize_list(unomol_b200 *h, int c) {
             L.pos_slot[o] = slot;
         }
         L.ntiles = (int)L.slot_pos.size() / TILE_SLOTS;
-        std::vector<ShellPair> tp(L.slot_pos.size());
-        for (size_t sl = 0; sl < tp.size(); ++sl) {
-            if (L.slot_pos[sl] >= 0) tp[sl] = L.pairs[L.slot_pos[sl]];
-            else { memset(&tp[sl], 0, sizeof(ShellPair)); tp[sl].sha = tp[sl].shb = -1; tp[sl].pairid = -1; }
+        L.tp_host.resize(L.slot_pos.size());
+        for (size_t sl = 0; sl < L.tp_host.size(); ++sl) {
+            if (L.slot_pos[sl] >= 0) L.tp_host[sl] = L.pairs[L.slot_pos[sl]];
+            else { memset(&L.tp_host[sl], 0, sizeof(ShellPair)); L.tp_host[sl].sha = L.tp_host[sl].shb = -1; L.tp_host[sl].pairid = -1; }
         }
-        CUDA_TRY(h, cudaMalloc(&L.d_tpairs, sizeof(ShellPair) * tp.size()));
-        CUDA_TRY(h, cudaMemcpy(L.d_tpairs, tp.data(), sizeof(ShellPair) * tp.size(), cudaMemcpyHostToDevice));
+        if (L.tp_host.size() > L.cap_tp) {
+            if (L.d_tpairs) cudaFree(L.d_tpairs);
+            L.d_tpairs = nullptr;
+            L.cap_tp = L.tp_host.size() + L.tp_host.size() / 8 + 64 * TILE_SLOTS;
+            CUDA_TRY(h, cudaMalloc(&L.d_tpairs, sizeof(ShellPair) * L.cap_tp));
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(L.d_tpairs, L.tp_host.data(), sizeof(ShellPair) * L.tp_host.size(), cudaMemcpyHostToDevice, h->stream));
     }
     return UNOMOL_OK;
 }
@@ -316,10 +320,17 @@ static int finalize_list(unomol_b200 *h, int c) {
 static int schwarz_of_pairs(unomol_b200 *h, int cls, std::vector<ShellPair> &pairs) {
     const int n = (int)pairs.size();
     if (!n) return UNOMOL_OK;
-    DevBuf<ShellPair> d_p;
-    DevBuf<int2> d_tl;
-    DevBuf<double> d_q;
-    if (!d_p.alloc(n) || !d_tl.alloc(n) || !d_q.alloc(n)) return UNOMOL_E_NOMEM;
+    // grow-only scratch: [ShellPair n][int2 n][double n]
+    const size_t need = (sizeof(ShellPair) + sizeof(int2) + sizeof(double)) * (size_t)n + 64;
+    if (need > h->schwarz_scratch_cap) {
+        if (h->d_schwarz_scratch) cudaFree(h->d_schwarz_scratch);
+        h->d_schwarz_scratch = nullptr;
+        h->schwarz_scratch_cap = need + need / 4;
+        if (cudaMalloc(&h->d_schwarz_scratch, h->schwarz_scratch_cap) != cudaSuccess) { h->schwarz_scratch_cap = 0; return UNOMOL_E_NOMEM; }
+    }
+    struct { ShellPair *p; } d_p{reinterpret_cast<ShellPair *>(h->d_schwarz_scratch)};
+    struct { int2 *p; } d_tl{reinterpret_cast<int2 *>(h->d_schwarz_scratch + sizeof(ShellPair) * (size_t)n)};
+    struct { double *p; } d_q{reinterpret_cast<double *>(h->d_schwarz_scratch + (sizeof(ShellPair) + sizeof(int2)) * (size_t)n)};
     std::vector<int2> tl(n);
     for (int i = 0; i < n; ++i) tl[i] = make_int2(i, i);
     CUDA_TRY(h, cudaMemcpyAsync(d_p.p, pairs.data(), sizeof(ShellPair) * n, cudaMemcpyHostToDevice, h->stream));
@@ -469,6 +480,9 @@ static int build_pairs(unomol_b200 *h) {
 // in d_prims and their bounds.  The plans (Schwarz prefixes, tile orders) are rebuilt.
 static int update_pairs_incremental(unomol_b200 *h, const std::vector<int> &moved) {
     cudaEventRecord(h->ev2, h->stream);
+    static const bool trace = std::getenv("UNOMOL_TIME_UPDATE") != nullptr;
+    auto tnow = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = tnow(), t1 = t0, t2 = t0, t3 = t0, t4 = t0;
     const HostBasis &B = h->basis;
     const int ns = B.nshell;
     std::vector<char> mark(ns, 0);
@@ -515,10 +529,12 @@ static int update_pairs_incremental(unomol_b200 *h, const std::vector<int> &move
     if (!dprims.empty())
         CUDA_TRY(h, cudaMemcpyAsync(h->d_prims + h->n_prims_full, dprims.data(), sizeof(PrimPair) * dprims.size(), cudaMemcpyHostToDevice,
                                     h->stream));
+    t1 = tnow();
     for (int cls = 0; cls < NPAIRCLASS; ++cls) {
         int rc = schwarz_of_pairs(h, cls, dyn[cls]);
         if (rc) return rc;
     }
+    t2 = tnow();
     // drop the old records of the moved shells, merge the new ones in by Q
     std::vector<char> touched(NGROUP, 0);
     for (int c = 0; c < NGROUP; ++c) {
@@ -529,6 +545,8 @@ static int update_pairs_incremental(unomol_b200 *h, const std::vector<int> &move
         P.erase(std::remove_if(P.begin(), P.end(), [&](const ShellPair &sp) { return mark[sp.sha] || mark[sp.shb]; }), P.end());
         if (P.size() != before) touched[c] = 1;
     }
+    std::vector<size_t> nstatic(NGROUP);
+    for (int c = 0; c < NGROUP; ++c) nstatic[c] = h->cls[c].pairs.size();
     for (int cls = 0; cls < NPAIRCLASS; ++cls)
         for (auto &sp : dyn[cls]) {
             const int c = group_of_pair(h, sp, cls);
@@ -536,10 +554,13 @@ static int update_pairs_incremental(unomol_b200 *h, const std::vector<int> &move
             touched[c] = 1;
         }
     long long nkept = 0, nprim = 0;
+    const auto byQ = [](const ShellPair &x, const ShellPair &y) { return x.Q > y.Q; };
     for (int c = 0; c < NGROUP; ++c) {
         if (touched[c]) {
             auto &P = h->cls[c].pairs;
-            std::stable_sort(P.begin(), P.end(), [](const ShellPair &x, const ShellPair &y) { return x.Q > y.Q; });
+            // the kept records are still sorted: sort the few new ones and merge (linear)
+            std::stable_sort(P.begin() + nstatic[c], P.end(), byQ);
+            std::inplace_merge(P.begin(), P.begin() + nstatic[c], P.end(), byQ);
             int rc = finalize_list(h, c);
             if (rc) return rc;
         }
@@ -549,8 +570,13 @@ static int update_pairs_incremental(unomol_b200 *h, const std::vector<int> &move
     h->stats.n_pairs_kept = nkept;
     h->stats.n_prim_pairs = nprim;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    t3 = tnow();
     int rc = build_plans(h);
     if (rc) return rc;
+    t4 = tnow();
+    if (trace)
+        fprintf(stderr, "unomol_b200: incremental update: pairs+prims %.3f ms, Schwarz %.3f ms, lists %.3f ms, plans %.3f ms\n", t1 - t0, t2 - t1,
+                t3 - t2, t4 - t3);
     h->xyz_built = h->basis.xyz;
     cudaEventRecord(h->ev3, h->stream);
     cudaEventSynchronize(h->ev3);
@@ -563,33 +589,48 @@ static int update_pairs_incremental(unomol_b200 *h, const std::vector<int> &move
 
 // per (bra class >= ket class): prefix counts of kets passing Q_bra*Q_ket >= tau (kets sorted descending)
 static int build_plans(unomol_b200 *h) {
-    for (auto &p : h->plans) {
-        if (p.d_ket_count) cudaFree(p.d_ket_count);
-        if (p.d_ket_prefix) cudaFree(p.d_ket_prefix);
-        if (p.d_kc_tile) cudaFree(p.d_kc_tile);
-        if (p.d_tile_order) cudaFree(p.d_tile_order);
-    }
+    // The per-plan arrays (ket counts, tile ket counts, tile orders, ket prefixes) live in ONE device pool filled by one copy:
+    // a plan rebuild used to cost ~100 cudaMalloc/cudaFree/synchronize calls, most of an incremental geometry update.
     h->plans.clear();
+    // pinned, grow-only staging buffer (no zero-fill, DMA straight from it)
+    size_t stage_size = 0;
+    bool stage_oom = false;
+    struct PoolRef { size_t kc = (size_t)-1, kct = (size_t)-1, order = (size_t)-1, pre = (size_t)-1; };
+    std::vector<PoolRef> refs;
+    auto push = [&](const void *src, size_t bytes) {
+        const size_t off = (stage_size + 255) & ~(size_t)255;
+        const size_t end = off + std::max<size_t>(bytes, 16);
+        if (end > h->plan_stage_cap) {
+            const size_t ncap = end + end / 2 + (1 << 16);
+            unsigned char *np = nullptr;
+            if (cudaMallocHost(&np, ncap) != cudaSuccess) { stage_oom = true; return (size_t)0; }
+            if (h->plan_stage && stage_size) memcpy(np, h->plan_stage, stage_size);
+            if (h->plan_stage) cudaFreeHost(h->plan_stage);
+            h->plan_stage = np;
+            h->plan_stage_cap = ncap;
+        }
+        memcpy(h->plan_stage + off, src, bytes);
+        stage_size = end;
+        return off;
+    };
     long long total = 0;
+    std::vector<int> kc, kct, order;
+    std::vector<std::pair<long long, int>> cost;
     for (int cb = 0; cb < NGROUP; ++cb)
         for (int ck = 0; ck <= cb; ++ck) {
             const PairClassList &Lb = h->cls[cb], &Lk = h->cls[ck];
             if (!Lb.n || !Lk.n) continue;
             ComboPlan plan;
             plan.cb = cb; plan.ck = ck;
-            std::vector<int> kc(Lb.n, 0);
+            kc.assign(Lb.n, 0);
+            int sweep = Lk.n;     // both lists are sorted by Q descending: the ket prefix only shrinks along the bras
             for (int i = 0; i < Lb.n; ++i) {
                 int cnt;
                 if (h->tau <= 0.0) cnt = Lk.n;
                 else {
                     const double need = h->tau / Lb.pairs[i].Q;   // Q_ket >= need
-                    // first index with Q < need in a descending list
-                    int lo = 0, hi = Lk.n;
-                    while (lo < hi) {
-                        int mid = (lo + hi) / 2;
-                        if (Lk.pairs[mid].Q >= need) lo = mid + 1; else hi = mid;
-                    }
-                    cnt = lo;
+                    while (sweep > 0 && !(Lk.pairs[sweep - 1].Q >= need)) --sweep;   // = first index with Q < need
+                    cnt = sweep;
                 }
                 if (cb == ck) cnt = std::min(cnt, i + 1);   // canonical: ket position <= bra position
                 kc[i] = cnt;
@@ -634,10 +675,10 @@ static int build_plans(unomol_b200 *h) {
                 while (plan.kslots > 0 && tile_smem_bytes(cb / NSUB, ck / NSUB, plan.maxbp, plan.kslots, h->rys.rys2_exact) > 100 * 1024) --plan.kslots;
                 if (tile_smem_bytes(cb / NSUB, ck / NSUB, plan.maxbp, plan.kslots, h->rys.rys2_exact) > 200 * 1024) plan.use_tile = false;
             }
-            std::vector<int> kct, order;
+            kct.clear(); order.clear();
             if (plan.use_tile) {
                 kct.assign(Lb.slot_pos.size(), 0);
-                std::vector<std::pair<long long, int>> cost(Lb.ntiles);
+                cost.assign(Lb.ntiles, std::pair<long long, int>(0, 0));
                 for (int t = 0; t < Lb.ntiles; ++t) {
                     long long w = 0;
                     for (int j = 0; j < TILE_SLOTS; ++j) {
@@ -658,31 +699,46 @@ static int build_plans(unomol_b200 *h) {
                 // launch for tiles of 8 bras to pay off
                 if (plan.nquartets < 1000000 && h->use_tile_kernels != 2) plan.use_tile = false;
             }
+            PoolRef ref;
             if (plan.use_tile) {
-                if (cudaMalloc(&plan.d_kc_tile, sizeof(int) * kct.size()) != cudaSuccess) return UNOMOL_E_NOMEM;
-                if (cudaMalloc(&plan.d_tile_order, sizeof(int) * std::max<size_t>(1, order.size())) != cudaSuccess) return UNOMOL_E_NOMEM;
-                cudaMemcpyAsync(plan.d_kc_tile, kct.data(), sizeof(int) * kct.size(), cudaMemcpyHostToDevice, h->stream);
-                cudaMemcpyAsync(plan.d_tile_order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, h->stream);
-                cudaStreamSynchronize(h->stream);
+                ref.kct = push(kct.data(), sizeof(int) * kct.size());
+                ref.order = push(order.data(), sizeof(int) * order.size());
             }
-            if (cudaMalloc(&plan.d_ket_count, sizeof(int) * Lb.n) != cudaSuccess) return UNOMOL_E_NOMEM;
-            cudaMemcpyAsync(plan.d_ket_count, kc.data(), sizeof(int) * Lb.n, cudaMemcpyHostToDevice, h->stream);
-            std::vector<long long> pre;
+            ref.kc = push(kc.data(), sizeof(int) * Lb.n);
             if (plan.highl) {
-                pre.assign(plan.nbra_eff + 1, 0);
+                std::vector<long long> pre(plan.nbra_eff + 1, 0);
                 for (int i = 0; i < plan.nbra_eff; ++i) pre[i + 1] = pre[i] + kc[i];
-                if (cudaMalloc(&plan.d_ket_prefix, sizeof(long long) * pre.size()) != cudaSuccess) return UNOMOL_E_NOMEM;
-                cudaMemcpyAsync(plan.d_ket_prefix, pre.data(), sizeof(long long) * pre.size(), cudaMemcpyHostToDevice, h->stream);
+                ref.pre = push(pre.data(), sizeof(long long) * pre.size());
             }
-            cudaStreamSynchronize(h->stream);
+            refs.push_back(ref);
             h->plans.push_back(plan);
         }
+    if (stage_oom) return UNOMOL_E_NOMEM;
+    if (stage_size > h->plan_pool_cap) {
+        if (h->d_plan_pool) cudaFree(h->d_plan_pool);
+        h->d_plan_pool = nullptr;
+        h->plan_pool_cap = stage_size + stage_size / 4 + 4096;
+        if (cudaMalloc(&h->d_plan_pool, h->plan_pool_cap) != cudaSuccess) { h->plan_pool_cap = 0; return UNOMOL_E_NOMEM; }
+    }
+    if (stage_size) CUDA_TRY(h, cudaMemcpyAsync(h->d_plan_pool, h->plan_stage, stage_size, cudaMemcpyHostToDevice, h->stream));
+    for (size_t ip = 0; ip < h->plans.size(); ++ip) {
+        ComboPlan &pl = h->plans[ip];
+        const PoolRef &r = refs[ip];
+        pl.d_ket_count = reinterpret_cast<int *>(h->d_plan_pool + r.kc);
+        pl.d_kc_tile = r.kct != (size_t)-1 ? reinterpret_cast<int *>(h->d_plan_pool + r.kct) : nullptr;
+        pl.d_tile_order = r.order != (size_t)-1 ? reinterpret_cast<int *>(h->d_plan_pool + r.order) : nullptr;
+        pl.d_ket_prefix = r.pre != (size_t)-1 ? reinterpret_cast<long long *>(h->d_plan_pool + r.pre) : nullptr;
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     const long long np = (long long)h->basis.nshell * (h->basis.nshell + 1) / 2;
     h->stats.n_quartets_total = np * (np + 1) / 2;
     (void)total;
-    if (h->d_counters) cudaFree(h->d_counters);
-    h->d_counters = nullptr;
-    if (cudaMalloc(&h->d_counters, sizeof(unsigned long long) * 2 * (h->plans.size() + 1)) != cudaSuccess) return UNOMOL_E_NOMEM;
+    if (h->plans.size() + 1 > h->counters_cap) {
+        if (h->d_counters) cudaFree(h->d_counters);
+        h->d_counters = nullptr;
+        h->counters_cap = h->plans.size() + 17;
+        if (cudaMalloc(&h->d_counters, sizeof(unsigned long long) * 2 * h->counters_cap) != cudaSuccess) { h->counters_cap = 0; return UNOMOL_E_NOMEM; }
+    }
     return UNOMOL_OK;
 }
 
@@ -932,6 +988,8 @@ void unomol_b200_destroy(unomol_b200_t *h) {
         cudaFree(h->d_Ppacked[s]); cudaFree(h->d_Gpacked[s]); cudaFree(h->d_PK[s]); cudaFree(h->d_K[s]);
     }
     cudaFree(h->d_PJ); cudaFree(h->d_J); cudaFree(h->d_counters); cudaFree(h->d_hl_scratch);
+    cudaFree(h->d_plan_pool); cudaFree(h->d_schwarz_scratch);
+    if (h->plan_stage) cudaFreeHost(h->plan_stage);
     cudaFree(h->d_work_local);
     if (h->d_work_shared && !h->work_borrowed) { if (h->work_owner) cudaFree(h->d_work_shared); else cudaIpcCloseMemHandle(h->d_work_shared); }
     if (h->h_pinned) cudaFreeHost(h->h_pinned);

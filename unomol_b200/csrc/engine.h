@@ -62,6 +62,9 @@ struct PairClassList {
     std::vector<int> pos_slot;      // [n]: slot of a pair
     int ntiles = 0;
     int maxnp = 0;                  // largest primitive-pair count in the list
+    size_t cap_pairs = 0, cap_tp = 0;       // capacities of d_pairs / d_hot and of d_tpairs (grow-only)
+    std::vector<KetHot> hot_host;           // host mirrors of d_hot / d_tpairs: sources of asynchronous uploads
+    std::vector<ShellPair> tp_host;
 };
 
 struct ComboPlan {                  // one (bra class, ket class) launch
@@ -124,6 +127,13 @@ struct unomol_b200 {
     double *d_PJ = nullptr, *d_PK[2] = {nullptr, nullptr}, *d_J = nullptr, *d_K[2] = {nullptr, nullptr};
     double *h_pinned = nullptr;               // staging for host<->device copies (4 * no2 doubles)
     unsigned long long *d_counters = nullptr; // 2 per combo
+    size_t counters_cap = 0;
+    unsigned char *d_plan_pool = nullptr;     // every plan's ket counts / tile orders / prefixes, one upload per build_plans
+    size_t plan_pool_cap = 0;
+    unsigned char *plan_stage = nullptr;      // pinned staging of the pool
+    size_t plan_stage_cap = 0;
+    unsigned char *d_schwarz_scratch = nullptr;
+    size_t schwarz_scratch_cap = 0;
     // runtime-L kernel (f/g shells): per-CTA slabs for the Cartesian block of a quartet; its launches share one stream
     double *d_hl_scratch = nullptr;
     long long hl_slab = 0;
@@ -145,6 +155,8 @@ struct unomol_b200 {
     int lwork = 0;
     // device-resident RHF iteration: packed core Hamiltonian, previous density, two reduction scalars
     double *d_scfH = nullptr, *d_scfPold = nullptr, *d_scfRed = nullptr;
+    // ... and UHF: previous beta density, beta orbital energies, {E, |dPA|^2 (slot 1), -, |dPB|^2 (slot 3)}
+    double *d_scfPoldB = nullptr, *d_evalsB = nullptr, *d_scfRed4 = nullptr;
     // NCCL
     void *nccl_comm = nullptr;
     std::string last_error;

@@ -106,6 +106,34 @@ __global__ void scf_pack_diff_kernel(const double *__restrict__ Pfull, const dou
     block_sum_to(d2, red + 1);
 }
 
+// ---- device-resident UHF iteration ------------------------------------------------------------------------------
+// E = tr(PA H) + tr(PB H) + (tr(PA GA) + tr(PB GB)) / 2 with full-matrix traces (reference UHF.hpp:111-114)
+__global__ void scf_energy_uhf_kernel(const double *__restrict__ PA, const double *__restrict__ PB, const double *__restrict__ H,
+                                      const double *__restrict__ GA, const double *__restrict__ GB, int n, double *__restrict__ red) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t no2 = (size_t)n * (n + 1) / 2;
+    double e = 0.0;
+    if (idx < no2) {
+        const int i = packed_row(idx), j = (int)(idx - (size_t)i * (i + 1) / 2);
+        const double pa = PA[idx], pb = PB[idx], hh = H[idx];
+        e = (i == j ? 1.0 : 2.0) * ((pa + pb) * hh + 0.5 * (pa * GA[idx] + pb * GB[idx]));
+    }
+    block_sum_to(e, red);
+}
+
+// F = H + G unpacked to the square work matrix; Pold <- P
+__global__ void scf_fock_unpack_kernel(const double *__restrict__ P, const double *__restrict__ H, const double *__restrict__ G,
+                                       double *__restrict__ Pold, double *__restrict__ Ffull, int n) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t no2 = (size_t)n * (n + 1) / 2;
+    if (idx >= no2) return;
+    const int i = packed_row(idx), j = (int)(idx - (size_t)i * (i + 1) / 2);
+    const double f = H[idx] + G[idx];
+    Ffull[(size_t)i * n + j] = f;
+    Ffull[(size_t)j * n + i] = f;
+    Pold[idx] = P[idx];
+}
+
 int scf_ensure(unomol_b200 *h) {
     if (h->cusolver) return UNOMOL_OK;
     const int n = h->basis.nbf;
@@ -156,7 +184,9 @@ void unomol_scf_free(unomol_b200 *h) {
     cudaFree(h->d_X); cudaFree(h->d_F); cudaFree(h->d_W); cudaFree(h->d_T);
     cudaFree(h->d_evals); cudaFree(h->d_work); cudaFree(h->d_info);
     cudaFree(h->d_scfH); cudaFree(h->d_scfPold); cudaFree(h->d_scfRed);
+    cudaFree(h->d_scfPoldB); cudaFree(h->d_evalsB); cudaFree(h->d_scfRed4);
     h->d_scfH = h->d_scfPold = h->d_scfRed = nullptr;
+    h->d_scfPoldB = h->d_evalsB = h->d_scfRed4 = nullptr;
     h->d_X = h->d_F = h->d_W = h->d_T = h->d_evals = h->d_work = nullptr;
     h->d_info = nullptr;
 }
@@ -312,6 +342,89 @@ int unomol_b200_scf_iterate_rhf(unomol_b200_t *h, int nocc, int damp, double *e_
     int rc = unomol_b200_scf_iterate_rhf_begin(h, damp);
     if (rc) return rc;
     return unomol_b200_scf_iterate_rhf_finish(h, nocc, e_elec, pdiff);
+}
+
+// ---- device-resident UHF iteration = UnRestrictedHartreeFock::scf_converger + update (reference UHF.hpp:690-740, 101-134) ----
+int unomol_b200_scf_load_uhf(unomol_b200_t *h, const double *H, const double *PA, const double *PB) {
+    if (!h || !H || !PA || !PB) return UNOMOL_E_ARG;
+    int rc = unomol_b200_scf_load(h, H, PA);
+    if (rc) return rc;
+    double *dP[2], *dG[2];
+    rc = unomol_b200_device_buffers(h, nullptr, dP, dG);
+    if (rc) return rc;
+    const size_t n = h->basis.nbf, no2 = n * (n + 1) / 2;
+    if (!h->d_scfPoldB) {
+        if (cudaMalloc(&h->d_scfPoldB, sizeof(double) * no2) != cudaSuccess) return UNOMOL_E_NOMEM;
+        if (cudaMalloc(&h->d_evalsB, sizeof(double) * n) != cudaSuccess) return UNOMOL_E_NOMEM;
+        if (cudaMalloc(&h->d_scfRed4, sizeof(double) * 4) != cudaSuccess) return UNOMOL_E_NOMEM;
+    }
+    cudaMemcpyAsync(dP[1], PB, sizeof(double) * no2, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(h->d_scfPoldB, PB, sizeof(double) * no2, cudaMemcpyHostToDevice, h->stream);
+    return cudaStreamSynchronize(h->stream) == cudaSuccess ? UNOMOL_OK : UNOMOL_E_CUDA;
+}
+
+int unomol_b200_scf_iterate_uhf(unomol_b200_t *h, int nocc_a, int nocc_b, int damp, double *e_elec, double *pdiff) {
+    if (!h || !e_elec || !pdiff || nocc_a < 0 || nocc_b < 0 || nocc_a > h->basis.nbf || nocc_b > h->basis.nbf) return UNOMOL_E_ARG;
+    if (!h->d_scfH || !h->d_scfPoldB) return UNOMOL_E_STATE;
+    cudaSetDevice(h->device);
+    double *dP[2], *dG[2];
+    int rc = unomol_b200_device_buffers(h, nullptr, dP, dG);
+    if (rc) return rc;
+    const int n = h->basis.nbf;
+    const size_t nn = (size_t)n * n, no2 = (size_t)n * (n + 1) / 2;
+    const unsigned blocks = (unsigned)((no2 + 255) / 256);
+    cublasHandle_t cb = (cublasHandle_t)h->cublas;
+    double *Pold[2] = {h->d_scfPold, h->d_scfPoldB};
+    double *ev[2] = {h->d_evals, h->d_evalsB};
+    const int nocc[2] = {nocc_a, nocc_b};
+    if (damp) {
+        scf_damp_kernel<<<blocks, 256, 0, h->stream>>>(dP[0], Pold[0], no2);
+        scf_damp_kernel<<<blocks, 256, 0, h->stream>>>(dP[1], Pold[1], no2);
+    }
+    rc = unomol_b200_fock_uhf_device(h, dP[0], dP[1], dG[0], dG[1], /*async=*/1);
+    if (rc) return rc;
+    cudaMemsetAsync(h->d_scfRed4, 0, sizeof(double) * 4, h->stream);
+    scf_energy_uhf_kernel<<<blocks, 256, 0, h->stream>>>(dP[0], dP[1], h->d_scfH, dG[0], dG[1], n, h->d_scfRed4);
+    const double one = 1.0, zero = 0.0;
+    for (int sp = 0; sp < 2; ++sp) {
+        scf_fock_unpack_kernel<<<blocks, 256, 0, h->stream>>>(dP[sp], h->d_scfH, dG[sp], Pold[sp], h->d_F, n);
+        cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, &one, h->d_F, n, h->d_X, n, &zero, h->d_T, n);
+        cublasDgemm(cb, CUBLAS_OP_T, CUBLAS_OP_N, n, n, n, &one, h->d_X, n, h->d_T, n, &zero, h->d_W, n);
+        cudaMemsetAsync(h->d_info, 0, sizeof(int) * 2, h->stream);
+        if (cusolverDnDsyevd((cusolverDnHandle_t)h->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, h->d_W, n, ev[sp],
+                             h->d_work, h->lwork, h->d_info) != CUSOLVER_STATUS_SUCCESS)
+            return UNOMOL_E_CUDA;
+        int info = 0;
+        cudaMemcpyAsync(&info, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_N, n, n, n, &one, h->d_X, n, h->d_W, n, &zero, h->d_T, n);   // C = X W
+        if (nocc[sp] > 0)
+            cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_T, n, n, nocc[sp], &one, h->d_T, n, h->d_T, n, &zero, h->d_F, n);
+        else
+            cudaMemsetAsync(h->d_F, 0, sizeof(double) * nn, h->stream);
+        scf_pack_diff_kernel<<<blocks, 256, 0, h->stream>>>(h->d_F, Pold[sp], dP[sp], n, h->d_scfRed4 + 2 * sp);
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess || info != 0) return UNOMOL_E_CUDA;
+    }
+    double red[4] = {0.0, 0.0, 0.0, 0.0};
+    cudaMemcpyAsync(red, h->d_scfRed4, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return UNOMOL_E_CUDA;
+    *e_elec = red[0];
+    *pdiff = sqrt(red[1]) / n + sqrt(red[3]) / n;      // SymmPackDiffNorm per spin, summed (UHF.hpp:124,132)
+    return UNOMOL_OK;
+}
+
+int unomol_b200_scf_fetch_uhf(unomol_b200_t *h, double *PA, double *PB, double *evals_a, double *evals_b) {
+    if (!h) return UNOMOL_E_ARG;
+    if (!h->d_scfH || !h->d_scfPoldB) return UNOMOL_E_STATE;
+    cudaSetDevice(h->device);
+    double *dP[2], *dG[2];
+    int rc = unomol_b200_device_buffers(h, nullptr, dP, dG);
+    if (rc) return rc;
+    const size_t n = h->basis.nbf, no2 = n * (n + 1) / 2;
+    if (PA) cudaMemcpyAsync(PA, dP[0], sizeof(double) * no2, cudaMemcpyDeviceToHost, h->stream);
+    if (PB) cudaMemcpyAsync(PB, dP[1], sizeof(double) * no2, cudaMemcpyDeviceToHost, h->stream);
+    if (evals_a) cudaMemcpyAsync(evals_a, h->d_evals, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
+    if (evals_b) cudaMemcpyAsync(evals_b, h->d_evalsB, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
+    return cudaStreamSynchronize(h->stream) == cudaSuccess ? UNOMOL_OK : UNOMOL_E_CUDA;
 }
 
 int unomol_b200_scf_fetch(unomol_b200_t *h, double *P, double *evals, double *C) {

@@ -267,6 +267,15 @@ class UnRestrictedHartreeFock {
     }
 
     void update() noexcept {   // UHF.hpp:101-134
+        if (on_device) {
+            // device-resident iteration: both densities, both G, F and H stay on the GPU; the mixing of scf_converger too
+            scf_check(unomol_b200_scf_iterate_uhf(tints.handle(), noccA, noccB, mix_next ? 1 : 0, &energy, &pdiff), "scf_iterate_uhf");
+            mix_next = false;
+            ediff = energy - eold;
+            eold = energy;
+            ++iteration;
+            return;
+        }
         for (int i = 0; i < no2; ++i) GmatA[i] = GmatB[i] = 0.0;
         tints.formGmatrix(PmatA.data(), PmatB.data(), GmatA.data(), GmatB.data());
         energy = SymmPack::TraceSymmPackProduct(PmatA.data(), Hmat.data(), no) + SymmPack::TraceSymmPackProduct(PmatB.data(), Hmat.data(), no) +
@@ -299,6 +308,9 @@ class UnRestrictedHartreeFock {
             scf_check(unomol_b200_scf_diag(tints.handle(), Hmat.data(), noccA, EvalsA.data(), nullptr, PmatA.data()), "scf_diag");
             scf_check(unomol_b200_scf_diag(tints.handle(), Hmat.data(), noccB, EvalsB.data(), nullptr, PmatB.data()), "scf_diag");
         }
+        // One GPU: the whole iteration stays on the device (UNOMOL_HOST_SCF=1 forces the host bookkeeping of the reference's update())
+        on_device = tints.number_of_gpus() == 1 && !std::getenv("UNOMOL_HOST_SCF");
+        if (on_device) scf_check(unomol_b200_scf_load_uhf(tints.handle(), Hmat.data(), PmatA.data(), PmatB.data()), "scf_load_uhf");
         iteration = 0;
         eold = 0.0;
         update();
@@ -312,6 +324,8 @@ class UnRestrictedHartreeFock {
             if (is_converged()) break;
             fprintf(stderr, "Iteration    =     %5d\nDelta Energy =  %25.15le\n", iteration, ediff);
         }
+        if (on_device)
+            scf_check(unomol_b200_scf_fetch_uhf(tints.handle(), PmatA.data(), PmatB.data(), EvalsA.data(), EvalsB.data()), "scf_fetch_uhf");
         FILE *fp = fopen("PMATRIX.DAT", "w");
         if (fp) { fwrite(PmatA.data(), sizeof(double), no2, fp); fwrite(PmatB.data(), sizeof(double), no2, fp); fclose(fp); }
         FILE *out = fopen("short.gs.out", "w");
@@ -346,6 +360,10 @@ class UnRestrictedHartreeFock {
     }
 
     void scf_converger() {   // UHF.hpp:690-740, serial path (extrap never set)
+        if (on_device) {      // the device keeps the previous densities; mixing happens at the start of the next iteration
+            mix_next = !(ediff < 0.0);
+            return;
+        }
         if (ediff < 0.0) {
             Pold2A = PoldA; PoldA = PmatA;
             Pold2B = PoldB; PoldB = PmatB;
@@ -364,6 +382,7 @@ class UnRestrictedHartreeFock {
     Basis &basis;
     TwoElectronInts &tints;
     int no = 0, no2 = 0, ncen = 0, noccA = 0, noccB = 0, maxits = 0, scf_accel = 0, cflag = 0, iteration = 0;
+    bool on_device = false, mix_next = false;
     double eps = 0, ediff = 10.0, pdiff = 10.0, eold = 0, nucrep = 0, energy = 0;
     std::vector<double> Pold2A, PoldA, PmatA, GmatA, Pold2B, PoldB, PmatB, GmatB, Hmat, Fock, Tmat, Smat, EvalsA, EvalsB;
 };
