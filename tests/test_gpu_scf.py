@@ -309,3 +309,28 @@ def test_driver_refuses_a_silent_partial_run(tmp_path):
     p = subprocess.run([BIN], cwd=tmp_path, capture_output=True, text=True, timeout=300, env=env)
     assert p.returncode == 3 and "finite-field" in p.stderr
     assert os.path.exists(tmp_path / "short.gs.out")          # the ground-state outputs are still written
+
+
+# final energies of the reference rebuilt with -DUNOMOL_MD_INTS (McMurchie-Davidson for every quartet,
+# i.e. without Rys::root2's missing 15 < X <= 33 band)
+MD_BUILD_ENERGIES = {"631.nh3": -56.195204585590417, "631.co": -112.73732120148594, "dh95.co2": -187.69058574482662,
+                     "3g.h2o": -74.962940006949680}
+
+
+@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "631.co", "dh95.co2"])
+def test_exact_two_root_mode_follows_the_md_build(name, tmp_path):
+    """UNOMOL_RYS2_EXACT=1 (engine option rys2_exact): the exact two-root quadrature.  The energy then leaves the default
+    (parity) build by what the reference's own two algorithms differ by (+2.8e-9 NH3, +8.3e-7 CO, -5.5e-7 CO2) and lands on the
+    reference's McMurchie-Davidson build, whose Boys function is good to 7e-11."""
+    e0, e1, de, out = run_scf(name, tmp_path, env={"UNOMOL_RYS2_EXACT": "1"})
+    assert abs(e1 - MD_BUILD_ENERGIES[name]) < 2e-9, (e1, MD_BUILD_ENERGIES[name], e1 - RUNS[name]["e_final"])
+    _, e1p, _, _ = run_scf(name, tmp_path)
+    shift_ref = MD_BUILD_ENERGIES[name] - RUNS[name]["e_final"]
+    assert abs((e1 - e1p) - shift_ref) < 2e-9, (e1 - e1p, shift_ref)
+
+
+def test_direct_form_g_matrix_entry_point(tmp_path):
+    """the shim's directFormGMatrix (reference TwoElectronInts.hpp:106) drives a whole SCF: same energy as formGmatrix.  (The
+    reference's own directFormGMatrix is dead code with extra cuts, |AB|^2 > 20 and 1e-12 on values, that are NOT reproduced.)"""
+    e0, e1, _, _ = run_scf("631.nh3", tmp_path, env={"UNOMOL_HOST_SCF": "1", "UNOMOL_DIRECT_G": "1"})
+    assert abs(e1 - SHORT["631.nh3"][1]) < E_TOL and abs(e0 - SHORT["631.nh3"][0]) < E_TOL

@@ -100,7 +100,9 @@ class RestrictedHartreeFock {
             return;
         }
         for (int i = 0; i < no2; ++i) Gmat[i] = 0.0;
-        tints.formGmatrix(Pmat.data(), Gmat.data());
+        // UNOMOL_DIRECT_G=1: through the reference's directFormGMatrix entry (TwoElectronInts.hpp:106; uncalled in the reference)
+        if (std::getenv("UNOMOL_DIRECT_G")) tints.directFormGMatrix(Pmat.data(), Gmat.data(), basis);
+        else tints.formGmatrix(Pmat.data(), Gmat.data());
         const double e1 = SymmPack::TraceSymmPackProduct(Pmat.data(), Hmat.data(), no) * 2.0;
         const double e2 = SymmPack::TraceSymmPackProduct(Pmat.data(), Gmat.data(), no);
         energy = e1 + e2;

@@ -84,6 +84,13 @@ class TwoElectronInts {
             check(unomol_b200_set_option(h, "work_stealing", 0), "set_option");
             for (auto *x : extra) check(unomol_b200_set_option(x, "work_stealing", 0), "set_option");
         }
+        // UNOMOL_RYS2_EXACT=1: the exact two-root Rys quadrature instead of the reference-compatible band 15 < X <= 40
+        // (reference Rys.cpp:614-624, off by up to 8.7e-7 there); energies then follow the reference's -DUNOMOL_MD_INTS build
+        const char *r2 = getenv("UNOMOL_RYS2_EXACT");
+        if (r2 && atoi(r2)) {
+            check(unomol_b200_set_option(h, "rys2_exact", 1), "set_option");
+            for (auto *x : extra) check(unomol_b200_set_option(x, "rys2_exact", 1), "set_option");
+        }
         const char *tau = getenv("UNOMOL_SCHWARZ_TAU");
         if (tau) {
             check(unomol_b200_set_option(h, "schwarz_tau", atof(tau)), "set_option");
