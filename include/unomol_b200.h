@@ -75,6 +75,7 @@ typedef struct unomol_b200_stats_t {
     int n_highl_launches;         /* runtime-L kernel (f/g shells) */
     int last_dump_kernel;         /* eri_quartet: 0 = generic kernel produced the block, 1 = the Fock build's own kernel */
     int n_incremental_updates;    /* set_geometry calls served by the incremental path (few moved centres) since create */
+    double onee_ms;               /* device time of the last unomol_b200_one_electron kernel */
 } unomol_b200_stats_t;
 
 /* Replaces the TwoElectronInts constructor (TwoElectronInts.hpp:83-88) + calculate() set-up
@@ -187,6 +188,13 @@ int unomol_b200_scf_fetch(unomol_b200_t *h, double *P, double *evals, double *C)
 int unomol_b200_scf_load_uhf(unomol_b200_t *h, const double *H, const double *PA, const double *PB);
 int unomol_b200_scf_iterate_uhf(unomol_b200_t *h, int nocc_a, int nocc_b, int damp, double *e_elec, double *pdiff);
 int unomol_b200_scf_fetch_uhf(unomol_b200_t *h, double *PA, double *PB, double *evals_a, double *evals_b);
+
+/* One-electron matrices on the device: replaces OneElectronInts(bas, S, T, H) (reference OneElectronInts.cpp:127-202) and,
+ * with M != NULL, MomentInts (Moments.cpp:94-187).  charge[ncen] = nuclear charges (a centre with charge 0, e.g. the skip
+ * centre of the polarisation scan, attracts nothing).  Outputs are packed lower-triangular host arrays [no2]: overlap S,
+ * kinetic energy T, core Hamiltonian H = T + V; M = 9 consecutive matrices dx dy dz qxx qxy qxz qyy qyz qzz (the reference's
+ * MomInts order) about the origin, or NULL.  Geometry = the handle's current one (create / set_geometry). */
+int unomol_b200_one_electron(unomol_b200_t *h, const double *charge, double *S, double *T, double *H, double *M);
 
 /* Bench support (no reference counterpart).
  * sample_quartets: draws nsample shell quartets uniformly from the screened canonical quartet list the Fock

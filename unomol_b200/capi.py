@@ -42,7 +42,7 @@ class Stats(ctypes.Structure):
                 ("nshell", _I), ("rank", _I), ("nranks", _I),
                 ("n_prim_quartets", ctypes.c_longlong), ("n_prim_candidates", ctypes.c_longlong),
                 ("n_tile_launches", _I), ("n_reg_launches", _I), ("n_rows_launches", _I), ("n_generic_launches", _I),
-                ("n_highl_launches", _I), ("last_dump_kernel", _I), ("n_incremental_updates", _I)]
+                ("n_highl_launches", _I), ("last_dump_kernel", _I), ("n_incremental_updates", _I), ("onee_ms", _D)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -54,7 +54,7 @@ EXPORTS = [
     "unomol_b200_eri_quartet", "unomol_b200_dump_eris", "unomol_b200_schwarz", "unomol_b200_stats",
     "unomol_b200_attach_nccl", "unomol_b200_steal_export", "unomol_b200_steal_import", "unomol_b200_steal_share", "unomol_b200_device_buffers", "unomol_b200_scf_set_overlap", "unomol_b200_scf_diag",
     "unomol_b200_scf_load", "unomol_b200_scf_iterate_rhf", "unomol_b200_scf_iterate_rhf_begin", "unomol_b200_scf_iterate_rhf_finish", "unomol_b200_scf_fetch",
-    "unomol_b200_scf_load_uhf", "unomol_b200_scf_iterate_uhf", "unomol_b200_scf_fetch_uhf",
+    "unomol_b200_one_electron", "unomol_b200_scf_load_uhf", "unomol_b200_scf_iterate_uhf", "unomol_b200_scf_fetch_uhf",
     "unomol_b200_sample_quartets", "unomol_b200_fp64_peak", "unomol_b200_model_flops", "unomol_b200_strerror", "unomol_b200_version",
 ]
 
@@ -88,6 +88,7 @@ def _load():
     L.unomol_b200_scf_iterate_rhf_begin.argtypes = [_P, _I]
     L.unomol_b200_scf_iterate_rhf_finish.argtypes = [_P, _I, _pd, _pd]
     L.unomol_b200_scf_fetch.argtypes = [_P, _pd, _pd, _pd]
+    L.unomol_b200_one_electron.argtypes = [_P, _pd, _pd, _pd, _pd, _pd]
     L.unomol_b200_scf_load_uhf.argtypes = [_P, _pd, _pd, _pd]
     L.unomol_b200_scf_iterate_uhf.argtypes = [_P, _I, _I, _I, _pd, _pd]
     L.unomol_b200_scf_fetch_uhf.argtypes = [_P, _pd, _pd, _pd, _pd]
@@ -248,6 +249,14 @@ class Handle:
         C = np.zeros((self.nbf, self.nbf)) if want_c else None
         _chk(lib.unomol_b200_scf_fetch(self.h, _dp(P), _dp(ev), _dp(C) if want_c else None), "scf_fetch")
         return (P, ev, C) if want_c else (P, ev)
+
+    def one_electron(self, charge, moments=False):
+        """packed S, T, H (and the 9 moment matrices) from the device kernel (csrc/onee_device.cu)"""
+        charge = np.ascontiguousarray(charge, float)
+        S = np.zeros(self.no2); T = np.zeros(self.no2); H = np.zeros(self.no2)
+        M = np.zeros((9, self.no2)) if moments else None
+        _chk(lib.unomol_b200_one_electron(self.h, _dp(charge), _dp(S), _dp(T), _dp(H), _dp(M) if moments else None), "one_electron")
+        return (S, T, H, M) if moments else (S, T, H)
 
     def scf_load_uhf(self, H, PA, PB):
         _chk(lib.unomol_b200_scf_load_uhf(self.h, _dp(np.ascontiguousarray(H, float)), _dp(np.ascontiguousarray(PA, float)),

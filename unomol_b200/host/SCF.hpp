@@ -13,7 +13,8 @@
 //                    (RHF.hpp:404-459); PMATRIX.DAT checkpoint (RHF.hpp:172-174)
 // What changes: the packed EISPACK-style eigensolver / transforms (SymmPack.cpp:272-348) are replaced by
 // cuSOLVER / cuBLAS on the device through unomol_b200_scf_set_overlap / unomol_b200_scf_diag (no CPU fallback).
-//                    moments.out / mol_dipmom.out through host/Moments.hpp (reference RHF.hpp:457-458, UHF.hpp:483)
+//                    moments.out / mol_dipmom.out through host/Moments.hpp (reference RHF.hpp:457-458, UHF.hpp:483);
+//                    the one-electron and moment INTEGRALS come from the device (unomol_b200_one_electron)
 // Finite-field and polarisation-potential drivers are outside the hot-path scope.
 #pragma once
 #include <cmath>
@@ -27,6 +28,33 @@
 #include "TwoElectronInts.hpp"
 
 namespace unomol {
+
+// One-electron and moment matrices: on the device through the C ABI (unomol_b200_one_electron, csrc/onee_device.cu) unless
+// UNOMOL_HOST_ONEE=1 asks for the threaded host versions (host/OneElectron.hpp, host/Moments.hpp), which are the cross-check.
+template <class BasisT>
+inline void OneElectronIntsAuto(const BasisT &basis, TwoElectronInts &t, double *S, double *T, double *H) {
+    if (std::getenv("UNOMOL_HOST_ONEE")) { OneElectronInts(basis, S, T, H); return; }
+    std::vector<double> z(basis.number_of_centers());
+    for (int c = 0; c < basis.number_of_centers(); ++c) z[c] = basis.center_ptr()[c].charge();
+    const int rc = unomol_b200_one_electron(t.handle(), z.data(), S, T, H, nullptr);
+    if (rc != UNOMOL_OK) {
+        fprintf(stderr, "unomol_b200 one_electron: %s\n", unomol_b200_strerror(rc));
+        exit(EXIT_FAILURE);
+    }
+}
+template <class BasisT>
+inline void MomentIntsAuto(const BasisT &basis, TwoElectronInts &t, MomentMatrices &M) {
+    if (std::getenv("UNOMOL_HOST_ONEE")) { MomentInts(basis, M); return; }
+    const size_t no = basis.number_of_orbitals(), no2 = no * (no + 1) / 2;
+    std::vector<double> z(basis.number_of_centers()), S(no2), T(no2), H(no2), buf(9 * no2);
+    for (int c = 0; c < basis.number_of_centers(); ++c) z[c] = basis.center_ptr()[c].charge();
+    const int rc = unomol_b200_one_electron(t.handle(), z.data(), S.data(), T.data(), H.data(), buf.data());
+    if (rc != UNOMOL_OK) {
+        fprintf(stderr, "unomol_b200 one_electron (moments): %s\n", unomol_b200_strerror(rc));
+        exit(EXIT_FAILURE);
+    }
+    for (int m = 0; m < 9; ++m) M.m[m].assign(buf.begin() + m * no2, buf.begin() + (m + 1) * no2);
+}
 
 namespace SymmPack {
 inline double TraceSymmPackProduct(const double *a, const double *b, int n) noexcept {   // SymmPack.cpp:7-18
@@ -118,7 +146,7 @@ class RestrictedHartreeFock {
 
     void findEnergy() noexcept {
         nucrep = nuclear_repulsion_energy(ncen, basis.center_ptr());
-        OneElectronInts(basis, Smat.data(), Tmat.data(), Hmat.data());
+        OneElectronIntsAuto(basis, tints, Smat.data(), Tmat.data(), Hmat.data());
         scf_check(unomol_b200_scf_set_overlap(tints.handle(), Smat.data()), "scf_set_overlap");   // formXmatrix
         if (basis.scf_flags(2)) {
             FILE *in = fopen("PMATRIX.DAT", "r");
@@ -200,7 +228,7 @@ class RestrictedHartreeFock {
         fclose(out);
         // reference RHF.hpp:457-458
         MomentMatrices mom;
-        MomentInts(basis, mom);
+        MomentIntsAuto(basis, tints, mom);
         AnalyzeMoments(mom, Pmat.data(), (const double *)nullptr, basis.center_ptr(), ncen, no);
         // O(N^3) on the host and N(N+1)/2 text lines: written like the reference up to 1000 functions, beyond that only on
         // request (UNOMOL_MOL_DIPMOM=1) -- at 2002 functions it is a 100 MB file and a minute of host time
@@ -299,7 +327,7 @@ class UnRestrictedHartreeFock {
 
     void findEnergy() noexcept {   // UHF.hpp:137-177
         nucrep = nuclear_repulsion_energy(ncen, basis.center_ptr());
-        OneElectronInts(basis, Smat.data(), Tmat.data(), Hmat.data());
+        OneElectronIntsAuto(basis, tints, Smat.data(), Tmat.data(), Hmat.data());
         scf_check(unomol_b200_scf_set_overlap(tints.handle(), Smat.data()), "scf_set_overlap");
         if (basis.scf_flags(2)) {
             FILE *in = fopen("PMATRIX.DAT", "r");
@@ -349,7 +377,7 @@ class UnRestrictedHartreeFock {
         // reference UHF.hpp:483 (moments.out from (PA + PB)/2; the MO transition dipoles need the eigenvectors, which this
         // driver does not bring back from the device for UHF)
         MomentMatrices mom;
-        MomentInts(basis, mom);
+        MomentIntsAuto(basis, tints, mom);
         AnalyzeMoments(mom, PmatA.data(), PmatB.data(), basis.center_ptr(), ncen, no);
     }
 
