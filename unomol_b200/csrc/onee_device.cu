@@ -39,8 +39,9 @@ __device__ __forceinline__ void onee_comp(int l, int c, int *lmn) {
     lmn[0] = l - i; lmn[1] = i - j; lmn[2] = j;
 }
 __device__ __forceinline__ double onee_cnorm(const int *lmn) {
-    // 1 / sqrt((2lx-1)!! (2ly-1)!! (2lz-1)!!), reference AuxFunctions.hpp:49-64
-    const double df[5] = {1.0, 1.0, 3.0, 15.0, 105.0};
+    // per-component norm 1/sqrt(df[lx] df[ly] df[lz]) with the reference's OWN recurrence (AuxFunctions.hpp:49-64:
+    // df[i] = df[i-1] * dx, dx *= 2i+1), which is (2l-1)!! only up to l = 2: df = 1, 1, 3, 45, 4725
+    const double df[5] = {1.0, 1.0, 3.0, 45.0, 4725.0};
     return rsqrt(df[lmn[0]] * df[lmn[1]] * df[lmn[2]]);
 }
 
