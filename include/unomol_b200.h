@@ -195,6 +195,10 @@ int unomol_b200_scf_fetch_uhf(unomol_b200_t *h, double *PA, double *PB, double *
  * kinetic energy T, core Hamiltonian H = T + V; M = 9 consecutive matrices dx dy dz qxx qxy qxz qyy qyz qzz (the reference's
  * MomInts order) about the origin, or NULL.  Geometry = the handle's current one (create / set_geometry). */
 int unomol_b200_one_electron(unomol_b200_t *h, const double *charge, double *S, double *T, double *H, double *M);
+/* ... plus the positron charge model of the polarisation scan folded into H: H -= GDPMInts (reference GDPMInts.cpp:86-145,
+ * called at RHF.hpp:317,356) for the model centred on centre dpm_center (pass that centre with charge 0: the reference skips
+ * it in the nuclear attraction, OneElectronInts.cpp:43).  dpm_center = -1: same as unomol_b200_one_electron. */
+int unomol_b200_one_electron_dpm(unomol_b200_t *h, const double *charge, int dpm_center, double *S, double *T, double *H, double *M);
 
 /* Bench support (no reference counterpart).
  * sample_quartets: draws nsample shell quartets uniformly from the screened canonical quartet list the Fock

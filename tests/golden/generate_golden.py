@@ -205,14 +205,41 @@ def moments_fixtures():
 
 REFT0 = "/root/reference/test"
 
+
+def polscan_fixture():
+    """polarisation-potential scan (reference RHF.hpp:292-388): the reference ships no input for it, so this one is ours --
+    water/6-31G with int_flag[0] = 1, three extra shells (s2 s1 p1) in posin.bas, six grid points in pos.grid.dat -- and the
+    unmodified reference is run on it; vpol.out / spol.out are the goldens (tests/test_gpu_scf.py::test_polarisation_scan...)."""
+    d = os.path.join(HERE, "polscan")
+    os.makedirs(d, exist_ok=True)
+    txt = open(os.path.join(REFT0, "patin.dat.631.h2o")).read().split("\n")
+    k = [i for i, l in enumerate(txt) if l.strip()][3]
+    txt[k] = " 1 0"
+    open(os.path.join(d, "patin.dat"), "w").write("\n".join(txt))
+    open(os.path.join(d, "posin.bas"), "w").write(" 3 5 1\n 2 0\n   1.6000000000   0.4000000000\n   0.4500000000   0.7000000000\n"
+                                                  " 1 0\n   0.1200000000   1.0000000000\n 1 1\n   0.2500000000   1.0000000000\n")
+    open(os.path.join(d, "pos.grid.dat"), "w").write(" 6\n 0.0 0.0 6.0\n 0.0 0.0 4.5\n 0.3 0.2 3.5\n 0.6 0.4 2.8\n 1.5 -0.5 2.0\n 3.0 1.0 -1.5\n")
+    t = tempfile.mkdtemp()
+    for f in ("patin.dat", "posin.bas", "pos.grid.dat"):
+        shutil.copyfile(os.path.join(d, f), os.path.join(t, f))
+    subprocess.run([Reference.UNOMOL], cwd=t, capture_output=True, text=True, timeout=3600, check=True)
+    for f in ("vpol.out", "spol.out"):
+        shutil.copyfile(os.path.join(t, f), os.path.join(d, f))
+    shutil.rmtree(t, ignore_errors=True)
+
 if __name__ == "__main__":
     if "--moments-only" in sys.argv:
         moments_fixtures()
+    polscan_fixture()
         sys.exit(0)
     if "--highl-only" in sys.argv:
         highl_input()
+        sys.exit(0)
+    if "--polscan-only" in sys.argv:
+        polscan_fixture()
         sys.exit(0)
     main()
     cation_variants()
     highl_input()
     moments_fixtures()
+    polscan_fixture()

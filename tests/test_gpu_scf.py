@@ -334,3 +334,27 @@ def test_direct_form_g_matrix_entry_point(tmp_path):
     reference's own directFormGMatrix is dead code with extra cuts, |AB|^2 > 20 and 1e-12 on values, that are NOT reproduced.)"""
     e0, e1, _, _ = run_scf("631.nh3", tmp_path, env={"UNOMOL_HOST_SCF": "1", "UNOMOL_DIRECT_G": "1"})
     assert abs(e1 - SHORT["631.nh3"][1]) < E_TOL and abs(e0 - SHORT["631.nh3"][0]) < E_TOL
+
+
+def test_polarisation_scan_vs_reference_run(tmp_path):
+    """reference RHF.hpp:292-388 (findPolarizationPotential): water/6-31G + three positron shells (posin.bas) moved over six grid
+    points (pos.grid.dat); vpol.out / spol.out of the unmodified reference are the goldens (generate_golden.py: polscan_fixture).
+    Energies within 1e-9 Eh; V_pol and V_stat are differences of two such energies."""
+    import numpy as np
+    d = os.path.join(GOLDEN, "polscan")
+    for f in ("patin.dat", "posin.bas", "pos.grid.dat"):
+        shutil.copyfile(os.path.join(d, f), tmp_path / f)
+    p = subprocess.run([BIN], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    ours_v = np.loadtxt(tmp_path / "vpol.out"); ref_v = np.loadtxt(os.path.join(d, "vpol.out"))
+    ours_s = np.loadtxt(tmp_path / "spol.out"); ref_s = np.loadtxt(os.path.join(d, "spol.out"))
+    assert ours_v.shape == ref_v.shape == (6, 7) and ours_s.shape == ref_s.shape == (6, 6)
+    assert np.max(np.abs(ours_v[:, :3] - ref_v[:, :3])) == 0.0                      # grid points
+    assert np.max(np.abs(ours_s[:, 1:4] - ref_s[:, 1:4])) < 2e-9                    # E_ground, E_first, E_final (printed with 11 digits)
+    assert np.max(np.abs(ours_v[:, 3] - ref_v[:, 3])) < 2e-9                        # V_pol
+    assert np.max(np.abs(ours_v[:, 5] - ref_v[:, 5])) < 2e-9                        # V_stat (incl. the first point's doubled repulsion)
+    assert np.max(np.abs(ours_v[:, 6] - ref_v[:, 6])) < 4e-9
+    r4 = np.sum(ours_v[:, :3] ** 2, axis=1) ** 2
+    assert np.max(np.abs(ours_v[:, 4] - ref_v[:, 4]) / r4) < 4e-9                   # alpha = -2 V_pol r^4
+    # every point after the first reuses the pair tables of the frozen molecule
+    assert "(5 incremental so far)" in p.stderr

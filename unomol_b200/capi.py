@@ -54,7 +54,7 @@ EXPORTS = [
     "unomol_b200_eri_quartet", "unomol_b200_dump_eris", "unomol_b200_schwarz", "unomol_b200_stats",
     "unomol_b200_attach_nccl", "unomol_b200_steal_export", "unomol_b200_steal_import", "unomol_b200_steal_share", "unomol_b200_device_buffers", "unomol_b200_scf_set_overlap", "unomol_b200_scf_diag",
     "unomol_b200_scf_load", "unomol_b200_scf_iterate_rhf", "unomol_b200_scf_iterate_rhf_begin", "unomol_b200_scf_iterate_rhf_finish", "unomol_b200_scf_fetch",
-    "unomol_b200_one_electron", "unomol_b200_scf_load_uhf", "unomol_b200_scf_iterate_uhf", "unomol_b200_scf_fetch_uhf",
+    "unomol_b200_one_electron", "unomol_b200_one_electron_dpm", "unomol_b200_scf_load_uhf", "unomol_b200_scf_iterate_uhf", "unomol_b200_scf_fetch_uhf",
     "unomol_b200_sample_quartets", "unomol_b200_fp64_peak", "unomol_b200_model_flops", "unomol_b200_strerror", "unomol_b200_version",
 ]
 
@@ -89,6 +89,7 @@ def _load():
     L.unomol_b200_scf_iterate_rhf_finish.argtypes = [_P, _I, _pd, _pd]
     L.unomol_b200_scf_fetch.argtypes = [_P, _pd, _pd, _pd]
     L.unomol_b200_one_electron.argtypes = [_P, _pd, _pd, _pd, _pd, _pd]
+    L.unomol_b200_one_electron_dpm.argtypes = [_P, _pd, _I, _pd, _pd, _pd, _pd]
     L.unomol_b200_scf_load_uhf.argtypes = [_P, _pd, _pd, _pd]
     L.unomol_b200_scf_iterate_uhf.argtypes = [_P, _I, _I, _I, _pd, _pd]
     L.unomol_b200_scf_fetch_uhf.argtypes = [_P, _pd, _pd, _pd, _pd]
@@ -250,12 +251,14 @@ class Handle:
         _chk(lib.unomol_b200_scf_fetch(self.h, _dp(P), _dp(ev), _dp(C) if want_c else None), "scf_fetch")
         return (P, ev, C) if want_c else (P, ev)
 
-    def one_electron(self, charge, moments=False):
-        """packed S, T, H (and the 9 moment matrices) from the device kernel (csrc/onee_device.cu)"""
+    def one_electron(self, charge, moments=False, dpm_center=-1):
+        """packed S, T, H (and the 9 moment matrices) from the device kernel (csrc/onee_device.cu); dpm_center >= 0 folds the
+        positron charge model of the polarisation scan into H"""
         charge = np.ascontiguousarray(charge, float)
         S = np.zeros(self.no2); T = np.zeros(self.no2); H = np.zeros(self.no2)
         M = np.zeros((9, self.no2)) if moments else None
-        _chk(lib.unomol_b200_one_electron(self.h, _dp(charge), _dp(S), _dp(T), _dp(H), _dp(M) if moments else None), "one_electron")
+        _chk(lib.unomol_b200_one_electron_dpm(self.h, _dp(charge), int(dpm_center), _dp(S), _dp(T), _dp(H), _dp(M) if moments else None),
+             "one_electron")
         return (S, T, H, M) if moments else (S, T, H)
 
     def scf_load_uhf(self, H, PA, PB):

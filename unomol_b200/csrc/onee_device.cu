@@ -30,7 +30,14 @@ struct OneeArgs {
     RysTables rys;
     double *S, *T, *H;      // packed lower triangle
     double *M;              // 9 packed moment matrices (dx dy dz qxx qxy qxz qyy qyz qzz) or null
+    int dpm_cen;            // >= 0: centre that carries the reference's positron charge model (GDPMInts), else -1
 };
+
+// The dipole-polarisation model of the reference's polarisation scan (reference GDPMInts.cpp:5-83): the positron is a fixed
+// contraction of six s Gaussians at the scan centre, and H -= sum_i c_i (g_i | a b), a three-centre Coulomb integral.  In Rys
+// form it is the nuclear-attraction recursion with t^2 -> t^2 p/(p+q) (p = the model exponent): a smeared point charge.
+__constant__ double dpm_alf[6] = {6.8505018000, 4.0491646000, 3.5941062989, 1.2478274000, 0.7927690989, 0.3377107978};
+__constant__ double dpm_cof[6] = {0.0766926784, 0.1483475912, 0.0462334641, 0.0717376427, 0.0447149792, 0.0069678529};
 
 __device__ __forceinline__ void onee_comp(int l, int c, int *lmn) {
     int i = 0;
@@ -172,6 +179,47 @@ __global__ void __launch_bounds__(128) onee_kernel(const OneeArgs a) {
                     }
                 }
             }
+            // ---- positron charge model (GDPMInts): roots in the ERI path's mode (the reference calls Rys::Recur here)
+            if (a.dpm_cen >= 0) {
+                const double *rp = a.xyz + 3 * a.dpm_cen;
+                const double pq[3] = {rp[0] - P[0], rp[1] - P[1], rp[2] - P[2]};      // (model centre) - (product centre)
+                const double pq2 = pq[0] * pq[0] + pq[1] * pq[1] + pq[2] * pq[2];
+                for (int im = 0; im < 6; ++im) {
+                    const double pe = dpm_alf[im], txp = pe + p;
+                    const double X = pe * p / txp * pq2;
+                    // sr = 2 pi^(5/2) s34 / (pe q sqrt(pe + q))   (GDPMInts.cpp:53), q = p here
+                    const double sr = SR_TERM * kab / (pe * p * sqrt(txp)) * dpm_cof[im] * c12;
+                    double t2[5], w[5];
+                    switch (nroots) {
+                        case 1: rys_t2<1>(X, t2, w, a.rys); break;
+                        case 2: rys_t2<2>(X, t2, w, a.rys); break;
+                        case 3: rys_t2<3>(X, t2, w, a.rys); break;
+                        case 4: rys_t2<4>(X, t2, w, a.rys); break;
+                        default: rys_t2<5>(X, t2, w, a.rys); break;
+                    }
+                    for (int ir = 0; ir < nroots; ++ir) {
+                        const double te = t2[ir] * pe / txp, b1 = (1.0 - te) * ip2;      // B1p of Rys::Recur (Rys.hpp:131)
+                        double g[3][NG][NI];
+                        for (int x = 0; x < 3; ++x) {
+                            const double c0 = PA[x] + te * pq[x];                         // Cp = qc + p pq t^2/(p+q) (Rys.hpp:133)
+                            g[x][0][0] = 1.0;
+                            for (int i = 0; i < L; ++i) g[x][i + 1][0] = c0 * g[x][i][0] + (i > 0 ? i * b1 * g[x][i - 1][0] : 0.0);
+                            for (int j = 0; j < lb; ++j)
+                                for (int i = 0; i <= L - j - 1; ++i) g[x][i][j + 1] = g[x][i + 1][j] + abv[x] * g[x][i][j];
+                        }
+                        const double wz = -sr * w[ir];                                     // Hmat -= (GDPMInts.cpp:139)
+                        for (int ia = 0; ia < na; ++ia) {
+                            int l1[3];
+                            onee_comp(la, ia, l1);
+                            for (int ib = 0; ib < nb; ++ib) {
+                                int l2[3];
+                                onee_comp(lb, ib, l2);
+                                vv[ia * nb + ib] += wz * g[0][l1[0]][l2[0]] * g[1][l1[1]][l2[1]] * g[2][l1[2]][l2[2]];
+                            }
+                        }
+                    }
+                }
+            }
         }
     const size_t no2 = (size_t)a.nbf * (a.nbf + 1) / 2;
     for (int ia = 0; ia < na; ++ia) {
@@ -200,7 +248,12 @@ __global__ void __launch_bounds__(128) onee_kernel(const OneeArgs a) {
 using namespace ub200;
 
 extern "C" int unomol_b200_one_electron(unomol_b200_t *h, const double *charge, double *S, double *T, double *H, double *M) {
-    if (!h || !charge || !S || !T || !H) return UNOMOL_E_ARG;
+    return unomol_b200_one_electron_dpm(h, charge, -1, S, T, H, M);
+}
+
+extern "C" int unomol_b200_one_electron_dpm(unomol_b200_t *h, const double *charge, int dpm_center, double *S, double *T, double *H,
+                                            double *M) {
+    if (!h || !charge || !S || !T || !H || dpm_center >= h->basis.ncen) return UNOMOL_E_ARG;
     if (cudaSetDevice(h->device) != cudaSuccess) return UNOMOL_E_CUDA;
     const HostBasis &B = h->basis;
     const int ns = B.nshell, n = B.nbf;
@@ -233,6 +286,7 @@ extern "C" int unomol_b200_one_electron(unomol_b200_t *h, const double *charge, 
     a.rys = h->rys;
     a.S = d_out; a.T = d_out + no2; a.H = d_out + 2 * no2;
     a.M = M ? d_out + 3 * no2 : nullptr;
+    a.dpm_cen = dpm_center;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, h->stream);
     {

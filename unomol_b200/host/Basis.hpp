@@ -1,7 +1,8 @@
 // unomol_b200/host/Basis.hpp -- host-side data model with the reference's names and accessors
 // (reference Basis.hpp:17-356: Shell, Center, Basis).  Clean-room: flat std::vector storage, same file
 // format (Basis.hpp:181-255), same contraction normalisation (Basis.hpp:56-75), same eps floor (:249-254).
-// Only the int_flag[0]==0 path is implemented (no posin.bas positron basis augmentation).
+// int_flag[0] == 1: the extra shells of posin.bas on one extra centre (charge +1, the positron of the polarisation scan) are read
+// too and become active with dpm_augment(), exactly as in the reference (Basis.hpp:208-243, 341-345).
 #pragma once
 #include <cfloat>
 #include <cmath>
@@ -43,8 +44,10 @@ class Shell {
         for (int i = 0; i < npr; i++) co[i] = co[i] * sum * sqrt(pow(2 * al[i], lpow) / piterm);
     }
 
-    std::istream &read_shell(std::istream &is) {
-        is >> npr >> lsh >> cen;
+    std::istream &read_shell(std::istream &is, int cen_in = -1) {   // reference Basis.hpp:77-96
+        is >> npr >> lsh;
+        if (cen_in == -1) is >> cen;
+        else cen = cen_in;
         al.assign(npr, 0.0);
         co.assign(npr, 0.0);
         for (int i = 0; i < npr; ++i) is >> al[i] >> co[i];
@@ -69,6 +72,7 @@ class Basis {
     std::vector<int> offsets;
     double eps = 0.0;
     int nshell = 0, ncen = 0, norb = 0, maxl = 0, nelec = 0, maxits = 0;
+    int tnshell = 0, tncen = 0, tnorb = 0, skipcen = 0;
     int scf_flag[3] = {0, 0, 0}, int_flag[3] = {0, 0, 0}, prt_flag[4] = {0, 0, 0, 0};
 
   public:
@@ -79,10 +83,19 @@ class Basis {
         in >> int_flag[0] >> int_flag[1] >> scf_flag[0] >> scf_flag[1] >> scf_flag[2];
         in >> prt_flag[0] >> prt_flag[1] >> prt_flag[2];
         if (!in) fatal_error("malformed patin.dat header");
-        if (int_flag[0] == 1) fatal_error("posin.bas augmentation (int_flag[0]=1) is outside the GPU Fock-build path");
+        tnshell = nshell; tncen = ncen; tnorb = norb;
+        std::ifstream ain;
+        if (int_flag[0] == 1) {   // reference Basis.hpp:208-222
+            ain.open("posin.bas");
+            if (!ain) fatal_error("could not open posin.bas");
+            int xsh = 0, xno = 0, xmaxl = 0;
+            ain >> xsh >> xno >> xmaxl;
+            tnshell += xsh; tnorb += xno; ++tncen;
+            if (xmaxl > maxl) maxl = xmaxl;
+        }
         if (maxl > 4) fatal_error("Angular Momentum is too large for present program\n");
-        centers.resize(ncen);
-        shells.resize(nshell);
+        centers.resize(tncen);
+        shells.resize(tnshell);
         for (int i = 0; i < ncen; ++i) {
             double q, x, y, z;
             in >> q >> x >> y >> z;
@@ -97,6 +110,18 @@ class Basis {
             off += (lv + 1) * (lv + 2) / 2;
         }
         if (!in) fatal_error("malformed patin.dat body");
+        if (int_flag[0] == 1) {   // reference Basis.hpp:235-243
+            centers[ncen].setCharge(1.0);
+            centers[ncen].setPosition(0.0, 0.0, 0.0);
+            for (int ish = nshell; ish < tnshell; ++ish) {
+                shells[ish].read_shell(ain, ncen);
+                const int lv = shells[ish].Lvalue();
+                offsets.push_back(off);
+                off += (lv + 1) * (lv + 2) / 2;
+            }
+            if (!ain) fatal_error("malformed posin.bas");
+        }
+        skipcen = ncen;
         for (auto &s : shells) s.normalize();
         const double xeps = DBL_EPSILON * norb * norb * 0.5;
         if (eps < xeps) {
@@ -120,6 +145,15 @@ class Basis {
     const Center *center_ptr() const noexcept { return centers.data(); }
     double scf_eps() const noexcept { return eps; }
     void SetCenterPosition(double x, double y, double z, int n) noexcept { centers[n].setPosition(x, y, z); }
+    int total_number_of_shells() const noexcept { return tnshell; }
+    int total_number_of_centers() const noexcept { return tncen; }
+    int total_number_of_orbitals() const noexcept { return tnorb; }
+    int skip_center() const noexcept { return skipcen; }
+    void dpm_augment() noexcept {   // reference Basis.hpp:341-345
+        nshell = tnshell;
+        norb = tnorb;
+        ++ncen;
+    }
 };
 
 }  // namespace unomol

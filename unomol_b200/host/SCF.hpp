@@ -15,12 +15,14 @@
 // cuSOLVER / cuBLAS on the device through unomol_b200_scf_set_overlap / unomol_b200_scf_diag (no CPU fallback).
 //                    moments.out / mol_dipmom.out through host/Moments.hpp (reference RHF.hpp:457-458, UHF.hpp:483);
 //                    the one-electron and moment INTEGRALS come from the device (unomol_b200_one_electron)
-// Finite-field and polarisation-potential drivers are outside the hot-path scope.
+// The polarisation-potential scan (RHF.hpp:292-388) is RestrictedHartreeFock::findPolarizationPotential below; the finite-field
+// analysis is not implemented (the driver says so).
 #pragma once
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <vector>
 #include "Basis.hpp"
 #include "OneElectron.hpp"
@@ -175,9 +177,80 @@ class RestrictedHartreeFock {
             report();
         }
         if (on_device) scf_check(unomol_b200_scf_fetch(tints.handle(), Pmat.data(), Evals.data(), Cmat.data()), "scf_fetch");
+        PmatGs = Pmat;                       // RHF.hpp:169-171: the ground state seeds every point of the polarisation scan
+        energyGs = energy + nucrep;
         FILE *fp = fopen("PMATRIX.DAT", "w");
         if (fp) { fwrite(Pmat.data(), sizeof(double), no2, fp); fclose(fp); }
         final_output(init_energy);
+    }
+
+    // The polarisation-potential scan (reference RHF.hpp:292-388): the basis is augmented by the posin.bas shells on one extra
+    // centre (the positron, charge +1), that centre is moved over the points of pos.grid.dat, and at every point an SCF restarted
+    // from the ground-state density gives V_pol = E_final - E_first and V_stat = E_first - E_ground; vpol.out / spol.out as the
+    // reference writes them.  Per point here: one incremental pair-table update (only the pairs of the moved centre are rebuilt,
+    // engine.cu: update_pairs_incremental), S/T/H with the positron charge model on the device (unomol_b200_one_electron_dpm =
+    // OneElectronInts + GDPMInts), X = S^-1/2, and the device-resident RHF iteration.  The reference adds the integrals of the new
+    // shells (xints, start_shell = old shell count) to the cached molecular ones (tints); an integral-direct build has no cache
+    // to add to, so ONE engine over the augmented basis computes both parts in one pass (same G).
+    void findPolarizationPotential() {
+        const int pcen = basis.skip_center();
+        basis.dpm_augment();
+        no = basis.number_of_orbitals();
+        no2 = no * (no + 1) / 2;
+        ncen = basis.number_of_centers();
+        eps = 1.e-12;
+        PmatGs.resize(no2, 0.0);             // new functions start empty (RHF.hpp:170)
+        for (auto *v : {&Hmat, &Tmat, &Smat}) v->assign(no2, 0.0);
+        std::ifstream in("pos.grid.dat");
+        if (!in) fatal_error("could not open pos.grid.dat");
+        int npts = 0;
+        in >> npts;
+        FILE *vout = fopen("vpol.out", "w"), *sout = fopen("spol.out", "w");
+        std::vector<double> z(ncen);
+        for (int c = 0; c < ncen; ++c) z[c] = (c == pcen) ? 0.0 : basis.center_ptr()[c].charge();   // OneElectronInts.cpp:43 skips it
+        TwoElectronInts *x = nullptr;
+        for (int i = 0; i < npts; ++i) {
+            double px, py, pz;
+            in >> px >> py >> pz;
+            basis.SetCenterPosition(px, py, pz, pcen);
+            nucrep = nuclear_repulsion_energy(ncen, basis.center_ptr());
+            if (!x) x = new TwoElectronInts(basis, 0, std::string("XINTS.DAT"));
+            else x->recalculate(basis);
+            scf_check(unomol_b200_one_electron_dpm(x->handle(), z.data(), pcen, Smat.data(), Tmat.data(), Hmat.data(), nullptr), "one_electron_dpm");
+            scf_check(unomol_b200_scf_set_overlap(x->handle(), Smat.data()), "scf_set_overlap");
+            scf_check(unomol_b200_scf_load(x->handle(), Hmat.data(), PmatGs.data()), "scf_load");
+            iteration = 0;
+            eold = 0.0;
+            auto upd = [&](bool mix) {
+                scf_check(unomol_b200_scf_iterate_rhf(x->handle(), nocc, mix ? 1 : 0, &energy, &pdiff), "scf_iterate_rhf");
+                ediff = energy - eold;
+                eold = energy;
+                ++iteration;
+            };
+            upd(false);
+            const double e_first = energy + nucrep;
+            while (iteration < maxits) {
+                upd(!(ediff < 0.0));         // scf_converger: mix unless the last step lowered the energy
+                if (is_converged()) break;
+            }
+            const double e_final = energy + nucrep;
+            const double vpol = e_final - e_first;
+            // the reference adds the nuclear repulsion a second time at the first point only (RHF.hpp:337 vs :374); kept as is
+            const double vstat = (i == 0) ? e_first - energyGs + nucrep : e_first - energyGs;
+            const double r2 = px * px + py * py + pz * pz;
+            const double alfa = -2.0 * vpol * r2 * r2;
+            fprintf(vout, "%15.10lf %15.10lf %15.10lf %25.15le %25.15le %25.15le %25.15le\n", px, py, pz, vpol, alfa, vstat, (vstat + vpol));
+            fflush(vout);
+            fprintf(sout, "%3d %20.10le %20.10le %20.10le %20.10le %25.15le\n", i, energyGs, e_first, e_final, vstat, ediff);
+            fflush(sout);
+            unomol_b200_stats_t st;
+            unomol_b200_stats(x->handle(), &st);
+            fprintf(stderr, "polarisation scan point %d: %d iterations, pair-table update %.3f ms (%d incremental so far), one-electron kernel %.3f ms\n",
+                    i, iteration, st.precompute_ms, st.n_incremental_updates, st.onee_ms);
+        }
+        fclose(vout);
+        fclose(sout);
+        delete x;
     }
 
     void PmatrixGuess() {   // core-Hamiltonian guess, RHF.hpp:205-211
@@ -272,8 +345,8 @@ class RestrictedHartreeFock {
     Basis &basis;
     TwoElectronInts &tints;
     int no = 0, no2 = 0, ncen = 0, nocc = 0, maxits = 0, scf_accel = 0, cflag = 0, iteration = 0;
-    double eps = 0, ediff = 10.0, pdiff = 10.0, eold = 0, nucrep = 0, energy = 0, init_energy = 0;
-    std::vector<double> Pold2, Pold, Pmat, Gmat, Hmat, Fock, Tmat, Smat, Evals, Cmat;
+    double eps = 0, ediff = 10.0, pdiff = 10.0, eold = 0, nucrep = 0, energy = 0, init_energy = 0, energyGs = 0;
+    std::vector<double> Pold2, Pold, Pmat, Gmat, Hmat, Fock, Tmat, Smat, Evals, Cmat, PmatGs;
     bool on_device = false, mix_next = false;
 };
 

@@ -1,7 +1,8 @@
 // unomol_b200/host/main.cpp -- the reference's serial driver (reference Unomol.cc:8-26) on the GPU engine:
 // reads ./patin.dat (or argv[1]), builds the two-electron engine, picks UHF iff the electron count is odd,
 // runs the ground-state SCF and writes short.gs.out / scfout.gs.out / PMATRIX.DAT in the working directory.
-// The finite-field and polarisation-potential follow-ups (Unomol.cc:16-17) are outside the hot-path scope.
+// The polarisation-potential scan (Unomol.cc:23) follows for closed shells when int_flag[0] is set; the finite-field analysis
+// (Unomol.cc:16,22) is not implemented and is refused loudly.
 #include <chrono>
 #include <cstdlib>
 #include <string>
@@ -29,11 +30,16 @@ int main(int argc, char **argv) {
     if (nelec % 2) {
         unomol::UnRestrictedHartreeFock uhf(&bas, &t);
         uhf.findEnergy();
+        if (bas.int_flags(0)) {
+            std::fprintf(stderr, "unomol_b200_scf: the polarisation scan is implemented for closed shells (RHF) only\n");
+            return 3;
+        }
         std::fprintf(stderr, "UHF energy %.15f after %d iterations\n", uhf.total_energy(), uhf.iterations());
     } else {
         unomol::RestrictedHartreeFock rhf(&bas, &t);
         rhf.findEnergy();
         std::fprintf(stderr, "RHF energy %.15f after %d iterations\n", rhf.total_energy(), rhf.iterations());
+        if (bas.int_flags(0)) rhf.findPolarizationPotential();   // reference Unomol.cc:23
     }
     auto t2 = std::chrono::steady_clock::now();
     std::fprintf(stderr, "SCF time = %g s\n", std::chrono::duration<double>(t2 - t1).count());
