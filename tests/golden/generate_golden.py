@@ -230,7 +230,6 @@ def polscan_fixture():
 if __name__ == "__main__":
     if "--moments-only" in sys.argv:
         moments_fixtures()
-    polscan_fixture()
         sys.exit(0)
     if "--highl-only" in sys.argv:
         highl_input()
