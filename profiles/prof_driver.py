@@ -12,6 +12,8 @@ h = capi.Handle(basis)
 import os
 if os.environ.get('UNOMOL_BUCKET_MIN'):
     h.set_option('bucket_min_pairs', float(os.environ['UNOMOL_BUCKET_MIN']))
+for kv in filter(None, os.environ.get('UNOMOL_OPTS', '').split(',')):
+    h.set_option(kv.split('=')[0], float(kv.split('=')[1]))
 P = bench.synthetic_density(basis)
 for _ in range(nb):
     G = h.fock_rhf(P)

@@ -814,9 +814,15 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
     std::vector<size_t> order(h->plans.size());
     std::iota(order.begin(), order.end(), (size_t)0);
     std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return h->plans[x].cost > h->plans[y].cost; });
+    static const bool debug_plans = getenv("UNOMOL_DEBUG_PLANS") != nullptr;   // launch list of the first build on stderr
     for (size_t io = 0; io < order.size(); ++io) {
         const size_t ip = order[io];
         const ComboPlan &pl = h->plans[ip];
+        if (debug_plans && h->build_count == 1)
+            fprintf(stderr, "launch %3zu: class (%d|%d) bucket (%d|%d) block (%d|%d) %s quartets %lld nbra %d nket %d tiles %d slices %d kslots %d maxbp %d ket maxnp %d\n",
+                    io, pl.cb / NSUB, pl.ck / NSUB, pl.cb % NSUB / NBLOCK, pl.ck % NSUB / NBLOCK, pl.cb % NBLOCK, pl.ck % NBLOCK,
+                    pl.highl ? "highl" : pl.use_tile ? "tile" : pl.use_reg ? "reg" : "generic", pl.nquartets, pl.nbra_eff, h->cls[pl.ck].n,
+                    pl.ntiles, pl.tile_slices, pl.kslots, pl.maxbp, h->cls[pl.ck].maxnp);
         // the runtime-L launches share one scratch area: keep them on one stream
         cudaStream_t st = pl.highl ? h->aux[0] : h->aux[io % unomol_b200::NAUX];
         ClassTask task{};
