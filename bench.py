@@ -16,6 +16,10 @@ roofline= FP64: algorithmic FLOPs of SURVEY.md 8(d) (reference Rys algorithm, pe
           measured in this run (MEASURED_PEAKS.json carries no FP64 number).
 cpu_baseline / --impl reference = the UNMODIFIED reference's calc_two_electron_ints_rys (oracle/_ref, built
           from /root/reference) timed on the host cores over a bounded, seeded sample of screened quartets.
+reference_mpi = the reference's own MPI work distribution (UnomolMPI.cc / TwoElectronIntsMPI.cpp / RHF_MPI.hpp, unmodified,
+          compiled against oracle/mpi_shim/mpi.h because the image has no MPI) run to convergence on SF6/TZ2P with one
+          rank per host core: its integral pass and its seconds per SCF iteration, as the program reports them.  The
+          >= 2000-function cluster cannot run there (its cache would hold ~10^12 integrals), see DESIGN.md.
 """
 import argparse
 import json
@@ -184,6 +188,23 @@ def load_workload(name, want_gpu_density=True):
     return basis, np.ascontiguousarray(P), dens, path, desc
 
 
+def reference_mpi_block(cores):
+    """The reference's MPI path on the host cores (north_star: 'CPU (and MPI) path timed on the GPU box's own host cores')"""
+    try:
+        from oracle.oracle import run_reference_mpi
+        from unomol_b200 import basis as B
+        r = run_reference_mpi(B.test_input("tz2p.sf6"), cores)
+    except Exception as e:      # the baseline must never take the bench line down
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+    if r is None:
+        return {"unavailable": "oracle/_ref/UnomolMPI is not built"}
+    r["workload"] = WORKLOADS["sf6"][0]
+    r["what"] = ("unmodified reference MPI driver over oracle/mpi_shim (fork + shared memory), RHF to convergence; integral pass = "
+                 "TwoElectronIntsMPI::calculate (round-robin over the lsh loop, every rank stores its share), one SCF iteration = "
+                 "MPI_Bcast(P) + digestion of the stored share + MPI_Reduce(G) + serial diagonalisation")
+    return r
+
+
 def oracle_parity(path, P, G_gpu, nelem=6, seed=20261017):
     """max relative deviation of a few G elements from the unscreened CPU oracle (sum over every shell quartet that touches
     the element, reference primitive cut and storage threshold), relative to max|G|"""
@@ -221,6 +242,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-extra", action="store_true", help="skip the SF6 / (H2O)_308 / UHF side measurements")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity block")
+    ap.add_argument("--no-mpi", action="store_true", help="skip the run of the reference's MPI driver (SF6/TZ2P on all host cores)")
     ap.add_argument("--set", action="append", default=[], metavar="OPTION=VALUE",
                     help="engine option for experiments (unomol_b200_set_option), e.g. --set tile_kernels=0")
     args = ap.parse_args()
@@ -276,6 +298,8 @@ def main():
                                            "looped in C (oracle/ref_harness.cc:ref_quartet_batch), %d host threads"
                                            % (len(shells), sample_desc, cores)},
                 "e2e": {"value": val, "unit": "quartets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        if not args.no_mpi:
+            line["reference_mpi"] = reference_mpi_block(cores)
         print(json.dumps(line))
         return 0
 
@@ -560,6 +584,8 @@ def main():
                                               "the reference's calc_two_electron_ints_rys as calculate() calls it + storage threshold + "
                                               "formGMatrixKernel digestion (%d stored integrals), looped in C (oracle/ref_harness.cc:"
                                               "ref_quartet_batch)" % (n, ntot, dt, stored)}
+            if not args.no_mpi:
+                line["reference_mpi"] = reference_mpi_block(os.cpu_count() or 1)
         print(json.dumps(line))
     sync_all()
     if world > 1:

@@ -301,3 +301,42 @@ class Reference:
         S = np.zeros(no2); T = np.zeros(no2); H = np.zeros(no2)
         self.lib.ref_one_electron(h, _dp(S), _dp(T), _dp(H))
         return S, T, H
+
+
+def run_reference_mpi(patin_path, nranks, timeout_s=600):
+    """Run the reference's UNMODIFIED MPI driver (oracle/_ref/UnomolMPI: UnomolMPI.cc + TwoElectronIntsMPI.cpp + RHF_MPI.hpp /
+    UHF_MPI.hpp compiled against oracle/mpi_shim/mpi.h) on `nranks` forked ranks of this host, in a scratch directory.
+    Returns what the program itself reports: its integral pass ("Time for Two Electrons Integrals", slowest rank; reference
+    TwoElectronIntsMPI.cpp:440-442), its SCF loop ("SCF time", RHF_MPI.hpp:229), iterations, final energy (short.gs.out).
+    Test / bench infrastructure only."""
+    import re
+    import shutil
+    import subprocess
+    import tempfile
+    import time
+    exe = os.path.join(HERE, "_ref", "UnomolMPI")
+    if not os.path.exists(exe):
+        return None
+    d = tempfile.mkdtemp(prefix="unomol_mpi_")
+    try:
+        lines = open(patin_path).read().split("\n")
+        lines[3] = " 0 0"                      # no finite-field analysis, no polarisation scan: the SCF alone
+        open(os.path.join(d, "patin.dat"), "w").write("\n".join(lines))
+        env = dict(os.environ, UNOMOL_MPI_SHIM_NP=str(nranks))
+        t0 = time.perf_counter()
+        r = subprocess.run([exe], cwd=d, env=env, capture_output=True, text=True, timeout=timeout_s)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            return {"error": "exit status %d: %s" % (r.returncode, r.stderr[-300:])}
+        logs = [r.stderr] + [open(os.path.join(d, f)).read() for f in sorted(os.listdir(d)) if f.startswith("mpi_rank") and f.endswith(".err")]
+        eri = [float(x) for log in logs for x in re.findall(r"Time for Two Electrons Integrals = ([0-9.eE+-]+)", log)]
+        scf = [float(x) for log in logs for x in re.findall(r"SCF time = ([0-9.eE+-]+)", log)]
+        head = r.stderr.split("SCF time")[0]
+        nums = [int(x) for x in re.findall(r"Iteration\s+=\s+(\d+)", head)]
+        its = nums[-1] if nums else 0
+        short = open(os.path.join(d, "short.gs.out")).read().split()
+        return {"ranks": nranks, "eri_pass_s_slowest_rank": max(eri) if eri else None, "eri_pass_s_fastest_rank": min(eri) if eri else None,
+                "scf_s": max(scf) if scf else None, "iterations": its, "scf_s_per_iteration": (max(scf) / its) if scf and its else None,
+                "wall_s": wall, "energy": float(short[1]) if len(short) > 1 else None}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)

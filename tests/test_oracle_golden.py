@@ -120,3 +120,19 @@ def test_short_dat_fixture_is_consistent_with_fresh_reference_runs():
     for name, r in runs.items():
         if name in short:
             assert abs(r["e_final"] - short[name][1]) < 5e-12, name   # HEAD reproduces goldens to 1.3e-12
+
+
+def test_reference_mpi_build_over_the_shim():
+    """The reference's MPI driver (unmodified sources, oracle/mpi_shim/mpi.h instead of an MPI library) on 3 forked ranks
+    reproduces the serial reference's H2O/STO-3G energy: the round-robin split of TwoElectronIntsMPI.cpp:350-354 plus the
+    MPI_Reduce of RHF_MPI.hpp:108 lose nothing."""
+    import os
+    from oracle.oracle import run_reference_mpi, HERE
+    if not os.path.exists(os.path.join(HERE, "_ref", "UnomolMPI")):
+        pytest.skip("oracle/_ref/UnomolMPI not built (no /root/reference at build time)")
+    from unomol_b200.basis import test_input
+    r1 = run_reference_mpi(test_input("3g.h2o"), 1)
+    r3 = run_reference_mpi(test_input("3g.h2o"), 3)
+    assert r3["ranks"] == 3 and r3["iterations"] > 3
+    assert abs(r3["energy"] - (-74.962940006948)) < 1e-9      # BASELINE.json config 1
+    assert abs(r3["energy"] - r1["energy"]) < 1e-11
