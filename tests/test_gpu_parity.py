@@ -432,6 +432,40 @@ def test_in_process_handles_share_work_counters(capi, two_devices):
     assert n0 > 0 and n1 > 0 and n0 + n1 == hf.stats()["n_quartets"]
 
 
+@pytest.mark.parametrize("static_fraction", [0.0, 0.75, 1.0])
+def test_static_plus_stealing_split(capi, static_fraction):
+    """SURVEY 8(e) / north_star (4): the blocks of a launch are dealt to the ranks block-cyclically (static share) and the
+    tail is stolen from the shared counter.  Two ranks as two handles of this process (one GPU is enough), every kernel family
+    (tile and register kernels forced on the small cluster, generic kernel on SF6): the partial G's add up to the 1-rank G and
+    every quartet is evaluated exactly once, for a purely stolen (0), mixed (0.75) and purely static (1) hand-out."""
+    import threading
+    from unomol_b200.basis import Basis, water_cluster
+    for b, opts in ((Basis.from_patin(golden_input("tz2p.sf6")), {}), (water_cluster(8), {"tile_kernels": 2, "reg_kernels": 2})):
+        rng = np.random.default_rng(67)
+        P = rng.standard_normal(b.no2)
+        hf = capi.Handle(b)
+        hs = [capi.Handle(b, device=0, rank=r, nranks=2) for r in range(2)]
+        for h in [hf] + hs:
+            for k, v in opts.items():
+                h.set_option(k, v)
+        full = hf.fock_rhf(P)
+        hs[0].steal_share(hs[1])
+        for h in hs:
+            h.set_option("static_fraction", static_fraction)
+        for rep in range(3):
+            parts = [None, None]
+
+            def run(i):
+                parts[i] = hs[i].fock_rhf(P)
+            t = threading.Thread(target=run, args=(1,))
+            t.start(); run(0); t.join()
+            assert np.max(np.abs(parts[0] + parts[1] - full)) < 1e-12 * np.max(np.abs(full)), (static_fraction, rep)
+        n0, n1 = hs[0].stats()["n_quartets"], hs[1].stats()["n_quartets"]
+        assert n0 + n1 == hf.stats()["n_quartets"]
+        if static_fraction > 0:
+            assert n0 > 0 and n1 > 0      # a static share guarantees both ranks work, whoever starts first
+
+
 def test_device_pair_tables_match_host_pair_tables(capi):
     """pair tables built on the GPU (pair_device.cu) against the threaded host path (engine.cu)"""
     for name in ("631.nh3", "tz2p.sf6"):

@@ -798,6 +798,18 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         CUDA_TRY(h, cudaMemsetAsync(h->d_work_local, 0, sizeof(unsigned long long) * std::max<size_t>(1, h->plans.size()), st));
         work = h->d_work_local;
     }
+    // static-plus-stealing split (ClassTask::local_counter): this rank's own counters for the statically dealt blocks
+    unsigned long long *local = nullptr;
+    if (work && h->nranks > 1 && h->static_fraction > 0.0) {
+        if (!h->d_work_local) CUDA_TRY(h, cudaMalloc(&h->d_work_local, sizeof(unsigned long long) * unomol_b200::MAXPLAN));
+        CUDA_TRY(h, cudaMemsetAsync(h->d_work_local, 0, sizeof(unsigned long long) * std::max<size_t>(1, h->plans.size()), st));
+        local = h->d_work_local;
+    }
+    // blocks of a launch that are dealt statically: the given share of its blocks, a whole number per rank
+    auto static_blocks = [&](long long items, int chunk) -> long long {
+        const long long nblocks = (items + chunk - 1) / chunk;
+        return (long long)(h->static_fraction * (double)nblocks / h->nranks) * h->nranks;
+    };
     ++h->build_count;
     // The class launches are independent (they only meet in the FP64 reds on J/K): spread them over a few streams,
     // largest first, so that the small launches of small molecules (SF6: 24 launches of a few hundred CTAs)
@@ -844,12 +856,15 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
         task.counters = h->d_counters + 2 * ip;
         task.debug_flags = h->debug_flags;
         task.work_counter = work ? work + ip : nullptr;
+        task.local_counter = local ? local + ip : nullptr;
         task.cand_counter = h->d_counters + 2 * h->plans.size();
         const int nmine = work ? pl.nbra_eff : (pl.nbra_eff + h->nranks - 1) / h->nranks;
         task.chunk = std::max(1, std::min(8, pl.nbra_eff / (h->nsm * 16 * 8 * h->nranks)));
         if (pl.highl) {
             // work items of the runtime-L kernel are single quartets
             const long long nq = work ? pl.nquartets_eff : (pl.nquartets_eff + h->nranks - 1) / h->nranks;
+            task.chunk = 1;
+            task.static_blocks = static_blocks(pl.nquartets_eff, 1);
             CUDA_TRY(h, launch_any_class(h, pl.cb / NSUB, pl.ck / NSUB, task, MODE_DIGEST, (int)std::min<long long>(nq, 1 << 20), st));
             ++n_hl;
         } else if (pl.use_tile) {
@@ -864,9 +879,11 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
             task.chunk = 1;
             task.tile_slices = pl.tile_slices;
             const int items = pl.ntiles * pl.tile_slices;
+            task.static_blocks = static_blocks(items, 1);
             const int tmine = work ? items : (items + h->nranks - 1) / h->nranks;
             CUDA_TRY(h, launch_tile_class(pl.cb / NSUB, pl.ck / NSUB, task, std::min(tmine, h->nsm * 8), st));
         } else if (pl.use_reg) {
+            task.static_blocks = static_blocks(pl.nbra_eff, task.chunk);
             CUDA_TRY(h, launch_reg_class(pl.cb / NSUB, pl.ck / NSUB, task, std::min(nmine, h->nsm * 16), st, h->stage_rows != 0));
             ++n_reg;
             if (h->stage_rows && nspin == 1 && reg_rows_fit(pl.cb / NSUB, ld)) ++n_rows;
@@ -878,6 +895,8 @@ static int fock_device(unomol_b200 *h, int nspin, const double *dPA, const doubl
             if (!h->bra_split_enabled) split = 1;
             task.bra_split = split;
             const long long items = (long long)(work ? pl.nbra_eff : nmine) * split;
+            task.chunk = 1;      // the generic kernel's warps claim single (bra, slice) items
+            task.static_blocks = static_blocks((long long)pl.nbra_eff * split, 1);
             const int ctas = (int)std::min<long long>((items + 3) / 4, h->nsm * 32);   // 4 warps per CTA
             CUDA_TRY(h, launch_quartet_class(pl.cb / NSUB, pl.ck / NSUB, task, MODE_DIGEST, std::max(ctas, 1), st));
             ++n_gen;
@@ -1021,6 +1040,9 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
     if (!strcmp(name, "prim_cut")) { h->prim_cut = value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "bucket_min_pairs")) { h->bucket_min_pairs = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "work_stealing")) { h->steal_enabled = value != 0.0; return UNOMOL_OK; }
+    // share of a launch's blocks that is dealt to the ranks statically (block-cyclic over the cost-sorted blocks); the rest is
+    // stolen from the shared counter.  0 = every block from the shared counter (round-2 behaviour up to this option).
+    if (!strcmp(name, "static_fraction")) { h->static_fraction = std::min(1.0, std::max(0.0, value)); return UNOMOL_OK; }
     if (!strcmp(name, "device_pairs")) { h->device_pairs = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "col_blocks")) { h->col_blocks = (int)value; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "stage_rows")) { h->stage_rows = (int)value; return UNOMOL_OK; }

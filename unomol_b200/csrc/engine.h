@@ -145,6 +145,7 @@ struct unomol_b200 {
     static constexpr int MAXPLAN = ub200::NGROUP * (ub200::NGROUP + 1) / 2;
     unsigned long long *d_work_local = nullptr, *d_work_shared = nullptr;
     bool work_owner = false, work_imported = false, steal_enabled = true;   // option "work_stealing"
+    double static_fraction = 0.5;             // option "static_fraction": share of a launch's work blocks dealt statically (N > 1)
     bool work_borrowed = false;               // d_work_shared is another handle's allocation in this process (peer access)
     long long build_count = 0;
     unomol_b200_stats_t stats{};

@@ -177,12 +177,13 @@ eri_class_kernel(const ClassTask task) {
     const int nitems = (MODE == MODE_DIGEST) ? task.nbra * nsplit : 0;
     const int nouter = (MODE == MODE_DIGEST) ? nitems : (task.ntask + C::GROUPS - 1) / C::GROUPS;
     int wseq = blockIdx.x * warps_per_cta + warp;   // static sequence position of this warp
+    bool static_done = false;                       // lane 0's state of claim_block
     for (int outer = (MODE == MODE_DIGEST) ? 0 : blockIdx.x;; outer += (MODE == MODE_DIGEST) ? 1 : gridDim.x) {
         int bi = 0, kfirst = 0, kcount = 0, kstep = 1;
         if (MODE == MODE_DIGEST) {
             int item;
             if (task.work_counter) {
-                if (lane == 0) item = (int)atomicAdd_system(task.work_counter, 1ULL);
+                if (lane == 0) item = (int)min(claim_block(task, static_done), (long long)INT_MAX);
                 item = __shfl_sync(0xffffffffu, item, 0);
             } else {
                 item = task.nranks * wseq + ((wseq & 1) ? task.nranks - 1 - task.rank : task.rank);

@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(HL_THREADS) eri_highl_kernel(const ClassTask t
     double *red = sm + HL_OFF_RED;
     unsigned long long n_quart = 0, n_primq = 0;
     long long seq = blockIdx.x;
+    bool static_done = false;      // thread 0's state of claim_block
     for (int outer = blockIdx.x;; outer += gridDim.x) {
         int bi = 0, kfirst = 0, kcount = 0;
         if (MODE == MODE_DIGEST) {
@@ -27,7 +28,7 @@ __global__ void __launch_bounds__(HL_THREADS) eri_highl_kernel(const ClassTask t
             long long q;
             if (task.work_counter) {
                 __syncthreads();
-                if (threadIdx.x == 0) s_q = (long long)atomicAdd_system(task.work_counter, 1ULL);
+                if (threadIdx.x == 0) s_q = claim_block(task, static_done);
                 __syncthreads();
                 q = s_q;
             } else {

@@ -148,10 +148,12 @@ __global__ void __launch_bounds__(ROWS ? REG_THREADS_ROWS : REG_THREADS) eri_reg
     // when the counter lives in IPC-mapped peer memory, across the GPUs of the box).  Static fallback: snake order.
     __shared__ int s_next;
     int jb = blockIdx.x, cpos = 0, cend = 0;   // thread 0's sequencer state
+    bool static_done = false;
     auto advance = [&]() -> int {             // thread 0 only
         if (task.work_counter) {
             if (cpos >= cend) {
-                cpos = (int)atomicAdd_system(task.work_counter, (unsigned long long)task.chunk);
+                const long long blk = claim_block(task, static_done) * task.chunk;
+                cpos = (int)min(blk, (long long)INT_MAX - task.chunk);
                 cend = cpos + task.chunk;
             }
             return cpos < task.nbra ? cpos++ : task.nbra;

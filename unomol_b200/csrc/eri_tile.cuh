@@ -127,11 +127,13 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
     // from a counter shared by every CTA of every rank (work stealing; see eri_reg.cuh); static fallback: snake order.
     auto pos_of = [&](int j) { return task.nranks * j + ((j & 1) ? task.nranks - 1 - task.rank : task.rank); };
     int jb = blockIdx.x, cpos = 0, cend = 0;
+    bool static_done = false;
     auto advance = [&]() -> int {   // thread 0 only; returns a tile id or -1
         int p;
         if (task.work_counter) {
             if (cpos >= cend) {
-                cpos = (int)atomicAdd_system(task.work_counter, (unsigned long long)task.chunk);
+                const long long blk = claim_block(task, static_done) * task.chunk;
+                cpos = (int)min(blk, (long long)INT_MAX - task.chunk);
                 cend = cpos + task.chunk;
             }
             p = cpos++;

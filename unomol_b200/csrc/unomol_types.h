@@ -1,5 +1,6 @@
 // unomol_b200/csrc/unomol_types.h -- plain structs shared by host and device code.
 #pragma once
+#include <climits>
 #include <cstdint>
 #include "rys_roots.cuh"
 
@@ -80,7 +81,13 @@ struct ClassTask {
     int rank, nranks;         // static fallback: bras are dealt to ranks in snake order
     unsigned long long *work_counter;  // dynamic self-scheduling: next unclaimed bra of this launch (device-local, or on rank 0's
                               // GPU and IPC/NVLink-mapped into every rank: work stealing across the GPUs of the box); null = static
-    int chunk;                // bras claimed per atomic
+    // Static-plus-stealing split across the GPUs of the box: the launch's work is cut into blocks of `chunk`
+    // items, heaviest first.  Blocks [0, static_blocks) are dealt to the ranks in turn (block B belongs to rank B % nranks: a
+    // cost-weighted block-cyclic assignment, the blocks being cost-sorted) and a rank walks ITS blocks through a counter in its
+    // own memory; the remaining blocks, the light tail, are claimed by whoever is free from the shared counter on rank 0's GPU.
+    unsigned long long *local_counter; // null: every block comes from work_counter (single GPU, or option static_fraction = 0)
+    long long static_blocks;           // multiple of nranks
+    int chunk;                // items per block (bras claimed per atomic)
     int bra_split;            // generic kernel: warps that share the kets of one bra (work item = (bra, slice)); >= 1
     double prim_cut;          // reference's sr < 1e-12 cut
     double value_cut;         // reference's |val| > 1e-14 storage threshold (TwoElectronInts.cpp:513)
@@ -103,5 +110,20 @@ struct ClassTask {
 };
 
 enum Mode { MODE_DIGEST = 0, MODE_DUMP = 1, MODE_SCHWARZ = 2 };
+
+#ifdef __CUDACC__
+// Next block of work of a launch (see ClassTask::local_counter): this rank's next static block while there is one, then a
+// block of the shared tail.  `static_done` is the caller's (one claiming thread's) state, initially false.  The caller
+// compares the returned block with the number of blocks of the launch.
+__device__ __forceinline__ long long claim_block(const ClassTask &task, bool &static_done) {
+    if (task.local_counter && !static_done) {
+        const long long q = (long long)atomicAdd(task.local_counter, 1ULL);
+        const long long b = q * task.nranks + task.rank;
+        if (b < task.static_blocks) return b;
+        static_done = true;
+    }
+    return (task.local_counter ? task.static_blocks : 0) + (long long)atomicAdd_system(task.work_counter, 1ULL);
+}
+#endif
 
 }  // namespace ub200
