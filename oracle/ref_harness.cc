@@ -56,6 +56,20 @@ int ref_rys_roots(int nroots, double x, double* roots, double* weights) {
     return 0;
 }
 
+// Rys::rootN (Rys.cpp:231-312), 6..9 roots.  It crashes or hangs for 2 <~ X <~ 15: callers probe it
+// in a child process with a timeout (tests/golden/generate_golden.py) and keep the points where it returns.
+int ref_rys_rootN(int nroots, double x, double* roots, double* weights) {
+    static Rys* rys = nullptr;
+    if (!rys) rys = new Rys(4);
+    if (nroots < 6 || nroots > 9) return -1;
+    rys->calculate_roots(x, nroots);
+    for (int i = 0; i < nroots; ++i) {
+        roots[i] = rys->roots[i];
+        weights[i] = rys->weights[i];
+    }
+    return 0;
+}
+
 // ---- Basis ---------------------------------------------------------------------------------------
 void* ref_basis_open(const char* patin_path) { return new Basis(std::string(patin_path)); }
 void ref_basis_close(void* b) { delete static_cast<Basis*>(b); }

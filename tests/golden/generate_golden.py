@@ -8,6 +8,7 @@ Writes, next to this script:
   short_dat.json          the reference's own golden energies test/short.dat.* (E_iter0, E_final, dE)
   ref_runs.json           fresh runs of oracle/_ref/Unomol (finite-field flag off): E_iter0, E_final, iterations
   rys_grid.npz            roots/weights of the reference's Rys::root1..5 on a fixed X grid
+  rys_rootn_grid.npz      roots/weights of the reference's Rys::rootN (6..9 roots) at the X where it returns
   eri_3g_h2o.npz          every stored unique integral of H2O/STO-3G (reference cache dump)
   eri_631_nh3.npz, eri_631_co.npz   ditto (108 345 computed each)
   g_<input>.npz           reference formGmatrix for seeded random P (RHF and UHF), several inputs
@@ -227,7 +228,45 @@ def polscan_fixture():
         shutil.copyfile(os.path.join(t, f), os.path.join(d, f))
     shutil.rmtree(t, ignore_errors=True)
 
+def rootn_fixture():
+    """rys_rootn_grid.npz: the reference's general routine Rys::rootN (Rys.cpp:231-312) for 6..9 roots wherever it returns.  It
+    smashes its stack or hangs for 2 <~ X <~ 15, so every point is probed in a child process with a
+    timeout; the fixture keeps the points that came back (r = t^2/(1-t^2) and weights as the reference stores them)."""
+    probe = (
+        "import ctypes, sys\n"
+        "L = ctypes.CDLL(sys.argv[1])\n"
+        "L.ref_rys_rootN.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]\n"
+        "n = int(sys.argv[2]); r = (ctypes.c_double * 9)(); w = (ctypes.c_double * 9)()\n"
+        "for x in sys.argv[3:]:\n"
+        "    rc = L.ref_rys_rootN(n, float(x), r, w)\n"
+        "    print('OK', x, rc, ' '.join(repr(v) for v in list(r)[:n] + list(w)[:n]), flush=True)\n")
+    lib = os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "libunomol_ref.so")
+    xs = [0.0, 1e-6, 0.01, 0.1, 0.25, 0.5, 0.75, 1.0, 1.25, 1.5, 1.75, 2.0, 2.5, 3.0, 5.0, 8.0, 12.0, 14.0, 15.0, 15.5] + \
+         [16.0 + 0.5 * i for i in range(60)] + [47.0, 50.0, 55.0, 60.0, 66.0, 70.0, 75.0, 80.0, 88.0, 95.0, 110.0, 150.0, 300.0]
+    out = {}
+    for n in range(6, 10):
+        good_x, good_v = [], []
+        for x in xs:                      # one child per point: a crash must not take its neighbours down
+            try:
+                p = subprocess.run([sys.executable, "-c", probe, lib, str(n), repr(x)], capture_output=True, text=True, timeout=10)
+            except subprocess.TimeoutExpired:
+                continue
+            for line in p.stdout.splitlines():
+                t = line.split()
+                if t and t[0] == "OK" and int(t[2]) == 0 and p.returncode == 0:
+                    v = [float(u) for u in t[3:]]
+                    if all(np.isfinite(v)):
+                        good_x.append(float(t[1])); good_v.append(v)
+        out["x%d" % n] = np.array(good_x)
+        out["r%d" % n] = np.array([v[:n] for v in good_v]); out["w%d" % n] = np.array([v[n:] for v in good_v])
+        sys.stderr.write("rootN n=%d: %d of %d points returned (X = %s ...)\n" % (n, len(good_x), len(xs), good_x[:14]))
+    np.savez_compressed(os.path.join(HERE, "rys_rootn_grid.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--rootn-only" in sys.argv:
+        rootn_fixture()
+        sys.exit(0)
     if "--moments-only" in sys.argv:
         moments_fixtures()
         sys.exit(0)
@@ -242,3 +281,4 @@ if __name__ == "__main__":
     highl_input()
     moments_fixtures()
     polscan_fixture()
+    rootn_fixture()

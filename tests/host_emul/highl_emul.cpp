@@ -71,7 +71,12 @@ Pairs build_pairs(const Basis &B) {
 bool one_centre(const ShellPair &s) { return s.AB[0] == 0.0 && s.AB[1] == 0.0 && s.AB[2] == 0.0; }
 }  // namespace
 
+static int g_all_rys = 0;
+
 extern "C" {
+
+// 1: quartets with l_tot > 8 through the Rys quadrature (6..9 roots) instead of McMurchie-Davidson (engine option "all_rys")
+void hl_emul_set_all_rys(int v) { g_all_rys = v; }
 
 // (ish jsh | ksh lsh), every Cartesian component, out[((i*n2 + j)*n3 + k)*n4 + l]
 int hl_emul_quartet(int ns, int nbf, const int *npr, const int *lv, const int *cen, const int *off, const int *poff,
@@ -88,6 +93,7 @@ int hl_emul_quartet(int ns, int nbf, const int *npr, const int *lv, const int *c
     std::vector<double> sm(HL_SMEM_DOUBLES + 4 * HL_NC);
     hl.scratch = V.data(); hl.slab = (long long)V.size();
     hl.rys = rys_host_tables();
+    hl.all_rys = g_all_rys;
     hl_init_tables(hl, sm.data());
     hl_quartet_block(hl, bra, ket, P.prims.data(), prim_cut, one_centre(bra), one_centre(ket), sm.data(), V.data());
     const bool sw1 = (ish != jsh) && bra.sha != ish, sw2 = (ksh != lsh) && ket.sha != ksh;
@@ -134,6 +140,7 @@ int hl_emul_fock(int ns, int nbf, const int *npr, const int *lv, const int *cen,
             if (only_highl && std::max(std::max(hl.la, hl.lb), std::max(hl.lc, hl.ld)) <= 2) continue;
             hl.scratch = V.data(); hl.slab = 50625;
             hl.rys = rys_host_tables();
+            hl.all_rys = g_all_rys;
             hl_init_tables(hl, sm.data());
             hl_quartet_block(hl, bra, ket, P.prims.data(), prim_cut, one_centre(bra), one_centre(ket), sm.data(), V.data());
             double sym = 1.0;

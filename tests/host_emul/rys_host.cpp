@@ -13,6 +13,10 @@ extern "C" int unomol_rys_host(int n, double x, int exact, double *r, double *w)
         case 3: rys_roots<3>(x, r, w, T); return 0;
         case 4: rys_roots<4>(x, r, w, T); return 0;
         case 5: rys_roots<5>(x, r, w, T); return 0;
+        case 6: rys_roots<6>(x, r, w, T); return 0;
+        case 7: rys_roots<7>(x, r, w, T); return 0;
+        case 8: rys_roots<8>(x, r, w, T); return 0;
+        case 9: rys_roots<9>(x, r, w, T); return 0;
     }
     return -1;
 }

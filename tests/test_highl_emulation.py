@@ -23,6 +23,7 @@ def emul():
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, os.path.join(d, "highl_emul.cpp")])
     L = ctypes.CDLL(so)
     L.hl_emul_quartet.argtypes = [_I, _I] + [ctypes.POINTER(_I)] * 5 + [ctypes.POINTER(_D)] * 3 + [_D, _I, _I, _I, _I, ctypes.POINTER(_D)]
+    L.hl_emul_set_all_rys.argtypes = [_I]
     L.hl_emul_fock.argtypes = [_I, _I] + [ctypes.POINTER(_I)] * 5 + [ctypes.POINTER(_D)] * 3 + [_D, _D, _I] + [ctypes.POINTER(_D)] * 4 + [_I]
     return L
 
@@ -74,3 +75,37 @@ def test_kernel_body_fock_build_vs_reference_fixture(emul, oracle):
     scale = np.max(np.abs(g["G"]))
     assert np.max(np.abs(G - g["G"])) < 1e-12 * scale
     assert np.max(np.abs(GA - g["GA"])) < 1e-12 * scale and np.max(np.abs(GB - g["GB"])) < 1e-12 * scale
+
+
+def test_all_rys_mode_six_to_nine_roots_vs_the_md_fixture(emul, oracle):
+    """SURVEY 8(a) row a8.  The reference's MPI build has no McMurchie-Davidson dispatch: it sends quartets with l_tot > 8 to the
+    Rys quadrature with 6..9 roots from Rys::rootN (which crashes on them, SURVEY.md section 7).  Option all_rys does that with
+    the generated 6..9-root tables.  The blocks agree with the serial reference's McMurchie-Davidson values (the fixture) to
+    1e-10 -- the Rys branch applies the reference's primitive cut sr < 1e-12, its McMurchie-Davidson routine has none -- with ONE
+    exception: the two-centre block (ff|ff) of the two hydrogens, where the reference's McMurchie-Davidson value is off by 3.3e-7.
+    That is the reference's error, not the quadrature's: the 7-root result is reproduced to 1e-15 by an 8-root evaluation of the
+    same block (one root more than needed; checked with a modified copy of the kernel header, profiles/experiments/), and the
+    default path (McMurchie-Davidson, parity mode) reproduces the reference's value to 3e-16 as the tests above show."""
+    g = np.load(os.path.join(GOLDEN, "quartets_fg_h2o.npz"))
+    b = oracle.basis(golden_input("fg.h2o"))
+    emul.hl_emul_set_all_rys(1)
+    try:
+        worst = 0.0
+        nhigh = 0
+        roots = set()
+        for q, (i, j, k, l) in enumerate(g["quartets"]):
+            ltot = int(b.lv[i] + b.lv[j] + b.lv[k] + b.lv[l])
+            if ltot <= 8:
+                continue
+            nhigh += 1
+            roots.add(ltot // 2 + 1)
+            ref = g["values"][g["offsets"][q]:g["offsets"][q + 1]]
+            err = float(np.max(np.abs(_block(emul, b, int(i), int(j), int(k), int(l)).ravel() - ref)))
+            if (int(i), int(j), int(k), int(l)) == (8, 8, 11, 11):
+                assert 1e-7 < err < 1e-6, err          # the reference's own defect, see above
+            else:
+                worst = max(worst, err)
+    finally:
+        emul.hl_emul_set_all_rys(0)
+    assert nhigh >= 20 and roots == {5, 6, 7, 8}, (nhigh, roots)
+    assert worst < 1e-10, worst

@@ -33,7 +33,7 @@ def rys():
     L.unomol_f0_host.argtypes = [_D]; L.unomol_f0_host.restype = _D
 
     def f(n, x, exact=0):
-        r = np.zeros(5); w = np.zeros(5)
+        r = np.zeros(9); w = np.zeros(9)
         assert L.unomol_rys_host(n, float(x), exact, _dp(r), _dp(w)) == 0
         return r[:n].copy(), w[:n].copy()
     f.lib = L
@@ -109,3 +109,49 @@ def test_f0_only_path_matches_the_one_root_weight(rys):
         r, w = rys(1, x)
         worst = max(worst, abs(rys.lib.unomol_f0_host(float(x)) / w[0] - 1.0))
     assert worst < 1e-15, worst
+
+
+@pytest.mark.parametrize("n", [6, 7, 8, 9])
+def test_six_to_nine_roots_reproduce_the_boys_moments(rys, n):
+    """SURVEY 8(a) row a8: the range of the reference's Rys::rootN (Rys.cpp:231-312), here degree-12 tables generated at 80
+    digits (tools/gen_rys_tables.py --hi).  Defining property: the n-point rule integrates t^(2k), k < 2n, exactly."""
+    import mpmath as mp
+    mp.mp.dps = 40
+
+    def boys_mp(m, x):
+        if x == 0:
+            return 1.0 / (2 * m + 1)
+        return float(mp.gammainc(m + mp.mpf(1) / 2, 0, x) / (2 * mp.mpf(x) ** (m + mp.mpf(1) / 2)))
+    rng = np.random.default_rng(n)
+    xa = {6: 72.0, 7: 78.0, 8: 84.0, 9: 90.0}[n]
+    xs = np.concatenate([rng.uniform(0.0, 100.0, 150), [0.0, 1e-9, 0.999999, 1.0, 1.000001, 2.0, 8.5, 15.0, xa - 1e-9, xa, xa + 1e-9, 250.0]])
+    worst = 0.0
+    for x in xs:
+        r, w = rys(n, x)
+        assert np.all(np.diff(r) > 0) and np.all(w > 0)
+        t2 = r / (1.0 + r)
+        for k in range(2 * n):
+            ex = boys_mp(k, float(x))
+            worst = max(worst, abs(np.sum(w * t2 ** k) - ex) / ex)
+    assert worst < 2e-13, worst
+
+
+def test_six_to_nine_roots_vs_the_reference_rootN_where_it_returns(rys):
+    """The reference's general routine smashes its stack or hangs for 2 <~ X <~ 15; the fixture
+    (tests/golden/generate_golden.py: rootn_fixture, one child process per point) holds the points where it came back: X <= 2.5
+    and X >= 18.  There it is an orthogonal-polynomial construction from Boys moments in double precision, good to ~1e-9 on the
+    small weights; the table evaluator is compared at the tolerance that construction allows."""
+    g = np.load(os.path.join(GOLDEN, "rys_rootn_grid.npz"))
+    # measured differences (the moment tests above put the table evaluator at 2e-13 of the exact quadrature, so these are the
+    # reference's own errors): small X 3e-10 / 6e-9 / 2e-7 / 1.2e-5 for 6 / 7 / 8 / 9 roots, X >= 18 7e-13 / 1e-11 / 1e-10 / 7e-10
+    tol_small = {6: 1e-9, 7: 2e-8, 8: 1e-6, 9: 5e-5}
+    tol_large = {6: 5e-12, 7: 5e-11, 8: 5e-10, 9: 5e-9}
+    npts = 0
+    for n in range(6, 10):
+        for i, x in enumerate(g["x%d" % n]):
+            r, w = rys(n, x)
+            tol = tol_small[n] if x < 10.0 else tol_large[n]
+            assert np.max(np.abs(r / g["r%d" % n][i] - 1.0)) < tol, (n, x)
+            assert np.max(np.abs(w - g["w%d" % n][i])) / np.max(w) < tol, (n, x)
+            npts += 1
+    assert npts > 250

@@ -96,6 +96,7 @@ cudaError_t launch_any_class(unomol_b200 *h, int cb, int ck, const ClassTask &ta
     hl.scratch = h->d_hl_scratch;
     hl.slab = h->hl_slab;
     hl.rys = h->rys;
+    hl.all_rys = h->all_rys;
     return launch_highl(task, hl, mode, std::min(grid, unomol_b200::HL_GRID), s);
 }
 static int any_groups_per_cta(int cb, int ck) { return is_highl(cb, ck) ? 1 : class_groups_per_cta(cb, ck); }
@@ -1058,6 +1059,10 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
         return UNOMOL_OK;
     }
     if (!strcmp(name, "dump_kernel")) { h->dump_kernel = (int)value; return UNOMOL_OK; }
+    // 1: quartets with l_tot > 8 also go through the Rys quadrature (6..9 roots), which is what the reference's MPI build asks of
+    // its Rys::rootN (Rys.cpp:231-312); 0 (default): the serial reference's rule, McMurchie-Davidson above l_tot = 8.  Schwarz
+    // bounds of f/g pairs come from the same kernel, so the pair tables are rebuilt.
+    if (!strcmp(name, "all_rys")) { h->all_rys = value != 0.0; h->pairs_ready = false; return UNOMOL_OK; }
     if (!strcmp(name, "incremental_geometry")) { h->incremental = (int)value; return UNOMOL_OK; }
     if (!strcmp(name, "reg_kernels")) {
         h->use_reg_kernels = (int)value;     // 0 = generic kernel only, 1 = by class and list length, 2 = every available class

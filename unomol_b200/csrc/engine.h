@@ -99,6 +99,7 @@ struct unomol_b200 {
     double tau = 1e-12, prim_cut = 1e-12, value_cut = 1e-14;
     int use_reg_kernels = 1;
     int use_tile_kernels = 1;       // option "tile_kernels": 0 falls back to the one-bra-per-CTA register kernels
+    int all_rys = 0;                // option "all_rys": Rys quadrature with 6..9 roots for l_tot > 8 instead of McMurchie-Davidson
     int dump_kernel = 0;            // option "dump_kernel": 1 = eri_quartet / dump_eris run the kernel a Fock build uses for the class
     int device_pairs = 1;           // option "device_pairs": build the pair tables on the GPU (0 = threaded host path)
     int col_blocks = 0;             // option "col_blocks": spatial blocks per pair list (0 = choose from N so a launch fits L2)

@@ -55,9 +55,12 @@ constexpr int HL_OFF_R = HL_OFF_AY + HL_RD * HL_RD * (HL_RD + 1);   // [17][17][
 constexpr int HL_OFF_END = HL_OFF_R + HL_RD * HL_RD * HL_RD;
 constexpr int HL_OFF_G = 0;                                     // Rys: [3*5][<=25] 2-D tables
 constexpr int HL_OFF_S = HL_OFF_G + 15 * 25;                    // Rys: [3*5][<=81] shifted per-axis integrals
+constexpr int HL_RYS_BATCH = 5;                                 // roots whose tables are in shared memory at a time
+constexpr int HL_OFF_S_HI = HL_OFF_G + 3 * HL_RYS_BATCH * HL_TD * HL_TD;   // l_tot > 8 through Rys: G [15][<=81], S [15][<=625]
 constexpr int HL_OFF_NRM = HL_OFF_END;                          // [4][15] per-component norms
 constexpr int HL_OFF_RED = HL_OFF_NRM + 4 * HL_NC;              // [HL_THREADS] reduction scratch
 constexpr int HL_SMEM_DOUBLES = HL_OFF_RED + HL_THREADS;
+static_assert(HL_OFF_S_HI + 3 * HL_RYS_BATCH * HL_LD * HL_LD * HL_LD * HL_LD <= HL_OFF_END, "the all-Rys tables fit the McMurchie-Davidson region");
 constexpr size_t HL_SMEM_BYTES = sizeof(double) * HL_SMEM_DOUBLES + sizeof(int) * 4 * HL_NC;
 
 struct HighLArgs {
@@ -65,6 +68,8 @@ struct HighLArgs {
     double *scratch;             // per-CTA slabs for the Cartesian block
     long long slab;              // doubles per slab (>= ncart(la) ncart(lb) ncart(lc) ncart(ld))
     RysTables rys;               // Boys grid / piecewise root tables (device pointers; host arrays in the emulation build)
+    int all_rys;                 // 1: Rys quadrature also for l_tot > 8 (6..9 roots), as the reference's MPI build does through
+                                 // Rys::rootN (TwoElectronIntsMPI.cpp has no McMurchie-Davidson dispatch); 0: the serial reference's rule
 };
 
 HL_FN int hl_ncart(int l) { return (l + 1) * (l + 2) / 2; }
@@ -147,7 +152,12 @@ HL_FN void hl_roots(int nr, double X, double *rt, double *wt, const RysTables &T
         case 2: hl_roots_n<2>(X, rt, wt, T); break;
         case 3: hl_roots_n<3>(X, rt, wt, T); break;
         case 4: hl_roots_n<4>(X, rt, wt, T); break;
-        default: hl_roots_n<5>(X, rt, wt, T); break;
+        case 5: hl_roots_n<5>(X, rt, wt, T); break;
+        // all-Rys mode only (l_tot > 8): the range of the reference's Rys::rootN
+        case 6: hl_roots_n<6>(X, rt, wt, T); break;
+        case 7: hl_roots_n<7>(X, rt, wt, T); break;
+        case 8: hl_roots_n<8>(X, rt, wt, T); break;
+        default: hl_roots_n<9>(X, rt, wt, T); break;
     }
 }
 
@@ -182,11 +192,12 @@ HL_FN unsigned long long hl_quartet_block(const HighLArgs &hl, const ShellPair &
     unsigned long long nprimq = 0;
     for (int o = tid; o < NINT; o += nt) V[o] = 0.0;
     HL_SYNC();
-    if (ltot <= 8) {
+    if (ltot <= 8 || hl.all_rys) {
         // ------------------------------------------------ Rys branch
         const int nr = ltot / 2 + 1, GJ = Lb + 1, GSZ = (La + 1) * GJ;
         const int nS = (la + 1) * (lb + 1) * (lc + 1) * (ld + 1);
-        double *G = sm + HL_OFF_G, *S = sm + HL_OFF_S;
+        // l_tot > 8 (all-Rys mode, 6..9 roots): the tables of at most HL_RYS_BATCH roots at a time, in the larger layout
+        double *G = sm + HL_OFF_G, *S = sm + (ltot <= 8 ? HL_OFF_S : HL_OFF_S_HI);
         const double cut2 = prim_cut * prim_cut;
         for (int ib = 0; ib < bra.nprim; ++ib) {
             const PrimPair b = bp[ib];
@@ -200,22 +211,24 @@ HL_FN unsigned long long hl_quartet_block(const HighLArgs &hl, const ShellPair &
                 const double sr = t0 * sqrt(itx) * (b.c * k.c);
                 const double pq[3] = {b.P[0] - k.P[0], b.P[1] - k.P[1], b.P[2] - k.P[2]};
                 const double X = b.p * k.p * itx * (pq[0] * pq[0] + pq[1] * pq[1] + pq[2] * pq[2]);
-                double rt[5], wt[5];
+                double rt[9], wt[9];
                 hl_roots(nr, X, rt, wt, hl.rys);
-                for (int tsk = tid; tsk < 3 * nr; tsk += nt) {
+                for (int r0 = 0; r0 < nr; r0 += HL_RYS_BATCH) {
+                const int nrb = (nr - r0 < HL_RYS_BATCH) ? nr - r0 : HL_RYS_BATCH;      // roots of this batch (all of them when nr <= 5)
+                for (int tsk = tid; tsk < 3 * nrb; tsk += nt) {
                     const int ir = tsk / 3, ax = tsk - 3 * ir;
-                    const double dr = rt[ir];
+                    const double dr = rt[r0 + ir];
                     const double fff = dr * itx;
                     const double B00 = 0.5 * fff;
                     const double B1 = (0.5 - B00 * k.p) * b.ip;
                     const double B1p = (0.5 - B00 * b.p) * k.ip;
                     const double Cc = b.PA[ax] - k.p * pq[ax] * fff;
                     const double Cp = k.PA[ax] + b.p * pq[ax] * fff;
-                    hl_vrr(G + tsk * GSZ, La, Lb, B00, B1, B1p, Cc, Cp, ax == 2 ? wt[ir] * sr : 1.0);   // weight and prefactor ride on z
+                    hl_vrr(G + tsk * GSZ, La, Lb, B00, B1, B1p, Cc, Cp, ax == 2 ? wt[r0 + ir] * sr : 1.0);   // weight and prefactor ride on z
                 }
                 HL_SYNC();
                 // horizontal transfer per axis (reference Rys.hpp:173-192): exponents (ia, ib | ic, id) of one axis
-                for (int o = tid; o < 3 * nr * nS; o += nt) {
+                for (int o = tid; o < 3 * nrb * nS; o += nt) {
                     const int tsk = o / nS;
                     int r = o - tsk * nS;
                     const int ax = tsk % 3;
@@ -250,13 +263,14 @@ HL_FN unsigned long long hl_quartet_block(const HighLArgs &hl, const ShellPair &
                         idx[ax] = ((((pa >> sh) & 15) * (lb + 1) + ((pb >> sh) & 15)) * (lc + 1) + ((pc >> sh) & 15)) * (ld + 1) + ((pd >> sh) & 15);
                     }
                     double s = 0.0;
-                    for (int ir = 0; ir < nr; ++ir) {
+                    for (int ir = 0; ir < nrb; ++ir) {
                         const double *Sr = S + 3 * ir * nS;
                         s = fma(Sr[idx[0]] * Sr[nS + idx[1]], Sr[2 * nS + idx[2]], s);
                     }
                     V[o] += s;
                 }
                 HL_SYNC();
+                }
             }
         }
     } else {

@@ -46,6 +46,21 @@ constexpr double rys_herm(int weights, int i) {
 #undef RYS_CONST
     return weights ? rys_herm_w[i] : rys_herm_r[i];
 }
+// ... and of 6..9 roots (rys_consts_hi.inc): row n - 6 holds n entries
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr double rys_herm_hi(int weights, int i) {
+#define RYS_CONST(name, n) constexpr double name[n]
+#include "rys_consts_hi.inc"
+#undef RYS_CONST
+    return weights ? rys_herm_hi_w[i] : rys_herm_hi_r[i];
+}
+template <int N>
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr double rys_herm_n(int weights, int i) { return N <= 5 ? rys_herm(weights, 5 * (N - 1) + i) : rys_herm_hi(weights, 9 * (N - 6) + i); }
 
 // Table pointers in the caller's address space: device global memory (rys_tables.cu) or a shared-memory copy of the
 // Boys grid inside kernels, the host arrays of rys_host_tables() in host code.
@@ -54,6 +69,8 @@ struct RysTables {
     const double *boys1;       // [RYS_BOYS1_NPTS][2] = {F_8(X_i), exp(-X_i)}, X_i <= 35: one root (two recursion steps less)
     const double *boys0;       // [RYS_BOYS1_NPTS][2] = {F_7(X_i), exp(-X_i)}: F_0 alone ((ss|ss))
     const double *piece[3];    // 3, 4, 5 roots: [interval][k = 0..12][y_0..y_{n-1}, w_0..w_{n-1}], y = t^2
+    const double *piece_hi[4]; // 6..9 roots, same layout (rys_tables_hi.inc): all-Rys mode of the runtime-L kernel, the range of
+                               // the reference's Rys::rootN (Rys.cpp:231-312)
     int rys2_exact;            // 0: reference-compatible two-root band (see above); 1: exact two-root quadrature
     int pad;
 };
@@ -170,8 +187,8 @@ UNOMOL_HD void rys_hermite_limit_t2(double x, double *t2, double *w) {
     const double s = RYS_SQRT_PI_4 * rx, ix = rx * rx;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        t2[i] = rys_herm(0, 5 * (N - 1) + i) * ix;
-        w[i] = rys_herm(1, 5 * (N - 1) + i) * s;
+        t2[i] = rys_herm_n<N>(0, i) * ix;
+        w[i] = rys_herm_n<N>(1, i) * s;
     }
 }
 
@@ -300,6 +317,19 @@ UNOMOL_HD void rys_t2<4>(double x, double *t2, double *w, const RysTables &T) { 
 template <>
 UNOMOL_HD void rys_t2<5>(double x, double *t2, double *w, const RysTables &T) { rys_piecewise_t2<5>(x, t2, w, T.piece[2], RYS_P5_XA); }
 
+// 6..9 roots: the range of the reference's general routine Rys::rootN (Rys.cpp:231-312: Boys moments -> orthogonal polynomials ->
+// bracketed roots -> Christoffel weights, which crashes or hangs for 2 <~ X <~ 15).  Here the same kind of
+// table as for 3..5 roots, generated from the definition of the quadrature at 80 digits.
+static_assert(RYS_P6_DEG == RYS_P3_DEG && RYS_P7_DEG == RYS_P3_DEG && RYS_P8_DEG == RYS_P3_DEG && RYS_P9_DEG == RYS_P3_DEG, "one degree for all piecewise tables");
+template <>
+UNOMOL_HD void rys_t2<6>(double x, double *t2, double *w, const RysTables &T) { rys_piecewise_t2<6>(x, t2, w, T.piece_hi[0], RYS_P6_XA); }
+template <>
+UNOMOL_HD void rys_t2<7>(double x, double *t2, double *w, const RysTables &T) { rys_piecewise_t2<7>(x, t2, w, T.piece_hi[1], RYS_P7_XA); }
+template <>
+UNOMOL_HD void rys_t2<8>(double x, double *t2, double *w, const RysTables &T) { rys_piecewise_t2<8>(x, t2, w, T.piece_hi[2], RYS_P8_XA); }
+template <>
+UNOMOL_HD void rys_t2<9>(double x, double *t2, double *w, const RysTables &T) { rys_piecewise_t2<9>(x, t2, w, T.piece_hi[3], RYS_P9_XA); }
+
 // the reference's form: r[i] = t_i^2 / (1 - t_i^2)  (Rys.hpp:145-164); used by the evaluator's own tests
 template <int N>
 UNOMOL_HD void rys_roots(double x, double *r, double *w, const RysTables &T) {
@@ -313,6 +343,7 @@ UNOMOL_HD void rys_roots(double x, double *r, double *w, const RysTables &T) {
 namespace rys_host {
 #define RYS_TABLE(name, n) static const double name[n]
 #include "rys_tables.inc"
+#include "rys_tables_hi.inc"
 #undef RYS_TABLE
 }  // namespace rys_host
 inline RysTables rys_host_tables(int rys2_exact = 0) {
@@ -323,6 +354,10 @@ inline RysTables rys_host_tables(int rys2_exact = 0) {
     T.piece[0] = rys_host::rys_piece3_tab;
     T.piece[1] = rys_host::rys_piece4_tab;
     T.piece[2] = rys_host::rys_piece5_tab;
+    T.piece_hi[0] = rys_host::rys_piece6_tab;
+    T.piece_hi[1] = rys_host::rys_piece7_tab;
+    T.piece_hi[2] = rys_host::rys_piece8_tab;
+    T.piece_hi[3] = rys_host::rys_piece9_tab;
     T.rys2_exact = rys2_exact;
     T.pad = 0;
     return T;

@@ -7,6 +7,7 @@ namespace ub200 {
 
 #define RYS_TABLE(name, n) __device__ __align__(16) const double name[n]
 #include "rys_tables.inc"
+#include "rys_tables_hi.inc"
 #undef RYS_TABLE
 
 // Device addresses of the tables on the CURRENT device (symbols exist once per device).
@@ -25,6 +26,14 @@ cudaError_t rys_device_tables(RysTables *out) {
     out->piece[1] = (const double *)p;
     if ((e = cudaGetSymbolAddress(&p, rys_piece5_tab)) != cudaSuccess) return e;
     out->piece[2] = (const double *)p;
+    if ((e = cudaGetSymbolAddress(&p, rys_piece6_tab)) != cudaSuccess) return e;
+    out->piece_hi[0] = (const double *)p;
+    if ((e = cudaGetSymbolAddress(&p, rys_piece7_tab)) != cudaSuccess) return e;
+    out->piece_hi[1] = (const double *)p;
+    if ((e = cudaGetSymbolAddress(&p, rys_piece8_tab)) != cudaSuccess) return e;
+    out->piece_hi[2] = (const double *)p;
+    if ((e = cudaGetSymbolAddress(&p, rys_piece9_tab)) != cudaSuccess) return e;
+    out->piece_hi[3] = (const double *)p;
     out->rys2_exact = 0;
     out->pad = 0;
     return cudaSuccess;

@@ -33,7 +33,10 @@ BOYS1_MTOP = 8
 NTERMS = 8                 # Taylor terms: (1/32)^8/8! = 2e-17
 
 # n: (interval width, polynomial degree, XA_n)
-PIECE = {3: (1.0, 12, 52.0), 4: (1.0, 12, 58.0), 5: (1.0, 12, 64.0)}   # measured: degree 11 leaves 1.1e-16, XA: limit good to 4e-16
+PIECE = {3: (1.0, 12, 52.0), 4: (1.0, 12, 58.0), 5: (1.0, 12, 64.0),   # measured: degree 11 leaves 1.1e-16, XA: limit good to 4e-16
+         # 6..9 roots (--hi: rys_tables_hi.inc; the reference's Rys::rootN range, Rys.cpp:231-312): Gauss-Hermite limit measured
+         # good to 4e-16 (roots) / 1e-15 (weights) at 70 / 76 / 82 / 88
+         6: (1.0, 12, 72.0), 7: (1.0, 12, 78.0), 8: (1.0, 12, 84.0), 9: (1.0, 12, 90.0)}
 
 
 def boys(m, x):
@@ -213,5 +216,47 @@ def main():
     sys.stderr.write("wrote %s\n" % os.path.normpath(OUT))
 
 
+def main_hi():
+    """rys_tables_hi.inc / rys_consts_hi.inc: 6..9 roots (all-Rys mode for quartets with l_tot > 8).  Separate files so that the
+    tables of the default path stay byte-identical."""
+    mp.mp.dps = 80                 # the Hankel systems of 9 roots lose ~25 digits
+    check = "--check" in sys.argv
+    L = ["// unomol_b200/csrc/rys_tables_hi.inc -- GENERATED by unomol_b200/tools/gen_rys_tables.py --hi (mpmath, 80 digits) from the",
+         "// definition of the Rys quadrature: 6..9 roots.  Do not edit by hand."]
+    C = ["// unomol_b200/csrc/rys_consts_hi.inc -- GENERATED by unomol_b200/tools/gen_rys_tables.py --hi.  Do not edit by hand.",
+         "// large-X limit of 6..9 roots: t_i^2 = R_i / X, w_i = W_i sqrt(pi/(4X)); row n-6 holds n entries"]
+    hr, hw = [], []
+    for n in range(6, 10):
+        R, W = hermite_limits(n)
+        hr.append(R + [mp.mpf(0)] * (9 - n))
+        hw.append(W + [mp.mpf(0)] * (9 - n))
+    for name, rows in (("rys_herm_hi_r", hr), ("rys_herm_hi_w", hw)):
+        C.append("RYS_CONST(%s, 36) = {" % name)
+        for row in rows:
+            C.append("    " + ", ".join(fmt(v) for v in row) + ",")
+        C.append("};")
+    for n in (6, 7, 8, 9):
+        width, deg, xa, nint, rows, worst = gen_piece(n, check)
+        sys.stderr.write("n=%d: %d intervals of width %g, degree %d, XA %g, worst rel err on check points %.2e\n"
+                         % (n, nint, width, deg, xa, worst))
+        C.append("#define RYS_P%d_DEG %d" % (n, deg))
+        C.append("#define RYS_P%d_XA %.17g" % (n, xa))
+        C.append("#define RYS_P%d_NINT %d" % (n, nint))
+        L.append("// layout [interval][k = 0..deg][y_0..y_%d, w_0..w_%d], y = t^2" % (n - 1, n - 1))
+        L.append("RYS_TABLE(rys_piece%d_tab, %d) = {" % (n, nint * (deg + 1) * 2 * n))
+        for iv in range(nint):
+            for k in range(deg + 1):
+                L.append("    " + ", ".join(fmt(rows[iv][f][k]) for f in range(2 * n)) + ",")
+        L.append("};")
+    with open(os.path.join(HERE, "..", "csrc", "rys_tables_hi.inc"), "w") as f:
+        f.write("\n".join(L) + "\n")
+    with open(os.path.join(HERE, "..", "csrc", "rys_consts_hi.inc"), "w") as f:
+        f.write("\n".join(C) + "\n")
+    sys.stderr.write("wrote rys_tables_hi.inc, rys_consts_hi.inc\n")
+
+
 if __name__ == "__main__":
-    main()
+    if "--hi" in sys.argv:
+        main_hi()
+    else:
+        main()
