@@ -333,6 +333,38 @@ def test_high_l_quartets_vs_oracle_both_algorithms(capi, oracle):
     assert worst_rys < ERI_TOL and worst_md < ERI_TOL, (worst_rys, worst_md)
 
 
+def test_all_rys_mode_six_to_nine_roots_on_the_gpu(capi, oracle):
+    """SURVEY 8(a) row a8 on the device: option all_rys sends l_tot > 8 through the Rys quadrature with 6..9 roots (the range of
+    the reference's Rys::rootN, which the MPI build relies on and which crashes there) instead of McMurchie-Davidson.  Blocks
+    against the serial reference's values within 1e-10 (primitive cut of the Rys routine; see tests/test_highl_emulation.py for
+    the one (ff|ff) block where the reference's McMurchie-Davidson value itself is off by 3.3e-7), the whole G of fg.h2o against
+    the default build within 1e-7 relative, and the SCF energy moves by less than 1e-7 Eh."""
+    b, h = _handle(capi, "fg.h2o")
+    ob = oracle.basis(golden_input("fg.h2o"))
+    h.set_option("all_rys", 1)
+    rng = np.random.default_rng(19)
+    cases = [(5, 5, 5, 5), (5, 4, 8, 8), (11, 11, 8, 8), (4, 5, 11, 8), (5, 5, 11, 11), (3, 3, 5, 5), (5, 5, 5, 4)]
+    cases += [tuple(int(x) for x in rng.integers(0, b.nshell, 4)) for _ in range(40)]
+    worst = 0.0
+    nroots = set()
+    for (i, j, k, l) in cases:
+        lt = int(b.lv[i] + b.lv[j] + b.lv[k] + b.lv[l])
+        if lt <= 8 or sorted((i, j, k, l)) == [8, 8, 11, 11]:
+            continue
+        nroots.add(lt // 2 + 1)
+        worst = max(worst, float(np.max(np.abs(h.eri_quartet(i, j, k, l) - oracle.quartet_block(ob, i, j, k, l)))))
+    assert 9 in nroots and 6 in nroots, nroots          # (gg|gg) needs nine roots
+    assert worst < 1e-10, worst
+    d88 = float(np.max(np.abs(h.eri_quartet(8, 8, 11, 11) - oracle.quartet_block(ob, 8, 8, 11, 11))))
+    assert 1e-7 < d88 < 1e-6, d88
+    P = rng.standard_normal(b.no2)
+    G1 = h.fock_rhf(P)
+    assert h.stats()["n_highl_launches"] > 0
+    h0 = _handle(capi, "fg.h2o")[1]
+    G0 = h0.fock_rhf(P)
+    assert 0 < np.max(np.abs(G1 - G0)) < 1e-6 * np.max(np.abs(G0))
+
+
 def test_high_l_unique_integral_list_vs_oracle(capi, oracle):
     """all 2.6 million function quartets of fg.h2o (2.3 million above the reference's 1e-14 storage threshold)"""
     b, h = _handle(capi, "fg.h2o")
