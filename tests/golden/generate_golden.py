@@ -207,15 +207,20 @@ def moments_fixtures():
 REFT0 = "/root/reference/test"
 
 
-def polscan_fixture():
-    """polarisation-potential scan (reference RHF.hpp:292-388): the reference ships no input for it, so this one is ours --
-    water/6-31G with int_flag[0] = 1, three extra shells (s2 s1 p1) in posin.bas, six grid points in pos.grid.dat -- and the
-    unmodified reference is run on it; vpol.out / spol.out are the goldens (tests/test_gpu_scf.py::test_polarisation_scan...)."""
-    d = os.path.join(HERE, "polscan")
+def polscan_fixture(uhf=False):
+    """polarisation-potential scan (reference RHF.hpp:292-388, UHF.hpp:293-383): the reference ships no input for it, so this one
+    is ours -- water/6-31G (uhf: its cation, 9 electrons) with int_flag[0] = 1, three extra shells (s2 s1 p1) in posin.bas, six
+    grid points in pos.grid.dat -- and the unmodified reference is run on it; vpol.out / spol.out are the goldens
+    (tests/test_gpu_scf.py::test_polarisation_scan...)."""
+    d = os.path.join(HERE, "polscan_uhf" if uhf else "polscan")
     os.makedirs(d, exist_ok=True)
     txt = open(os.path.join(REFT0, "patin.dat.631.h2o")).read().split("\n")
-    k = [i for i, l in enumerate(txt) if l.strip()][3]
-    txt[k] = " 1 0"
+    nb = [i for i, l in enumerate(txt) if l.strip()]
+    txt[nb[3]] = " 1 0"
+    if uhf:
+        t1 = txt[nb[1]].split()
+        assert int(t1[0]) == 10
+        txt[nb[1]] = "      9 " + " ".join(t1[1:])
     open(os.path.join(d, "patin.dat"), "w").write("\n".join(txt))
     open(os.path.join(d, "posin.bas"), "w").write(" 3 5 1\n 2 0\n   1.6000000000   0.4000000000\n   0.4500000000   0.7000000000\n"
                                                   " 1 0\n   0.1200000000   1.0000000000\n 1 1\n   0.2500000000   1.0000000000\n")
@@ -275,10 +280,12 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--polscan-only" in sys.argv:
         polscan_fixture()
+        polscan_fixture(uhf=True)
         sys.exit(0)
     main()
     cation_variants()
     highl_input()
     moments_fixtures()
     polscan_fixture()
+    polscan_fixture(uhf=True)
     rootn_fixture()

@@ -358,3 +358,24 @@ def test_polarisation_scan_vs_reference_run(tmp_path):
     assert np.max(np.abs(ours_v[:, 4] - ref_v[:, 4]) / r4) < 4e-9                   # alpha = -2 V_pol r^4
     # every point after the first reuses the pair tables of the frozen molecule
     assert "(5 incremental so far)" in p.stderr
+
+
+def test_polarisation_scan_uhf_vs_reference_run(tmp_path):
+    """reference UHF.hpp:293-383: the same scan for an open shell (water cation, 9 electrons); vpol.out (five columns) / spol.out
+    of the unmodified reference are the goldens (generate_golden.py: polscan_fixture(uhf=True))."""
+    import numpy as np
+    d = os.path.join(GOLDEN, "polscan_uhf")
+    for f in ("patin.dat", "posin.bas", "pos.grid.dat"):
+        shutil.copyfile(os.path.join(d, f), tmp_path / f)
+    p = subprocess.run([BIN], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    ours_v = np.loadtxt(tmp_path / "vpol.out"); ref_v = np.loadtxt(os.path.join(d, "vpol.out"))
+    ours_s = np.loadtxt(tmp_path / "spol.out"); ref_s = np.loadtxt(os.path.join(d, "spol.out"))
+    assert ours_v.shape == ref_v.shape == (6, 5) and ours_s.shape == ref_s.shape == (6, 6)
+    assert np.max(np.abs(ours_v[:, :3] - ref_v[:, :3])) == 0.0
+    assert np.max(np.abs(ours_s[:, 1:4] - ref_s[:, 1:4])) < 2e-9                    # E_ground, E_first, E_final
+    assert np.max(np.abs(ours_s[:, 4] - ref_s[:, 4])) < 2e-9                        # V_stat
+    assert np.max(np.abs(ours_v[:, 3] - ref_v[:, 3])) < 2e-9                        # V_pol
+    r4 = np.sum(ours_v[:, :3] ** 2, axis=1) ** 2
+    assert np.max(np.abs(ours_v[:, 4] - ref_v[:, 4]) / r4) < 4e-9
+    assert "(5 incremental so far)" in p.stderr

@@ -15,7 +15,7 @@
 // cuSOLVER / cuBLAS on the device through unomol_b200_scf_set_overlap / unomol_b200_scf_diag (no CPU fallback).
 //                    moments.out / mol_dipmom.out through host/Moments.hpp (reference RHF.hpp:457-458, UHF.hpp:483);
 //                    the one-electron and moment INTEGRALS come from the device (unomol_b200_one_electron)
-// The polarisation-potential scan (RHF.hpp:292-388) is RestrictedHartreeFock::findPolarizationPotential below; the finite-field
+// The polarisation-potential scan (RHF.hpp:292-388, UHF.hpp:293-383) is findPolarizationPotential of both classes below; the finite-field
 // analysis is not implemented (the driver says so).
 #pragma once
 #include <cmath>
@@ -429,6 +429,9 @@ class UnRestrictedHartreeFock {
         }
         if (on_device)
             scf_check(unomol_b200_scf_fetch_uhf(tints.handle(), PmatA.data(), PmatB.data(), EvalsA.data(), EvalsB.data()), "scf_fetch_uhf");
+        PmatGsA = PmatA;                     // UHF.hpp:166-170: the ground state seeds every point of the polarisation scan
+        PmatGsB = PmatB;
+        energyGs = energy + nucrep;
         FILE *fp = fopen("PMATRIX.DAT", "w");
         if (fp) { fwrite(PmatA.data(), sizeof(double), no2, fp); fwrite(PmatB.data(), sizeof(double), no2, fp); fclose(fp); }
         FILE *out = fopen("short.gs.out", "w");
@@ -452,6 +455,72 @@ class UnRestrictedHartreeFock {
         MomentMatrices mom;
         MomentIntsAuto(basis, tints, mom);
         AnalyzeMoments(mom, PmatA.data(), PmatB.data(), basis.center_ptr(), ncen, no);
+    }
+
+    // The polarisation-potential scan for open shells (reference UHF.hpp:293-383); same construction as
+    // RestrictedHartreeFock::findPolarizationPotential above -- ONE engine over the augmented basis, incremental pair tables per
+    // grid point, S/T/H with the positron charge model on the device -- with the device-resident UHF iteration.  vpol.out has the
+    // reference's five columns here (UHF.hpp:337-338 writes no V_stat columns).
+    void findPolarizationPotential() {
+        const int pcen = basis.skip_center();
+        basis.dpm_augment();
+        no = basis.number_of_orbitals();
+        no2 = no * (no + 1) / 2;
+        ncen = basis.number_of_centers();
+        eps = 1.e-12;
+        PmatGsA.resize(no2, 0.0);            // new functions start empty (UHF.hpp:167,169)
+        PmatGsB.resize(no2, 0.0);
+        for (auto *v : {&Hmat, &Tmat, &Smat}) v->assign(no2, 0.0);
+        std::ifstream in("pos.grid.dat");
+        if (!in) fatal_error("could not open pos.grid.dat");
+        int npts = 0;
+        in >> npts;
+        FILE *vout = fopen("vpol.out", "w"), *sout = fopen("spol.out", "w");
+        std::vector<double> z(ncen);
+        for (int c = 0; c < ncen; ++c) z[c] = (c == pcen) ? 0.0 : basis.center_ptr()[c].charge();
+        TwoElectronInts *x = nullptr;
+        for (int i = 0; i < npts; ++i) {
+            double px, py, pz;
+            in >> px >> py >> pz;
+            basis.SetCenterPosition(px, py, pz, pcen);
+            nucrep = nuclear_repulsion_energy(ncen, basis.center_ptr());
+            if (!x) x = new TwoElectronInts(basis, 0, std::string("XINTS.DAT"));
+            else x->recalculate(basis);
+            scf_check(unomol_b200_one_electron_dpm(x->handle(), z.data(), pcen, Smat.data(), Tmat.data(), Hmat.data(), nullptr), "one_electron_dpm");
+            scf_check(unomol_b200_scf_set_overlap(x->handle(), Smat.data()), "scf_set_overlap");
+            scf_check(unomol_b200_scf_load_uhf(x->handle(), Hmat.data(), PmatGsA.data(), PmatGsB.data()), "scf_load_uhf");
+            iteration = 0;
+            eold = 0.0;
+            auto upd = [&](bool mix) {
+                scf_check(unomol_b200_scf_iterate_uhf(x->handle(), noccA, noccB, mix ? 1 : 0, &energy, &pdiff), "scf_iterate_uhf");
+                ediff = energy - eold;
+                eold = energy;
+                ++iteration;
+            };
+            upd(false);
+            const double e_first = energy + nucrep;
+            while (iteration < maxits) {
+                upd(!(ediff < 0.0));         // scf_converger: mix unless the last step lowered the energy
+                if (is_converged()) break;
+            }
+            const double e_final = energy + nucrep;
+            const double vpol = e_final - e_first;
+            // the reference adds the nuclear repulsion a second time at the first point only (UHF.hpp:334 vs :371); kept as is
+            const double vstat = (i == 0) ? e_first - energyGs + nucrep : e_first - energyGs;
+            const double r2 = px * px + py * py + pz * pz;
+            const double alfa = -2.0 * vpol * r2 * r2;
+            fprintf(vout, "%15.10lf %15.10lf %15.10lf %25.15le %25.15le\n", px, py, pz, vpol, alfa);
+            fflush(vout);
+            fprintf(sout, "%3d %20.10le %20.10le %20.10le %20.10le %25.15le\n", i, energyGs, e_first, e_final, vstat, ediff);
+            fflush(sout);
+            unomol_b200_stats_t st;
+            unomol_b200_stats(x->handle(), &st);
+            fprintf(stderr, "polarisation scan point %d (UHF): %d iterations, pair-table update %.3f ms (%d incremental so far), one-electron kernel %.3f ms\n",
+                    i, iteration, st.precompute_ms, st.n_incremental_updates, st.onee_ms);
+        }
+        fclose(vout);
+        fclose(sout);
+        delete x;
     }
 
     bool is_converged() const noexcept {
@@ -486,8 +555,8 @@ class UnRestrictedHartreeFock {
     TwoElectronInts &tints;
     int no = 0, no2 = 0, ncen = 0, noccA = 0, noccB = 0, maxits = 0, scf_accel = 0, cflag = 0, iteration = 0;
     bool on_device = false, mix_next = false;
-    double eps = 0, ediff = 10.0, pdiff = 10.0, eold = 0, nucrep = 0, energy = 0;
-    std::vector<double> Pold2A, PoldA, PmatA, GmatA, Pold2B, PoldB, PmatB, GmatB, Hmat, Fock, Tmat, Smat, EvalsA, EvalsB;
+    double eps = 0, ediff = 10.0, pdiff = 10.0, eold = 0, nucrep = 0, energy = 0, energyGs = 0;
+    std::vector<double> Pold2A, PoldA, PmatA, GmatA, Pold2B, PoldB, PmatB, GmatB, Hmat, Fock, Tmat, Smat, EvalsA, EvalsB, PmatGsA, PmatGsB;
 };
 
 }  // namespace unomol

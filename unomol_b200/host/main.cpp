@@ -30,11 +30,8 @@ int main(int argc, char **argv) {
     if (nelec % 2) {
         unomol::UnRestrictedHartreeFock uhf(&bas, &t);
         uhf.findEnergy();
-        if (bas.int_flags(0)) {
-            std::fprintf(stderr, "unomol_b200_scf: the polarisation scan is implemented for closed shells (RHF) only\n");
-            return 3;
-        }
         std::fprintf(stderr, "UHF energy %.15f after %d iterations\n", uhf.total_energy(), uhf.iterations());
+        if (bas.int_flags(0)) uhf.findPolarizationPotential();   // reference Unomol.cc:18
     } else {
         unomol::RestrictedHartreeFock rhf(&bas, &t);
         rhf.findEnergy();
