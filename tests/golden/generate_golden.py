@@ -233,6 +233,27 @@ def polscan_fixture(uhf=False):
         shutil.copyfile(os.path.join(t, f), os.path.join(d, f))
     shutil.rmtree(t, ignore_errors=True)
 
+def finitefield_fixtures():
+    """finitefield/<input>.out: finitefield.out of the unmodified reference run on the shipped inputs as they are (int_flag[1] = 1:
+    Unomol.cc:16-17 -> RHF.hpp:235-271 / UHF.hpp:239-272, three SCFs in a field of 5e-3 a.u. along x, y, z)."""
+    d = os.path.join(HERE, "finitefield")
+    os.makedirs(d, exist_ok=True)
+    # open shell: the water cation (non-degenerate hole; the CO2 / C2H2 cations have a degenerate pi hole and their UHF solutions in
+    # a field depend on which component the ground state happened to pick -- the reference's own x and y values differ there)
+    for name in ["3g.h2o", "631.nh3", "631.co", "631.h2o.cation"]:
+        t = tempfile.mkdtemp()
+        txt = open(os.path.join(HERE, "inputs", "patin.dat." + name.replace(".cation", ""))).read().split("\n")
+        nb = [i for i, l in enumerate(txt) if l.strip()]
+        k = nb[3]
+        if name.endswith(".cation"):
+            f = txt[nb[1]].split(); txt[nb[1]] = "     %d    %s" % (int(f[0]) - 1, f[1])
+        txt[k] = " 0 1"
+        open(os.path.join(t, "patin.dat"), "w").write("\n".join(txt))
+        subprocess.run([Reference.UNOMOL], cwd=t, capture_output=True, text=True, timeout=3600, check=True)
+        shutil.copyfile(os.path.join(t, "finitefield.out"), os.path.join(d, name + ".out"))
+        shutil.rmtree(t, ignore_errors=True)
+
+
 def rootn_fixture():
     """rys_rootn_grid.npz: the reference's general routine Rys::rootN (Rys.cpp:231-312) for 6..9 roots wherever it returns.  It
     smashes its stack or hangs for 2 <~ X <~ 15, so every point is probed in a child process with a
@@ -269,6 +290,9 @@ def rootn_fixture():
 
 
 if __name__ == "__main__":
+    if "--finitefield-only" in sys.argv:
+        finitefield_fixtures()
+        sys.exit(0)
     if "--rootn-only" in sys.argv:
         rootn_fixture()
         sys.exit(0)
@@ -288,4 +312,5 @@ if __name__ == "__main__":
     moments_fixtures()
     polscan_fixture()
     polscan_fixture(uhf=True)
+    finitefield_fixtures()
     rootn_fixture()

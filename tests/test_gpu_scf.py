@@ -301,14 +301,35 @@ def test_mo_transition_dipoles_written(tmp_path):
     assert abs(diag[0] - 0.0) < 1e-2        # oxygen 1s sits at the origin
 
 
-def test_driver_refuses_a_silent_partial_run(tmp_path):
-    """reference Unomol.cc runs FiniteFieldAnalysis() when int_flag[1] is set; this driver does not implement it and must say so
-    (exit status 3) unless the caller opts out with UNOMOL_SKIP_FINITE_FIELD=1"""
-    shutil.copyfile(golden_input("3g.h2o"), tmp_path / "patin.dat")
+@pytest.mark.parametrize("name", ["3g.h2o", "631.nh3", "631.co", "631.h2o.cation"])
+def test_finite_field_analysis_vs_reference_run(name, tmp_path):
+    """reference Unomol.cc:16-17,22: FiniteFieldAnalysis() when int_flag[1] is set (RHF.hpp:235-271, UHF.hpp:239-272; every
+    shipped input sets it): three SCFs in a field of 5e-3 a.u. restarted from the ground-state density.  finitefield.out of the
+    unmodified reference is the golden (generate_golden.py: finitefield_fixtures); polarisation energies within 2e-9 Eh, hence
+    alpha = -2 dE / E^2 within 2e-4.  Open shell: the water cation (a non-degenerate hole; the UHF solutions of the CO2 / C2H2
+    cations in a field depend on which pi component the ground state picked -- the reference's own x and y values differ)."""
+    lines = open(golden_input(name.replace(".cation", ""))).read().split("\n")
+    nb = [i for i, l in enumerate(lines) if l.strip()]
+    k = nb[3]
+    if name.endswith(".cation"):
+        f = lines[nb[1]].split(); lines[nb[1]] = "     %d    %s" % (int(f[0]) - 1, f[1])
+    lines[k] = " 0 1"
+    open(tmp_path / "patin.dat", "w").write("\n".join(lines))
     env = {k: v for k, v in os.environ.items() if k != "UNOMOL_SKIP_FINITE_FIELD"}
-    p = subprocess.run([BIN], cwd=tmp_path, capture_output=True, text=True, timeout=300, env=env)
-    assert p.returncode == 3 and "finite-field" in p.stderr
-    assert os.path.exists(tmp_path / "short.gs.out")          # the ground-state outputs are still written
+    p = subprocess.run([BIN], cwd=tmp_path, capture_output=True, text=True, timeout=900, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+
+    def parse(path):
+        rows = [ln.split() for ln in open(path).read().splitlines()]
+        return {r[0]: (float(r[1]), float(r[2])) for r in rows if len(r) == 3 and r[0] in ("x", "y", "z")}
+    ours = parse(tmp_path / "finitefield.out"); ref = parse(os.path.join(GOLDEN, "finitefield", name + ".out"))
+    assert set(ours) == set(ref) == {"x", "y", "z"}
+    for ax in "xyz":
+        assert abs(ours[ax][1] - ref[ax][1]) < 2e-9, (ax, ours[ax], ref[ax])
+        assert abs(ours[ax][0] - ref[ax][0]) < 2e-4, (ax, ours[ax], ref[ax])
+    # and the opt-out leaves the analysis out, loudly
+    p = subprocess.run([BIN], cwd=tmp_path, capture_output=True, text=True, timeout=900, env=dict(env, UNOMOL_SKIP_FINITE_FIELD="1"))
+    assert p.returncode == 0 and "finite-field analysis skipped" in p.stderr
 
 
 # BASELINE.md section 2: final energies of the reference rebuilt with -DUNOMOL_MD_INTS (McMurchie-Davidson for every quartet,

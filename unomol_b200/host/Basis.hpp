@@ -149,6 +149,7 @@ class Basis {
     int total_number_of_centers() const noexcept { return tncen; }
     int total_number_of_orbitals() const noexcept { return tnorb; }
     int skip_center() const noexcept { return skipcen; }
+    constexpr double FiniteFieldValue() const noexcept { return 5.e-3; }   // reference Basis.hpp:233,349-351
     void dpm_augment() noexcept {   // reference Basis.hpp:341-345
         nshell = tnshell;
         norb = tnorb;

@@ -15,8 +15,8 @@
 // cuSOLVER / cuBLAS on the device through unomol_b200_scf_set_overlap / unomol_b200_scf_diag (no CPU fallback).
 //                    moments.out / mol_dipmom.out through host/Moments.hpp (reference RHF.hpp:457-458, UHF.hpp:483);
 //                    the one-electron and moment INTEGRALS come from the device (unomol_b200_one_electron)
-// The polarisation-potential scan (RHF.hpp:292-388, UHF.hpp:293-383) is findPolarizationPotential of both classes below; the finite-field
-// analysis is not implemented (the driver says so).
+// The polarisation-potential scan (RHF.hpp:292-388, UHF.hpp:293-383) is findPolarizationPotential of both classes below, the
+// finite-field analysis (RHF.hpp:235-271, UHF.hpp:239-272) FiniteFieldAnalysis.
 #pragma once
 #include <cmath>
 #include <cstdio>
@@ -182,6 +182,44 @@ class RestrictedHartreeFock {
         FILE *fp = fopen("PMATRIX.DAT", "w");
         if (fp) { fwrite(Pmat.data(), sizeof(double), no2, fp); fclose(fp); }
         final_output(init_energy);
+    }
+
+    // Finite-field analysis (reference RHF.hpp:235-271, FField.cpp:5-19): three SCFs restarted from the ground-state density with
+    // H - E.(dx, dy, dz), E = 5e-3 a.u. along x, y, z; polarisation energies and alpha = -2 dE / E^2 into finitefield.out.
+    // The dipole matrices are the device one-electron kernel's (the reference reads the same numbers back from RMOM.DAT).
+    void FiniteFieldAnalysis() {
+        double polnrg[3], alfpol[3];
+        const double Emag = basis.FiniteFieldValue();
+        MomentMatrices mom;
+        MomentIntsAuto(basis, tints, mom);
+        for (int ix = 0; ix < 3; ++ix) {
+            OneElectronIntsAuto(basis, tints, Smat.data(), Tmat.data(), Hmat.data());
+            for (int i = 0; i < no2; ++i) Hmat[i] -= Emag * mom.m[ix][i];
+            scf_check(unomol_b200_scf_set_overlap(tints.handle(), Smat.data()), "scf_set_overlap");
+            Pmat = PmatGs;
+            if (on_device) scf_check(unomol_b200_scf_load(tints.handle(), Hmat.data(), Pmat.data()), "scf_load");
+            iteration = 0;
+            eold = 0.0;
+            mix_next = false;
+            update();
+            while (iteration < maxits) {
+                scf_converger();
+                update();
+                if (is_converged()) break;
+            }
+            polnrg[ix] = energy + nucrep - energyGs;
+            alfpol[ix] = -polnrg[ix] * 2.0 / Emag / Emag;
+        }
+        FILE *out = fopen("finitefield.out", "w");
+        fprintf(out, "        Unomol Finite Field Analysis\n");
+        fprintf(out, "        Electric field magnitude = %20.12le\n", Emag);
+        fprintf(out, "     alfa                pol energy\n");
+        fprintf(out, " x   %20.12le %20.12le\n", alfpol[0], polnrg[0]);
+        fprintf(out, " y   %20.12le %20.12le\n", alfpol[1], polnrg[1]);
+        fprintf(out, " z   %20.12le %20.12le\n", alfpol[2], polnrg[2]);
+        fprintf(out, " alf isotropic = %20.12le\n", (alfpol[0] + alfpol[1] + alfpol[2]) / 3.0);
+        fprintf(out, " alf aniso     = %20.12le\n", (2. * alfpol[2] - alfpol[1] - alfpol[0]) / 3.0);
+        fclose(out);
     }
 
     // The polarisation-potential scan (reference RHF.hpp:292-388): the basis is augmented by the posin.bas shells on one extra
@@ -455,6 +493,41 @@ class UnRestrictedHartreeFock {
         MomentMatrices mom;
         MomentIntsAuto(basis, tints, mom);
         AnalyzeMoments(mom, PmatA.data(), PmatB.data(), basis.center_ptr(), ncen, no);
+    }
+
+    // Finite-field analysis for open shells (reference UHF.hpp:239-272); see RestrictedHartreeFock::FiniteFieldAnalysis
+    void FiniteFieldAnalysis() {
+        double polnrg[3], alfpol[3];
+        const double Emag = basis.FiniteFieldValue();
+        MomentMatrices mom;
+        MomentIntsAuto(basis, tints, mom);
+        for (int ix = 0; ix < 3; ++ix) {
+            OneElectronIntsAuto(basis, tints, Smat.data(), Tmat.data(), Hmat.data());
+            for (int i = 0; i < no2; ++i) Hmat[i] -= Emag * mom.m[ix][i];
+            scf_check(unomol_b200_scf_set_overlap(tints.handle(), Smat.data()), "scf_set_overlap");
+            PmatA = PmatGsA;
+            PmatB = PmatGsB;
+            if (on_device) scf_check(unomol_b200_scf_load_uhf(tints.handle(), Hmat.data(), PmatA.data(), PmatB.data()), "scf_load_uhf");
+            iteration = 0;
+            eold = 0.0;
+            mix_next = false;
+            update();
+            while (iteration < maxits) {
+                scf_converger();
+                update();
+                if (is_converged()) break;
+            }
+            polnrg[ix] = energy + nucrep - energyGs;
+            alfpol[ix] = -polnrg[ix] * 2.0 / Emag / Emag;
+        }
+        FILE *out = fopen("finitefield.out", "w");
+        fprintf(out, "        Unomol Finite Field Analysis\n");
+        fprintf(out, "        Electric field magnitude = %20.12le\n", Emag);
+        fprintf(out, "     alfa                pol energy\n");
+        fprintf(out, " x   %20.12le %20.12le\n", alfpol[0], polnrg[0]);
+        fprintf(out, " y   %20.12le %20.12le\n", alfpol[1], polnrg[1]);
+        fprintf(out, " z   %20.12le %20.12le\n", alfpol[2], polnrg[2]);
+        fclose(out);
     }
 
     // The polarisation-potential scan for open shells (reference UHF.hpp:293-383); same construction as
