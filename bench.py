@@ -43,6 +43,8 @@ WORKLOADS = {
     "co2": ("CO2 / DZP (test/patin.dat.dh95.co2), 90 basis functions", lambda B: B.Basis.from_patin(B.test_input("dh95.co2"))),
     "c2h2": ("C2H2 / DZP (test/patin.dat.dh95.c2h2), 90 basis functions", lambda B: B.Basis.from_patin(B.test_input("dh95.c2h2"))),
     "nh3": ("NH3 / 6-31G** (test/patin.dat.631.nh3), 30 basis functions", lambda B: B.Basis.from_patin(B.test_input("631.nh3"))),
+    "fgh2o": ("H2O-like 3-centre system with s..g shells (tests/golden/inputs/patin.dat.fg.h2o), 67 basis functions: the runtime-L kernel",
+              lambda B: B.Basis.from_patin(B.test_input("fg.h2o"))),
 }
 
 
@@ -539,7 +541,7 @@ def main():
 
     extra = None
     if not args.no_extra and args.workload == "water154":
-        extra = {"sf6_tz2p_rhf": side_build("sf6", 1, 10), "co2_dzp_uhf": side_build("co2", 2, 10),
+        extra = {"sf6_tz2p_rhf": side_build("sf6", 1, 10), "co2_dzp_uhf": side_build("co2", 2, 10), "fg_h2o_rhf": side_build("fgh2o", 1, 5),
                  "water154_uhf": side_build("water154", 2, 2), "water308_rhf": side_build("water308", 1, 2)}
 
     if rank == 0:

@@ -350,6 +350,18 @@ def test_exact_two_root_mode_follows_the_md_build(name, tmp_path):
     assert abs((e1 - e1p) - shift_ref) < 2e-9, (e1 - e1p, shift_ref)
 
 
+def test_exact_mode_with_f_and_g_shells(tmp_path):
+    """UNOMOL_EXACT=1 = rys2_exact + all_rys: every quartet, also l_tot > 8, through a Rys quadrature that is exact to rounding
+    (SURVEY section 7 'build both': parity mode is the default, this is the production mode).  On fg.h2o the energy moves away
+    from the parity build by the reference's own defects -- the two-root band and, above all, its McMurchie-Davidson two-centre
+    (ff|ff) values (3e-7 per integral) -- i.e. by a small but non-zero amount; the SCF converges as before."""
+    _, e_par, _, _ = run_scf("fg.h2o", tmp_path)
+    _, e_ex, de, out = run_scf("fg.h2o", tmp_path, env={"UNOMOL_EXACT": "1"})
+    assert "NOT_ REACHED" not in out
+    assert 1e-10 < abs(e_ex - e_par) < 1e-5, (e_ex, e_par)
+    assert abs(e_par - RUNS["fg.h2o"]["e_final"]) < E_TOL
+
+
 def test_direct_form_g_matrix_entry_point(tmp_path):
     """the shim's directFormGMatrix (reference TwoElectronInts.hpp:106) drives a whole SCF: same energy as formGmatrix.  (The
     reference's own directFormGMatrix is dead code with extra cuts, |AB|^2 > 20 and 1e-12 on values, that are NOT reproduced.)"""

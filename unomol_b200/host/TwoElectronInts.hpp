@@ -91,6 +91,17 @@ class TwoElectronInts {
             check(unomol_b200_set_option(h, "rys2_exact", 1), "set_option");
             for (auto *x : extra) check(unomol_b200_set_option(x, "rys2_exact", 1), "set_option");
         }
+        // UNOMOL_EXACT=1: production mode without the reference's numerical defects -- the exact two-root quadrature AND the Rys
+        // quadrature with 6..9 roots for l_tot > 8 (option all_rys) instead of the reference's McMurchie-Davidson routine, whose
+        // Boys function switches to the bare asymptote at t = 20 (7e-11) and whose two-centre variant is off by up to 3e-7 on
+        // (ff|ff) blocks (tests/test_highl_emulation.py).  Every quartet is then evaluated by a quadrature that is exact to rounding.
+        const char *ex = getenv("UNOMOL_EXACT");
+        if (ex && atoi(ex)) {
+            for (const char *opt : {"rys2_exact", "all_rys"}) {
+                check(unomol_b200_set_option(h, opt, 1), "set_option");
+                for (auto *x : extra) check(unomol_b200_set_option(x, opt, 1), "set_option");
+            }
+        }
         const char *tau = getenv("UNOMOL_SCHWARZ_TAU");
         if (tau) {
             check(unomol_b200_set_option(h, "schwarz_tau", atof(tau)), "set_option");
