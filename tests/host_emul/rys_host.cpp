@@ -21,8 +21,13 @@ extern "C" int unomol_rys_host(int n, double x, int exact, double *r, double *w)
     return -1;
 }
 
-// F_0(x) .. F_3(x) through the grid path (x < 46)
+// F_0(x) .. F_3(x) through the two-root moment path (x < 46): Taylor row of F_3 + downward recursion (boys_poly03)
 extern "C" void unomol_boys_host(double x, double *F) {
+    const RysTables T = rys_host_tables(0);
+    boys_poly03(x, T.f3poly, F);
+}
+// ... and through the recursion-based grid of round 2's first evaluator (still used by nothing but this cross-check)
+extern "C" void unomol_boys_grid_host(double x, double *F) {
     const RysTables T = rys_host_tables(0);
     boys_grid<3, RYS_BOYS_MTOP>(x, T.boys, F);
 }

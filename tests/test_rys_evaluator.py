@@ -30,6 +30,7 @@ def rys():
     L = ctypes.CDLL(so)
     L.unomol_rys_host.argtypes = [ctypes.c_int, _D, ctypes.c_int, ctypes.POINTER(_D), ctypes.POINTER(_D)]
     L.unomol_boys_host.argtypes = [_D, ctypes.POINTER(_D)]
+    L.unomol_boys_grid_host.argtypes = [_D, ctypes.POINTER(_D)]
     L.unomol_f0_host.argtypes = [_D]; L.unomol_f0_host.restype = _D
 
     def f(n, x, exact=0):
@@ -100,6 +101,13 @@ def test_boys_grid_path(rys):
             ex = boys_exact(m, x)
             worst = max(worst, abs(F[m] - ex) / ex)
     assert worst < 2e-14, worst       # scipy's gammainc is the limit here; against mpmath the grid path is good to 7e-16
+    # the Taylor-row path the kernels use against the recursion-based grid: two independent evaluations of the same moments
+    G = np.zeros(4)
+    worst = 0.0
+    for x in np.linspace(0.0, 45.99, 4603):
+        rys.lib.unomol_boys_host(float(x), _dp(F)); rys.lib.unomol_boys_grid_host(float(x), _dp(G))
+        worst = max(worst, float(np.max(np.abs(F / G - 1.0))))
+    assert worst < 2e-15, worst
 
 
 def test_f0_only_path_matches_the_one_root_weight(rys):

@@ -44,8 +44,8 @@ __host__ __device__ inline TileLayout tile_layout(int maxbp, int tile_b, int nab
 // Boys grid entries a class needs in shared memory (rys_roots.cuh): one root up to X = 35, two roots up to X = 15
 // (parity mode) or 46 (exact mode); three and more roots read their polynomial tables from global memory
 __host__ __device__ inline int tile_boys_entries(int nroots, int rys2_exact) {
-    if (nroots == 1) return RYS_BOYS1_NPTS;
-    if (nroots == 2) return (rys2_exact ? RYS_BOYS_XMAX : 15) * RYS_BOYS_HINV + 2;
+    if (nroots == 1) return RYS_F0POLY_TAB_NPTS * RYS_FP_STRIDE / 2;      // 16-byte entries of the F_0 Taylor rows
+    if (nroots == 2) return ((rys2_exact ? RYS_BOYS_XMAX : 15) * RYS_FP_HINV + 2) * RYS_FP_STRIDE / 2;
     return 0;
 }
 
@@ -77,19 +77,18 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int maxbp = task.tile_maxbp, kslots = task.kslots;
-    const int nboys = tile_boys_entries(NR, task.rys.rys2_exact);
+    const int nboys = task.stage_table ? tile_boys_entries(NR, task.rys.rys2_exact) : 0;   // 0: the table is read through L1
     const TileLayout lay = tile_layout(maxbp, task.tile_b, NAB, kslots, NF2, nboys);
     double *sjab = reinterpret_cast<double *>(tsm + lay.off_jab);       // [(j * NAB + ab) * T + tid]
     double2 *skp = reinterpret_cast<double2 *>(tsm + lay.off_kp);       // [(prim * NF2 + field) * T + tid]
     RysTables rys = task.rys;
     if (nboys > 0) {
+        // one root: the Taylor rows of F_0 (boys_poly01); two roots: those of F_3 over the moment range (boys_poly03)
         double2 *sb = reinterpret_cast<double2 *>(tsm + lay.off_boys);
-        constexpr bool F0_ONLY = (NR == 1 && GI * GJ == 1);
-        const double2 *gb = reinterpret_cast<const double2 *>(F0_ONLY ? task.rys.boys0 : (NR == 1 ? task.rys.boys1 : task.rys.boys));
+        const double2 *gb = reinterpret_cast<const double2 *>(NR == 1 ? task.rys.f0poly : task.rys.f3poly_glob);
         for (int i = tid; i < nboys; i += T) sb[i] = gb[i];
-        if (F0_ONLY) rys.boys0 = reinterpret_cast<const double *>(sb);
-        else if (NR == 1) rys.boys1 = reinterpret_cast<const double *>(sb);
-        else rys.boys = reinterpret_cast<const double *>(sb);
+        if (NR == 1) rys.f0poly = reinterpret_cast<const double *>(sb);
+        else rys.f3poly = reinterpret_cast<const double *>(sb);
     }
     if (tid == 0) {
         mbar_init(&bars[0], 1);

@@ -6,15 +6,26 @@
 namespace ub200 {
 
 template <int LA, int LB, int LC, int LD, int NSPIN>
-static cudaError_t launch_tile_inst(const ClassTask &task, int grid, size_t smem, cudaStream_t stream) {
+static cudaError_t launch_tile_inst(ClassTask task, int grid, size_t smem_staged, size_t smem_plain, cudaStream_t stream) {
     static std::atomic<size_t> attr_smem_dev[64];   // per device: largest dynamic shared memory size enabled so far
     int dev = 0;
     cudaGetDevice(&dev);
     std::atomic<size_t> &have = attr_smem_dev[dev & 63];
-    if (smem > have) {
-        cudaError_t e = cudaFuncSetAttribute(eri_tile_kernel<LA, LB, LC, LD, NSPIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem_staged > have) {
+        cudaError_t e = cudaFuncSetAttribute(eri_tile_kernel<LA, LB, LC, LD, NSPIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged);
         if (e != cudaSuccess) return e;
-        have = smem;
+        have = smem_staged;
+    }
+    // The Boys table is staged in shared memory unless that costs a resident CTA (these kernels are bound by the latency of
+    // dependent FP64 instructions, i.e. by warps per scheduler: (ps|ss) with six ket-primitive slots dropped from three CTAs to
+    // two when the table grew by 4.6 KB, 16 -> 21 ms); then it is read through L1 instead.
+    size_t smem = smem_staged;
+    task.stage_table = 1;
+    if (smem_plain < smem_staged) {
+        int occ_staged = 0, occ_plain = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_staged, eri_tile_kernel<LA, LB, LC, LD, NSPIN>, TILE_THREADS, smem_staged);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_plain, eri_tile_kernel<LA, LB, LC, LD, NSPIN>, TILE_THREADS, smem_plain);
+        if (occ_plain > occ_staged) { smem = smem_plain; task.stage_table = 0; }
     }
     eri_tile_kernel<LA, LB, LC, LD, NSPIN><<<grid, TILE_THREADS, smem, stream>>>(task);
     return cudaGetLastError();
@@ -24,10 +35,11 @@ template <int LA, int LB, int LC, int LD>
 static cudaError_t launch_tile(const ClassTask &task, int grid, cudaStream_t stream) {
     using C = QC<LA, LB, LC, LD>;
     if (grid <= 0) return cudaSuccess;
-    const TileLayout lay = tile_layout(task.tile_maxbp, task.tile_b, C::NAB, task.kslots, C::GJ > 1 ? 5 : 3,
-                                       tile_boys_entries(C::NR, task.rys.rys2_exact));
-    if (task.nspin == 2) return launch_tile_inst<LA, LB, LC, LD, 2>(task, grid, lay.total, stream);
-    return launch_tile_inst<LA, LB, LC, LD, 1>(task, grid, lay.total, stream);
+    const int nf2 = C::GJ > 1 ? 5 : 3;
+    const TileLayout lay = tile_layout(task.tile_maxbp, task.tile_b, C::NAB, task.kslots, nf2, tile_boys_entries(C::NR, task.rys.rys2_exact));
+    const TileLayout plain = tile_layout(task.tile_maxbp, task.tile_b, C::NAB, task.kslots, nf2, 0);
+    if (task.nspin == 2) return launch_tile_inst<LA, LB, LC, LD, 2>(task, grid, lay.total, plain.total, stream);
+    return launch_tile_inst<LA, LB, LC, LD, 1>(task, grid, lay.total, plain.total, stream);
 }
 
 bool tile_class_available(int cb, int ck) {

@@ -67,7 +67,12 @@ constexpr double rys_herm_n(int weights, int i) { return N <= 5 ? rys_herm(weigh
 struct RysTables {
     const double *boys;        // [RYS_BOYS_NPTS][2] = {F_10(X_i), exp(-X_i)}, X_i = i / RYS_BOYS_HINV, X_i <= 46: two roots
     const double *boys1;       // [RYS_BOYS1_NPTS][2] = {F_8(X_i), exp(-X_i)}, X_i <= 35: one root (two recursion steps less)
-    const double *boys0;       // [RYS_BOYS1_NPTS][2] = {F_7(X_i), exp(-X_i)}: F_0 alone ((ss|ss))
+    const double *boys0;       // [RYS_BOYS1_NPTS][2] = {F_7(X_i), exp(-X_i)}: F_0 alone (superseded by f0poly; kept for the tests)
+    const double *f3poly;      // [RYS_F3POLY_TAB_NPTS][RYS_FP_STRIDE]: Taylor rows F_{3+j}(X_i) / j! + exp(-X_i), X_i = i / 4 <= 46: the moments
+                               // F_0..F_3 of the two-root classes (boys_poly03); kernels may point this at a shared-memory copy
+    const double *f3poly_glob; // the same table in global memory, whole range (exp(-X_i) for the two-root band 15 < X <= 40)
+    const double *f0poly;      // [RYS_F0POLY_TAB_NPTS][RYS_FP_STRIDE]: Taylor rows F_k(X_i) / k!, X_i = i / 4 <= 35: F_0 and F_1 of
+                               // the one-root classes (boys_poly01)
     const double *piece[3];    // 3, 4, 5 roots: [interval][k = 0..12][y_0..y_{n-1}, w_0..w_{n-1}], y = t^2
     const double *piece_hi[4]; // 6..9 roots, same layout (rys_tables_hi.inc): all-Rys mode of the runtime-L kernel, the range of
                                // the reference's Rys::rootN (Rys.cpp:231-312)
@@ -173,6 +178,92 @@ UNOMOL_HD void boys_grid(double x, const double *tab, double *F) {
     }
 }
 
+// F_0(x) and, with WITH_F1, F_1(x) for 0 <= x < 35 from the Taylor row of the nearest point of a coarse grid (X_i = i/4):
+//   F_0(x) = sum_k a_k d^k,  a_k = F_k(X_i) / k!,  d = X_i - x, |d| <= 1/8, degree 10 ((1/8)^11 / 11! = 3e-18);
+//   F_1(x) = -dF_0/dx = sum_k k a_k d^(k-1): the derivative comes out of the same Horner pass (q <- q d + p before p <- p d + a_k).
+// 17 (F_0: even / odd halves in d^2, 7 dependent FP64 operations) or 31 instructions against the 48 / 65 of the recursion-based
+// boys_grid<0, 7> / boys_grid<1, 8>.  This is the branch of the root evaluation that the few lanes of a warp whose ket is NEAR the
+// bra take while the others wait (ncu: 17..23 % of the warp instructions of the one-root tile kernels ran there with <= 4 lanes),
+// so its length is paid almost in full per primitive quartet.
+#include "rys_consts_poly.inc"
+template <bool WITH_F1>
+UNOMOL_HD void boys_poly01(double x, const double *tab, double &f0, double &f1) {
+    static_assert(RYS_FP_DEG == 10 && RYS_FP_STRIDE == 12, "coefficient rows of 11 + 1 doubles");
+    const int i = (int)fma(x, (double)RYS_FP_HINV, 0.5);
+    const double d = (double)i * (1.0 / RYS_FP_HINV) - x;
+    double a[12];
+#ifdef __CUDA_ARCH__
+    const double2 *c2 = reinterpret_cast<const double2 *>(tab + i * RYS_FP_STRIDE);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { const double2 v = c2[k]; a[2 * k] = v.x; a[2 * k + 1] = v.y; }
+#else
+    for (int k = 0; k < 12; ++k) a[k] = tab[i * RYS_FP_STRIDE + k];
+#endif
+    if (WITH_F1) {
+        double p = a[10], q = 0.0;
+#pragma unroll
+        for (int k = 9; k >= 0; --k) { q = fma(q, d, p); p = fma(p, d, a[k]); }
+        f0 = p;
+        f1 = q;
+    } else {
+        const double d2 = d * d;
+        double e = a[10], o = a[9];
+#pragma unroll
+        for (int k = 8; k >= 0; k -= 2) e = fma(e, d2, a[k]);
+#pragma unroll
+        for (int k = 7; k >= 1; k -= 2) o = fma(o, d2, a[k]);
+        f0 = fma(o, d, e);
+        f1 = 0.0;
+    }
+}
+
+// exp(d) for |d| <= 1/8: Taylor series of degree 10 ((1/8)^11 / 11! = 3e-18), even / odd halves in d^2
+UNOMOL_HD double rys_exp_small(double d) {
+    const double d2 = d * d;
+    double e = 1.0 / 3628800.0, o = 1.0 / 362880.0;
+    e = fma(e, d2, 1.0 / 40320.0); o = fma(o, d2, 1.0 / 5040.0);
+    e = fma(e, d2, 1.0 / 720.0);   o = fma(o, d2, 1.0 / 120.0);
+    e = fma(e, d2, 1.0 / 24.0);    o = fma(o, d2, 1.0 / 6.0);
+    e = fma(e, d2, 0.5);           o = fma(o, d2, 1.0);
+    e = fma(e, d2, 1.0);
+    return fma(o, d, e);
+}
+
+// exp(-x) for 0 <= x < RYS_BOYS_XMAX from the exp(-X_i) column of the F_3 rows: exp(-x) = exp(-X_i) exp(X_i - x)
+UNOMOL_HD double rys_exp_neg(double x, const double *f3rows) {
+    const int i = (int)fma(x, (double)RYS_FP_HINV, 0.5);
+    const double d = (double)i * (1.0 / RYS_FP_HINV) - x;
+    return f3rows[i * RYS_FP_STRIDE + RYS_FP_DEG + 1] * rys_exp_small(d);
+}
+
+// F[0..3] = F_0(x) .. F_3(x) for 0 <= x < RYS_BOYS_XMAX: F_3 from its Taylor row (degree 10, even / odd halves), exp(-x) from the
+// row's last slot, F_2, F_1, F_0 by the downward recursion at x (positive terms: stable).  About 40 instructions against the
+// 100 of boys_grid<3, 10>; see boys_poly01 for why the length of this branch matters.
+UNOMOL_HD void boys_poly03(double x, const double *tab, double *F) {
+    const int i = (int)fma(x, (double)RYS_FP_HINV, 0.5);
+    const double d = (double)i * (1.0 / RYS_FP_HINV) - x;
+    double a[12];
+#ifdef __CUDA_ARCH__
+    const double2 *c2 = reinterpret_cast<const double2 *>(tab + i * RYS_FP_STRIDE);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { const double2 v = c2[k]; a[2 * k] = v.x; a[2 * k + 1] = v.y; }
+#else
+    for (int k = 0; k < 12; ++k) a[k] = tab[i * RYS_FP_STRIDE + k];
+#endif
+    const double d2 = d * d;
+    double e = a[10], o = a[9];
+#pragma unroll
+    for (int k = 8; k >= 0; k -= 2) e = fma(e, d2, a[k]);
+#pragma unroll
+    for (int k = 7; k >= 1; k -= 2) o = fma(o, d2, a[k]);
+    const double ex = a[11] * rys_exp_small(d);
+    const double xx = x + x;
+    F[3] = fma(o, d, e);
+    F[2] = fma(xx, F[3], ex) * (1.0 / 5.0);
+    F[1] = fma(xx, F[2], ex) * (1.0 / 3.0);
+    F[0] = fma(xx, F[1], ex);
+}
+
 // ---- nodes as t^2 --------------------------------------------------------------------------------------------------
 // The two-dimensional recurrences need t_i^2 (reference Rys.hpp:127: t2 = r/(1+r)); the reference's root routines return
 // r = t^2/(1-t^2) only to divide it back.  rys_t2<N> returns t2[i] = t_i^2 (ascending) and w[i] directly -- the kernels
@@ -195,10 +286,7 @@ UNOMOL_HD void rys_hermite_limit_t2(double x, double *t2, double *w) {
 // One root as moments: w = F_0(x), f1 = F_1(x) = w t^2.  The (ps|ss) kernels use these directly.
 UNOMOL_HD void rys1_f0f1(double x, double &w, double &f1, const RysTables &T) {
     if (x < RYS_X_ASYM1) {
-        double F[2];
-        boys_grid<1, RYS_BOYS1_MTOP>(x, T.boys1, F);
-        w = F[0];
-        f1 = F[1];
+        boys_poly01<true>(x, T.f0poly, w, f1);
     } else {
         const double rx = rys_rsqrt(x);
         w = RYS_SQRT_PI_4 * rx;
@@ -208,9 +296,9 @@ UNOMOL_HD void rys1_f0f1(double x, double &w, double &f1, const RysTables &T) {
 
 UNOMOL_HD double rys1_f0(double x, const RysTables &T) {
     if (x < RYS_X_ASYM1) {
-        double F[1];
-        boys_grid<0, RYS_BOYS0_MTOP>(x, T.boys0, F);
-        return F[0];
+        double f0, f1;
+        boys_poly01<false>(x, T.f0poly, f0, f1);
+        return f0;
     }
     return RYS_SQRT_PI_4 * rys_rsqrt(x);
 }
@@ -219,8 +307,8 @@ UNOMOL_HD double rys1_f0(double x, const RysTables &T) {
 //     r_i = (a_i X + b_i) exp(-X) + R_i / (X - R_i),   w_1 = (a_w X + b_w) exp(-X) + W_1 sqrt(pi/4X),   w_0 = sqrt(pi/4X) - w_1,
 // evaluated for t_i^2 = r_i / (1 + r_i) = N_i / (N_i + u_i) with u_i = X - R_i, N_i = (a_i X + b_i) exp(-X) u_i + R_i: one
 // reciprocal for both nodes instead of four divisions (same numbers to rounding).
-UNOMOL_HD void rys2_compat_band_t2(double x, double *t2, double *w) {
-    const double g = exp(-x);
+UNOMOL_HD void rys2_compat_band_t2(double x, double *t2, double *w, const double *f3rows) {
+    const double g = rys_exp_neg(x, f3rows);      // exp(-x) to 2e-16 without the library routine's range reduction (x <= 40 here)
     const double wsum = 0.886226925452758 * rys_rsqrt(x);           // sqrt(.785398163397448 / x)
     const double u0 = x - 0.275255128608411, u1 = x - 2.72474487139158;
     const double n0 = fma(fma(-0.87894730749888, x, 10.9243702330261) * g, u0, 0.275255128608411);
@@ -248,7 +336,7 @@ UNOMOL_HD void rys_t2<2>(double x, double *t2, double *w, const RysTables &T) {
     const double xmom = T.rys2_exact ? (double)RYS_BOYS_XMAX : 15.0;
     if (x <= xmom && x < (double)RYS_BOYS_XMAX) {
         double m[4];
-        boys_grid<3, RYS_BOYS_MTOP>(x, T.boys, m);
+        boys_poly03(x, T.f3poly, m);
         // orthogonal polynomial D y^2 + n1 y + n0 in y = t^2 from the Hankel system [m0 m1; m1 m2] (c0, c1)^T = -(m2, m3)^T:
         // D = m0 m2 - m1^2 > 0, n0 = m1 m3 - m2^2 > 0, n1 = m1 m2 - m0 m3 < 0.  With S = sqrt(n1^2 - 4 D n0):
         // y1 = (S - n1) / (2 D), y0 = 2 n0 / (S - n1), y1 - y0 = S / D, w1 = (m1 - y0 m0) D / S.  One rsqrt (S and 1/S)
@@ -267,7 +355,7 @@ UNOMOL_HD void rys_t2<2>(double x, double *t2, double *w, const RysTables &T) {
         w[1] = fma(-y0, m[0], m[1]) * D * iS;
         w[0] = m[0] - w[1];
     } else if (!T.rys2_exact && x <= 40.0) {
-        rys2_compat_band_t2(x, t2, w);
+        rys2_compat_band_t2(x, t2, w, T.f3poly_glob);
     } else {
         rys_hermite_limit_t2<2>(x, t2, w);
     }
@@ -344,6 +432,7 @@ namespace rys_host {
 #define RYS_TABLE(name, n) static const double name[n]
 #include "rys_tables.inc"
 #include "rys_tables_hi.inc"
+#include "rys_tables_poly.inc"
 #undef RYS_TABLE
 }  // namespace rys_host
 inline RysTables rys_host_tables(int rys2_exact = 0) {
@@ -351,6 +440,8 @@ inline RysTables rys_host_tables(int rys2_exact = 0) {
     T.boys = rys_host::rys_boys_tab;
     T.boys1 = rys_host::rys_boys1_tab;
     T.boys0 = rys_host::rys_boys0_tab;
+    T.f0poly = rys_host::rys_f0poly_tab;
+    T.f3poly = T.f3poly_glob = rys_host::rys_f3poly_tab;
     T.piece[0] = rys_host::rys_piece3_tab;
     T.piece[1] = rys_host::rys_piece4_tab;
     T.piece[2] = rys_host::rys_piece5_tab;

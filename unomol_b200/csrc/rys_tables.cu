@@ -8,6 +8,7 @@ namespace ub200 {
 #define RYS_TABLE(name, n) __device__ __align__(16) const double name[n]
 #include "rys_tables.inc"
 #include "rys_tables_hi.inc"
+#include "rys_tables_poly.inc"
 #undef RYS_TABLE
 
 // Device addresses of the tables on the CURRENT device (symbols exist once per device).
@@ -20,6 +21,10 @@ cudaError_t rys_device_tables(RysTables *out) {
     out->boys1 = (const double *)p;
     if ((e = cudaGetSymbolAddress(&p, rys_boys0_tab)) != cudaSuccess) return e;
     out->boys0 = (const double *)p;
+    if ((e = cudaGetSymbolAddress(&p, rys_f0poly_tab)) != cudaSuccess) return e;
+    out->f0poly = (const double *)p;
+    if ((e = cudaGetSymbolAddress(&p, rys_f3poly_tab)) != cudaSuccess) return e;
+    out->f3poly = out->f3poly_glob = (const double *)p;
     if ((e = cudaGetSymbolAddress(&p, rys_piece3_tab)) != cudaSuccess) return e;
     out->piece[0] = (const double *)p;
     if ((e = cudaGetSymbolAddress(&p, rys_piece4_tab)) != cudaSuccess) return e;

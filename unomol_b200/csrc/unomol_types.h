@@ -72,6 +72,7 @@ struct ClassTask {
                               // TILE_THREADS (lists with few tiles would not fill the GPU otherwise); >= 1
     int tile_b;               // bras per tile of this bra class (<= TILE_MAXB)
     int tile_maxbp;           // largest primitive-pair count of a bra (stride of the staged primitive slots)
+    int stage_table;          // tile kernel: copy the Boys table of the class into shared memory (set by the launcher)
     int kslots;               // ket primitive pairs a thread keeps in its shared-memory slots (kets with more read global memory)
     const long long *ket_prefix;  // runtime-L kernel only: exclusive prefix sum of ket_count over the bras [nbra + 1]; its work
                               // items are single shell quartets (a (gg|gg) block is 50 625 integrals), not bras

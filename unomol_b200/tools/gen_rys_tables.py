@@ -255,8 +255,49 @@ def main_hi():
     sys.stderr.write("wrote rys_tables_hi.inc, rys_consts_hi.inc\n")
 
 
+def main_poly():
+    """rys_tables_poly.inc / rys_consts_poly.inc: Taylor coefficient tables of the Boys function about the points of a coarse grid,
+    a_k = F_{m+k}(X_i) / k! (dF_m/dX = -F_{m+1}, so F_m(x) = sum_k a_k (X_i - x)^k), X_i = i / HINV.  One row of coefficients
+    replaces the downward recursion + Taylor chain of boys_grid for the order the kernels need most: the near branch of the root
+    evaluation runs with few active lanes, so its LENGTH is what costs."""
+    mp.mp.dps = 50
+    hinv, deg, stride = 4, 10, 12             # |X_i - x| <= 1/8: (1/8)^11 / 11! = 3e-18
+    L = ["// unomol_b200/csrc/rys_tables_poly.inc -- GENERATED by unomol_b200/tools/gen_rys_tables.py --poly (mpmath, 50 digits).",
+         "// Do not edit by hand."]
+    C = ["// unomol_b200/csrc/rys_consts_poly.inc -- GENERATED by unomol_b200/tools/gen_rys_tables.py --poly.  Do not edit by hand.",
+         "#define RYS_FP_HINV %d" % hinv, "#define RYS_FP_DEG %d" % deg, "#define RYS_FP_STRIDE %d" % stride]
+    for name, m, xmax in (("rys_f0poly_tab", 0, BOYS1_XMAX),):
+        npts = xmax * hinv + 2
+        C.append("#define %s_NPTS %d" % (name.upper(), npts))
+        L.append("// [point][k = 0..%d (+ padding to %d)]: F_%d+k(X_i) / k!" % (deg, stride, m))
+        L.append("RYS_TABLE(%s, %d) = {" % (name, npts * stride))
+        for i in range(npts):
+            x = mp.mpf(i) / hinv
+            row = [boys(m + k, x) / mp.factorial(k) for k in range(deg + 1)] + [mp.mpf(0)] * (stride - deg - 1)
+            L.append("    " + ", ".join(fmt(v) for v in row) + ",")
+        L.append("};")
+    # two roots: Taylor rows of F_3 (F_{3+j}(X_i) / j!, j = 0..10) with exp(-X_i) in the twelfth slot, up to the end of the moment
+    # range of the exact mode; F_2, F_1, F_0 follow by the downward recursion at x with exp(-x) = exp(-X_i) exp(X_i - x)
+    npts = BOYS_XMAX * hinv + 2
+    C.append("#define RYS_F3POLY_TAB_NPTS %d" % npts)
+    L.append("// [point][j = 0..%d: F_3+j(X_i) / j!][exp(-X_i)]" % deg)
+    L.append("RYS_TABLE(rys_f3poly_tab, %d) = {" % (npts * stride))
+    for i in range(npts):
+        x = mp.mpf(i) / hinv
+        row = [boys(3 + k, x) / mp.factorial(k) for k in range(deg + 1)] + [mp.exp(-x)]
+        L.append("    " + ", ".join(fmt(v) for v in row) + ",")
+    L.append("};")
+    with open(os.path.join(HERE, "..", "csrc", "rys_tables_poly.inc"), "w") as f:
+        f.write("\n".join(L) + "\n")
+    with open(os.path.join(HERE, "..", "csrc", "rys_consts_poly.inc"), "w") as f:
+        f.write("\n".join(C) + "\n")
+    sys.stderr.write("wrote rys_tables_poly.inc, rys_consts_poly.inc\n")
+
+
 if __name__ == "__main__":
-    if "--hi" in sys.argv:
+    if "--poly" in sys.argv:
+        main_poly()
+    elif "--hi" in sys.argv:
         main_hi()
     else:
         main()
