@@ -664,8 +664,9 @@ static int build_plans(unomol_b200 *h) {
             }
             const bool roots_ok = nroots <= 2 || (nroots == 3 && plan.nquartets >= 1000000) || h->use_reg_kernels == 2;
             plan.use_reg = !plan.highl && h->use_reg_kernels && roots_ok && reg_class_available(cb / NSUB, ck / NSUB) && maxbp <= reg_max_bra_prims();
+            // (the tile kernels address the square matrices with 32-bit element offsets: leading dimension <= 65535)
             plan.use_tile = plan.use_reg && h->use_tile_kernels && tile_class_available(cb / NSUB, ck / NSUB) && Lb.ntiles > 0 &&
-                            Lb.maxnp <= TILE_MAX_BRA_PRIMS;
+                            Lb.maxnp <= TILE_MAX_BRA_PRIMS && h->basis.nbf < 65535;
             if (plan.use_tile) {
                 plan.maxbp = Lb.maxnp;
                 // ket primitives a thread keeps in shared memory: every ket of the list when that fits the budget

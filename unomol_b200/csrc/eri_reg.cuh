@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(ROWS ? REG_THREADS_ROWS : REG_THREADS) eri_reg
                 {
                     const double bpv = bp[ib].p;
                     const double txp = bpv + k.p;
-                    const double rtx = rsqrt(txp);
+                    const double rtx = rys_rsqrt(txp);
                     const double itx = rtx * rtx;
                     double sr = tk * bp[ib].u * rtx;
                     sr *= bp[ib].c * k.c;

@@ -157,6 +157,9 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
     unsigned long long n_quart = 0, n_primq = 0, n_cand = 0;
     const double cut2 = task.prim_cut * task.prim_cut;
     const int n = task.nbf;
+    // element (r, c) of the square matrices as a 32-bit offset (leading dimension <= 65535, enforced in build_plans): the address is
+    // then one IMAD.WIDE.U32 instead of a 64-bit multiply-add chain, ~25 integer instructions per quartet in the digestion
+#define EIDX(r, c) ((unsigned)(r) * (unsigned)n + (unsigned)(c))
 
     while (wi >= 0) {
         if (tid == 0) {
@@ -201,6 +204,12 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                 const ShellPair *kfull = task.ket + ki;
                 cdx = kfull->AB[0]; cdy = kfull->AB[1]; cdz = kfull->AB[2];
             }
+            // statistics of this ket in 32 bits (at most 8 x 36 x 36 per ket), added to the 64-bit totals once per ket: a 64-bit
+            // increment per candidate and per survivor is two instructions in the innermost loops
+            unsigned c_quart = 0, c_primq = 0, c_cand = 0;
+            const bool dump = task.out != nullptr;
+            const double half = dump ? 1.0 : 0.5;
+            const double ksym = (ket.sha == ket.shb) ? half : 1.0;
             // per-ket digestion state (registers): gathered once, flushed once per tile
             double pjcd[NCD], jcd[NCD], pac[NSPIN][NA * NC], pad[NSPIN][NA * ND], kac[NSPIN][NA * NC], kad[NSPIN][NA * ND];
             bool loaded = false, touched = false;
@@ -242,7 +251,7 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                         }
                         while (ib < nbp) {
                             const double t = tk * bp[ib].u;
-                            ++n_cand;
+                            ++c_cand;
                             if (t * t >= cut2 * (bp[ib].p + kp_)) { found = true; break; }
                             if (t * t < cut2 * (pminb + kp_)) { ib = nbp; break; }
                             ++ib;
@@ -255,11 +264,11 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                     {
                         const double bpv = bp[ib].p;
                         const double txp = bpv + kp_;
-                        const double rtx = rsqrt(txp);
+                        const double rtx = rys_rsqrt(txp);
                         const double itx = rtx * rtx;
                         double sr = tk * bp[ib].u * rtx;
                         sr *= bp[ib].c * kcf;
-                        ++n_primq;
+                        ++c_primq;
                         const double pq0 = bp[ib].P[0] - kP0, pq1 = bp[ib].P[1] - kP1, pq2 = bp[ib].P[2] - kP2;
                         const double X = bpv * kp_ * itx * (pq0 * pq0 + pq1 * pq1 + pq2 * pq2);
                         if constexpr (NR == 1 && GI * GJ == 1) {
@@ -320,7 +329,7 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                     }
                     ++ib;
                 }
-                ++n_quart;
+                ++c_quart;
                 // ---- horizontal transfer in registers: ket, then bra (reference Rys.hpp:173-192, once per contracted quartet)
                 const double abx = bra.AB[0], aby = bra.AB[1], abz = bra.AB[2];
                 double h1[NE * NCD];
@@ -351,12 +360,10 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                     });
                     h1[O] = v;
                 });
-                double sym = 1.0;
-                if (!task.out) {
-                    if (sha == bra.shb) sym *= 0.5;
-                    if (ket.sha == ket.shb) sym *= 0.5;
-                    if (task.same_class && bra.pairid == ket.pairid) sym *= 0.5;
-                }
+                // symmetry weight of the quartet in the triangular sums: 1/2 per pair of identical shells, 1/2 on the diagonal of a
+                // same-list launch (the ket's own factor is per-ket state; dump mode takes the plain block)
+                double sym = (sha == bra.shb) ? half * ksym : ksym;
+                if (task.same_class && bra.pairid == ket.pairid) sym *= half;
                 double V[NINT];
                 static_for<NINT>([&](auto oo) {
                     constexpr int O = decltype(oo)::value;
@@ -386,7 +393,7 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                     constexpr double nrm = c_norm(LA, a) * c_norm(LB, b) * c_norm(LC, c) * c_norm(LD, d);
                     V[O] = v * (nrm * sym);
                 });
-                if (task.out) {
+                if (__builtin_expect(dump, 0)) {
                     // dump mode (test hook): the contracted block as computed by THIS kernel, no symmetry factor
                     double *dst = task.out + task.task_out[(size_t)ti * TILE_MAXB + j] + (size_t)ki * NINT;
 #pragma unroll
@@ -407,7 +414,7 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                     for (int c = 0; c < NC; ++c)
 #pragma unroll
                         for (int d = 0; d < ND; ++d) {
-                            pjcd[c * ND + d] = task.PJ[(size_t)(oc + c) * n + od + d];
+                            pjcd[c * ND + d] = task.PJ[EIDX(oc + c, od + d)];
                             jcd[c * ND + d] = 0.0;
                         }
 #pragma unroll
@@ -416,9 +423,9 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
 #pragma unroll
                         for (int a = 0; a < NA; ++a) {
 #pragma unroll
-                            for (int c = 0; c < NC; ++c) { pac[sp][a * NC + c] = P[(size_t)(oa + a) * n + oc + c]; kac[sp][a * NC + c] = 0.0; }
+                            for (int c = 0; c < NC; ++c) { pac[sp][a * NC + c] = P[EIDX(oa + a, oc + c)]; kac[sp][a * NC + c] = 0.0; }
 #pragma unroll
-                            for (int d = 0; d < ND; ++d) { pad[sp][a * ND + d] = P[(size_t)(oa + a) * n + od + d]; kad[sp][a * ND + d] = 0.0; }
+                            for (int d = 0; d < ND; ++d) { pad[sp][a * ND + d] = P[EIDX(oa + a, od + d)]; kad[sp][a * ND + d] = 0.0; }
                         }
                     }
                 }
@@ -438,7 +445,7 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
 #pragma unroll
                     for (int a = 0; a < NA; ++a)
 #pragma unroll
-                        for (int b = 0; b < NB; ++b) pab[a * NB + b] = task.PJ[(size_t)(oa + a) * n + ob + b];
+                        for (int b = 0; b < NB; ++b) pab[a * NB + b] = task.PJ[EIDX(oa + a, ob + b)];
 #pragma unroll
                     for (int cd = 0; cd < NCD; ++cd) {
                         double sacc = jcd[cd];
@@ -456,9 +463,9 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
 #pragma unroll
                     for (int b = 0; b < NB; ++b) {
 #pragma unroll
-                        for (int d = 0; d < ND; ++d) pbd[b * ND + d] = P[(size_t)(ob + b) * n + od + d];
+                        for (int d = 0; d < ND; ++d) pbd[b * ND + d] = P[EIDX(ob + b, od + d)];
 #pragma unroll
-                        for (int c = 0; c < NC; ++c) pbc[b * NC + c] = P[(size_t)(ob + b) * n + oc + c];
+                        for (int c = 0; c < NC; ++c) pbc[b * NC + c] = P[EIDX(ob + b, oc + c)];
                     }
 #pragma unroll
                     for (int a = 0; a < NA; ++a) {
@@ -491,7 +498,7 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                             for (int a = 0; a < NA; ++a)
 #pragma unroll
                                 for (int d = 0; d < ND; ++d) sacc = fma(V[((a * NB + b) * NC + c) * ND + d], pad[sp][a * ND + d], sacc);
-                            atomicAdd(K + (size_t)(ob + b) * n + oc + c, sacc);
+                            atomicAdd(K + EIDX(ob + b, oc + c), sacc);
                         }
 #pragma unroll
                         for (int d = 0; d < ND; ++d) {
@@ -500,24 +507,25 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                             for (int a = 0; a < NA; ++a)
 #pragma unroll
                                 for (int c = 0; c < NC; ++c) sacc = fma(V[((a * NB + b) * NC + c) * ND + d], pac[sp][a * NC + c], sacc);
-                            atomicAdd(K + (size_t)(ob + b) * n + od + d, sacc);
+                            atomicAdd(K + EIDX(ob + b, od + d), sacc);
                         }
                     }
                 }
             }
+            n_quart += c_quart; n_primq += c_primq; n_cand += c_cand;
             if (touched) {
                 // flush this ket's register accumulators: J[c,d], K[a,c], K[a,d]
 #pragma unroll
-                for (int cd = 0; cd < NCD; ++cd) atomicAdd(task.J + (size_t)(oc + cd / ND) * n + od + cd % ND, task.jscale * jcd[cd]);
+                for (int cd = 0; cd < NCD; ++cd) atomicAdd(task.J + EIDX(oc + cd / ND, od + cd % ND), task.jscale * jcd[cd]);
 #pragma unroll
                 for (int sp = 0; sp < NSPIN; ++sp) {
                     double *K = task.K[sp];
 #pragma unroll
                     for (int a = 0; a < NA; ++a) {
 #pragma unroll
-                        for (int c = 0; c < NC; ++c) atomicAdd(K + (size_t)(oa + a) * n + oc + c, kac[sp][a * NC + c]);
+                        for (int c = 0; c < NC; ++c) atomicAdd(K + EIDX(oa + a, oc + c), kac[sp][a * NC + c]);
 #pragma unroll
-                        for (int d = 0; d < ND; ++d) atomicAdd(K + (size_t)(oa + a) * n + od + d, kad[sp][a * ND + d]);
+                        for (int d = 0; d < ND; ++d) atomicAdd(K + EIDX(oa + a, od + d), kad[sp][a * ND + d]);
                     }
                 }
             }
@@ -535,7 +543,7 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                 if (lane == 0 && v != 0.0) {
                     const int j = e / NAB, ab = e % NAB;
-                    atomicAdd(task.J + (size_t)(oa + ab / NB) * n + bras[j].offb + ab % NB, task.jscale * v);
+                    atomicAdd(task.J + EIDX(oa + ab / NB, bras[j].offb + ab % NB), task.jscale * v);
                 }
             }
         }
@@ -557,5 +565,7 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
         }
     }
 }
+
+#undef EIDX
 
 }  // namespace ub200

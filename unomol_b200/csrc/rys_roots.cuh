@@ -83,9 +83,24 @@ struct RysTables {
 constexpr double RYS_SQRT_PI_4 = 0.88622692545275801;   // sqrt(pi/4)
 constexpr double RYS_X_ASYM1 = (double)RYS_BOYS1_XMAX;    // F_0 = sqrt(pi/4X) to 6e-17 beyond (exp(-35)/70 = 9e-18)
 
+// 1/sqrt(x) and 1/x for POSITIVE NORMAL x (sums of exponents, X >= 35, discriminants): the hardware seed (MUFU.RSQ64H /
+// MUFU.RCP64H, 2^-22) refined by the same steps the CUDA library routines use -- one cubic step for the square root (2^-66), two
+// Newton steps for the reciprocal -- without their tests for zero / infinity / subnormal arguments, which cost seven non-FP64
+// instructions and a divergence point per call (SASS of the tile kernels: ISETP + BRA + BSSY / BSYNC + three moves around the
+// five DFMA / DMUL).  UNOMOL_FAST_RSQRT=0 restores the library calls.
+#ifndef UNOMOL_FAST_RSQRT
+#define UNOMOL_FAST_RSQRT 1
+#endif
 UNOMOL_HD double rys_rsqrt(double x) {
 #ifdef __CUDA_ARCH__
+#if UNOMOL_FAST_RSQRT
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(x, -(y * y), 1.0);
+    return fma(fma(e, 0.375, 0.5), y * e, y);
+#else
     return rsqrt(x);
+#endif
 #else
     return 1.0 / sqrt(x);
 #endif
@@ -269,7 +284,16 @@ UNOMOL_HD void boys_poly03(double x, const double *tab, double *F) {
 // r = t^2/(1-t^2) only to divide it back.  rys_t2<N> returns t2[i] = t_i^2 (ascending) and w[i] directly -- the kernels
 // call it -- and rys_roots<N> converts to the reference's r for the parity tests of the evaluator itself.
 
-UNOMOL_HD double rys_rcp(double x) { return 1.0 / x; }
+UNOMOL_HD double rys_rcp(double x) {
+#if defined(__CUDA_ARCH__) && UNOMOL_FAST_RSQRT
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(fma(-x, y, 1.0), y, y);
+    return fma(fma(-x, y, 1.0), y, y);
+#else
+    return 1.0 / x;
+#endif
+}
 
 // Gauss-Hermite limit (all exp(-X) terms below double precision): t_i^2 = R_i / X, w_i = W_i sqrt(pi/4X)
 template <int N>
