@@ -673,7 +673,7 @@ static int build_plans(unomol_b200 *h) {
                 int maxkp = 0;
                 const int kmaxvis = *std::max_element(kc.begin(), kc.end());
                 for (int i = 0; i < kmaxvis; ++i) maxkp = std::max(maxkp, Lk.pairs[i].nprim);
-                plan.kslots = std::min(maxkp, 6);
+                plan.kslots = std::min(maxkp, h->tile_kslots);
                 while (plan.kslots > 0 && tile_smem_bytes(cb / NSUB, ck / NSUB, plan.maxbp, plan.kslots, h->rys.rys2_exact) > 100 * 1024) --plan.kslots;
                 if (tile_smem_bytes(cb / NSUB, ck / NSUB, plan.maxbp, plan.kslots, h->rys.rys2_exact) > 200 * 1024) plan.use_tile = false;
             }
@@ -1060,6 +1060,7 @@ int unomol_b200_set_option(unomol_b200_t *h, const char *name, double value) {
         return UNOMOL_OK;
     }
     if (!strcmp(name, "dump_kernel")) { h->dump_kernel = (int)value; return UNOMOL_OK; }
+    if (!strcmp(name, "tile_kslots")) { h->tile_kslots = std::max(0, std::min(6, (int)value)); h->pairs_ready = false; return UNOMOL_OK; }
     // 1: quartets with l_tot > 8 also go through the Rys quadrature (6..9 roots), which is what the reference's MPI build asks of
     // its Rys::rootN (Rys.cpp:231-312); 0 (default): the serial reference's rule, McMurchie-Davidson above l_tot = 8.  Schwarz
     // bounds of f/g pairs come from the same kernel, so the pair tables are rebuilt.

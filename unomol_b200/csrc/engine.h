@@ -98,6 +98,7 @@ struct unomol_b200 {
     ub200::RysTables rys{};         // device table pointers + option "rys2_exact"
     double tau = 1e-12, prim_cut = 1e-12, value_cut = 1e-14;
     int use_reg_kernels = 1;
+    int tile_kslots = 6;            // option "tile_kslots": ket primitives a thread of the tile kernels keeps in shared memory (<= 6)
     int use_tile_kernels = 1;       // option "tile_kernels": 0 falls back to the one-bra-per-CTA register kernels
     int all_rys = 0;                // option "all_rys": Rys quadrature with 6..9 roots for l_tot > 8 instead of McMurchie-Davidson
     int dump_kernel = 0;            // option "dump_kernel": 1 = eri_quartet / dump_eris run the kernel a Fock build uses for the class

@@ -28,6 +28,10 @@ constexpr int TILE_THREADS = 128;
 constexpr int TILE_MAXB = 8;       // bras per tile (slots of the padded tile-ordered bra list)
 constexpr int TILE_KC_BYTES = 32;  // TILE_MAXB ints
 
+#ifndef TILE_STAGE_EXP    // A/B switch: exp(-X_i) column of the two-root band in shared memory
+#define TILE_STAGE_EXP 1
+#endif
+
 struct TileLayout {
     unsigned stage_bytes, off_jab, off_kp, off_boys, total;
 };
@@ -43,10 +47,20 @@ __host__ __device__ inline TileLayout tile_layout(int maxbp, int tile_b, int nab
 }
 // Boys grid entries a class needs in shared memory (rys_roots.cuh): one root up to X = 35, two roots up to X = 15
 // (parity mode) or 46 (exact mode); three and more roots read their polynomial tables from global memory
-__host__ __device__ inline int tile_boys_entries(int nroots, int rys2_exact) {
-    if (nroots == 1) return RYS_F0POLY_TAB_NPTS * RYS_FP_STRIDE / 2;      // 16-byte entries of the F_0 Taylor rows
-    if (nroots == 2) return ((rys2_exact ? RYS_BOYS_XMAX : 15) * RYS_FP_HINV + 2) * RYS_FP_STRIDE / 2;
+// rows of the exp(-X_i) column the reference-compatible two-root band reads (X <= 40 and a rounding error), kept compact (stride 1)
+// behind the F_3 rows in parity mode: the band's exp(-X_i) came from global memory and was 7.8 % of the stall samples of (ps|ps)
+constexpr int TILE_EXPCOL_N = 40 * RYS_FP_HINV + 2;
+__host__ __device__ inline int tile_boys_rows(int nroots, int rys2_exact) {
+    if (nroots == 1) return RYS_F0POLY_TAB_NPTS;
+    if (nroots == 2) return (rys2_exact ? RYS_BOYS_XMAX : 15) * RYS_FP_HINV + 2;
     return 0;
+}
+__host__ __device__ inline int tile_boys_entries(int nroots, int rys2_exact) {   // 16-byte entries
+    int n = tile_boys_rows(nroots, rys2_exact) * RYS_FP_STRIDE / 2;
+#if TILE_STAGE_EXP
+    if (nroots == 2 && !rys2_exact) n += TILE_EXPCOL_N / 2;
+#endif
+    return n;
 }
 
 // resident CTAs per SM the register allocation is capped for (ncu: the FP64 pipe waits on dependent results, "wait" is the top
@@ -54,18 +68,57 @@ __host__ __device__ inline int tile_boys_entries(int nroots, int rys2_exact) {
 #ifndef TILE_MINB_SET
 #define TILE_MINB_SET 0
 #endif
-__host__ __device__ constexpr int tile_minb(int lab, int lcd) {
+#ifndef TILE_MINB_PPSS
+#define TILE_MINB_PPSS 3
+#endif
+#ifndef TILE_MINB_PSPS
+#define TILE_MINB_PSPS 1
+#endif
+// A/B switches of round-2 changes (1 = on): far / near split of the root evaluation (one reciprocal square root per far primitive
+// quartet), fused right-hand side of the primitive screen, integer comparison of the block maximum with the storage threshold
+#ifdef TILE_NO_STATS      // experiment: what the per-launch statistics counters cost (the bench needs them: quartets, model flops)
+#define TILE_STAT(x)
+#else
+#define TILE_STAT(x) x
+#endif
+#ifndef TILE_FAR_SPLIT
+#define TILE_FAR_SPLIT 1
+#endif
+#ifndef TILE_SCAN_FMA
+#define TILE_SCAN_FMA 1
+#endif
+#ifndef TILE_SPEC_SCAN
+#define TILE_SPEC_SCAN 1
+#endif
+#if TILE_SPEC_SCAN && !TILE_SCAN_FMA
+#error "TILE_SPEC_SCAN uses the per-ket-primitive bounds of TILE_SCAN_FMA"
+#endif
+#ifndef TILE_PREFETCH_P
+#define TILE_PREFETCH_P 1
+#endif
+#ifndef TILE_INT_VMAX
+#define TILE_INT_VMAX 1
+#endif
+__host__ __device__ constexpr int tile_minb(int lab, int lcd, int nspin) {
 #if TILE_MINB_SET == 1
     return lab == 0 ? 6 : (lab == 1 && lcd == 0) ? 5 : (lab == 1) ? 3 : (lcd == 0) ? 4 : 2;
 #elif TILE_MINB_SET == 2
     return lab == 0 ? 8 : (lab == 1 && lcd == 0) ? 6 : (lab == 1) ? 4 : (lcd == 0) ? 5 : 3;
+#elif TILE_MINB_SET == 3
+    return lab == 0 ? 4 : (lab == 1 && lcd == 0) ? 4 : (lab == 1) ? 3 : (lcd == 0) ? 3 : 2;
+#elif TILE_MINB_SET == 4
+    return (lab == 1 && lcd == 0) ? 4 : 1;
 #else
-    return 1;
+    // (ss|ss) needs 134 registers with the speculative screen and fits 128 without a spill: four resident CTAs instead of three
+    // (360.5 against 370.3 ms per (H2O)154 build); the UHF instance of (ps|ss) needs 200 and fits the 168 of three resident
+    // CTAs (UHF build 496 -> 472 ms); the RHF instance of (pp|ss) gains a third CTA at 168 registers
+    // (40 bytes spilled, 353.5 -> 350.9 ms).  Every other cap tried costs more than the extra warps give back.
+    return (lab == 0 && lcd == 0) ? 4 : (lab == 1 && lcd == 0) ? 3 : (lab == 2 && lcd == 0 && nspin == 1) ? TILE_MINB_PPSS : (lab == 1 && lcd == 1) ? TILE_MINB_PSPS : 1;
 #endif
 }
 
 template <int LA, int LB, int LC, int LD, int NSPIN>
-__global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri_tile_kernel(const ClassTask task) {
+__global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD, NSPIN)) eri_tile_kernel(const ClassTask task) {
     using C = QC<LA, LB, LC, LD>;
     constexpr int NR = C::NR, GI = C::GI, GJ = C::GJ, NE = C::NE, NF = C::NF, NEF = C::NEF;
     constexpr int NA = C::NA, NB = C::NB, NC = C::NC, ND = C::ND, NAB = C::NAB, NCD = C::NCD, NINT = C::NINT;
@@ -86,9 +139,18 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
         // one root: the Taylor rows of F_0 (boys_poly01); two roots: those of F_3 over the moment range (boys_poly03)
         double2 *sb = reinterpret_cast<double2 *>(tsm + lay.off_boys);
         const double2 *gb = reinterpret_cast<const double2 *>(NR == 1 ? task.rys.f0poly : task.rys.f3poly_glob);
-        for (int i = tid; i < nboys; i += T) sb[i] = gb[i];
+        const int nrow2 = tile_boys_rows(NR, task.rys.rys2_exact) * RYS_FP_STRIDE / 2;
+        for (int i = tid; i < nrow2; i += T) sb[i] = gb[i];
         if (NR == 1) rys.f0poly = reinterpret_cast<const double *>(sb);
         else rys.f3poly = reinterpret_cast<const double *>(sb);
+#if TILE_STAGE_EXP
+        if (NR == 2 && !task.rys.rys2_exact) {
+            double *se = reinterpret_cast<double *>(sb + nrow2);
+            for (int i = tid; i < TILE_EXPCOL_N; i += T) se[i] = task.rys.expcol[i * task.rys.exp_stride];
+            rys.expcol = se;
+            rys.exp_stride = 1;
+        }
+#endif
     }
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -185,6 +247,10 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
         for (int ki = slice * T + tid; ki < kmax; ki += T * nslice) {
             const KetHot ket = load_streaming(task.ket_hot + ki);   // 32 B per thread, coalesced
             const int oc = ket.offa, od = ket.offb, nkp = ket.nprim;
+            const bool dump = task.out != nullptr;
+            // per-ket digestion state (registers): gathered once, flushed once per tile
+            double pjcd[NCD], jcd[NCD], pac[NSPIN][NA * NC], pad[NSPIN][NA * ND], kac[NSPIN][NA * NC], kad[NSPIN][NA * ND];
+            bool loaded = false, touched = false;
             // ket primitives: into this thread's shared-memory slots when they fit, else read from global memory per bra
             const double2 *kbase;
             int kpstride, kfstride;
@@ -207,12 +273,8 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
             // statistics of this ket in 32 bits (at most 8 x 36 x 36 per ket), added to the 64-bit totals once per ket: a 64-bit
             // increment per candidate and per survivor is two instructions in the innermost loops
             unsigned c_quart = 0, c_primq = 0, c_cand = 0;
-            const bool dump = task.out != nullptr;
             const double half = dump ? 1.0 : 0.5;
             const double ksym = (ket.sha == ket.shb) ? half : 1.0;
-            // per-ket digestion state (registers): gathered once, flushed once per tile
-            double pjcd[NCD], jcd[NCD], pac[NSPIN][NA * NC], pad[NSPIN][NA * ND], kac[NSPIN][NA * NC], kad[NSPIN][NA * ND];
-            bool loaded = false, touched = false;
 
             for (int j = 0; j < nb; ++j) {
                 if (ki >= kc[j]) continue;
@@ -221,6 +283,33 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                 const PrimPair *bp = bprims + (size_t)j * maxbp;
                 const int nbp = bra.nprim;
                 const double bumax = bra.umax, pminb = bra.pmin;
+                // The density elements this quartet's digestion gathers from rows b_j are independent of the integrals: they are requested
+                // HERE, before the primitive loop, so that the L2 round trip of the scattered gathers (the long-scoreboard stalls of the
+                // digestion, ncu: 9..18 % of the stall samples) runs in the shadow of the loop.  Only where that costs few registers (the UHF
+                // instances lose more to the registers than they gain: 467 -> 485 ms), and not in dump mode (no density there).
+                constexpr bool PREF_K = TILE_PREFETCH_P && NSPIN == 1 && NB * (NC + ND) <= 8;
+                constexpr bool PREF_J = PREF_K && NAB <= 3;
+                const int ob = bra.offb;
+                double qbd[NSPIN][NB * ND], qbc[NSPIN][NB * NC], qab[NAB];
+                if (PREF_K && !dump) {
+#pragma unroll
+                    for (int sp = 0; sp < NSPIN; ++sp) {
+                        const double *P = task.PK[sp];
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+                            for (int d = 0; d < ND; ++d) qbd[sp][b * ND + d] = P[EIDX(ob + b, od + d)];
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) qbc[sp][b * NC + c] = P[EIDX(ob + b, oc + c)];
+                        }
+                    }
+                }
+                if (PREF_J && !dump) {
+#pragma unroll
+                    for (int a = 0; a < NA; ++a)
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) qab[a * NB + b] = task.PJ[EIDX(oa + a, ob + b)];
+                }
                 double acc[NEF];
 #pragma unroll
                 for (int m = 0; m < NEF; ++m) acc[m] = 0.0;
@@ -230,8 +319,19 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                 bool have_k = false;
                 double ku = 0.0, kp_ = 0.0, kcf = 0.0, kP0 = 0.0, kP1 = 0.0, kP2 = 0.0, kip = 0.0, kA0 = 0.0, kA1 = 0.0, kA2 = 0.0;
                 double tk = 0.0;
+#if TILE_SCAN_FMA
+                double ck = 0.0, ckm = 0.0;
+#endif
+#if TILE_SPEC_SCAN
+                bool spec_ok = false, spec_end = false;
+#endif
                 for (;;) {
+#if TILE_SPEC_SCAN
+                    bool found = spec_ok;      // the candidate after the last survivor was tested while that one was evaluated
+                    if (!found)
+#else
                     bool found = false;
+#endif
                     while (ik < nkp) {
                         if (!have_k) {
                             const double2 up = kbase[ik * kpstride];
@@ -239,7 +339,13 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                             tk = SR_TERM * ku;
                             const double tb = tk * bumax;
                             if (tb * tb < cut2 * pminb) { ik = nkp; break; }
+#if TILE_SCAN_FMA
+                            ckm = cut2 * (pminb + kp_);
+                            if (tb * tb < ckm) { ++ik; continue; }
+                            ck = cut2 * kp_;
+#else
                             if (tb * tb < cut2 * (pminb + kp_)) { ++ik; continue; }
+#endif
                             have_k = true;
                             ib = 0;
                             const double2 c1 = kbase[ik * kpstride + kfstride], c2 = kbase[ik * kpstride + 2 * kfstride];
@@ -251,9 +357,17 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                         }
                         while (ib < nbp) {
                             const double t = tk * bp[ib].u;
-                            ++c_cand;
+                            TILE_STAT(++c_cand);
+#if TILE_SCAN_FMA
+                            // (SR u_b u_k)^2 against cut^2 (p + q) as one fma on the candidate's p (cut^2 q and the list-end bound
+                            // cut^2 (p_min + q) are per-ket-primitive values)
+                            const double t2c = t * t;
+                            if (t2c >= fma(cut2, bp[ib].p, ck)) { found = true; break; }
+                            if (t2c < ckm) { ib = nbp; break; }
+#else
                             if (t * t >= cut2 * (bp[ib].p + kp_)) { found = true; break; }
                             if (t * t < cut2 * (pminb + kp_)) { ib = nbp; break; }
+#endif
                             ++ib;
                         }
                         if (found) break;
@@ -261,15 +375,94 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                         ++ik;
                     }
                     if (!found) break;
+#if TILE_SPEC_SCAN
+                    {
+                        // The survivors of one ket primitive are (all but) a prefix of the bra primitives, so the candidate after a survivor
+                        // is the next survivor two times out of three.  Its test is independent of the evaluation below and is issued
+                        // first: the screen's chain (LDS, 2 DMUL, DFMA, DSETP) then runs in the shadow of the evaluation's instead of in
+                        // series with it (ncu source view: the scan was 34 % of the stall samples of (ps|ss)).  Reading one record past
+                        // the bra's primitives is harmless (shared memory), the result is masked.
+                        const int ibn = ib + 1;
+                        const double tn = tk * bp[ibn].u;
+                        const double t2n = tn * tn;
+                        const bool inb = ibn < nbp;
+                        spec_ok = inb && (t2n >= fma(cut2, bp[ibn].p, ck));
+                        spec_end = !inb || (t2n < ckm);
+                        TILE_STAT(c_cand += inb ? 1u : 0u);
+                    }
+#endif
                     {
                         const double bpv = bp[ib].p;
                         const double txp = bpv + kp_;
+                        TILE_STAT(++c_primq);
+                        const double pq0 = bp[ib].P[0] - kP0, pq1 = bp[ib].P[1] - kP1, pq2 = bp[ib].P[2] - kP2;
+#if TILE_FAR_SPLIT
+                        // X = p q |PQ|^2 / (p + q).  Most primitive quartets of a large molecule are FAR (X beyond the asymptotic limit
+                        // of the quadrature), and there every factor 1 / (p + q) cancels: sr w_i = k0 sqrt(pi/4) W_i (p q |PQ|^2)^(-1/2),
+                        // t_i^2 / (p + q) = R_i / (p q |PQ|^2).  The far branch is decided without a division (p q |PQ|^2 against
+                        // x_far (p + q)) and needs ONE reciprocal square root; the near branch keeps 1/sqrt(p + q) and the tables.
+                        const double k0 = (tk * bp[ib].u) * (bp[ib].c * kcf);
+                        const double pqr = bpv * kp_ * (pq0 * pq0 + pq1 * pq1 + pq2 * pq2);
+                        const double xfar = (NR == 1) ? RYS_X_ASYM1 : (rys.rys2_exact ? (double)RYS_BOYS_XMAX : 40.0);
+                        const bool far = pqr > xfar * txp;
+                        if constexpr (NR == 1 && GI * GJ == 1) {
+                            if (far) {
+                                acc[0] = fma(k0 * RYS_SQRT_PI_4, rys_rsqrt(pqr), acc[0]);
+                            } else {
+                                const double rtx = rys_rsqrt(txp);
+                                double f0, f1;
+                                boys_poly01<false>(pqr * (rtx * rtx), rys.f0poly, f0, f1);
+                                acc[0] = fma(k0 * rtx, f0, acc[0]);
+                            }
+                        } else if constexpr (NR == 1) {
+                            // (ps|ss): one root, G[1][0] = C per axis: sr*w*C = sr*(PA*w - q/(p+q)*PQ*F1)
+                            double a, bq;
+                            if (far) {
+                                const double rs = rys_rsqrt(pqr);
+                                a = k0 * RYS_SQRT_PI_4 * rs;              // sr F_0
+                                bq = (0.5 * a) * kp_ * (rs * rs);         // sr F_1 q / (p + q),  F_1 = F_0 / 2X
+                            } else {
+                                const double rtx = rys_rsqrt(txp);
+                                const double itx = rtx * rtx, sr = k0 * rtx;
+                                double w, f1;
+                                boys_poly01<true>(pqr * itx, rys.f0poly, w, f1);
+                                a = sr * w;
+                                bq = sr * f1 * kp_ * itx;
+                            }
+                            acc[0] = fma(a, bp[ib].PA[0], fma(-bq, pq0, acc[0]));
+                            acc[1] = fma(a, bp[ib].PA[1], fma(-bq, pq1, acc[1]));
+                            acc[2] = fma(a, bp[ib].PA[2], fma(-bq, pq2, acc[2]));
+                        } else {
+                            static_assert(NR == 2, "the tile kernels cover the classes with one and two roots");
+                            double fr[NR], ws[NR];     // t_i^2 / (p + q) and sr w_i
+                            if (far) {
+                                const double rs = rys_rsqrt(pqr);
+                                const double rs2 = rs * rs, ksr = k0 * RYS_SQRT_PI_4 * rs;
+#pragma unroll
+                                for (int ir = 0; ir < NR; ++ir) {
+                                    fr[ir] = rys_herm_n<NR>(0, ir) * rs2;
+                                    ws[ir] = rys_herm_n<NR>(1, ir) * ksr;
+                                }
+                            } else {
+                                const double rtx = rys_rsqrt(txp);
+                                const double itx = rtx * rtx, sr = k0 * rtx;
+                                double rt[NR], wt[NR];
+                                rys2_near_t2(pqr * itx, rt, wt, rys);      // rt[] = t^2
+#pragma unroll
+                                for (int ir = 0; ir < NR; ++ir) {
+                                    fr[ir] = rt[ir] * itx;
+                                    ws[ir] = wt[ir] * sr;
+                                }
+                            }
+#pragma unroll
+                            for (int ir = 0; ir < NR; ++ir) {
+                                const double fff = fr[ir];
+                                const double wsr = ws[ir];
+#else
                         const double rtx = rys_rsqrt(txp);
                         const double itx = rtx * rtx;
                         double sr = tk * bp[ib].u * rtx;
                         sr *= bp[ib].c * kcf;
-                        ++c_primq;
-                        const double pq0 = bp[ib].P[0] - kP0, pq1 = bp[ib].P[1] - kP1, pq2 = bp[ib].P[2] - kP2;
                         const double X = bpv * kp_ * itx * (pq0 * pq0 + pq1 * pq1 + pq2 * pq2);
                         if constexpr (NR == 1 && GI * GJ == 1) {
                             acc[0] = fma(sr, rys1_f0(X, rys), acc[0]);
@@ -286,8 +479,9 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                             rys_t2<NR>(X, rt, wt, rys);      // rt[] = t^2
 #pragma unroll
                             for (int ir = 0; ir < NR; ++ir) {
-                                const double dr = rt[ir];
-                                const double fff = dr * itx;
+                                const double fff = rt[ir] * itx;
+                                const double wsr = wt[ir] * sr;
+#endif
                                 const double B00 = 0.5 * fff;
                                 const double B1 = (0.5 - B00 * kp_) * bp[ib].ip;
                                 const double B1p = (0.5 - B00 * bpv) * kip;
@@ -298,7 +492,7 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                                     const double kA = ax == 0 ? kA0 : (ax == 1 ? kA1 : kA2);
                                     const double Cc = bp[ib].PA[ax] - kp_ * pq * fff;
                                     const double Cp = kA + bpv * pq * fff;
-                                    const double scale = (ax == 2) ? wt[ir] * sr : 1.0;
+                                    const double scale = (ax == 2) ? wsr : 1.0;
                                     g[ax][0][0] = scale;
                                     if constexpr (GJ > 1) {
                                         g[ax][0][1] = Cp * scale;
@@ -327,9 +521,14 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                             }
                         }
                     }
+#if TILE_SPEC_SCAN
+                    // next candidate of the general scan: ib + 1 is a survivor (spec_ok), ends this ket primitive's run, or is skipped
+                    ib = spec_ok ? ib + 1 : (spec_end ? nbp : ib + 2);
+#else
                     ++ib;
+#endif
                 }
-                ++c_quart;
+                TILE_STAT(++c_quart);
                 // ---- horizontal transfer in registers: ket, then bra (reference Rys.hpp:173-192, once per contracted quartet)
                 const double abx = bra.AB[0], aby = bra.AB[1], abz = bra.AB[2];
                 double h1[NE * NCD];
@@ -402,10 +601,27 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                 }
                 // blocks entirely at or below the reference's storage threshold never reach its G (TwoElectronInts.cpp:513,667-671)
                 {
+#if TILE_INT_VMAX
+                    // max |V| against the threshold on the high words (|x| orders like its bit pattern: two integer instructions per
+                    // element instead of three on the FP64 pipe); only a tie of the high words needs the exact comparison
+                    const double thr = task.value_cut * sym;
+                    unsigned hmax = 0u;
+#pragma unroll
+                    for (int o = 0; o < NINT; ++o) hmax = max(hmax, (unsigned)__double2hiint(V[o]) & 0x7fffffffu);
+                    const unsigned hthr = (unsigned)__double2hiint(thr);
+                    if (hmax < hthr) continue;
+                    if (hmax == hthr) {
+                        double vmax = 0.0;
+#pragma unroll
+                        for (int o = 0; o < NINT; ++o) vmax = fmax(vmax, fabs(V[o]));
+                        if (vmax <= thr) continue;
+                    }
+#else
                     double vmax = 0.0;
 #pragma unroll
                     for (int o = 0; o < NINT; ++o) vmax = fmax(vmax, fabs(V[o]));
                     if (vmax <= task.value_cut * sym) continue;
+#endif
                 }
                 // ---- J/K digestion (reference TwoElectronInts.cpp:699-820, shell-block form)
                 if (!loaded) {
@@ -430,7 +646,6 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
                     }
                 }
                 touched = true;
-                const int ob = bra.offb;
                 {
                     // J[a,b_j] += sum_cd V PJ[c,d]   (per-thread partials in shared memory, reduced once per tile)
 #pragma unroll
@@ -445,7 +660,7 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
 #pragma unroll
                     for (int a = 0; a < NA; ++a)
 #pragma unroll
-                        for (int b = 0; b < NB; ++b) pab[a * NB + b] = task.PJ[EIDX(oa + a, ob + b)];
+                        for (int b = 0; b < NB; ++b) pab[a * NB + b] = PREF_J ? qab[a * NB + b] : task.PJ[EIDX(oa + a, ob + b)];
 #pragma unroll
                     for (int cd = 0; cd < NCD; ++cd) {
                         double sacc = jcd[cd];
@@ -463,9 +678,9 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD)) eri
 #pragma unroll
                     for (int b = 0; b < NB; ++b) {
 #pragma unroll
-                        for (int d = 0; d < ND; ++d) pbd[b * ND + d] = P[EIDX(ob + b, od + d)];
+                        for (int d = 0; d < ND; ++d) pbd[b * ND + d] = PREF_K ? qbd[sp][b * ND + d] : P[EIDX(ob + b, od + d)];
 #pragma unroll
-                        for (int c = 0; c < NC; ++c) pbc[b * NC + c] = P[EIDX(ob + b, oc + c)];
+                        for (int c = 0; c < NC; ++c) pbc[b * NC + c] = PREF_K ? qbc[sp][b * NC + c] : P[EIDX(ob + b, oc + c)];
                     }
 #pragma unroll
                     for (int a = 0; a < NA; ++a) {

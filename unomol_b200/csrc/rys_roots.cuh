@@ -70,14 +70,16 @@ struct RysTables {
     const double *boys0;       // [RYS_BOYS1_NPTS][2] = {F_7(X_i), exp(-X_i)}: F_0 alone (superseded by f0poly; kept for the tests)
     const double *f3poly;      // [RYS_F3POLY_TAB_NPTS][RYS_FP_STRIDE]: Taylor rows F_{3+j}(X_i) / j! + exp(-X_i), X_i = i / 4 <= 46: the moments
                                // F_0..F_3 of the two-root classes (boys_poly03); kernels may point this at a shared-memory copy
-    const double *f3poly_glob; // the same table in global memory, whole range (exp(-X_i) for the two-root band 15 < X <= 40)
+    const double *f3poly_glob; // the same table in global memory, whole range
+    const double *expcol;      // exp(-X_i), X_i = i / 4, as expcol[i * exp_stride]: the exp(-X) of the two-root band 15 < X <= 40.  The last
+                               // column of f3poly_glob (stride RYS_FP_STRIDE) or a kernel's compact shared-memory copy (stride 1)
     const double *f0poly;      // [RYS_F0POLY_TAB_NPTS][RYS_FP_STRIDE]: Taylor rows F_k(X_i) / k!, X_i = i / 4 <= 35: F_0 and F_1 of
                                // the one-root classes (boys_poly01)
     const double *piece[3];    // 3, 4, 5 roots: [interval][k = 0..12][y_0..y_{n-1}, w_0..w_{n-1}], y = t^2
     const double *piece_hi[4]; // 6..9 roots, same layout (rys_tables_hi.inc): all-Rys mode of the runtime-L kernel, the range of
                                // the reference's Rys::rootN (Rys.cpp:231-312)
     int rys2_exact;            // 0: reference-compatible two-root band (see above); 1: exact two-root quadrature
-    int pad;
+    int exp_stride;
 };
 
 constexpr double RYS_SQRT_PI_4 = 0.88622692545275801;   // sqrt(pi/4)
@@ -201,10 +203,13 @@ UNOMOL_HD void boys_grid(double x, const double *tab, double *F) {
 // bra take while the others wait (ncu: 17..23 % of the warp instructions of the one-root tile kernels ran there with <= 4 lanes),
 // so its length is paid almost in full per primitive quartet.
 #include "rys_consts_poly.inc"
-template <bool WITH_F1>
+// CLAMP: x may be anything (NaN included); the row index is clamped to the table and the result is then garbage for x beyond the
+// grid -- for callers that evaluate this branch-free beside the asymptotic form and select afterwards (eri_tile.cuh).
+template <bool WITH_F1, bool CLAMP = false>
 UNOMOL_HD void boys_poly01(double x, const double *tab, double &f0, double &f1) {
     static_assert(RYS_FP_DEG == 10 && RYS_FP_STRIDE == 12, "coefficient rows of 11 + 1 doubles");
-    const int i = (int)fma(x, (double)RYS_FP_HINV, 0.5);
+    int i = (int)fma(x, (double)RYS_FP_HINV, 0.5);
+    if (CLAMP) i = i < 0 ? 0 : (i > RYS_F0POLY_TAB_NPTS - 1 ? RYS_F0POLY_TAB_NPTS - 1 : i);
     const double d = (double)i * (1.0 / RYS_FP_HINV) - x;
     double a[12];
 #ifdef __CUDA_ARCH__
@@ -245,10 +250,10 @@ UNOMOL_HD double rys_exp_small(double d) {
 }
 
 // exp(-x) for 0 <= x < RYS_BOYS_XMAX from the exp(-X_i) column of the F_3 rows: exp(-x) = exp(-X_i) exp(X_i - x)
-UNOMOL_HD double rys_exp_neg(double x, const double *f3rows) {
+UNOMOL_HD double rys_exp_neg(double x, const double *expcol, int stride) {
     const int i = (int)fma(x, (double)RYS_FP_HINV, 0.5);
     const double d = (double)i * (1.0 / RYS_FP_HINV) - x;
-    return f3rows[i * RYS_FP_STRIDE + RYS_FP_DEG + 1] * rys_exp_small(d);
+    return expcol[i * stride] * rys_exp_small(d);
 }
 
 // F[0..3] = F_0(x) .. F_3(x) for 0 <= x < RYS_BOYS_XMAX: F_3 from its Taylor row (degree 10, even / odd halves), exp(-x) from the
@@ -331,8 +336,8 @@ UNOMOL_HD double rys1_f0(double x, const RysTables &T) {
 //     r_i = (a_i X + b_i) exp(-X) + R_i / (X - R_i),   w_1 = (a_w X + b_w) exp(-X) + W_1 sqrt(pi/4X),   w_0 = sqrt(pi/4X) - w_1,
 // evaluated for t_i^2 = r_i / (1 + r_i) = N_i / (N_i + u_i) with u_i = X - R_i, N_i = (a_i X + b_i) exp(-X) u_i + R_i: one
 // reciprocal for both nodes instead of four divisions (same numbers to rounding).
-UNOMOL_HD void rys2_compat_band_t2(double x, double *t2, double *w, const double *f3rows) {
-    const double g = rys_exp_neg(x, f3rows);      // exp(-x) to 2e-16 without the library routine's range reduction (x <= 40 here)
+UNOMOL_HD void rys2_compat_band_t2(double x, double *t2, double *w, const double *expcol, int exp_stride) {
+    const double g = rys_exp_neg(x, expcol, exp_stride);      // exp(-x) to 2e-16 without the library routine's range reduction (x <= 40 here)
     const double wsum = 0.886226925452758 * rys_rsqrt(x);           // sqrt(.785398163397448 / x)
     const double u0 = x - 0.275255128608411, u1 = x - 2.72474487139158;
     const double n0 = fma(fma(-0.87894730749888, x, 10.9243702330261) * g, u0, 0.275255128608411);
@@ -355,10 +360,10 @@ UNOMOL_HD void rys_t2<1>(double x, double *t2, double *w, const RysTables &T) {
     t2[0] = f1 / w[0];
 }
 
-template <>
-UNOMOL_HD void rys_t2<2>(double x, double *t2, double *w, const RysTables &T) {
-    const double xmom = T.rys2_exact ? (double)RYS_BOYS_XMAX : 15.0;
-    if (x <= xmom && x < (double)RYS_BOYS_XMAX) {
+// Two roots below the Gauss-Hermite limit (x <= 40 in parity mode, x < RYS_BOYS_XMAX in exact mode; callers that decide "far" on
+// their own -- eri_tile.cuh -- may be a rounding error beyond: the table rows and the band formula extend that far)
+UNOMOL_HD void rys2_near_t2(double x, double *t2, double *w, const RysTables &T) {
+    if (T.rys2_exact || x <= 15.0) {
         double m[4];
         boys_poly03(x, T.f3poly, m);
         // orthogonal polynomial D y^2 + n1 y + n0 in y = t^2 from the Hankel system [m0 m1; m1 m2] (c0, c1)^T = -(m2, m3)^T:
@@ -378,11 +383,15 @@ UNOMOL_HD void rys_t2<2>(double x, double *t2, double *w, const RysTables &T) {
         t2[1] = y1;
         w[1] = fma(-y0, m[0], m[1]) * D * iS;
         w[0] = m[0] - w[1];
-    } else if (!T.rys2_exact && x <= 40.0) {
-        rys2_compat_band_t2(x, t2, w, T.f3poly_glob);
     } else {
-        rys_hermite_limit_t2<2>(x, t2, w);
+        rys2_compat_band_t2(x, t2, w, T.expcol, T.exp_stride);
     }
+}
+
+template <>
+UNOMOL_HD void rys_t2<2>(double x, double *t2, double *w, const RysTables &T) {
+    if (T.rys2_exact ? x < (double)RYS_BOYS_XMAX : x <= 40.0) rys2_near_t2(x, t2, w, T);
+    else rys_hermite_limit_t2<2>(x, t2, w);
 }
 
 template <int N>
@@ -473,8 +482,9 @@ inline RysTables rys_host_tables(int rys2_exact = 0) {
     T.piece_hi[1] = rys_host::rys_piece7_tab;
     T.piece_hi[2] = rys_host::rys_piece8_tab;
     T.piece_hi[3] = rys_host::rys_piece9_tab;
+    T.expcol = T.f3poly_glob + RYS_FP_DEG + 1;
+    T.exp_stride = RYS_FP_STRIDE;
     T.rys2_exact = rys2_exact;
-    T.pad = 0;
     return T;
 }
 #endif

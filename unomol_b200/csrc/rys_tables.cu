@@ -25,6 +25,8 @@ cudaError_t rys_device_tables(RysTables *out) {
     out->f0poly = (const double *)p;
     if ((e = cudaGetSymbolAddress(&p, rys_f3poly_tab)) != cudaSuccess) return e;
     out->f3poly = out->f3poly_glob = (const double *)p;
+    out->expcol = out->f3poly_glob + RYS_FP_DEG + 1;
+    out->exp_stride = RYS_FP_STRIDE;
     if ((e = cudaGetSymbolAddress(&p, rys_piece3_tab)) != cudaSuccess) return e;
     out->piece[0] = (const double *)p;
     if ((e = cudaGetSymbolAddress(&p, rys_piece4_tab)) != cudaSuccess) return e;
@@ -40,7 +42,6 @@ cudaError_t rys_device_tables(RysTables *out) {
     if ((e = cudaGetSymbolAddress(&p, rys_piece9_tab)) != cudaSuccess) return e;
     out->piece_hi[3] = (const double *)p;
     out->rys2_exact = 0;
-    out->pad = 0;
     return cudaSuccess;
 }
 
