@@ -19,7 +19,9 @@
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
+#include <functional>
 #include <numeric>
+#include <vector>
 #include "engine.h"
 #include "eri_highl.cuh"
 
@@ -1114,6 +1116,20 @@ int unomol_b200_fock_uhf_device(unomol_b200_t *h, const double *dPA, const doubl
     return finish_stats(h);
 }
 
+// Host passes over the packed matrices of the host-pointer entry (staging copy of P, G += result): at 2002 functions they are
+// 16 MB each and, single-threaded, were ~5 ms of the 8 ms the host-pointer call costs over the device-resident one.  Large
+// matrices are cut into one range per worker thread; small ones (every molecule of the reference's test set) stay inline.
+static void host_ranges(size_t n, const std::function<void(size_t, size_t)> &fn) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t nt = n < (size_t)1 << 19 ? 1 : std::min<size_t>(8, hw ? hw : 1);
+    if (nt <= 1) { fn((size_t)0, n); return; }
+    std::vector<std::thread> th;
+    const size_t chunk = (n + nt - 1) / nt;
+    for (size_t t = 1; t < nt; ++t) th.emplace_back([=, &fn] { fn(std::min(n, t * chunk), std::min(n, (t + 1) * chunk)); });
+    fn((size_t)0, std::min(n, chunk));
+    for (auto &x : th) x.join();
+}
+
 static int fock_host(unomol_b200 *h, int nspin, const double *PA, const double *PB, double *GA, double *GB) {
     cudaSetDevice(h->device);
     int rc = ensure_buffers(h);
@@ -1122,7 +1138,9 @@ static int fock_host(unomol_b200 *h, int nspin, const double *PA, const double *
     const double *Ph[2] = {PA, PB};
     double *Gh[2] = {GA, GB};
     for (int s = 0; s < nspin; ++s) {
-        memcpy(h->h_pinned + s * no2, Ph[s], sizeof(double) * no2);
+        double *stage = h->h_pinned + s * no2;
+        const double *srcp = Ph[s];
+        host_ranges(no2, [=](size_t a, size_t b) { memcpy(stage + a, srcp + a, sizeof(double) * (b - a)); });
         CUDA_TRY(h, cudaMemcpyAsync(h->d_Ppacked[s], h->h_pinned + s * no2, sizeof(double) * no2, cudaMemcpyHostToDevice,
                                     h->stream));
     }
@@ -1135,7 +1153,7 @@ static int fock_host(unomol_b200 *h, int nspin, const double *PA, const double *
     for (int s = 0; s < nspin; ++s) {
         const double *src = h->h_pinned + (2 + s) * no2;
         double *dst = Gh[s];
-        for (size_t i = 0; i < no2; ++i) dst[i] += src[i];   // the reference accumulates into G
+        host_ranges(no2, [=](size_t a, size_t b) { for (size_t i = a; i < b; ++i) dst[i] += src[i]; });   // the reference accumulates into G
     }
     return finish_stats(h);
 }
