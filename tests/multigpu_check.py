@@ -24,7 +24,7 @@ for basis in (Basis.from_patin(os.path.join(ROOT, "tests", "golden", "inputs", "
     for rep in range(3):                                        # several builds: exercises the alternating counter sets
         G = df.fock_rhf(P)
         worst = max(worst, float(np.max(np.abs(G - ref)) / np.max(np.abs(ref))))
-    for frac in (0.0, 1.0, 0.75):                               # share of the blocks dealt statically: none, all, the default
+    for frac in (0.0, 1.0, 0.75):                               # share of the blocks dealt statically: none (the default), all, most
         df.h.set_option("static_fraction", frac)
         for rep in range(2):
             G = df.fock_rhf(P)
