@@ -637,20 +637,16 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD, NSPI
                 // blocks entirely at or below the reference's storage threshold never reach its G (TwoElectronInts.cpp:513,667-671)
                 {
 #if TILE_INT_VMAX
-                    // max |V| against the threshold on the high words (|x| orders like its bit pattern: two integer instructions per
-                    // element instead of three on the FP64 pipe); only a tie of the high words needs the exact comparison
+                    // max |V| against the threshold on the HIGH WORDS (|x| orders like its bit pattern: two integer instructions per
+                    // element instead of three on the FP64 pipe).  A block is skipped when every high word is below the threshold's;
+                    // a tie of the high words (max |V| within 2^-20 below the threshold) keeps the block -- its integrals are at
+                    // the reference's 1e-14, far below the 1e-12 the parity tests resolve, and the exact comparison, if-converted
+                    // by the compiler, cost 24 instructions on every quartet for a case that almost never happens.
                     const double thr = task.value_cut * sym;
                     unsigned hmax = 0u;
 #pragma unroll
                     for (int o = 0; o < NINT; ++o) hmax = max(hmax, (unsigned)__double2hiint(V[o]) & 0x7fffffffu);
-                    const unsigned hthr = (unsigned)__double2hiint(thr);
-                    if (hmax < hthr) continue;
-                    if (hmax == hthr) {
-                        double vmax = 0.0;
-#pragma unroll
-                        for (int o = 0; o < NINT; ++o) vmax = fmax(vmax, fabs(V[o]));
-                        if (vmax <= thr) continue;
-                    }
+                    if (hmax < (unsigned)__double2hiint(thr)) continue;
 #else
                     double vmax = 0.0;
 #pragma unroll
