@@ -430,7 +430,9 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD, NSPI
                         const double bpv = bp[ib].p;
                         const double txp = bpv + kp_;
                         TILE_STAT(++c_primq);
-                        const double pq0 = bp[ib].P[0] - kP0, pq1 = bp[ib].P[1] - kP1, pq2 = bp[ib].P[2] - kP2;
+                        const double bP0 = bp[ib].P[0], bP1 = bp[ib].P[1], bP2 = bp[ib].P[2];
+                        const double pq0 = bP0 - kP0, pq1 = bP1 - kP1, pq2 = bP2 - kP2;
+                        const double bPA0 = bp[ib].PA[0], bPA1 = bp[ib].PA[1], bPA2 = bp[ib].PA[2];
 #if TILE_FAR_SPLIT
                         // X = p q |PQ|^2 / (p + q).  Most primitive quartets of a large molecule are FAR (X beyond the asymptotic limit
                         // of the quadrature), and there every factor 1 / (p + q) cancels: sr w_i = k0 sqrt(pi/4) W_i (p q |PQ|^2)^(-1/2),
@@ -464,9 +466,9 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD, NSPI
                                 a = sr * w;
                                 bq = sr * f1 * kp_ * itx;
                             }
-                            acc[0] = fma(a, bp[ib].PA[0], fma(-bq, pq0, acc[0]));
-                            acc[1] = fma(a, bp[ib].PA[1], fma(-bq, pq1, acc[1]));
-                            acc[2] = fma(a, bp[ib].PA[2], fma(-bq, pq2, acc[2]));
+                            acc[0] = fma(a, bPA0, fma(-bq, pq0, acc[0]));
+                            acc[1] = fma(a, bPA1, fma(-bq, pq1, acc[1]));
+                            acc[2] = fma(a, bPA2, fma(-bq, pq2, acc[2]));
                         } else {
                             static_assert(NR == 2, "the tile kernels cover the classes with one and two roots");
                             double fr[NR], ws[NR];     // t_i^2 / (p + q) and sr w_i
@@ -506,9 +508,9 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD, NSPI
                             double w, f1;
                             rys1_f0f1(X, w, f1, rys);
                             const double a = sr * w, bq = sr * f1 * kp_ * itx;
-                            acc[0] = fma(a, bp[ib].PA[0], fma(-bq, pq0, acc[0]));
-                            acc[1] = fma(a, bp[ib].PA[1], fma(-bq, pq1, acc[1]));
-                            acc[2] = fma(a, bp[ib].PA[2], fma(-bq, pq2, acc[2]));
+                            acc[0] = fma(a, bPA0, fma(-bq, pq0, acc[0]));
+                            acc[1] = fma(a, bPA1, fma(-bq, pq1, acc[1]));
+                            acc[2] = fma(a, bPA2, fma(-bq, pq2, acc[2]));
                         } else {
                             double rt[NR], wt[NR];
                             rys_t2<NR>(X, rt, wt, rys);      // rt[] = t^2
@@ -525,7 +527,7 @@ __global__ void __launch_bounds__(TILE_THREADS, tile_minb(LA + LB, LC + LD, NSPI
                                 for (int ax = 0; ax < 3; ++ax) {
                                     const double pq = ax == 0 ? pq0 : (ax == 1 ? pq1 : pq2);
                                     const double kA = ax == 0 ? kA0 : (ax == 1 ? kA1 : kA2);
-                                    const double Cc = bp[ib].PA[ax] - kp_ * pq * fff;
+                                    const double Cc = (ax == 0 ? bPA0 : (ax == 1 ? bPA1 : bPA2)) - kp_ * pq * fff;
                                     const double Cp = kA + bpv * pq * fff;
                                     const double scale = (ax == 2) ? wsr : 1.0;
                                     g[ax][0][0] = scale;
